@@ -1,0 +1,163 @@
+"""Shared test helpers: fixture loading, the two CPU checkers (oracle restatement + compiled reference).
+
+Everything under oracle/ is TEST INFRASTRUCTURE: it is loaded here (tests), in __graft_entry__.smoke()
+and in bench.py's cpu_baseline / --impl reference legs only.
+"""
+import ctypes as C
+import hashlib
+import json
+import os
+import subprocess
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+ORACLE_DIR = os.path.join(ROOT, "oracle")
+
+
+def load_pnm(path):
+    """Minimal PNM reader with the reference loader's conventions (imageio_pnm.c:73-148):
+    maxval is NOT rescaled, PBM 1 -> 0 and 0 -> 255.  Returns (array HxW or HxWx3 u8, is_rgb)."""
+    data = open(path, "rb").read()
+    assert data[0:1] == b"P"
+    t = data[1] - ord("0")
+    pos = 2
+    nums = []
+    want = 2 if t in (1, 4) else 3
+
+    def next_number(pos):
+        while True:
+            ch = data[pos:pos + 1]
+            if ch == b"#":
+                while data[pos:pos + 1] not in (b"\r", b"\n", b""):
+                    pos += 1
+            elif ch.isdigit():
+                v = 0
+                while data[pos:pos + 1].isdigit():
+                    v = v * 10 + int(data[pos:pos + 1])
+                    pos += 1
+                return v, pos + 1          # the reference consumes one char after the number
+            elif ch == b"":
+                return -1, pos
+            pos += 1
+
+    last_ch_pos = pos
+    while len(nums) < want:
+        v, pos = next_number(pos)
+        nums.append(v)
+    w, h = nums[0], nums[1]
+    # skip to end of the header line (imageio_pnm.c:100-102)
+    if data[pos - 1:pos] != b"\n":
+        while data[pos:pos + 1] not in (b"\n", b""):
+            pos += 1
+        pos += 1
+    is_rgb = t in (3, 6)
+    n = w * h * (3 if is_rgb else 1)
+    if t in (5, 6):
+        arr = np.frombuffer(data, dtype=np.uint8, count=n, offset=pos).copy()
+    elif t == 4:
+        rowbytes = (w + 7) // 8
+        bits = np.unpackbits(np.frombuffer(data, dtype=np.uint8, count=rowbytes * h, offset=pos).reshape(h, rowbytes), axis=1)[:, :w]
+        arr = np.where(bits != 0, 0, 255).astype(np.uint8).reshape(-1)
+    else:
+        vals = []
+        while len(vals) < n:
+            v, pos = next_number(pos)
+            vals.append(v)
+        arr = np.array(vals, dtype=np.int64)
+        if t == 1:
+            arr = np.where(arr != 0, 0, 255)
+        arr = arr.astype(np.uint8)
+    return (arr.reshape(h, w, 3) if is_rgb else arr.reshape(h, w)), is_rgb
+
+
+def sha256(b):
+    return hashlib.sha256(bytes(b)).hexdigest()
+
+
+def golden_table():
+    with open(os.path.join(GOLDEN, "known_answers.json")) as f:
+        return json.load(f)
+
+
+def _build_oracle():
+    subprocess.run(["make", "-C", ORACLE_DIR, "-s"], check=True, capture_output=True)
+
+
+_libs = {}
+
+
+def oracle_lib():
+    """ctypes handle of oracle/liboracle.so (this repo's plain-C restatement)."""
+    if "oracle" not in _libs:
+        path = os.path.join(ORACLE_DIR, "liboracle.so")
+        if not os.path.exists(path):
+            _build_oracle()
+        lib = C.CDLL(path)
+        lib.oracle_jls_encode.restype = C.c_size_t
+        lib.oracle_jls_encode.argtypes = [C.c_void_p, C.c_int, C.c_uint32, C.c_uint32, C.c_int, C.c_void_p, C.c_size_t]
+        if hasattr(lib, "oracle_hevc_encode"):
+            lib.oracle_hevc_encode.restype = C.c_long
+            lib.oracle_hevc_encode.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int), C.c_int]
+        _libs["oracle"] = lib
+    return _libs["oracle"]
+
+
+def ref_lib():
+    """ctypes handle of oracle/_ref/libimcvt_ref.so (the UNMODIFIED reference, compiled by oracle/Makefile),
+    or None when it has not been built (it can only be built where /root/reference exists)."""
+    if "ref" not in _libs:
+        path = os.path.join(ORACLE_DIR, "_ref", "libimcvt_ref.so")
+        if not os.path.exists(path) and os.path.isdir("/root/reference/src"):
+            _build_oracle()
+        if not os.path.exists(path):
+            _libs["ref"] = None
+        else:
+            lib = C.CDLL(path)
+            lib.ref_jls_encode.restype = C.c_size_t
+            lib.ref_jls_encode.argtypes = [C.c_void_p, C.c_int, C.c_uint32, C.c_uint32, C.c_int, C.c_void_p, C.c_size_t]
+            lib.HEVCImageEncoder.restype = C.c_int
+            lib.HEVCImageEncoder.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int), C.c_int]
+            _libs["ref"] = lib
+    return _libs["ref"]
+
+
+def _jls_call(fn, img, near):
+    img = np.ascontiguousarray(img, dtype=np.uint8)
+    is_rgb = int(img.ndim == 3)
+    h, w = img.shape[:2]
+    cap = 8 * h * w * (3 if is_rgb else 1) + 65536
+    out = np.empty(cap, dtype=np.uint8)
+    n = fn(img.ctypes.data, is_rgb, h, w, near, out.ctypes.data, cap)
+    assert n > 0
+    return out[:n].tobytes()
+
+
+def oracle_jls(img, near):
+    return _jls_call(oracle_lib().oracle_jls_encode, img, near)
+
+
+def ref_jls(img, near):
+    return _jls_call(ref_lib().ref_jls_encode, img, near)
+
+
+def _hevc_call(fn, img, qpd6):
+    img = np.ascontiguousarray(img, dtype=np.uint8)
+    assert img.ndim == 2
+    h, w = img.shape
+    hp, wp = (min(h, 8192) + 31) // 32 * 32, (min(w, 8192) + 31) // 32 * 32
+    out = np.zeros(2 * (wp + 32) * (hp + 32) + 65536, dtype=np.uint8)
+    rcon = np.zeros(hp * wp + 64, dtype=np.uint8)
+    ch, cw = C.c_int(h), C.c_int(w)
+    n = fn(out.ctypes.data, img.ctypes.data, rcon.ctypes.data, C.byref(ch), C.byref(cw), qpd6)
+    assert n > 0 and ch.value == hp and cw.value == wp
+    return out[:n].tobytes(), rcon[:hp * wp].reshape(hp, wp).copy()
+
+
+def oracle_hevc(img, qpd6):
+    return _hevc_call(oracle_lib().oracle_hevc_encode, img, qpd6)
+
+
+def ref_hevc(img, qpd6):
+    return _hevc_call(ref_lib().HEVCImageEncoder, img, qpd6)
