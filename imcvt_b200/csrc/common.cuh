@@ -1,0 +1,70 @@
+// common.cuh -- engine context, device workspace, launch instrumentation (host side) for libimcvt_b200.so
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stddef.h>
+#include <stdio.h>
+#include <string>
+#include <vector>
+#include <map>
+
+namespace imcvt {
+
+void set_error(const char *fmt, ...);
+
+#define IMCVT_CUDA(call)                                                                        \
+    do {                                                                                        \
+        cudaError_t e__ = (call);                                                               \
+        if (e__ != cudaSuccess) {                                                               \
+            imcvt::set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e__)); \
+            return 1;                                                                           \
+        }                                                                                       \
+    } while (0)
+
+// One growable device allocation carved into aligned sub-buffers per call (bump allocator).
+// Kept across calls so steady-state encoding does no cudaMalloc.
+struct Workspace {
+    char  *base = nullptr;
+    size_t cap = 0, used = 0;
+    int reserve(size_t bytes);                      // grow (frees + reallocates) if needed; resets the bump pointer
+    void reset() { used = 0; }
+    template <class T> T *take(size_t count) {      // 256-byte aligned slice; nullptr on overflow
+        size_t bytes = (count * sizeof(T) + 255) & ~(size_t)255;
+        if (used + bytes > cap) return nullptr;
+        T *p = reinterpret_cast<T *>(base + used);
+        used += bytes;
+        return p;
+    }
+    void release();
+};
+
+struct KernelStat { int launches = 0; double ms = 0.0; };
+
+struct Engine {
+    int device = -1;
+    bool ready = false;
+    Workspace ws;           // scratch for the device pipelines
+    Workspace io;           // staging for the host-buffer entry points (frames in, streams out)
+    cudaStream_t stream = nullptr;      // engine-owned stream for the host-buffer entry points
+    bool profile = false;
+    long launches = 0;
+    std::map<std::string, KernelStat> stats;
+    struct Pending { std::string name; cudaEvent_t a, b; };
+    std::vector<Pending> pending;
+    std::vector<cudaEvent_t> event_pool;
+    bool jls_force_serial = false;
+    int sm_count = 148;
+};
+
+Engine &engine();
+int ensure_engine();
+
+// RAII bracket around one kernel launch: counts it and (when profiling) times it with events on `s`.
+struct LaunchScope {
+    cudaStream_t s; const char *name; cudaEvent_t a = nullptr, b = nullptr;
+    LaunchScope(const char *name_, cudaStream_t s_);
+    ~LaunchScope();
+};
+void profile_collect();     // resolves pending event pairs (synchronises on them)
+
+}  // namespace imcvt

@@ -1,0 +1,88 @@
+/* imcvt_b200.h -- C-ABI of the B200-native encode engine (libimcvt_b200.so).
+ *
+ * Drop-in boundary for the two compute-bound paths of WangXuan95/ImCvt:
+ *   - JPEG-LS encoder   (reference: src/imageio_jls.c)
+ *   - H.265 intra encoder (reference: src/HEVCe/HEVCe.c, wrapper src/imageio_hevc.c)
+ *
+ * Plain C linkage, plain pointers and sizes, no torch / C++ types.  All functions are synchronous at
+ * return unless they take a `stream`.  Every function returns 0 on success and non-zero on failure
+ * (the reference's convention, src/imageio.h:15); imcvtLastError() gives the reason.  There is NO CPU
+ * fallback: without a CUDA device every encode entry point fails.
+ *
+ * The reference-compatible file API (writeJLSImageFile / writeHEVCImageFile / HEVCImageEncoder) is
+ * declared in imcvt_imageio.h and exported by the same library.
+ */
+#ifndef IMCVT_B200_H
+#define IMCVT_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- life cycle ------------------------------------------------------------------------------ */
+int         imcvtInit(int device);          /* optional: binds the engine to a CUDA device (default: current) */
+void        imcvtShutdown(void);            /* frees the device workspace */
+const char *imcvtLastError(void);           /* message of the last failure on this thread */
+int         imcvtVersion(void);
+
+/* ---- sizes ----------------------------------------------------------------------------------- */
+/* Upper bound of one encoded JPEG-LS image: the reference's own allocation bound 8*W*H+65536
+ * (src/imageio_jls.c:439) is far above what 8-bit data can produce; the engine guarantees
+ * len <= imcvtJLSBound().  is_rgb: 0 gray8, 1 RGB24. */
+size_t imcvtJLSBound(int is_rgb, uint32_t height, uint32_t width);
+/* Upper bound of one encoded HEVC picture = the reference's stream allocation (src/imageio_hevc.c:14). */
+size_t imcvtHEVCBound(uint32_t height, uint32_t width);
+
+/* ---- JPEG-LS, batch, host buffers (replaces N calls of writeJLSImageFile's codec part,
+ *      src/imageio_jls.c:428-465: same pixels in, same .jls bytes out) -------------------------------
+ * frames      : n images, image i at frames + i*frame_stride, interleaved u8 H*W (gray) or H*W*3 (RGB)
+ * near        : 0..4 (NEAR); 0 = lossless
+ * out         : n output slots, slot i at out + i*out_stride, each >= imcvtJLSBound() bytes is always enough
+ * out_len[i]  : bytes produced for image i
+ * Bad dimensions (outside 1..32767, src/imageio_jls.c:436) or a too small slot fail the call. */
+int imcvtEncodeBatchJLS(const uint8_t *frames, size_t frame_stride, int n, int is_rgb,
+                        uint32_t height, uint32_t width, int near_,
+                        uint8_t *out, size_t out_stride, size_t *out_len);
+
+/* Same, but `d_frames`, `d_out`, `d_out_len` (uint64 per image) are DEVICE pointers and the work is queued
+ * on `stream` (a cudaStream_t passed as void*; NULL = default stream) without synchronising. */
+int imcvtEncodeBatchJLSDevice(const void *d_frames, size_t frame_stride, int n, int is_rgb,
+                              uint32_t height, uint32_t width, int near_,
+                              void *d_out, size_t out_stride, void *d_out_len, void *stream);
+
+/* ---- H.265 intra, batch (replaces N calls of HEVCImageEncoder, src/HEVCe/HEVCe.h:5-12) ---------------
+ * frames      : n gray8 images H*W, image i at frames + i*frame_stride
+ * qpd6        : 0..4  (QP = 6*qpd6 + 4, src/HEVCe/HEVCe.c:727)
+ * out/out_len : as above, slot >= imcvtHEVCBound()
+ * rcon        : optional (may be NULL): n reconstructed pictures of the PADDED size
+ *               (ceil32(H) x ceil32(W)), picture i at rcon + i*rcon_stride */
+int imcvtEncodeBatchHEVC(const uint8_t *frames, size_t frame_stride, int n,
+                         uint32_t height, uint32_t width, int qpd6,
+                         uint8_t *out, size_t out_stride, size_t *out_len,
+                         uint8_t *rcon, size_t rcon_stride);
+
+int imcvtEncodeBatchHEVCDevice(const void *d_frames, size_t frame_stride, int n,
+                               uint32_t height, uint32_t width, int qpd6,
+                               void *d_out, size_t out_stride, void *d_out_len,
+                               void *d_rcon, size_t rcon_stride, void *stream);
+
+/* ---- instrumentation ------------------------------------------------------------------------- */
+/* When enabled, every kernel launch of the engine is bracketed by CUDA events on its own stream;
+ * imcvtProfileGet() returns launch count and summed device milliseconds per kernel name
+ * ("jls_chain", "hevc_frame", ...).  Used by bench.py for the roofline line. */
+void imcvtProfileEnable(int on);
+void imcvtProfileReset(void);
+int  imcvtProfileGet(const char *kernel, int *launches, double *total_ms);
+int  imcvtProfileList(char *buf, size_t cap);        /* "name:launches:ms\n..." */
+long imcvtLaunchCount(void);                         /* total kernels launched since ProfileReset */
+
+/* Debug / cross-check: force the fully serial JPEG-LS scan kernel also for NEAR=0 (default 0). */
+void imcvtDebugJLSForceSerial(int on);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* IMCVT_B200_H */

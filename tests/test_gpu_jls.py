@@ -1,0 +1,121 @@
+"""GPU: parity of the CUDA JPEG-LS path (through the C-ABI) with the oracle and the golden fixtures."""
+import os
+import tempfile
+
+import numpy as np
+import pytest
+
+import imcvt_b200
+from imcvt_b200 import synth
+from tests._util import GOLDEN, golden_table, load_pnm, oracle_jls, sha256
+from tests.test_oracle_jls import edge_images
+
+pytestmark = pytest.mark.gpu
+
+
+def first_diff(a, b):
+    n = min(len(a), len(b))
+    for i in range(n):
+        if a[i] != b[i]:
+            return f"first difference at byte {i} of {len(a)}/{len(b)}"
+    return f"lengths differ: {len(a)} vs {len(b)}"
+
+
+def check(img, near):
+    got = imcvt_b200.encode_jls_batch(img[None], near)[0]
+    want = oracle_jls(img, near)
+    assert got == want, first_diff(got, want)
+
+
+@pytest.mark.parametrize("serial", [False, True], ids=["pipeline", "serial"])
+@pytest.mark.parametrize("entry", [e for e in golden_table() if e["codec"] == "jls"],
+                         ids=lambda e: f"{e['fixture']}-near{e['setting']}")
+def test_known_answers(entry, serial):
+    img, _ = load_pnm(os.path.join(GOLDEN, entry["fixture"] + ".pnm"))
+    imcvt_b200.debug_jls_force_serial(serial)
+    try:
+        s = imcvt_b200.encode_jls_batch(img[None], entry["setting"])[0]
+    finally:
+        imcvt_b200.debug_jls_force_serial(False)
+    assert len(s) == entry["length"]
+    assert sha256(s) == entry["sha256"]
+
+
+@pytest.mark.parametrize("near", [0, 1, 2, 3, 4])
+def test_edge_cases_match_oracle(near):
+    for name, img in edge_images():
+        got = imcvt_b200.encode_jls_batch(img[None], near)[0]
+        want = oracle_jls(img, near)
+        assert got == want, f"{name}: {first_diff(got, want)}"
+
+
+def test_random_shapes_lossless():
+    rng = np.random.default_rng(11)
+    for _ in range(40):
+        h, w = int(rng.integers(1, 70)), int(rng.integers(1, 300))
+        kind = rng.integers(0, 4)
+        if kind == 0:
+            img = rng.integers(0, 256, (h, w), dtype=np.uint8)
+        elif kind == 1:
+            img = rng.integers(0, 4, (h, w), dtype=np.uint8) * 85          # few levels: many runs + interruptions
+        elif kind == 2:
+            img = np.repeat(rng.integers(0, 256, (h, (w + 15) // 16), dtype=np.uint8), 16, axis=1)[:, :w].copy()
+        else:
+            img = (rng.integers(0, 2, (h, w)) * 255).astype(np.uint8)       # 0xFF stuffing stress
+        check(img, 0)
+
+
+def test_batch_of_synthetic_frames_all_kinds():
+    for kind in ["natural", "texture", "noise", "constant"]:
+        frames = synth.batch(kind, 3, 135, 240)
+        got = imcvt_b200.encode_jls_batch(frames, 0)
+        for i in range(3):
+            want = oracle_jls(frames[i], 0)
+            assert got[i] == want, f"{kind}[{i}]: {first_diff(got[i], want)}"
+
+
+def test_rgb_batch_lossless_and_lossy():
+    frames = synth.batch("natural", 2, 90, 160, rgb=True)
+    for near in (0, 2):
+        got = imcvt_b200.encode_jls_batch(frames, near)
+        for i in range(2):
+            want = oracle_jls(frames[i], near)
+            assert got[i] == want, f"near={near}[{i}]: {first_diff(got[i], want)}"
+
+
+def test_full_hd_frame_matches_oracle():
+    for kind in ["natural", "texture"]:
+        f = synth.frame(kind, 5, 1080, 1920)
+        check(f, 0)
+
+
+def test_serial_kernel_equals_pipeline_at_full_size():
+    frames = synth.batch("natural", 4, 1080, 1920)
+    a = imcvt_b200.encode_jls_batch(frames, 0)
+    imcvt_b200.debug_jls_force_serial(True)
+    try:
+        b = imcvt_b200.encode_jls_batch(frames, 0)
+    finally:
+        imcvt_b200.debug_jls_force_serial(False)
+    assert a == b
+
+
+def test_write_jls_image_file_is_a_drop_in():
+    img, _ = load_pnm(os.path.join(GOLDEN, "P5.pnm"))
+    entry = [e for e in golden_table() if e["codec"] == "jls" and e["fixture"] == "P5" and e["setting"] == 0][0]
+    with tempfile.TemporaryDirectory() as d:
+        path = os.path.join(d, "a.jls")
+        assert imcvt_b200.write_jls_image_file(path, img, 0, img.shape[0], img.shape[1], 0) == 0
+        assert sha256(open(path, "rb").read()) == entry["sha256"]
+        # reference error behaviour: bad dimensions -> 1, nothing written (imageio_jls.c:436)
+        bad = os.path.join(d, "b.jls")
+        assert imcvt_b200.write_jls_image_file(bad, img, 0, 0, 10, 0) == 1
+        assert not os.path.exists(bad)
+        # unwritable path -> 1 (imageio_jls.c:467-472)
+        assert imcvt_b200.write_jls_image_file(os.path.join(d, "no/such/dir.jls"), img, 0, img.shape[0], img.shape[1], 0) == 1
+
+
+def test_small_output_slot_is_an_error_not_a_crash():
+    img = np.random.default_rng(1).integers(0, 256, (64, 64), dtype=np.uint8)
+    with pytest.raises(imcvt_b200.ImcvtError):
+        imcvt_b200.encode_jls_batch(img[None], 0, out_stride=512)
