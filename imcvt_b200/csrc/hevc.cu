@@ -1,9 +1,58 @@
-// hevc.cu -- H.265 intra encoder for sm_100a (placeholder until the frame kernel lands)
+// hevc.cu -- host side of the H.265 intra encoder: workspace carving and the launch of hevc_frame_kernel
+// (device code: hevc_kernel.cuh).  Replaces the codec part of writeHEVCImageFile / HEVCImageEncoder
+// (reference: src/imageio_hevc.c:9-53, src/HEVCe/HEVCe.c:1569-1646).
 #include "common.cuh"
-namespace imcvt { namespace hevc {
-int encode_device(const uint8_t *, size_t, int, uint32_t, uint32_t, int, uint8_t *, size_t, uint64_t *, uint8_t *, size_t, int *, cudaStream_t)
+#include "../../include/imcvt_b200.h"
+#include "hevc_kernel.cuh"
+
+namespace imcvt {
+namespace hevc {
+
+static inline int pad32(uint32_t v) { uint32_t c = v > 8192 ? 8192 : v; return (int)((c + 31) / 32 * 32); }   // HEVCe.c:1580-1581
+
+// d_frames: device, n gray8 images.  d_out / d_out_len / d_rcon (optional): device.  Queues everything on `st`.
+int encode_device(const uint8_t *d_frames, size_t frame_stride, int n, uint32_t H, uint32_t W, int qpd6,
+                  uint8_t *d_out, size_t out_stride, uint64_t *d_out_len, uint8_t *d_rcon, size_t rcon_stride,
+                  int *d_overflow, cudaStream_t st)
 {
-    set_error("HEVC device path not built yet");
-    return 1;
+    Engine &E = engine();
+    const int hp = pad32(H), wp = pad32(W);
+    const size_t rbytes = (size_t)hp * wp;
+    if (d_rcon && rcon_stride < rbytes) { set_error("rcon_stride smaller than one padded picture"); return 1; }
+    if (out_stride > 0xFFFFFFFFull) out_stride = 0xFFFFFFFFull;             // stream positions are 32-bit inside the kernel
+
+    static bool attr_set = false;
+    if (!attr_set) {
+        IMCVT_CUDA(cudaFuncSetAttribute(hevc_frame_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem)));
+        attr_set = true;
+    }
+    const int grid = n < E.sm_count ? n : E.sm_count;                       // one CTA per SM; frames come from a queue
+    const size_t rstride = (rbytes + 255) & ~(size_t)255;
+    size_t bytes = 4096 + (size_t)grid * NMODE * SCR_BYTES + 256;
+    if (!d_rcon) bytes += (size_t)n * rstride + 256;
+    if (E.ws.reserve(bytes)) return 1;
+    uint8_t *scratch = E.ws.take<uint8_t>((size_t)grid * NMODE * SCR_BYTES);
+    int *next = E.ws.take<int>(1);
+    uint8_t *rc = d_rcon;
+    size_t rcs = rcon_stride;
+    if (!rc) { rc = E.ws.take<uint8_t>((size_t)n * rstride); rcs = rstride; }
+    if (!scratch || !next || !rc) { set_error("workspace carve failed"); return 1; }
+    IMCVT_CUDA(cudaMemsetAsync(next, 0, sizeof(int), st));
+
+    Params P;
+    P.frames = d_frames; P.frame_stride = frame_stride;
+    P.n = n; P.H = (int)H; P.W = (int)W; P.hp = hp; P.wp = wp; P.qpd6 = qpd6;
+    P.out = d_out; P.out_stride = out_stride;
+    P.out_len = (unsigned long long *)d_out_len;
+    P.rcon = rc; P.rcon_stride = rcs;
+    P.scratch = scratch; P.overflow = d_overflow; P.next_frame = next;
+    {
+        LaunchScope ls("hevc_frame", st);
+        hevc_frame_kernel<<<grid, NT, sizeof(Smem), st>>>(P);
+    }
+    IMCVT_CUDA(cudaGetLastError());
+    return 0;
 }
-}}
+
+}  // namespace hevc
+}  // namespace imcvt

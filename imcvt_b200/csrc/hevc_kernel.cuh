@@ -1,0 +1,1241 @@
+// hevc_kernel.cuh -- H.265/HEVC intra-frame encoder kernel for sm_100a (device code only).
+//
+// Replaces HEVCImageEncoder and everything below it (reference: src/HEVCe/HEVCe.c:177-1646): 8-bit luma,
+// CTU 32, CU 32/16/8, TU 32..4, 35 intra modes, exhaustive RD search driven by REAL CABAC trial encodes,
+// simplified RDOQ.  Streams and reconstructions are bit-identical to the reference.
+//
+// Mapping: one CTA per frame walks the CTUs in raster order -- the picture has ONE
+// arithmetic coder and ONE adaptive context set (:1577-1578) whose exact bit counts feed every decision (:1437),
+// so CTUs of a frame form a chain.  Inside a CU the 35 modes are the parallel axis:
+//   phase A  warp-cooperative TU pipelines (32/TS transform units per warp, a lane owns a column, then a row):
+//            reference samples + smoothing (:196-257), prediction (:262-381), residual, forward transform
+//            (:497-516) as register partial butterflies, RDOQ (:540-594), de-quantisation (:599-614), inverse
+//            transform, reconstruction, SSE, last significant position / coefficient-group mask;
+//   phase B  one thread per candidate (spread across warps): CABAC trial encode from the CU's entry state
+//            (:1422-1423), bytes into a private scratch stream so emulation-prevention bytes count (:834);
+//   decide   reference candidate order, `>=` tie rule (:1439,1475,1520,1545); the winner's coder state, bytes,
+//            reconstruction and size/mode maps are committed.
+//
+// The file is also compiled for the host by tests/emu (a fiber SIMT emulator, test infrastructure only) so the
+// kernel logic is checked against the oracle in the CPU test tier.
+#pragma once
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef IMCVT_HOST_EMU
+#define IMCVT_CONSTANT static const
+#define IMCVT_DYN_SMEM() (emu::S().smem)
+#else
+#define IMCVT_CONSTANT __constant__ const
+extern __shared__ __align__(16) unsigned char imcvt_dyn_smem[];
+#define IMCVT_DYN_SMEM() (imcvt_dyn_smem)
+#endif
+
+namespace imcvt {
+namespace hevc {
+
+#include "hevc_tables.h"
+
+constexpr int NW = 12;                  // warps per CTA
+constexpr int NT = NW * 32;
+constexpr int NMODE = 35;
+constexpr int CTU = 32;
+constexpr int RCP = 72;                 // row pitch of the CTU reconstruction window (1 + 64 columns used)
+constexpr int LEV_STRIDE = 1152;        // int16 per candidate: one 32x(32+2) block or four 16x(16+2) blocks
+constexpr int REC_STRIDE = 1024;        // bytes per candidate reconstruction tile
+constexpr int WS_STRIDE = 32 * 34;      // int16 per warp: transpose scratch
+constexpr int REFS_BYTES = 448;         // per warp: reference samples of its transform units
+constexpr int CXN = 142, CXP = 144;     // context bytes (padded to words)
+constexpr int SCR_BYTES = 8192;         // private trial stream per candidate (reference bound: 3200, :794)
+constexpr int I32MAX = 0x7fffffff;
+constexpr int NSCAN = 1520;
+
+// context offsets: member order of the reference's ContextSet (:744-758)
+enum { CX_SPLIT_CU = 0, CX_PART = 3, CX_YMODE = 4, CX_UVMODE = 5, CX_SPLIT_TU = 6, CX_YCBF = 9, CX_UVCBF = 11,
+       CX_LASTX = 16, CX_LASTY = 41, CX_SIGCG = 66, CX_SIG = 68, CX_ONE = 112, CX_ABS = 136 };
+
+IMCVT_CONSTANT int c_dst4[4][4] = { {29, 55, 74, 84}, {74, 74, 0, -74}, {84, -29, -74, 55}, {55, -84, 74, -29} };   // :391-396
+IMCVT_CONSTANT signed char c_angle[35] = {0, 0, 32, 26, 21, 17, 13, 9, 5, 2, 0, -2, -5, -9, -13, -17, -21, -26, -32, -26, -21, -17, -13, -9, -5, -2, 0, 2, 5, 9, 13, 17, 21, 26, 32};
+IMCVT_CONSTANT short c_invang[35] = {0, 0, 256, 315, 390, 482, 630, 910, 1638, 4096, 0, 4096, 1638, 910, 630, 482, 390, 315, 256, 315, 390, 482, 630, 910, 1638, 4096, 0, 4096, 1638, 910, 630, 482, 390, 315, 256};
+IMCVT_CONSTANT int c_wd[5] = {11, 11, 11, 5, 1};             // calcRDcost weights :178-179
+IMCVT_CONSTANT int c_wb[5] = {1, 4, 16, 29, 23};
+
+// CABAC tables (:700-714); copied to shared memory at kernel start because lanes index them divergently
+IMCVT_CONSTANT unsigned char c_next_lps[128] = {1,0,0,1,2,3,4,5,4,5,8,9,8,9,10,11,12,13,14,15,16,17,18,19,18,19,22,23,22,23,24,25,26,27,26,27,30,31,30,31,32,33,32,33,36,37,36,37,38,39,38,39,42,43,42,43,44,45,44,45,46,47,48,49,48,49,50,51,52,53,52,53,54,55,54,55,56,57,58,59,58,59,60,61,60,61,60,61,62,63,64,65,64,65,66,67,66,67,66,67,68,69,68,69,70,71,70,71,70,71,72,73,72,73,72,73,74,75,74,75,74,75,76,77,76,77,126,127};
+IMCVT_CONSTANT unsigned char c_lps[64][4] = {
+  {128,176,208,240},{128,167,197,227},{128,158,187,216},{123,150,178,205},{116,142,169,195},{111,135,160,185},{105,128,152,175},{100,122,144,166},
+  { 95,116,137,158},{ 90,110,130,150},{ 85,104,123,142},{ 81, 99,117,135},{ 77, 94,111,128},{ 73, 89,105,122},{ 69, 85,100,116},{ 66, 80, 95,110},
+  { 62, 76, 90,104},{ 59, 72, 86, 99},{ 56, 69, 81, 94},{ 53, 65, 77, 89},{ 51, 62, 73, 85},{ 48, 59, 69, 80},{ 46, 56, 66, 76},{ 43, 53, 63, 72},
+  { 41, 50, 59, 69},{ 39, 48, 56, 65},{ 37, 45, 54, 62},{ 35, 43, 51, 59},{ 33, 41, 48, 56},{ 32, 39, 46, 53},{ 30, 37, 43, 50},{ 29, 35, 41, 48},
+  { 27, 33, 39, 45},{ 26, 31, 37, 43},{ 24, 30, 35, 41},{ 23, 28, 33, 39},{ 22, 27, 32, 37},{ 21, 26, 30, 35},{ 20, 24, 29, 33},{ 19, 23, 27, 31},
+  { 18, 22, 26, 30},{ 17, 21, 25, 28},{ 16, 20, 23, 27},{ 15, 19, 22, 25},{ 14, 18, 21, 24},{ 14, 17, 20, 23},{ 13, 16, 19, 22},{ 12, 15, 18, 21},
+  { 12, 14, 17, 20},{ 11, 14, 16, 19},{ 11, 13, 15, 18},{ 10, 12, 15, 17},{ 10, 12, 14, 16},{  9, 11, 13, 15},{  9, 11, 12, 14},{  8, 10, 12, 14},
+  {  8,  9, 11, 13},{  7,  9, 11, 12},{  7,  9, 10, 12},{  7,  8, 10, 11},{  6,  8,  9, 11},{  6,  7,  9, 10},{  6,  7,  8,  9},{  2,  2,  2,  2}};
+IMCVT_CONSTANT unsigned char c_ctx_init[CXN] = {           // newContextSet :762-776
+    139, 141, 157,  184,  184,  63,  153, 138, 138,  111, 141,  94, 138, 182, 154, 154,
+    110, 110, 124, 0, 0,  125, 140, 153, 0, 0,  125, 127, 140, 109, 0,  111, 143, 127, 111, 79,  108, 123, 63, 154, 0,
+    110, 110, 124, 0, 0,  125, 140, 153, 0, 0,  125, 127, 140, 109, 0,  111, 143, 127, 111, 79,  108, 123, 63, 154, 0,
+    91, 171,
+    111, 111, 125, 110, 110, 94, 124, 108, 124, 107, 125, 141, 179, 153, 125, 107, 125, 141, 179, 153, 125, 107, 125, 141, 179, 153, 125, 141, 140, 139, 182, 182, 152, 136, 152, 136, 153, 136, 139, 111, 136, 139, 111, 111,
+    140, 92, 137, 138, 140, 152, 138, 139, 153, 74, 149, 92, 139, 107, 122, 152, 140, 179, 166, 182, 140, 227, 122, 197,
+    138, 153, 136, 167, 152, 152 };
+// fixed parameter sets (putHeaderToBuffer :664-690)
+IMCVT_CONSTANT unsigned char c_vps[27] = {0x00,0x00,0x01,0x40,0x01,0x0C,0x01,0xFF,0xFF,0x03,0x10,0x00,0x00,0x03,0x00,0x00,0x03,0x00,0x00,0x03,0x00,0x00,0x03,0x00,0xB4,0xF0,0x24};
+IMCVT_CONSTANT unsigned char c_sps[22] = {0x00,0x00,0x01,0x42,0x01,0x01,0x03,0x10,0x00,0x00,0x03,0x00,0x00,0x03,0x00,0x00,0x03,0x00,0x00,0x03,0x00,0xB4};
+IMCVT_CONSTANT unsigned char c_pps[11] = {0x00,0x00,0x01,0x44,0x01,0xC0,0x90,0x91,0x81,0xD9,0x20};
+IMCVT_CONSTANT unsigned char c_slice_head[6] = {0x00,0x00,0x01,0x26,0x01,0xAC};
+IMCVT_CONSTANT unsigned char c_slice_tail[5][2] = {{0x16,0xDE},{0x10,0xDE},{0x2B,0x78},{0x4D,0xE0},{0x97,0x80}};
+
+// ------------------------------------------------------------------------------------------------
+// kernel parameters and shared-memory layout
+// ------------------------------------------------------------------------------------------------
+struct Params {
+    const uint8_t *frames; size_t frame_stride;     // n gray8 images H x W
+    int n, H, W, hp, wp, qpd6;                       // hp, wp: padded to x32 (and clipped to 8192, :1580-1581)
+    uint8_t *out; size_t out_stride;                 // output slots
+    unsigned long long *out_len;                     // [n]
+    uint8_t *rcon; size_t rcon_stride;               // [n][hp*wp] reconstruction (also the line buffer between CTU rows)
+    uint8_t *scratch;                                // [gridDim.x][NMODE][SCR_BYTES] private trial streams
+    int *overflow;                                   // set to 1 when a stream did not fit its slot
+    int *next_frame;                                 // dynamic frame queue
+};
+
+struct CoderRegs { int range, low, nbits, pending, held, zeros; unsigned nout; int pad_; };
+
+struct Smem {
+    short lev[NMODE][LEV_STRIDE];                   // quantised levels of the candidates
+    short ws[NW][WS_STRIDE];                        // per-warp transpose scratch
+    uint8_t rec[NMODE][REC_STRIDE];                 // candidate prediction -> reconstruction tiles
+    uint8_t refs[NW][REFS_BYTES];
+    uint8_t cctx[NMODE][CXP];                       // candidate context sets
+    CoderRegs ccoder[NMODE];
+    int cbits[NMODE], csse[NMODE];
+    int clast[NMODE][4];
+    unsigned ccg[NMODE][4][2];
+    short cmag[NMODE][16];
+    // CTU state
+    uint8_t orig[CTU][CTU];
+    uint8_t rc[CTU + 1][RCP];                       // reconstruction window: row 0 / column 0 are the neighbours (:1588-1589)
+    uint8_t msz[9][12], mmd[9][12];                 // CU size / luma mode per 4x4 cell; row 0 / column 0 = above / left CTU
+    uint8_t left_sz[8], left_md[8];                 // right-most column of the previous CTU
+    uint8_t best_rec[CTU * CTU + 16 * 16 + 8 * 8];  // best reconstruction so far per CU level
+    uint8_t nxn_rec[8 * 8];
+    short nxn_lev[4][4 * 6];
+    int nxn_mode[4], nxn_last[4];
+    unsigned nxn_cg[4];
+    CoderRegs cur, entry[3];
+    uint8_t cur_ctx[CXP], entry_ctx[3][CXP], init_ctx[CXP];
+    int best_cost[3];
+    int win, red[NW];
+    uint8_t lps[256], next_lps[128];
+    uint8_t scan[NSCAN][2];                         // coefficient scans (y, x): see scan_base()
+    uint8_t dord[4][64][2];                         // up-right diagonal orders of 1, 2x2, 4x4, 8x8 grids
+    uint8_t above_sz[2048];                         // CU sizes along the bottom of the CTU row above (4x4 cells)
+};
+
+// ------------------------------------------------------------------------------------------------
+// small helpers
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
+__device__ __forceinline__ int clip16(int v) { return clampi(v, -32768, 32767); }
+__device__ __forceinline__ int iabs(int v) { return v < 0 ? -v : v; }
+template <int TS> struct SizeClass { static constexpr int v = TS == 4 ? 0 : TS == 8 ? 1 : TS == 16 ? 2 : 3; };
+__device__ __forceinline__ int size_class(int sz) { return sz == 4 ? 0 : sz == 8 ? 1 : sz == 16 ? 2 : 3; }
+
+__device__ __forceinline__ int rd_cost(int qpd6, int dist, int bits)                   // calcRDcost :177-185
+{
+    const int wd = c_wd[qpd6], wb = c_wb[qpd6];
+    const int c1 = (I32MAX / wd <= dist) ? I32MAX : wd * dist;
+    const int c2 = (I32MAX / wb <= bits) ? I32MAX : wb * bits;
+    return (I32MAX - c1 <= c2) ? I32MAX : c1 + c2;
+}
+
+__device__ __forceinline__ int level_rate(int level)                                   // estimateCoeffRate :526-535
+{
+    if (level < 6) {
+        return level == 0 ? 0 : level == 1 ? 70000 : level == 2 ? 90000 : level == 3 ? 92000 : level == 4 ? 157536 : 190304;
+    }
+    const int i = 31 - __clz(level - 5);                // number of exp-Golomb prefix steps for level - 6
+    return 92000 + ((3 + i * 2 + 1) << 15);
+}
+
+__device__ __forceinline__ int scan_type_for(int sz, int mode)                         // getScanOrder :1133-1150
+{
+    if (sz <= 8) {
+        if (iabs(mode - 26) <= 4) return 1;
+        if (iabs(mode - 10) <= 4) return 2;
+    }
+    return 0;
+}
+
+// start of a scan table inside Smem::scan: diagonal 4/8/16/32, horizontal 4/8, vertical 4/8
+__device__ __forceinline__ int scan_base(int st, int sc)
+{
+    if (st == 0) return sc == 0 ? 0 : sc == 1 ? 16 : sc == 2 ? 80 : 336;
+    return (st == 1 ? 1360 : 1440) + (sc == 0 ? 0 : 16);
+}
+
+__device__ __forceinline__ bool uses_smoothed(int sz, int mode)                        // :274-280
+{
+    if (sz == 4 || mode == 1) return false;
+    if (sz == 8) return mode == 0 || mode == 2 || mode == 18 || mode == 34;
+    if (sz == 16) return !(mode >= 9 && mode <= 11) && !(mode >= 25 && mode <= 27);
+    return mode != 10 && mode != 26;
+}
+
+// ------------------------------------------------------------------------------------------------
+// CABAC engine (one thread).  State in registers, contexts and tables in shared memory.
+// ------------------------------------------------------------------------------------------------
+struct Coder {
+    int range, low, nbits, pending, held, zeros;
+    unsigned nout, cap;
+    uint8_t *ctx, *out;
+    const uint8_t *lps, *nlps;
+
+    __device__ __forceinline__ void load(const CoderRegs &r) { range = r.range; low = r.low; nbits = r.nbits; pending = r.pending; held = r.held; zeros = r.zeros; nout = r.nout; }
+    __device__ __forceinline__ void store(CoderRegs &r) const { r.range = range; r.low = low; r.nbits = nbits; r.pending = pending; r.held = held; r.zeros = zeros; r.nout = nout; }
+    __device__ __forceinline__ void fresh() { range = 510; low = 0; nbits = 23; pending = 0; held = 0xFF; zeros = 0; nout = 0; }     // newCABACcoder :808
+
+    __device__ __forceinline__ void byte(int b)                                        // CABACput :820-831
+    {
+        b &= 0xFF;
+        if (zeros >= 2 && b <= 3) { if (nout < cap) out[nout] = 3; nout++; zeros = 0; }
+        if (nout < cap) out[nout] = (uint8_t)b;
+        nout++;
+        zeros = b == 0 ? zeros + 1 : 0;
+    }
+    __device__ __forceinline__ int bits() const { return 8 * ((int)nout + pending) + 23 - nbits; }      // CABAClen :834
+    __device__ __forceinline__ void shift_out()                                        // CABACupdate :858-878
+    {
+        if (nbits >= 12) return;
+        const int lead = low >> (24 - nbits);
+        nbits += 8;
+        low &= (int)(0xFFFFFFFFu >> nbits);
+        if (lead == 0xFF) {
+            pending++;
+        } else if (pending > 0) {
+            const int carry = lead >> 8;
+            byte(held + carry);
+            held = lead & 0xFF;
+            for (; pending > 1; pending--) byte(0xFF + carry);
+        } else {
+            pending = 1;
+            held = lead;
+        }
+    }
+    __device__ __forceinline__ void bin(int b, int ci)                                 // CABACputBin :913-932
+    {
+        const int st = ctx[ci];
+        const int l = lps[(st >> 1) * 4 + ((range >> 6) & 3)];
+        range -= l;
+        if ((b != 0) != ((st & 1) != 0)) {
+            const int n = __clz(l >> 3) - 26;           // renormalisation shift (table :712-714 in closed form)
+            ctx[ci] = nlps[st];
+            low = (low + range) << n;
+            range = l << n;
+            nbits -= n;
+        } else {
+            ctx[ci] = (uint8_t)(st < 124 ? st + 2 : st);
+            if (range < 256) { low <<= 1; range <<= 1; nbits--; }
+        }
+        shift_out();
+    }
+    __device__ __forceinline__ void bypass(int bins, int len)                          // CABACputBins :898-910
+    {
+        bins &= (1 << len) - 1;
+        while (len > 0) {
+            const int n = len < 8 ? len : 8;
+            len -= n;
+            low = (low << n) + range * ((bins >> len) & ((1 << n) - 1));
+            nbits -= n;
+            shift_out();
+        }
+    }
+    __device__ __forceinline__ void terminate(int b)                                   // CABACputTerminate :881-895
+    {
+        range -= 2;
+        if (b) { low = (low + range) << 7; range = 256; nbits -= 7; }
+        else if (range < 256) { low <<= 1; range <<= 1; nbits--; }
+        shift_out();
+    }
+    __device__ __forceinline__ void finish()                                           // CABACfinish :839-855
+    {
+        int fill = 0;
+        if ((low >> (32 - nbits)) > 0) {
+            byte(held + 1);
+            low -= 1 << (32 - nbits);
+        } else {
+            if (pending > 0) byte(held);
+            fill = 0xFF;
+        }
+        for (; pending > 1; pending--) byte(fill);
+        const int tail = (low >> 8) << nbits;
+        byte(tail >> 16); byte(tail >> 8); byte(tail);
+    }
+};
+
+// ------------------------------------------------------------------------------------------------
+// syntax elements (one thread)
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void mpm_list(int l, int a, int m[3])                       // getProbablePmodes :957-976
+{
+    if (l != a) {
+        m[0] = l; m[1] = a;
+        m[2] = (l != 0 && a != 0) ? 0 : (l + a < 2 ? 26 : 1);
+    } else if (l > 1) {
+        m[0] = l; m[1] = ((l + 29) % 32) + 2; m[2] = ((l - 1) % 32) + 2;
+    } else { m[0] = 0; m[1] = 1; m[2] = 26; }
+}
+
+// all prev_intra_luma_pred flags first, then mpm_idx / rem_intra_luma_pred_mode (putYpmode :984-1017)
+__device__ inline void put_luma_modes(Coder &c, int count, const int *mode, const int *left, const int *above)
+{
+    int hit[4];
+    for (int i = 0; i < count; i++) {
+        int m[3];
+        mpm_list(left[i], above[i], m);
+        hit[i] = -1;
+        for (int j = 0; j < 3; j++) if (m[j] == mode[i]) hit[i] = j;
+        c.bin(hit[i] >= 0, CX_YMODE);
+    }
+    for (int i = 0; i < count; i++) {
+        if (hit[i] >= 0) {
+            c.bypass(hit[i] > 0, 1);
+            if (hit[i] > 0) c.bypass(hit[i] - 1, 1);
+        } else {
+            int m[3], t, rem = mode[i];
+            mpm_list(left[i], above[i], m);
+            if (m[0] < m[1]) { t = m[0]; m[0] = m[1]; m[1] = t; }
+            if (m[1] < m[2]) { t = m[1]; m[1] = m[2]; m[2] = t; }
+            if (m[0] < m[1]) { t = m[0]; m[0] = m[1]; m[1] = t; }
+            for (int j = 0; j < 3; j++) if (rem > m[j]) rem--;
+            c.bypass(rem, 5);
+        }
+    }
+}
+
+__device__ __forceinline__ int pos_group(int v)        // last-position group index (:1046)
+{
+    return v < 4 ? v : v < 6 ? 4 : v < 8 ? 5 : v < 12 ? 6 : v < 16 ? 7 : v < 24 ? 8 : 9;
+}
+__device__ __forceinline__ int group_min(int g)        // :1047
+{
+    return g < 4 ? g : g == 4 ? 4 : g == 5 ? 6 : g == 6 ? 8 : g == 7 ? 12 : g == 8 ? 16 : 24;
+}
+
+__device__ inline void put_last_pos(Coder &c, int sz, int scan_type, int y, int x)     // putLastSignificantXY :1045-1086 (luma)
+{
+    const int sc = size_class(sz), base = sc * 5, sft = sc == 0 ? 0 : 1;
+    int ty = scan_type == 2 ? x : y, tx = scan_type == 2 ? y : x;
+    const int gy = pos_group(ty), gx = pos_group(tx), gmax = pos_group(sz - 1);
+    int i;
+    for (i = 0; i < gx; i++) c.bin(1, CX_LASTX + base + (i >> sft));
+    if (gx < gmax) c.bin(0, CX_LASTX + base + (gx >> sft));
+    for (i = 0; i < gy; i++) c.bin(1, CX_LASTY + base + (i >> sft));
+    if (gy < gmax) c.bin(0, CX_LASTY + base + (gy >> sft));
+    if (gx > 3) { tx -= group_min(gx); for (i = ((gx - 2) >> 1) - 1; i >= 0; i--) c.bypass((tx >> i) & 1, 1); }
+    if (gy > 3) { ty -= group_min(gy); for (i = ((gy - 2) >> 1) - 1; i >= 0; i--) c.bypass((ty >> i) & 1, 1); }
+}
+
+__device__ __forceinline__ int sig_ctx_index(int sz, int scan_type, int y, int x, int nb)      // getSigCtxIdx :1091-1121 (luma)
+{
+    if (y == 0 && x == 0) return 0;
+    if (sz == 4) {
+        // {{0,1,4,5},{2,3,4,5},{6,6,8,8},{7,7,8,8}} packed 4 bits per entry, row-major
+        const unsigned long long map4 = 0x8877886654325410ull;
+        return (int)((map4 >> (4 * (y * 4 + x))) & 15);
+    }
+    int ci = 9;
+    if (sz >= 16) ci += 12;
+    if (sz == 8 && scan_type != 0) ci += 6;
+    if ((y >> 2) || (x >> 2)) ci += 3;
+    const int py = y & 3, px = x & 3;
+    int s;
+    if (nb == 0) s = py + px; else if (nb == 1) s = py << 1; else if (nb == 2) s = px << 1; else return ci + 2;
+    return ci + (s == 0 ? 2 : s < 3 ? 1 : 0);
+}
+
+__device__ inline void put_remaining(Coder &c, int v, int rice)                        // putRemainExGolomb :1153-1168
+{
+    if (v < (3 << rice)) {
+        const int len = v >> rice;
+        c.bypass((1 << (len + 1)) - 2, len + 1);
+        c.bypass(v & ((1 << rice) - 1), rice);
+    } else {
+        int len = rice;
+        v -= 3 << rice;
+        for (; v >= (1 << len); len++) v -= 1 << len;
+        c.bypass((1 << (4 + len - rice)) - 2, 4 + len - rice);
+        c.bypass(v, len);
+    }
+}
+
+struct LevBlock { const short *p; int pitch; int last; unsigned cg0, cg1; };           // cg: bit (yc*8+xc) = group has a non-zero level
+
+// residual_coding of one luma TU (putCoef :1172-1268)
+__device__ inline void put_coefs(Coder &c, int sz, int mode, const LevBlock &L, const uint8_t (*scan_all)[2], short *mag)
+{
+    const int st = scan_type_for(sz, mode), ncg = sz >> 2;
+    const uint8_t (*scan)[2] = scan_all + scan_base(st, size_class(sz));
+    const int last = L.last;
+    int nz = 0, signs = 0, nb = 0, c1 = 1, cgs = 0;
+
+    put_last_pos(c, sz, st, scan[last][0], scan[last][1]);
+
+    for (int i = last; i >= 0; i--) {
+        const int y = scan[i][0], x = scan[i][1], yc = y >> 2, xc = x >> 2;
+        const bool is_last = i == last, first_cg = (yc | xc) == 0;
+        const bool cg_begin = (i & 15) == 15 || is_last, cg_end = (i & 15) == 0;
+        if (cg_begin) {
+            const int b = yc * 8 + xc;
+            cgs = (int)(((b < 32 ? L.cg0 >> b : L.cg1 >> (b - 32))) & 1u);
+            const int br = b + 1, bb = b + 8;
+            const int right = xc < ncg - 1 && (((br < 32 ? L.cg0 >> br : L.cg1 >> (br - 32))) & 1u);
+            const int below = yc < ncg - 1 && (((bb < 32 ? L.cg0 >> bb : L.cg1 >> (bb - 32))) & 1u);
+            nb = (below << 1) | right;
+            nz = 0; signs = 0;
+            if (!first_cg && !is_last) {
+                c.bin(cgs, CX_SIGCG + (nb != 0));
+                if (!cgs) { i &= ~15; continue; }               // nothing else is coded for an all-zero group
+            }
+        }
+        const int v = L.p[y * L.pitch + x];
+        if (!is_last && (first_cg || (cgs && (!cg_end || nz > 0))))
+            c.bin(v != 0, CX_SIG + sig_ctx_index(sz, st, y, x, nb));
+        if (v != 0) { mag[nz++] = (short)iabs(v); signs = (signs << 1) | (v < 0); }
+
+        if (cg_end && nz > 0) {
+            const int set = (first_cg ? 0 : 2) + (c1 == 0);
+            int escape = nz > 8, g2 = -1;
+            c1 = 1;
+            for (int j = 0; j < 8 && j < nz; j++) {
+                const int big = mag[j] > 1;
+                c.bin(big, CX_ONE + 4 * set + c1);
+                if (big) {
+                    c1 = 0;
+                    if (g2 < 0) g2 = mag[j] > 2; else escape = 1;
+                } else if (c1 > 0 && c1 < 3) c1++;
+            }
+            if (c1 == 0 && g2 >= 0) { c.bin(g2, CX_ABS + set); escape |= g2; }
+            c.bypass(signs, nz);
+            if (escape) {
+                int base = 3, rice = 0;
+                for (int j = 0; j < nz; j++) {
+                    const int m = mag[j];
+                    const int ev = m - (j < 8 ? base : 1);
+                    if (ev >= 0) {
+                        put_remaining(c, ev, rice);
+                        if (m > (3 << rice)) rice = rice < 4 ? rice + 1 : 4;
+                    }
+                    if (m >= 2) base = 2;
+                }
+            }
+        }
+    }
+}
+
+// everything of a coding unit after split_cu_flag.
+// kind 0: 2Nx2N one TU (:1271-1290)   kind 1: 2Nx2N four TUs (:1293-1315)   kind 2: NxN (:1318-1339)
+__device__ inline void put_cu(Coder &c, int sz, int kind, const int *modes, const int *left, const int *above,
+                              const LevBlock *blk, const uint8_t (*scan_all)[2], short *mag)
+{
+    if (sz == 8) c.bin(kind != 2, CX_PART);                                            // putPartSize :951-954
+    put_luma_modes(c, kind == 2 ? 4 : 1, modes, left, above);
+    c.bin(0, CX_UVMODE);                                                               // chroma mode "derived" :1020-1022
+    if (kind != 2) c.bin(kind == 1, CX_SPLIT_TU + (sz == 32 ? 0 : sz == 16 ? 1 : 2));  // :1025-1032
+    c.bin(0, CX_UVCBF + 0);                                                            // cbf_cb, cbf_cr at depth 0
+    c.bin(0, CX_UVCBF + 0);
+    if (kind == 0) {
+        const int cbf = (blk[0].cg0 | blk[0].cg1) != 0;
+        c.bin(cbf, CX_YCBF + 1);                                                       // depth 0 (:1039)
+        if (cbf) put_coefs(c, sz, modes[0], blk[0], scan_all, mag);
+    } else {
+        for (int i = 0; i < 4; i++) {
+            const int cbf = (blk[i].cg0 | blk[i].cg1) != 0;
+            c.bin(cbf, CX_YCBF + 0);
+            if (cbf) put_coefs(c, sz >> 1, modes[kind == 2 ? i : 0], blk[i], scan_all, mag);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// 1-D transforms on register arrays.  out[k] = sum_n M[k][n] in[n] (forward) / out[n] = sum_k M[k][n] in[k]
+// (inverse), M = N-point HEVC matrix.  Even/odd decomposition regroups the reference's dense sums (:469-492)
+// before any rounding, so results are identical.
+// ------------------------------------------------------------------------------------------------
+template <int N> struct Dct {
+    template <int OS> static __device__ __forceinline__ void fwd(const int *in, int *out)
+    {
+        int E[N / 2], O[N / 2];
+#pragma unroll
+        for (int k = 0; k < N / 2; k++) { E[k] = in[k] + in[N - 1 - k]; O[k] = in[k] - in[N - 1 - k]; }
+#pragma unroll
+        for (int m = 0; m < N / 2; m++) {
+            int s = 0;
+#pragma unroll
+            for (int k = 0; k < N / 2; k++) s += c_dct[(2 * m + 1) * (32 / N)][k] * O[k];
+            out[(2 * m + 1) * OS] = s;
+        }
+        Dct<N / 2>::template fwd<2 * OS>(E, out);
+    }
+    template <int IS> static __device__ __forceinline__ void inv(const int *in, int *out)
+    {
+        int Ee[N / 2];
+        Dct<N / 2>::template inv<2 * IS>(in, Ee);
+#pragma unroll
+        for (int n = 0; n < N / 2; n++) {
+            int s = 0;
+#pragma unroll
+            for (int m = 0; m < N / 2; m++) s += c_dct[(2 * m + 1) * (32 / N)][n] * in[(2 * m + 1) * IS];
+            out[n] = Ee[n] + s;
+            out[N - 1 - n] = Ee[n] - s;
+        }
+    }
+};
+template <> struct Dct<2> {
+    template <int OS> static __device__ __forceinline__ void fwd(const int *in, int *out)
+    {
+        out[0] = 64 * (in[0] + in[1]);
+        out[OS] = 64 * (in[0] - in[1]);
+    }
+    template <int IS> static __device__ __forceinline__ void inv(const int *in, int *out)
+    {
+        out[0] = 64 * (in[0] + in[IS]);
+        out[1] = 64 * (in[0] - in[IS]);
+    }
+};
+
+template <int TS> __device__ __forceinline__ void fwd1d(const int *in, int *out)
+{
+    if constexpr (TS == 4) {
+#pragma unroll
+        for (int k = 0; k < 4; k++) out[k] = c_dst4[k][0] * in[0] + c_dst4[k][1] * in[1] + c_dst4[k][2] * in[2] + c_dst4[k][3] * in[3];
+    } else {
+        Dct<TS>::template fwd<1>(in, out);
+    }
+}
+template <int TS> __device__ __forceinline__ void inv1d(const int *in, int *out)
+{
+    if constexpr (TS == 4) {
+#pragma unroll
+        for (int n = 0; n < 4; n++) out[n] = c_dst4[0][n] * in[0] + c_dst4[1][n] * in[1] + c_dst4[2][n] * in[2] + c_dst4[3][n] * in[3];
+    } else {
+        Dct<TS>::template inv<1>(in, out);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// phase A: one transform unit per group of TS lanes
+// ------------------------------------------------------------------------------------------------
+// where reference samples come from: the CTU window, or (inside the CU under trial) a private tile
+struct Src {
+    const uint8_t *rc;          // Smem::rc
+    const uint8_t *priv;        // tile of the CU being tried (or nullptr)
+    int py0, px0, psz, ppitch;
+    __device__ __forceinline__ int at(int y, int x) const
+    {
+        if (priv && (unsigned)(y - py0) < (unsigned)psz && (unsigned)(x - px0) < (unsigned)psz)
+            return priv[(y - py0) * ppitch + (x - px0)];
+        return rc[(y + 1) * RCP + x + 1];
+    }
+};
+
+template <int TS> __device__ __forceinline__ int group_sum(int v)
+{
+#pragma unroll
+    for (int d = 1; d < TS; d <<= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+    return v;
+}
+template <int TS> __device__ __forceinline__ int group_max(int v)
+{
+#pragma unroll
+    for (int d = 1; d < TS; d <<= 1) { const int o = __shfl_xor_sync(0xffffffffu, v, d); v = o > v ? o : v; }
+    return v;
+}
+template <int TS> __device__ __forceinline__ unsigned group_or(unsigned v)
+{
+#pragma unroll
+    for (int d = 1; d < TS; d <<= 1) v |= __shfl_xor_sync(0xffffffffu, v, d);
+    return v;
+}
+
+struct TuResult { int sse, last; unsigned cg0, cg1; };
+
+// Must be called by all 32 lanes of a warp (it contains warp-level exchanges); `active` masks the stores of idle
+// groups.  (y0, x0): position of the TU inside the CTU.  avail: bit0 left, bit1 below-left, bit2 above, bit3 above-right.
+// lev: TS x TS levels with pitch TS+2.  rec: TS x TS tile (pitch rec_pitch) that receives the reconstruction.
+template <int TS>
+__device__ __forceinline__ TuResult tu_pipeline(Smem &sm, int warp, int lane, bool active, const Src &src, int y0, int x0,
+                                                int avail, int mode, int qpd6, short *lev, uint8_t *rec, int rec_pitch)
+{
+    constexpr int LOG = TS == 4 ? 2 : TS == 8 ? 3 : TS == 16 ? 4 : 5;
+    constexpr int SC = LOG - 2;
+    constexpr int GS = (11 * TS + 6 + 3) & ~3;
+    constexpr int LP = TS + 2;
+    const int g = lane / TS, l = lane % TS;
+    uint8_t *R = sm.refs[warp] + g * GS;
+    uint8_t *left = R + 4, *top = left + 2 * TS, *fleft = top + 2 * TS, *ftop = fleft + 2 * TS, *line = ftop + 2 * TS;
+    short *ws = sm.ws[warp] + g * TS * LP;
+    const bool hl = avail & 1, hbl = avail & 2, ha = avail & 4, har = avail & 8;
+
+    // ---- reference samples with substitution (getBorder :212-243) ----
+    const int corner = (hl && ha) ? src.at(y0 - 1, x0 - 1) : hl ? src.at(y0, x0 - 1) : ha ? src.at(y0 - 1, x0) : 128;
+#pragma unroll
+    for (int i = l; i < 2 * TS; i += TS) {
+        int vl, vt;
+        if (i < TS) {
+            vl = hl ? src.at(y0 + i, x0 - 1) : corner;
+            vt = ha ? src.at(y0 - 1, x0 + i) : corner;
+        } else {
+            vl = hbl ? src.at(y0 + i, x0 - 1) : (hl ? src.at(y0 + TS - 1, x0 - 1) : corner);
+            vt = har ? src.at(y0 - 1, x0 + i) : (ha ? src.at(y0 - 1, x0 + TS - 1) : corner);
+        }
+        left[i] = (uint8_t)vl; top[i] = (uint8_t)vt;
+    }
+    if (l == 0) R[0] = (uint8_t)corner;
+    __syncwarp();
+    // [1 2 1]/4 smoothing (:245-256)
+#pragma unroll
+    for (int i = l; i < 2 * TS; i += TS) {
+        if (i == 2 * TS - 1) { fleft[i] = left[i]; ftop[i] = top[i]; }
+        else {
+            const int pl = i > 0 ? left[i - 1] : corner, pt = i > 0 ? top[i - 1] : corner;
+            fleft[i] = (uint8_t)((2 + 2 * left[i] + pl + left[i + 1]) >> 2);
+            ftop[i]  = (uint8_t)((2 + 2 * top[i] + pt + top[i + 1]) >> 2);
+        }
+    }
+    if (l == 0) R[1] = (uint8_t)((2 + left[0] + top[0] + 2 * corner) >> 2);
+    __syncwarp();
+
+    // ---- prediction (predict :262-381), this lane owns column l ----
+    const bool smo = uses_smoothed(TS, mode);
+    const uint8_t *Lr = smo ? fleft : left, *Tr = smo ? ftop : top;
+    const int C = smo ? R[1] : R[0];
+    const int dcsum = group_sum<TS>((int)left[l] + (int)top[l]);        // DC never uses the smoothed samples
+    const bool angular = mode >= 2 && mode != 10 && mode != 26;
+    uint8_t *lineb = line + TS;                                         // lineb[0] = corner, lineb[1..] = main reference, lineb[<0] = projected side
+    if (angular) {
+        const bool horiz = mode < 18;
+        const int ang = c_angle[mode], inv = c_invang[mode];
+        const uint8_t *mainr = horiz ? Lr : Tr, *side = horiz ? Tr : Lr;
+        for (int i = l; i < 2 * TS + 2; i += TS) lineb[i] = (uint8_t)(i == 0 ? C : (i <= 2 * TS ? mainr[i - 1] : 0));
+        const int lim = (TS * ang) >> 5;
+        for (int i = -1 - l; i > lim; i -= TS) lineb[i] = side[((128 - inv * i) >> 8) - 1];
+    }
+    __syncwarp();
+
+    int v[TS];          // residual column
+    {
+        int p[TS];
+        if (mode == 0) {
+            const int tl = Tr[l], tr = Tr[TS], bl = Lr[TS];
+#pragma unroll
+            for (int y = 0; y < TS; y++) p[y] = (TS + (TS - 1 - l) * Lr[y] + (l + 1) * tr + (TS - 1 - y) * tl + (y + 1) * bl) >> (LOG + 1);
+        } else if (mode == 1) {
+            const int dc = (dcsum + TS) >> (LOG + 1);
+#pragma unroll
+            for (int y = 0; y < TS; y++) p[y] = dc;
+            if (TS <= 16) {
+                if (l == 0) {
+                    p[0] = (2 + 2 * dc + left[0] + top[0]) >> 2;
+#pragma unroll
+                    for (int y = 1; y < TS; y++) p[y] = (2 + 3 * dc + left[y]) >> 2;
+                } else {
+                    p[0] = (2 + 3 * dc + top[l]) >> 2;
+                }
+            }
+        } else if (mode == 10) {
+#pragma unroll
+            for (int y = 0; y < TS; y++) p[y] = Lr[y];
+            if (TS <= 16) p[0] = clampi(p[0] + ((Tr[l] - C) >> 1), 0, 255);
+        } else if (mode == 26) {
+#pragma unroll
+            for (int y = 0; y < TS; y++) p[y] = Tr[l];
+            if (TS <= 16 && l == 0) {
+#pragma unroll
+                for (int y = 0; y < TS; y++) p[y] = clampi(p[y] + ((Lr[y] - C) >> 1), 0, 255);
+            }
+        } else {
+            const int ang = c_angle[mode];
+            if (mode < 18) {
+                const int off = ang * (l + 1), oi = off >> 5, of = off & 31;
+#pragma unroll
+                for (int y = 0; y < TS; y++) p[y] = ((32 - of) * lineb[oi + y + 1] + of * lineb[oi + y + 2] + 16) >> 5;
+            } else {
+#pragma unroll
+                for (int y = 0; y < TS; y++) {
+                    const int off = ang * (y + 1), oi = off >> 5, of = off & 31;
+                    p[y] = ((32 - of) * lineb[oi + l + 1] + of * lineb[oi + l + 2] + 16) >> 5;
+                }
+            }
+        }
+#pragma unroll
+        for (int y = 0; y < TS; y++) {
+            if (active) rec[y * rec_pitch + l] = (uint8_t)p[y];
+            v[y] = (int)sm.orig[y0 + y][x0 + l] - p[y];
+        }
+    }
+
+    // ---- forward transform (:497-516, inverse = 0): columns, then rows ----
+    int t[TS];
+    fwd1d<TS>(v, t);
+#pragma unroll
+    for (int i = 0; i < TS; i++) ws[i * LP + l] = (short)((t[i] + (1 << (SC + 1) >> 1)) >> (SC + 1));
+    __syncwarp();
+#pragma unroll
+    for (int k = 0; k < TS; k++) v[k] = ws[l * LP + k];
+    fwd1d<TS>(v, t);
+    __syncwarp();
+
+    // ---- RDOQ-lite (quantize :540-594): this lane owns row l of the coefficient block ----
+    {
+        const int dist_sft = 8 - SC, sft = 19 - SC + qpd6;
+        const int add = 1 << sft >> 1, max_d = I32MAX - add, thr = 9 << sft >> 2;
+        int cgsum = 0;
+#pragma unroll
+        for (int n = 0; n < TS; n++) {
+            const int coef = (t[n] + (1 << (SC + 8) >> 1)) >> (SC + 8);
+            const int av = iabs(coef);
+            int d = (av & 0x1ffff) << 14;
+            d = (av > 0x1ffff || d > max_d) ? max_d : d;
+            int level = clip16((d + add) >> sft);
+            const int lo = level - 2 > 0 ? level - 2 : 0;
+            int best = I32MAX, pick = 0;
+            for (; level >= lo; level--) {
+                const int d1 = iabs(d - (level << sft)) >> dist_sft;
+                const int dist = (d1 < 46340 ? d1 * d1 : I32MAX) >> 7;
+                const int cost = rd_cost(qpd6, dist, level_rate(level));
+                if (cost < best) { best = cost; pick = level; }
+            }
+            t[n] = coef < 0 ? -pick : pick;
+            cgsum += d < thr ? d : thr;
+            if ((n & 3) == 3) {                         // coefficient group (rows l&~3.., columns n-3..n) complete
+                cgsum += __shfl_xor_sync(0xffffffffu, cgsum, 1);
+                cgsum += __shfl_xor_sync(0xffffffffu, cgsum, 2);
+                if (cgsum < thr) { t[n] = 0; t[n - 1] = 0; t[n - 2] = 0; t[n - 3] = 0; }
+                cgsum = 0;
+            }
+        }
+        if (active) {
+#pragma unroll
+            for (int n = 0; n < TS; n++) lev[l * LP + n] = (short)t[n];
+        } else {
+#pragma unroll
+            for (int n = 0; n < TS; n++) ws[l * LP + n] = (short)t[n];     // idle group: keep its data private
+        }
+    }
+    __syncwarp();
+    const short *lv = active ? lev : ws;
+
+    // ---- last significant position and coefficient-group mask (first pass of putCoef :1196-1203) ----
+    TuResult res;
+    {
+        const uint8_t (*scan)[2] = sm.scan + scan_base(scan_type_for(TS, mode), SC);
+        int last = 0;
+        unsigned cg0 = 0, cg1 = 0;
+#pragma unroll 4
+        for (int i = l; i < TS * TS; i += TS) {
+            const int y = scan[i][0], x = scan[i][1];
+            if (lv[y * LP + x] != 0) {
+                last = i;
+                const int b = (y >> 2) * 8 + (x >> 2);
+                if (b < 32) cg0 |= 1u << b; else cg1 |= 1u << (b - 32);
+            }
+        }
+        res.last = group_max<TS>(last);
+        res.cg0 = group_or<TS>(cg0);
+        res.cg1 = TS == 32 ? group_or<TS>(cg1) : 0u;
+    }
+
+    // ---- de-quantise (:599-614) + inverse transform: columns, then rows ----
+    {
+        const int s = 5 - SC + qpd6;
+#pragma unroll
+        for (int k = 0; k < TS; k++) v[k] = clip16((int)lv[k * LP + l] * (1 << s));
+    }
+    __syncwarp();                                       // idle groups keep their levels in ws: all reads done before it is reused
+    inv1d<TS>(v, t);
+#pragma unroll
+    for (int i = 0; i < TS; i++) ws[i * LP + l] = (short)clip16((t[i] + 64) >> 7);
+    __syncwarp();
+#pragma unroll
+    for (int k = 0; k < TS; k++) v[k] = ws[l * LP + k];
+    inv1d<TS>(v, t);
+    __syncwarp();
+
+    // ---- reconstruction of row l and its squared error ----
+    int sse = 0;
+    if (active) {
+#pragma unroll
+        for (int j = 0; j < TS; j++) {
+            const int r = clampi(clip16((t[j] + 2048) >> 12) + (int)rec[l * rec_pitch + j], 0, 255);
+            const int d = (int)sm.orig[y0 + l][x0 + j] - r;
+            sse += d * d;
+            rec[l * rec_pitch + j] = (uint8_t)r;
+        }
+    }
+    res.sse = group_sum<TS>(sse);
+    __syncwarp();
+    return res;
+}
+
+// ------------------------------------------------------------------------------------------------
+// block-level helpers
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int block_sum(Smem &sm, int v)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    v = group_sum<32>(v);
+    __syncthreads();
+    if (lane == 0) sm.red[warp] = v;
+    __syncthreads();
+    int s = 0;
+#pragma unroll
+    for (int w = 0; w < NW; w++) s += sm.red[w];
+    return s;
+}
+
+__device__ __forceinline__ void copy_words(void *dst, const void *src, int nwords, int tid, int nthreads)
+{
+    unsigned *d = (unsigned *)dst;
+    const unsigned *s = (const unsigned *)src;
+    for (int i = tid; i < nwords; i += nthreads) d[i] = s[i];
+}
+
+// candidate c is coded by lane c / NW of warp c % NW, so that concurrent trial encodes sit in different warps
+__device__ __forceinline__ int candidate_of_thread(int tid)
+{
+    const int lane = tid & 31, warp = tid >> 5;
+    const int c = lane * NW + warp;
+    return (lane < (NMODE + NW - 1) / NW && c < NMODE) ? c : -1;
+}
+
+struct Ctx {
+    Smem *sm;
+    const Params *P;
+    uint8_t *out;               // this frame's output slot
+    uint8_t *scratch;           // this CTA's [NMODE][SCR_BYTES]
+    int qpd6;
+};
+
+template <int SZ> struct Level { static constexpr int v = SZ == 32 ? 0 : SZ == 16 ? 1 : 2; static constexpr int best_off = SZ == 32 ? 0 : SZ == 16 ? 1024 : 1280; };
+
+// the winner of a step becomes the current state: coder, bytes, reconstruction, maps (:1439-1446)
+template <int SZ>
+__device__ __forceinline__ void commit_candidate(Ctx &K, int win, int y0, int x0)
+{
+    Smem &sm = *K.sm;
+    constexpr int LV = Level<SZ>::v;
+    const int tid = threadIdx.x;
+    const unsigned base = sm.entry[LV].nout, n = sm.ccoder[win].nout;
+    const uint8_t *src = K.scratch + (size_t)win * SCR_BYTES;
+    const unsigned cap = (unsigned)K.P->out_stride;
+    for (unsigned i = tid; i < n && i < SCR_BYTES; i += NT) if (base + i < cap) K.out[base + i] = src[i];
+    copy_words(sm.cur_ctx, sm.cctx[win], CXP / 4, tid, NT);
+    if (tid == 0) { sm.cur = sm.ccoder[win]; sm.cur.nout = base + n; }
+    uint8_t *best = sm.best_rec + Level<SZ>::best_off;
+    for (int i = tid; i < SZ * SZ / 4; i += NT) ((unsigned *)best)[i] = ((const unsigned *)sm.rec[win])[i];
+    (void)y0; (void)x0;
+}
+
+template <int SZ>
+__device__ __forceinline__ void fill_maps(Smem &sm, int y0, int x0, int mode)
+{
+    constexpr int NC = SZ / 4;
+    const int tid = threadIdx.x;
+    if (tid < NC * NC) {
+        const int r = 1 + y0 / 4 + tid / NC, c = 1 + x0 / 4 + tid % NC;
+        sm.msz[r][c] = (uint8_t)SZ;
+        sm.mmd[r][c] = (uint8_t)mode;
+    }
+}
+
+// RD search of one coding unit (processCURecurs :1349-1559).  Executed by the whole CTA in uniform control flow.
+template <int SZ>
+__device__ void search_cu(Ctx &K, int y0, int x0, int avail)
+{
+    Smem &sm = *K.sm;
+    constexpr int LV = Level<SZ>::v;
+    constexpr int H = SZ / 2;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int qpd6 = K.qpd6;
+    const int cy = y0 / 4, cx = x0 / 4;
+    const bool hl = avail & 1, hbl = avail & 2, ha = avail & 4, har = avail & 8;
+    uint8_t *best = sm.best_rec + Level<SZ>::best_off;
+
+    __syncthreads();
+    // ---- entry state (:1363-1372) ----
+    copy_words(sm.entry_ctx[LV], sm.cur_ctx, CXP / 4, tid, NT);
+    if (tid == 0) { sm.entry[LV] = sm.cur; sm.best_cost[LV] = I32MAX; }
+    const int split_ctx = (SZ > sm.msz[1 + cy][cx]) + (SZ > sm.msz[cy][1 + cx]);
+    const int mode_l = sm.mmd[1 + cy][cx], mode_a = sm.mmd[cy][1 + cx];
+    __syncthreads();
+    const CoderRegs entry = sm.entry[LV];
+    const int entry_bits_abs = 8 * ((int)entry.nout + entry.pending) + 23 - entry.nbits;
+    const int entry_bits_rel = 8 * entry.pending + 23 - entry.nbits;
+
+    const int sub_y[4] = {y0, y0, y0 + H, y0 + H}, sub_x[4] = {x0, x0 + H, x0, x0 + H};
+    const int sub_avail[4] = {                                                        // :1375-1378
+        (hl ? 1 : 0) | (hl ? 2 : 0) | (ha ? 4 : 0) | (ha ? 8 : 0),
+        1 | 0 | (ha ? 4 : 0) | (har ? 8 : 0),
+        (hl ? 1 : 0) | (hbl ? 2 : 0) | 4 | 8,
+        1 | 0 | 4 | 0 };
+
+    // ---- 1: four smaller CUs (:1402-1412) ----
+    if constexpr (SZ > 8) {
+        if (tid == 0) {
+            Coder c; c.load(sm.cur); c.ctx = sm.cur_ctx; c.out = K.out; c.cap = (unsigned)K.P->out_stride; c.lps = sm.lps; c.nlps = sm.next_lps;
+            c.bin(1, CX_SPLIT_CU + split_ctx);
+            c.store(sm.cur);
+        }
+        for (int i = 0; i < 4; i++) search_cu<H>(K, sub_y[i], sub_x[i], sub_avail[i]);
+        __syncthreads();
+        int sse = 0;
+        for (int i = tid; i < SZ * SZ; i += NT) {
+            const int y = i / SZ, x = i % SZ;
+            const int r = sm.rc[1 + y0 + y][1 + x0 + x];
+            best[i] = (uint8_t)r;
+            const int d = (int)sm.orig[y0 + y][x0 + x] - r;
+            sse += d * d;
+        }
+        sse = block_sum(sm, sse);
+        if (tid == 0) {
+            const int bits = 8 * ((int)sm.cur.nout + sm.cur.pending) + 23 - sm.cur.nbits;
+            sm.best_cost[LV] = rd_cost(qpd6, sse, bits - entry_bits_abs);
+        }
+        __syncthreads();
+    }
+
+    Src src; src.rc = &sm.rc[0][0]; src.priv = nullptr; src.py0 = y0; src.px0 = x0; src.psz = SZ; src.ppitch = SZ;
+
+    // ---- 2 and 3: one CU, 35 modes; one TU (kind 0, :1419-1447), then four TUs (kind 1, :1454-1483) ----
+    for (int kind = 0; kind < 2; kind++) {
+        // phase A
+        if (kind == 0) {
+            constexpr int G = 32 / SZ, NG = NW * G;
+            for (int base = 0; base < NMODE; base += NG) {
+                if (base + warp * G >= NMODE) break;                        // warp-uniform
+                const int item = base + warp * G + lane / SZ;
+                const bool active = item < NMODE;
+                const int m = active ? item : 0;
+                TuResult r = tu_pipeline<SZ>(sm, warp, lane, active, src, y0, x0, avail, m, qpd6, sm.lev[m], sm.rec[m], SZ);
+                if (active && lane % SZ == 0) { sm.csse[m] = r.sse; sm.clast[m][0] = r.last; sm.ccg[m][0][0] = r.cg0; sm.ccg[m][0][1] = r.cg1; }
+            }
+        } else {
+            constexpr int G = 32 / H, NG = NW * G;
+            for (int base = 0; base < NMODE; base += NG) {
+                if (base + warp * G >= NMODE) break;
+                const int item = base + warp * G + lane / H;
+                const bool active = item < NMODE;
+                const int m = active ? item : 0;
+                Src ps = src; ps.priv = sm.rec[m];                           // earlier sub-TUs of the same trial
+                int sse = 0;
+                for (int i = 0; i < 4; i++) {
+                    TuResult r = tu_pipeline<H>(sm, warp, lane, active, ps, sub_y[i], sub_x[i], sub_avail[i], m, qpd6,
+                                                sm.lev[m] + i * H * (H + 2), sm.rec[m] + (sub_y[i] - y0) * SZ + (sub_x[i] - x0), SZ);
+                    sse += r.sse;
+                    if (active && lane % H == 0) { sm.clast[m][i] = r.last; sm.ccg[m][i][0] = r.cg0; sm.ccg[m][i][1] = r.cg1; }
+                }
+                if (active && lane % H == 0) sm.csse[m] = sse;
+            }
+        }
+        __syncthreads();
+        // phase B: trial encodes from the entry state
+        for (int i = tid; i < NMODE * (CXP / 4); i += NT)
+            ((unsigned *)sm.cctx)[i] = ((const unsigned *)sm.entry_ctx[LV])[i % (CXP / 4)];
+        __syncthreads();
+        {
+            const int c = candidate_of_thread(tid);
+            if (c >= 0) {
+                Coder cd; cd.load(entry); cd.nout = 0;
+                cd.ctx = sm.cctx[c]; cd.out = K.scratch + (size_t)c * SCR_BYTES; cd.cap = SCR_BYTES; cd.lps = sm.lps; cd.nlps = sm.next_lps;
+                if (SZ >= 16) cd.bin(0, CX_SPLIT_CU + split_ctx);          // putSplitCUflag :942-946
+                LevBlock blk[4];
+                const int tsz = kind == 0 ? SZ : H;
+                for (int i = 0; i < (kind == 0 ? 1 : 4); i++) {
+                    blk[i].p = sm.lev[c] + i * H * (H + 2); blk[i].pitch = tsz + 2;
+                    blk[i].last = sm.clast[c][i]; blk[i].cg0 = sm.ccg[c][i][0]; blk[i].cg1 = sm.ccg[c][i][1];
+                }
+                const int mode = c;
+                put_cu(cd, SZ, kind, &mode, &mode_l, &mode_a, blk, sm.scan, sm.cmag[c]);
+                cd.store(sm.ccoder[c]);
+                sm.cbits[c] = cd.bits() - entry_bits_rel;
+            }
+        }
+        __syncthreads();
+        // decide (:1437-1446): candidates in mode order, a later candidate wins ties
+        if (tid == 0) {
+            int bc = sm.best_cost[LV], win = -1;
+            for (int m = 0; m < NMODE; m++) {
+                const int cost = rd_cost(qpd6, sm.csse[m], sm.cbits[m]);
+                if (bc >= cost) { bc = cost; win = m; }
+            }
+            sm.best_cost[LV] = bc;
+            sm.win = win;
+        }
+        __syncthreads();
+        const int win = sm.win;
+        if (win >= 0) {
+            commit_candidate<SZ>(K, win, y0, x0);
+            fill_maps<SZ>(sm, y0, x0, win);
+        }
+        __syncthreads();
+    }
+
+    // ---- 4: 8x8 only: four 4x4 PUs, each mode chosen by a stand-alone cost on a fresh coder (:1490-1556) ----
+    if constexpr (SZ == 8) {
+        Src ps = src; ps.priv = sm.nxn_rec; ps.ppitch = 8;
+        for (int i = 0; i < 4; i++) {
+            constexpr int G = 8, NG = NW * G;
+            for (int base = 0; base < NMODE; base += NG) {
+                if (base + warp * G >= NMODE) break;
+                const int item = base + warp * G + lane / 4;
+                const bool active = item < NMODE;
+                const int m = active ? item : 0;
+                TuResult r = tu_pipeline<4>(sm, warp, lane, active, ps, sub_y[i], sub_x[i], sub_avail[i], m, qpd6, sm.lev[m], sm.rec[m], 4);
+                if (active && lane % 4 == 0) { sm.csse[m] = r.sse; sm.clast[m][0] = r.last; sm.ccg[m][0][0] = r.cg0; sm.ccg[m][0][1] = r.cg1; }
+            }
+            for (int k = tid; k < NMODE * (CXP / 4); k += NT)
+                ((unsigned *)sm.cctx)[k] = ((const unsigned *)sm.init_ctx)[k % (CXP / 4)];
+            __syncthreads();
+            {
+                const int c = candidate_of_thread(tid);
+                if (c >= 0) {
+                    Coder cd; cd.fresh();
+                    cd.ctx = sm.cctx[c]; cd.out = K.scratch + (size_t)c * SCR_BYTES; cd.cap = SCR_BYTES; cd.lps = sm.lps; cd.nlps = sm.next_lps;
+                    LevBlock blk; blk.p = sm.lev[c]; blk.pitch = 6; blk.last = sm.clast[c][0]; blk.cg0 = sm.ccg[c][0][0]; blk.cg1 = 0;
+                    put_coefs(cd, 4, c, blk, sm.scan, sm.cmag[c]);
+                    sm.cbits[c] = cd.bits();
+                }
+            }
+            __syncthreads();
+            if (tid == 0) {
+                int bc = I32MAX, win = -1;
+                for (int m = 0; m < NMODE; m++) {
+                    const int cost = rd_cost(qpd6, sm.csse[m], sm.cbits[m]);
+                    if (bc >= cost) { bc = cost; win = m; }
+                }
+                sm.win = win;
+                sm.nxn_mode[i] = win; sm.nxn_last[i] = sm.clast[win][0]; sm.nxn_cg[i] = sm.ccg[win][0][0];
+            }
+            __syncthreads();
+            if (tid < 16) {
+                const int w = sm.win, y = tid >> 2, x = tid & 3;
+                sm.nxn_lev[i][y * 6 + x] = sm.lev[w][y * 6 + x];
+                sm.nxn_rec[(sub_y[i] - y0 + y) * 8 + (sub_x[i] - x0 + x)] = sm.rec[w][y * 4 + x];
+            }
+            __syncthreads();
+        }
+        // the NxN coding unit from the entry state (:1528-1545)
+        copy_words(sm.cctx[0], sm.entry_ctx[LV], CXP / 4, tid, NT);
+        int sse = 0;
+        if (tid < 64) { const int d = (int)sm.orig[y0 + (tid >> 3)][x0 + (tid & 7)] - (int)sm.nxn_rec[tid]; sse = d * d; }
+        sse = block_sum(sm, sse);                                           // contains the barriers the copy above needs
+        if (tid == 0) {
+            Coder cd; cd.load(entry); cd.nout = 0;
+            cd.ctx = sm.cctx[0]; cd.out = K.scratch; cd.cap = SCR_BYTES; cd.lps = sm.lps; cd.nlps = sm.next_lps;
+            int modes[4], left[4], above[4];
+            LevBlock blk[4];
+            for (int i = 0; i < 4; i++) {
+                modes[i] = sm.nxn_mode[i];
+                blk[i].p = sm.nxn_lev[i]; blk[i].pitch = 6; blk[i].last = sm.nxn_last[i]; blk[i].cg0 = sm.nxn_cg[i]; blk[i].cg1 = 0;
+            }
+            left[0] = mode_l;                  above[0] = mode_a;                               // :1530-1537
+            left[1] = modes[0];                above[1] = sm.mmd[cy][1 + cx + 1];
+            left[2] = sm.mmd[1 + cy + 1][cx];  above[2] = modes[0];
+            left[3] = modes[2];                above[3] = modes[1];
+            put_cu(cd, 8, 2, modes, left, above, blk, sm.scan, sm.cmag[0]);
+            cd.store(sm.ccoder[0]);
+            const int cost = rd_cost(qpd6, sse, cd.bits() - entry_bits_rel);
+            sm.win = (sm.best_cost[LV] >= cost) ? 1 : 0;
+        }
+        __syncthreads();
+        if (sm.win) {
+            // commit: coder, bytes, maps; the reconstruction is the four kept 4x4 tiles (:1546-1554)
+            const unsigned base = entry.nout, n = sm.ccoder[0].nout, cap = (unsigned)K.P->out_stride;
+            for (unsigned i = tid; i < n && i < SCR_BYTES; i += NT) if (base + i < cap) K.out[base + i] = K.scratch[i];
+            copy_words(sm.cur_ctx, sm.cctx[0], CXP / 4, tid, NT);
+            if (tid == 0) { sm.cur = sm.ccoder[0]; sm.cur.nout = base + n; }
+            if (tid < 4) {
+                const int r = 1 + cy + (tid >> 1), c = 1 + cx + (tid & 1);
+                sm.msz[r][c] = 8;
+                sm.mmd[r][c] = (uint8_t)sm.nxn_mode[tid];
+            }
+            if (tid < 64) sm.rc[1 + y0 + (tid >> 3)][1 + x0 + (tid & 7)] = sm.nxn_rec[tid];
+            __syncthreads();
+            return;
+        }
+    }
+
+    // ---- the best reconstruction becomes the CU's reconstruction (:1558) ----
+    for (int i = tid; i < SZ * SZ; i += NT) sm.rc[1 + y0 + i / SZ][1 + x0 + i % SZ] = best[i];
+    __syncthreads();
+}
+
+// ------------------------------------------------------------------------------------------------
+// parameter sets + slice header (putHeaderToBuffer :664-690); one thread
+// ------------------------------------------------------------------------------------------------
+struct HeaderBits {
+    uint8_t *p; int bit; unsigned acc;
+    __device__ void put(unsigned v, int n)
+    {
+        for (n--; n >= 0; n--) {
+            acc = (acc << 1) | ((v >> n) & 1u);
+            if (++bit == 8) { *p++ = (uint8_t)acc; acc = 0; bit = 0; }
+        }
+    }
+    __device__ void ue(unsigned v)                      // putUVLCtoBuffer :641-647
+    {
+        int len = 1;
+        v++;
+        for (unsigned t = v + 1; t != 1; t >>= 1) len += 2;
+        put(v & ((1u << ((len + 1) >> 1)) - 1u), (len >> 1) + ((len + 1) >> 1));
+    }
+    __device__ void align() { if (bit) { acc <<= (8 - bit); *p++ = (uint8_t)acc; acc = 0; bit = 0; } }
+};
+
+__device__ inline unsigned put_headers(uint8_t *out, int qpd6, int hp, int wp)
+{
+    uint8_t *p = out;
+    for (int i = 0; i < 27; i++) *p++ = c_vps[i];
+    for (int i = 0; i < 22; i++) *p++ = c_sps[i];
+    HeaderBits w; w.p = p; w.bit = 0; w.acc = 0;
+    w.put(0x0A, 4); w.ue((unsigned)wp); w.ue((unsigned)hp);
+    w.put(0x197EE4, 22); w.put(0x681ED1, 24);
+    w.align();
+    p = w.p;
+    for (int i = 0; i < 11; i++) *p++ = c_pps[i];
+    for (int i = 0; i < 6; i++) *p++ = c_slice_head[i];
+    *p++ = c_slice_tail[qpd6][0]; *p++ = c_slice_tail[qpd6][1];
+    return (unsigned)(p - out);
+}
+
+// ------------------------------------------------------------------------------------------------
+// the frame kernel (HEVCImageEncoder :1569-1646): one CTA per frame, frames taken from a queue
+// ------------------------------------------------------------------------------------------------
+__device__ inline void build_tables(Smem &sm, int qpd6)
+{
+    const int tid = threadIdx.x;
+    for (int i = tid; i < 256; i += NT) sm.lps[i] = c_lps[i >> 2][i & 3];
+    for (int i = tid; i < 128; i += NT) sm.next_lps[i] = c_next_lps[i];
+    if (tid < CXP) {                                                        // initContextValue :726-734
+        int s = 0;
+        if (tid < CXN) {
+            const int v = c_ctx_init[tid], qp = qpd6 * 6 + 4;
+            const int st = clampi(((((v >> 4) * 5 - 45) * qp) >> 4) + ((v & 15) << 3) - 16, 1, 126);
+            s = st >= 64 ? (((st - 64) << 1) | 1) : ((63 - st) << 1);
+        }
+        sm.init_ctx[tid] = (uint8_t)s;
+    }
+    if (tid < 4) {                                                          // up-right diagonal order of an n x n grid
+        const int n = 1 << tid;
+        int k = 0;
+        for (int d = 0; d <= 2 * n - 2; d++)
+            for (int y = d < n - 1 ? d : n - 1; y >= (d - n + 1 > 0 ? d - n + 1 : 0); y--) { sm.dord[tid][k][0] = (uint8_t)y; sm.dord[tid][k][1] = (uint8_t)(d - y); k++; }
+    }
+    __syncthreads();
+    for (int i = tid; i < NSCAN; i += NT) {                                 // scan tables (:1126-1150)
+        int y, x;
+        if (i < 1360) {
+            const int sc = i < 16 ? 0 : i < 80 ? 1 : i < 336 ? 2 : 3;
+            const int k = i - scan_base(0, sc), gidx = k >> 4, p = k & 15;
+            y = sm.dord[sc][gidx][0] * 4 + sm.dord[2][p][0];
+            x = sm.dord[sc][gidx][1] * 4 + sm.dord[2][p][1];
+        } else {
+            const int st = i < 1440 ? 1 : 2, r = i - (st == 1 ? 1360 : 1440);
+            const int sc = r < 16 ? 0 : 1, k = r - (sc ? 16 : 0), ncg = 1 << sc, gidx = k >> 4, p = k & 15;
+            const int a = (gidx / ncg) * 4 + p / 4, b = (gidx % ncg) * 4 + p % 4;
+            y = st == 1 ? a : b; x = st == 1 ? b : a;
+        }
+        sm.scan[i][0] = (uint8_t)y; sm.scan[i][1] = (uint8_t)x;
+    }
+    __syncthreads();
+}
+
+__device__ inline void encode_frame(Ctx &K, int f)
+{
+    Smem &sm = *K.sm;
+    const Params &P = *K.P;
+    const int tid = threadIdx.x;
+    const int H = P.H, W = P.W, hp = P.hp, wp = P.wp, qpd6 = P.qpd6;
+    const uint8_t *img = P.frames + (size_t)f * P.frame_stride;
+    uint8_t *rcon = P.rcon + (size_t)f * P.rcon_stride;
+    K.out = P.out + (size_t)f * P.out_stride;
+
+    __syncthreads();
+    copy_words(sm.cur_ctx, sm.init_ctx, CXP / 4, tid, NT);
+    for (int i = tid; i < 2048; i += NT) sm.above_sz[i] = 32;                // :1594-1599
+    if (tid == 0) {
+        Coder c; c.fresh(); c.store(sm.cur);
+        sm.cur.nout = P.out_stride >= 128 ? put_headers(K.out, qpd6, hp, wp) : 0;
+        if (P.out_stride < 128) atomicExch(P.overflow, 1);
+    }
+    __syncthreads();
+
+    for (int y = 0; y < hp; y += CTU) {
+        for (int x = 0; x < wp; x += CTU) {
+            const bool hl = x > 0, ha = y > 0, har = ha && (x + CTU < wp);      // :1605-1608
+            // original block with edge replication, neighbours of the reconstruction (:1613-1621)
+            for (int i = tid; i < CTU * CTU; i += NT) {
+                const int yy = min(y + i / CTU, H - 1), xx = min(x + i % CTU, W - 1);
+                sm.orig[i / CTU][i % CTU] = img[(size_t)yy * W + xx];
+            }
+            if (tid < CTU) sm.rc[1 + tid][0] = hl ? rcon[(size_t)(y + tid) * wp + x - 1] : 0;
+            if (tid >= 64 && tid < 64 + 1 + 2 * CTU) {
+                const int j = tid - 64 - 1;                                     // -1 .. 63
+                const int xx = clampi(x + j, 0, wp - 1);
+                sm.rc[0][1 + j] = ha ? rcon[(size_t)(y - 1) * wp + xx] : 0;
+            }
+            if (tid >= 160 && tid < 160 + 81) {
+                const int r = (tid - 160) / 9, c = (tid - 160) % 9;
+                uint8_t s = 32, m = 1;                                          // outside the picture: size 32, DC
+                if (r == 0) { if (c > 0) s = sm.above_sz[x / 4 + c - 1]; }
+                else if (c == 0) { if (hl) { s = sm.left_sz[r - 1]; m = sm.left_md[r - 1]; } }
+                if (r == 0 || c == 0) { sm.msz[r][c] = s; sm.mmd[r][c] = m; }
+            }
+            search_cu<CTU>(K, 0, 0, (hl ? 1 : 0) | (ha ? 4 : 0) | (har ? 8 : 0));
+
+            for (int i = tid; i < CTU * CTU / 4; i += NT) {                      // :1625-1627
+                const int r = i / 8, c4 = (i % 8) * 4;
+                const uint8_t *s = &sm.rc[1 + r][1 + c4];
+                *(unsigned *)(rcon + (size_t)(y + r) * wp + x + c4) = (unsigned)s[0] | ((unsigned)s[1] << 8) | ((unsigned)s[2] << 16) | ((unsigned)s[3] << 24);
+            }
+            if (tid < 8) { sm.left_sz[tid] = sm.msz[1 + tid][8]; sm.left_md[tid] = sm.mmd[1 + tid][8]; sm.above_sz[x / 4 + tid] = sm.msz[8][1 + tid]; }
+            if (tid == 0) {
+                Coder c; c.load(sm.cur); c.ctx = sm.cur_ctx; c.out = K.out; c.cap = (unsigned)P.out_stride; c.lps = sm.lps; c.nlps = sm.next_lps;
+                c.terminate(y + CTU >= hp && x + CTU >= wp);                     // :1629
+                c.store(sm.cur);
+            }
+            __syncthreads();
+        }
+    }
+    if (tid == 0) {
+        Coder c; c.load(sm.cur); c.ctx = sm.cur_ctx; c.out = K.out; c.cap = (unsigned)P.out_stride; c.lps = sm.lps; c.nlps = sm.next_lps;
+        c.finish();                                                             // :1639-1640
+        const bool fits = c.nout <= (unsigned)P.out_stride;
+        P.out_len[f] = fits ? c.nout : 0;
+        if (!fits) atomicExch(P.overflow, 1);
+    }
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(NT, 1) hevc_frame_kernel(Params P)
+{
+    Smem &sm = *reinterpret_cast<Smem *>(IMCVT_DYN_SMEM());
+    Ctx K;
+    K.sm = &sm; K.P = &P; K.qpd6 = P.qpd6;
+    K.scratch = P.scratch + (size_t)blockIdx.x * NMODE * SCR_BYTES;
+    K.out = nullptr;
+    build_tables(sm, P.qpd6);
+    for (;;) {                                                                  // frames vary 2-3x in cost: dynamic queue
+        __syncthreads();
+        if (threadIdx.x == 0) sm.win = atomicAdd(P.next_frame, 1);
+        __syncthreads();
+        const int f = sm.win;
+        if (f >= P.n) break;
+        encode_frame(K, f);
+    }
+}
+
+}  // namespace hevc
+}  // namespace imcvt

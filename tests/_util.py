@@ -161,3 +161,23 @@ def oracle_hevc(img, qpd6):
 
 def ref_hevc(img, qpd6):
     return _hevc_call(ref_lib().HEVCImageEncoder, img, qpd6)
+
+
+def emu_hevc(img, qpd6):
+    """The SOURCE of the CUDA HEVC kernel run under the CPU SIMT emulator (tests/emu, test infrastructure)."""
+    if "emu" not in _libs:
+        d = os.path.join(ROOT, "tests", "emu")
+        subprocess.run(["make", "-C", d, "-s"], check=True, capture_output=True)
+        lib = C.CDLL(os.path.join(d, "libhevc_emu.so"))
+        lib.emu_hevc_encode.restype = C.c_long
+        lib.emu_hevc_encode.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int), C.c_int]
+        _libs["emu"] = lib
+    img = np.ascontiguousarray(img, dtype=np.uint8)
+    h, w = img.shape
+    hp, wp = (min(h, 8192) + 31) // 32 * 32, (min(w, 8192) + 31) // 32 * 32
+    out = np.zeros(2 * (wp + 32) * (hp + 32) + 65536, dtype=np.uint8)
+    rcon = np.zeros(hp * wp, dtype=np.uint8)
+    ch, cw = C.c_int(h), C.c_int(w)
+    n = _libs["emu"].emu_hevc_encode(out.ctypes.data, out.size, img.ctypes.data, rcon.ctypes.data, C.byref(ch), C.byref(cw), qpd6)
+    assert n > 0 and ch.value == hp and cw.value == wp
+    return out[:n].tobytes(), rcon.reshape(hp, wp).copy()

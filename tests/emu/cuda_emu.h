@@ -1,0 +1,229 @@
+// tests/emu/cuda_emu.h -- TEST INFRASTRUCTURE ONLY (never part of libimcvt_b200.so).
+//
+// A minimal CPU SIMT emulator: runs the *source* of a CUDA kernel on the host so that the kernel's logic can be
+// checked bit-for-bit against the oracle in the CPU test tier (and debugged without a GPU).  Every CUDA thread
+// of a block is a fiber (ucontext); __syncthreads / __syncwarp / shuffles / ballots are cooperative yield
+// points resolved by a round-robin scheduler.  A barrier that can never complete (divergent __syncthreads,
+// a shuffle executed by part of a warp only) is reported as a deadlock instead of hanging -- which is exactly
+// the class of bug that would hang or corrupt a real GPU run.
+//
+// Blocks run one after the other, so there is no inter-block concurrency (kernels that need it cannot be
+// emulated).  Dynamic shared memory is filled with 0xCD to surface reads of uninitialised shared memory.
+#pragma once
+#include <ucontext.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <algorithm>
+#include <functional>
+#include <vector>
+
+#define __device__
+#define __host__
+#define __global__
+#define __forceinline__ inline __attribute__((always_inline))
+#define __noinline__ __attribute__((noinline))
+#define __constant__ static
+#define __launch_bounds__(...)
+#define IMCVT_HOST_EMU 1
+
+namespace emu {
+
+struct Dim3 { unsigned x = 1, y = 1, z = 1; };
+
+enum { RUNNABLE = 0, AT_BLOCK_BARRIER = 1, AT_WARP_BARRIER = 2, DONE = 3 };
+
+struct Fiber {
+    ucontext_t ctx;
+    char *stack = nullptr;
+    int state = RUNNABLE;
+};
+
+struct State {
+    Dim3 blockIdx, blockDim, gridDim;
+    int tid = 0, nthreads = 0;
+    ucontext_t sched;
+    std::vector<Fiber> fibers;
+    std::vector<uint64_t> slots;            // [warp][32] exchange slots for shuffles / ballots
+    unsigned char *smem = nullptr;
+    std::function<void()> body;
+    long n_block_barriers = 0, n_warp_barriers = 0;
+};
+
+inline State &S() { static State s; return s; }
+
+inline void yield_as(int st)
+{
+    State &s = S();
+    Fiber &f = s.fibers[s.tid];
+    f.state = st;
+    swapcontext(&f.ctx, &s.sched);
+}
+
+inline void trampoline()
+{
+    State &s = S();
+    s.body();
+    s.fibers[s.tid].state = DONE;
+    swapcontext(&s.fibers[s.tid].ctx, &s.sched);
+}
+
+constexpr size_t STACK_BYTES = 512 * 1024;
+
+// runs `body` once per CUDA thread for every block of the grid
+inline void launch(unsigned grid_x, unsigned block_x, size_t smem_bytes, std::function<void()> body)
+{
+    State &s = S();
+    s.gridDim.x = grid_x; s.blockDim.x = block_x;
+    s.nthreads = (int)block_x;
+    s.body = body;
+    s.fibers.resize(block_x);
+    s.slots.assign((size_t)((block_x + 31) / 32) * 32, 0);
+    for (auto &f : s.fibers) if (!f.stack) f.stack = (char *)malloc(STACK_BYTES);
+    s.smem = (unsigned char *)malloc(smem_bytes + 64);
+    for (unsigned b = 0; b < grid_x; b++) {
+        s.blockIdx.x = b;
+        memset(s.smem, 0xCD, smem_bytes + 64);
+        for (unsigned t = 0; t < block_x; t++) {
+            Fiber &f = s.fibers[t];
+            getcontext(&f.ctx);
+            f.ctx.uc_stack.ss_sp = f.stack;
+            f.ctx.uc_stack.ss_size = STACK_BYTES;
+            f.ctx.uc_link = nullptr;
+            makecontext(&f.ctx, (void (*)())trampoline, 0);
+            f.state = RUNNABLE;
+        }
+        const int nwarps = (int)(block_x + 31) / 32;
+        for (;;) {
+            bool ran = false;
+            for (int t = 0; t < s.nthreads; t++)
+                if (s.fibers[t].state == RUNNABLE) {
+                    s.tid = t;
+                    swapcontext(&s.sched, &s.fibers[t].ctx);
+                    ran = true;
+                }
+            bool released = false;
+            // warp barriers: every live lane of the warp waits at one
+            for (int w = 0; w < nwarps; w++) {
+                int live = 0, waiting = 0;
+                for (int l = 0; l < 32 && w * 32 + l < s.nthreads; l++) {
+                    int st = s.fibers[w * 32 + l].state;
+                    if (st != DONE) live++;
+                    if (st == AT_WARP_BARRIER) waiting++;
+                }
+                if (live > 0 && waiting == live) {
+                    for (int l = 0; l < 32 && w * 32 + l < s.nthreads; l++)
+                        if (s.fibers[w * 32 + l].state == AT_WARP_BARRIER) s.fibers[w * 32 + l].state = RUNNABLE;
+                    s.n_warp_barriers++;
+                    released = true;
+                }
+            }
+            // block barrier
+            int live = 0, waiting = 0;
+            for (int t = 0; t < s.nthreads; t++) {
+                int st = s.fibers[t].state;
+                if (st != DONE) live++;
+                if (st == AT_BLOCK_BARRIER) waiting++;
+            }
+            if (live == 0) break;
+            if (waiting == live) {
+                for (int t = 0; t < s.nthreads; t++)
+                    if (s.fibers[t].state == AT_BLOCK_BARRIER) s.fibers[t].state = RUNNABLE;
+                s.n_block_barriers++;
+                released = true;
+            }
+            if (!ran && !released) {
+                fprintf(stderr, "cuda_emu: DEADLOCK in block %u: threads wait at barriers that cannot complete\n", b);
+                for (int t = 0; t < s.nthreads; t++)
+                    if (s.fibers[t].state != DONE && (t % 32 == 0 || s.fibers[t].state != s.fibers[t - 1].state))
+                        fprintf(stderr, "   thread %d.. state %d\n", t, s.fibers[t].state);
+                abort();
+            }
+        }
+    }
+    free(s.smem);
+    s.smem = nullptr;
+}
+
+inline int lane_id() { return S().tid & 31; }
+inline uint64_t *warp_slots() { return &S().slots[(size_t)(S().tid >> 5) * 32]; }
+
+template <class T> inline uint64_t to_bits(T v) { uint64_t b = 0; memcpy(&b, &v, sizeof(T)); return b; }
+template <class T> inline T from_bits(uint64_t b) { T v; memcpy(&v, &b, sizeof(T)); return v; }
+
+template <class T> inline T exchange(T v, int src_lane)
+{
+    uint64_t *sl = warp_slots();
+    sl[lane_id()] = to_bits(v);
+    yield_as(AT_WARP_BARRIER);
+    T r = from_bits<T>(sl[src_lane & 31]);
+    yield_as(AT_WARP_BARRIER);
+    return r;
+}
+
+}  // namespace emu
+
+// ---- CUDA surface ------------------------------------------------------------------------------------
+#define threadIdx (emu::Dim3{(unsigned)emu::S().tid, 0, 0})
+#define blockIdx  (emu::S().blockIdx)
+#define blockDim  (emu::S().blockDim)
+#define gridDim   (emu::S().gridDim)
+
+inline void __syncthreads() { emu::yield_as(emu::AT_BLOCK_BARRIER); }
+inline void __syncwarp(unsigned = 0xffffffffu) { emu::yield_as(emu::AT_WARP_BARRIER); }
+inline void __threadfence_block() {}
+inline void __threadfence() {}
+
+template <class T> inline T __shfl_sync(unsigned, T v, int src, int width = 32)
+{
+    int lane = emu::lane_id();
+    return emu::exchange(v, (lane & ~(width - 1)) | (src & (width - 1)));
+}
+template <class T> inline T __shfl_xor_sync(unsigned, T v, int m, int width = 32)
+{
+    int lane = emu::lane_id(), src = lane ^ m;
+    if ((src & ~(width - 1)) != (lane & ~(width - 1))) src = lane;
+    return emu::exchange(v, src);
+}
+template <class T> inline T __shfl_up_sync(unsigned, T v, unsigned d, int width = 32)
+{
+    int lane = emu::lane_id();
+    int src = ((lane & (width - 1)) >= (int)d) ? lane - (int)d : lane;
+    return emu::exchange(v, src);
+}
+template <class T> inline T __shfl_down_sync(unsigned, T v, unsigned d, int width = 32)
+{
+    int lane = emu::lane_id();
+    int src = ((lane & (width - 1)) + (int)d < width) ? lane + (int)d : lane;
+    return emu::exchange(v, src);
+}
+inline unsigned __ballot_sync(unsigned, int pred)
+{
+    uint64_t *sl = emu::warp_slots();
+    sl[emu::lane_id()] = pred ? 1 : 0;
+    emu::yield_as(emu::AT_WARP_BARRIER);
+    unsigned r = 0;
+    int base = emu::S().tid & ~31;
+    for (int l = 0; l < 32 && base + l < emu::S().nthreads; l++)
+        if (emu::S().fibers[base + l].state != emu::DONE && sl[l]) r |= 1u << l;
+    emu::yield_as(emu::AT_WARP_BARRIER);
+    return r;
+}
+inline int __any_sync(unsigned m, int p) { return __ballot_sync(m, p) != 0; }
+
+inline int __clz(int v) { return v == 0 ? 32 : __builtin_clz((unsigned)v); }
+inline int __clzll(long long v) { return v == 0 ? 64 : __builtin_clzll((unsigned long long)v); }
+inline int __popc(unsigned v) { return __builtin_popcount(v); }
+inline int __ffs(int v) { return __builtin_ffs(v); }
+inline unsigned __funnelshift_l(unsigned lo, unsigned hi, unsigned sh)
+{
+    sh &= 31;
+    return sh ? (hi << sh) | (lo >> (32 - sh)) : hi;
+}
+template <class T> inline T __ldg(const T *p) { return *p; }
+using std::min;
+using std::max;
+inline unsigned atomicOr(unsigned *p, unsigned v) { unsigned o = *p; *p |= v; return o; }
+inline int atomicExch(int *p, int v) { int o = *p; *p = v; return o; }
+inline int atomicAdd(int *p, int v) { int o = *p; *p += v; return o; }

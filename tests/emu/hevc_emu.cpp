@@ -1,0 +1,27 @@
+// tests/emu/hevc_emu.cpp -- TEST INFRASTRUCTURE ONLY.
+// Runs the SOURCE of the CUDA HEVC frame kernel (imcvt_b200/csrc/hevc_kernel.cuh) under the fiber SIMT emulator
+// of cuda_emu.h, so that tests/test_emu_hevc.py can compare it bit-for-bit with the oracle without a GPU.
+// It is not linked into libimcvt_b200.so and nothing in the product loads it.
+#include "cuda_emu.h"
+#include "../../imcvt_b200/csrc/hevc_kernel.cuh"
+
+using namespace imcvt::hevc;
+
+extern "C" long emu_hevc_encode(uint8_t *stream, size_t cap, const uint8_t *img, uint8_t *img_rcon, int *ysz, int *xsz, int qpd6)
+{
+    const int H = *ysz, W = *xsz;
+    const int hp = (std::min(H, 8192) + 31) / 32 * 32, wp = (std::min(W, 8192) + 31) / 32 * 32;
+    Params P;
+    unsigned long long len = 0;
+    int overflow = 0, next = 0;
+    std::vector<uint8_t> scratch((size_t)NMODE * SCR_BYTES);
+    P.frames = img; P.frame_stride = (size_t)H * W; P.n = 1; P.H = H; P.W = W; P.hp = hp; P.wp = wp; P.qpd6 = qpd6;
+    P.out = stream; P.out_stride = cap; P.out_len = &len;
+    P.rcon = img_rcon; P.rcon_stride = (size_t)hp * wp;
+    P.scratch = scratch.data(); P.overflow = &overflow; P.next_frame = &next;
+    emu::launch(1, NT, sizeof(Smem), [&] { hevc_frame_kernel(P); });
+    *ysz = hp; *xsz = wp;
+    return overflow ? 0 : (long)len;
+}
+
+extern "C" long emu_barrier_count(int which) { return which ? emu::S().n_warp_barriers : emu::S().n_block_barriers; }

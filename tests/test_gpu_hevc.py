@@ -1,0 +1,76 @@
+"""GPU: parity of the CUDA H.265 intra path (through the C-ABI) with the oracle and the golden fixtures."""
+import os
+import tempfile
+
+import numpy as np
+import pytest
+
+import imcvt_b200
+from imcvt_b200 import synth
+from tests._util import GOLDEN, golden_table, load_pnm, oracle_hevc, sha256
+from tests.test_oracle_hevc import fixture_gray, hevc_edge_images
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("entry", [e for e in golden_table() if e["codec"] == "hevc"],
+                         ids=lambda e: f"{e['fixture']}-qpd6_{e['setting']}")
+def test_known_answers(entry):
+    img = fixture_gray(entry["fixture"])
+    s, _ = imcvt_b200.encode_hevc_batch(img[None], entry["setting"])
+    assert len(s[0]) == entry["length"]
+    assert sha256(s[0]) == entry["sha256"]
+
+
+@pytest.mark.parametrize("qpd6", [0, 1, 2, 3, 4])
+def test_edge_cases_match_oracle(qpd6):
+    for name, img in hevc_edge_images():
+        s, r = imcvt_b200.encode_hevc_batch(img[None], qpd6)
+        s2, r2 = oracle_hevc(img, qpd6)
+        assert s[0] == s2, name
+        assert np.array_equal(r[0], r2), name
+
+
+def test_batch_of_synthetic_frames_all_kinds():
+    for kind in ["natural", "texture", "noise", "constant"]:
+        frames = synth.batch(kind, 3, 72, 136)
+        s, r = imcvt_b200.encode_hevc_batch(frames, 4)
+        for i in range(3):
+            s2, r2 = oracle_hevc(frames[i], 4)
+            assert s[i] == s2, f"{kind}[{i}]"
+            assert np.array_equal(r[i], r2), f"{kind}[{i}]"
+
+
+def test_batch_larger_than_the_grid_uses_the_frame_queue():
+    frames = synth.batch("natural", 200, 32, 64)
+    s, _ = imcvt_b200.encode_hevc_batch(frames, 3, want_rcon=False)
+    for i in (0, 57, 147, 148, 199):
+        assert s[i] == oracle_hevc(frames[i], 3)[0], i
+    assert len(set(s)) > 150
+
+
+def test_hevc_image_encoder_and_file_writer_are_drop_ins():
+    img, _ = load_pnm(os.path.join(GOLDEN, "P5.pnm"))
+    entry = [e for e in golden_table() if e["codec"] == "hevc" and e["fixture"] == "P5" and e["setting"] == 4][0]
+    s, rcon = imcvt_b200.hevc_image_encoder(img, 4)
+    assert sha256(s) == entry["sha256"]
+    assert rcon.shape == (288, 320)
+    with tempfile.TemporaryDirectory() as d:
+        path = os.path.join(d, "a.h265")
+        assert imcvt_b200.write_hevc_image_file(path, img, 0, img.shape[0], img.shape[1], 4) == 0
+        assert sha256(open(path, "rb").read()) == entry["sha256"]
+        # RGB input: the green channel is coded (imageio_hevc.c:24-26)
+        rgb, _ = load_pnm(os.path.join(GOLDEN, "P6.pnm"))
+        e6 = [e for e in golden_table() if e["codec"] == "hevc" and e["fixture"] == "P6" and e["setting"] == 2][0]
+        assert imcvt_b200.write_hevc_image_file(path, rgb, 1, rgb.shape[0], rgb.shape[1], 2) == 0
+        assert sha256(open(path, "rb").read()) == e6["sha256"]
+        assert imcvt_b200.write_hevc_image_file(os.path.join(d, "no/such/dir.h265"), img, 0, img.shape[0], img.shape[1], 4) == 1
+
+
+def test_small_output_slot_is_an_error_not_a_crash():
+    import ctypes as C
+    img = np.random.default_rng(1).integers(0, 256, (64, 64), dtype=np.uint8)
+    out = np.zeros(600, dtype=np.uint8)
+    ln = (C.c_size_t * 1)()
+    rc = imcvt_b200.lib().imcvtEncodeBatchHEVC(img.ctypes.data, 64 * 64, 1, 64, 64, 0, out.ctypes.data, 600, C.cast(ln, C.c_void_p), None, 0)
+    assert rc == 1
