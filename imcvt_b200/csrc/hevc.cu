@@ -28,15 +28,16 @@ int encode_device(const uint8_t *d_frames, size_t frame_stride, int n, uint32_t 
     }
     const int grid = n < E.sm_count ? n : E.sm_count;                       // one CTA per SM; frames come from a queue
     const size_t rstride = (rbytes + 255) & ~(size_t)255;
-    size_t bytes = 4096 + (size_t)grid * NMODE * SCR_BYTES + 256;
+    size_t bytes = 4096 + (size_t)grid * NCAND * SCR_BYTES + 256 + (size_t)grid * NCAND * CAND_LIST_U16 * 2 + 256;
     if (!d_rcon) bytes += (size_t)n * rstride + 256;
     if (E.ws.reserve(bytes)) return 1;
-    uint8_t *scratch = E.ws.take<uint8_t>((size_t)grid * NMODE * SCR_BYTES);
+    uint8_t *scratch = E.ws.take<uint8_t>((size_t)grid * NCAND * SCR_BYTES);
+    unsigned short *lists = E.ws.take<unsigned short>((size_t)grid * NCAND * CAND_LIST_U16);
     int *next = E.ws.take<int>(1);
     uint8_t *rc = d_rcon;
     size_t rcs = rcon_stride;
     if (!rc) { rc = E.ws.take<uint8_t>((size_t)n * rstride); rcs = rstride; }
-    if (!scratch || !next || !rc) { set_error("workspace carve failed"); return 1; }
+    if (!scratch || !lists || !next || !rc) { set_error("workspace carve failed"); return 1; }
     IMCVT_CUDA(cudaMemsetAsync(next, 0, sizeof(int), st));
 
     Params P;
@@ -45,7 +46,7 @@ int encode_device(const uint8_t *d_frames, size_t frame_stride, int n, uint32_t 
     P.out = d_out; P.out_stride = out_stride;
     P.out_len = (unsigned long long *)d_out_len;
     P.rcon = rc; P.rcon_stride = rcs;
-    P.scratch = scratch; P.overflow = d_overflow; P.next_frame = next;
+    P.scratch = scratch; P.lists = lists; P.overflow = d_overflow; P.next_frame = next;
     {
         LaunchScope ls("hevc_frame", st);
         hevc_frame_kernel<<<grid, NT, sizeof(Smem), st>>>(P);

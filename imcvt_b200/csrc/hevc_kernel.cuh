@@ -49,6 +49,9 @@ constexpr int CXN = 142, CXP = 144;     // context bytes (padded to words)
 constexpr int SCR_BYTES = 8192;         // private trial stream per candidate (reference bound: 3200, :794)
 constexpr int I32MAX = 0x7fffffff;
 constexpr int NSCAN = 1520;
+constexpr int NCAND = 2 * NMODE;        // candidates coded together: 35 one-TU trials + 35 four-TU trials
+constexpr int SLOT = 112;               // bin-list entries per coefficient group (worst case 107)
+constexpr int CAND_LIST_U16 = 64 * SLOT + 64;   // 64 group slots + 64 group headers per candidate
 
 // context offsets: member order of the reference's ContextSet (:744-758)
 enum { CX_SPLIT_CU = 0, CX_PART = 3, CX_YMODE = 4, CX_UVMODE = 5, CX_SPLIT_TU = 6, CX_YCBF = 9, CX_UVCBF = 11,
@@ -95,24 +98,28 @@ struct Params {
     uint8_t *out; size_t out_stride;                 // output slots
     unsigned long long *out_len;                     // [n]
     uint8_t *rcon; size_t rcon_stride;               // [n][hp*wp] reconstruction (also the line buffer between CTU rows)
-    uint8_t *scratch;                                // [gridDim.x][NMODE][SCR_BYTES] private trial streams
+    uint8_t *scratch;                                // [gridDim.x][NCAND][SCR_BYTES] private trial streams
+    unsigned short *lists;                           // [gridDim.x][NCAND][CAND_LIST_U16] bin lists of the trials
     int *overflow;                                   // set to 1 when a stream did not fit its slot
     int *next_frame;                                 // dynamic frame queue
 };
 
 struct CoderRegs { int range, low, nbits, pending, held, zeros; unsigned nout; int pad_; };
 
+struct BinDesc { int active, lid, slot0, mode, lev_off, last; unsigned sg0, sg1; };   // one transform unit to binarise
+
 struct Smem {
-    short lev[NMODE][LEV_STRIDE];                   // quantised levels of the candidates
+    short lev[NMODE][LEV_STRIDE];                   // quantised levels of the candidates of the step in flight
     short ws[NW][WS_STRIDE];                        // per-warp transpose scratch
-    uint8_t rec[NMODE][REC_STRIDE];                 // candidate prediction -> reconstruction tiles
+    uint8_t rec[NCAND][REC_STRIDE];                 // candidate prediction -> reconstruction tiles
     uint8_t refs[NW][REFS_BYTES];
-    uint8_t cctx[NMODE][CXP];                       // candidate context sets
-    CoderRegs ccoder[NMODE];
-    int cbits[NMODE], csse[NMODE];
-    int clast[NMODE][4];
-    unsigned ccg[NMODE][4][2];
-    short cmag[NMODE][16];
+    BinDesc bdesc[NW][8];
+    uint8_t cctx[NCAND][CXP];                       // candidate context sets
+    CoderRegs ccoder[NCAND];
+    int cbits[NCAND], csse[NCAND];
+    int clast[NCAND][4];
+    unsigned ccg[NCAND][4][2];                      // significant groups by position: bit yc*8+xc
+    unsigned csg[NCAND][4][2];                      // significant groups by scan index
     // CTU state
     uint8_t orig[CTU][CTU];
     uint8_t rc[CTU + 1][RCP];                       // reconstruction window: row 0 / column 0 are the neighbours (:1588-1589)
@@ -120,14 +127,15 @@ struct Smem {
     uint8_t left_sz[8], left_md[8];                 // right-most column of the previous CTU
     uint8_t best_rec[CTU * CTU + 16 * 16 + 8 * 8];  // best reconstruction so far per CU level
     uint8_t nxn_rec[8 * 8];
-    short nxn_lev[4][4 * 6];
+    unsigned short nxn_list[4][SLOT], nxn_hdr[4];   // bin lists of the four kept 4x4 blocks
     int nxn_mode[4], nxn_last[4];
     unsigned nxn_cg[4];
     CoderRegs cur, entry[3];
     uint8_t cur_ctx[CXP], entry_ctx[3][CXP], init_ctx[CXP];
     int best_cost[3];
     int win, red[NW];
-    uint8_t lps[256], next_lps[128];
+    unsigned lpsw[64];                              // LPS range table, one word per state (4 range classes)
+    uint8_t next_lps[128];
     uint8_t scan[NSCAN][2];                         // coefficient scans (y, x): see scan_base()
     uint8_t dord[4][64][2];                         // up-right diagonal orders of 1, 2x2, 4x4, 8x8 grids
     uint8_t above_sz[2048];                         // CU sizes along the bottom of the CTU row above (4x4 cells)
@@ -142,13 +150,17 @@ __device__ __forceinline__ int iabs(int v) { return v < 0 ? -v : v; }
 template <int TS> struct SizeClass { static constexpr int v = TS == 4 ? 0 : TS == 8 ? 1 : TS == 16 ? 2 : 3; };
 __device__ __forceinline__ int size_class(int sz) { return sz == 4 ? 0 : sz == 8 ? 1 : sz == 16 ? 2 : 3; }
 
-__device__ __forceinline__ int rd_cost(int qpd6, int dist, int bits)                   // calcRDcost :177-185
-{
-    const int wd = c_wd[qpd6], wb = c_wb[qpd6];
-    const int c1 = (I32MAX / wd <= dist) ? I32MAX : wd * dist;
-    const int c2 = (I32MAX / wb <= bits) ? I32MAX : wb * bits;
-    return (I32MAX - c1 <= c2) ? I32MAX : c1 + c2;
-}
+// calcRDcost :177-185 with the two divisions (I32MAX / weight) taken out of the hot loops: they only depend on qpd6
+struct RdK {
+    int wd, wb, limd, limb;
+    __device__ __forceinline__ void init(int qpd6) { wd = c_wd[qpd6]; wb = c_wb[qpd6]; limd = I32MAX / wd; limb = I32MAX / wb; }
+    __device__ __forceinline__ int cost(int dist, int bits) const
+    {
+        const int c1 = (limd <= dist) ? I32MAX : wd * dist;
+        const int c2 = (limb <= bits) ? I32MAX : wb * bits;
+        return (I32MAX - c1 <= c2) ? I32MAX : c1 + c2;
+    }
+};
 
 __device__ __forceinline__ int level_rate(int level)                                   // estimateCoeffRate :526-535
 {
@@ -190,7 +202,8 @@ struct Coder {
     int range, low, nbits, pending, held, zeros;
     unsigned nout, cap;
     uint8_t *ctx, *out;
-    const uint8_t *lps, *nlps;
+    const unsigned *lps;
+    const uint8_t *nlps;
 
     __device__ __forceinline__ void load(const CoderRegs &r) { range = r.range; low = r.low; nbits = r.nbits; pending = r.pending; held = r.held; zeros = r.zeros; nout = r.nout; }
     __device__ __forceinline__ void store(CoderRegs &r) const { r.range = range; r.low = low; r.nbits = nbits; r.pending = pending; r.held = held; r.zeros = zeros; r.nout = nout; }
@@ -226,7 +239,7 @@ struct Coder {
     __device__ __forceinline__ void bin(int b, int ci)                                 // CABACputBin :913-932
     {
         const int st = ctx[ci];
-        const int l = lps[(st >> 1) * 4 + ((range >> 6) & 3)];
+        const int l = (int)((lps[st >> 1] >> (((range >> 6) & 3) * 8)) & 0xFFu);
         range -= l;
         if ((b != 0) != ((st & 1) != 0)) {
             const int n = __clz(l >> 3) - 26;           // renormalisation shift (table :712-714 in closed form)
@@ -250,6 +263,12 @@ struct Coder {
             nbits -= n;
             shift_out();
         }
+    }
+    __device__ __forceinline__ void bypass_chunk(int val, int n)                       // one step of CABACputBins: n <= 8 bins
+    {
+        low = (low << n) + range * val;
+        nbits -= n;
+        shift_out();
     }
     __device__ __forceinline__ void terminate(int b)                                   // CABACputTerminate :881-895
     {
@@ -355,89 +374,208 @@ __device__ __forceinline__ int sig_ctx_index(int sz, int scan_type, int y, int x
     return ci + (s == 0 ? 2 : s < 3 ? 1 : 0);
 }
 
-__device__ inline void put_remaining(Coder &c, int v, int rice)                        // putRemainExGolomb :1153-1168
+// ------------------------------------------------------------------------------------------------
+// Bin lists.  The residual syntax of a transform unit (putCoef :1172-1268) is binarised in parallel, one
+// coefficient group (16 scan positions) per half-warp, into a fixed slot of 16-bit entries; the arithmetic
+// coder lane of the trial then only walks entries.  Entry: bits 15..14 type
+//   0 context bin: bits 7..0 context index, bit 8 value
+//   1 context bin of the greater-than-1 class, 2 of the greater-than-2 class: as 0, but the context set of these
+//     depends on the PREVIOUS coded group (c1 == 0 there, :1229-1232); the coder lane adds 4 / 1 when that holds
+//   3 bypass chunk: bits 7..0 value, bits 11..8 length (1..8) -- chunked exactly like CABACputBins (:898-910)
+// Header per group: bits 6..0 entry count, bit 7 group has non-zero levels, bit 8 one of its first 8 levels is > 1.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned short ent_ctx(int cls, int ci, int bin) { return (unsigned short)((cls << 14) | (bin << 8) | ci); }
+__device__ __forceinline__ unsigned short ent_byp(int val, int len) { return (unsigned short)((3 << 14) | (len << 8) | val); }
+
+// number of chunk entries of one CABACputBins(value, len) call
+__device__ __forceinline__ int chunks_of(int len) { return (len + 7) >> 3; }
+__device__ __forceinline__ void emit_bypass(unsigned short *dst, int &o, int val, int len)
 {
-    if (v < (3 << rice)) {
-        const int len = v >> rice;
-        c.bypass((1 << (len + 1)) - 2, len + 1);
-        c.bypass(v & ((1 << rice) - 1), rice);
-    } else {
-        int len = rice;
-        v -= 3 << rice;
-        for (; v >= (1 << len); len++) v -= 1 << len;
-        c.bypass((1 << (4 + len - rice)) - 2, 4 + len - rice);
-        c.bypass(v, len);
+    val &= (1 << len) - 1;
+    while (len > 0) {
+        const int n = len < 8 ? len : 8;
+        len -= n;
+        dst[o++] = ent_byp((val >> len) & ((1 << n) - 1), n);
     }
 }
 
-struct LevBlock { const short *p; int pitch; int last; unsigned cg0, cg1; };           // cg: bit (yc*8+xc) = group has a non-zero level
+// One coefficient group by the 16 lanes of a half-warp; lane hl codes scan position cg*16 + 15 - hl, so lane order is
+// coding order.  Executed by all 32 lanes (ballots / shuffles inside); `has` masks a half without a task.
+__device__ __forceinline__ void binarize_cg(bool has, const BinDesc &D, int sz, int cg, int hl, int half,
+                                            const uint8_t (*scan_all)[2], const short *levbase,
+                                            unsigned cgp0, unsigned cgp1, unsigned short *lists)
+{
+    const int st = scan_type_for(sz, D.mode), ncg = sz >> 2, lp = sz + 2;
+    const uint8_t (*scan)[2] = scan_all + scan_base(st, size_class(sz));
+    const int i = cg * 16 + 15 - hl;
+    const int y = scan[i][0], x = scan[i][1], yc = y >> 2, xc = x >> 2;
+    const bool valid = has && i <= D.last;
+    const int v = valid ? (int)levbase[D.lev_off + y * lp + x] : 0;
+    const bool nzf = v != 0;
+    const int mag = iabs(v);
+    const bool first_cg = cg == 0;
+    const unsigned lt = (1u << hl) - 1u;
+    const int sh = half * 16;
 
-// residual_coding of one luma TU (putCoef :1172-1268)
-__device__ inline void put_coefs(Coder &c, int sz, int mode, const LevBlock &L, const uint8_t (*scan_all)[2], short *mag)
+    const unsigned nzball = (__ballot_sync(0xffffffffu, nzf) >> sh) & 0xFFFFu;
+    const int nzidx = __popc(nzball & lt), nz = __popc(nzball);
+    // significant_coeff_flag
+    const int bpos = yc * 8 + xc, br = bpos + 1, bb = bpos + 8;
+    const int cgs = (int)((bpos < 32 ? cgp0 >> bpos : cgp1 >> (bpos - 32)) & 1u);
+    const int right = xc < ncg - 1 && ((br < 32 ? cgp0 >> br : cgp1 >> (br - 32)) & 1u);
+    const int below = yc < ncg - 1 && ((bb < 32 ? cgp0 >> bb : cgp1 >> (bb - 32)) & 1u);
+    const int nb = (below << 1) | right;
+    const bool sig_coded = valid && i != D.last && (first_cg || (cgs && (hl != 15 || nzidx > 0)));
+    const unsigned sball = (__ballot_sync(0xffffffffu, sig_coded) >> sh) & 0xFFFFu;
+    const int n1 = __popc(sball);
+    // greater-than-1 flags of the first 8 levels, greater-than-2 flag of the first level > 1
+    const bool big = nzf && mag > 1 && nzidx < 8;
+    const unsigned bball = (__ballot_sync(0xffffffffu, big) >> sh) & 0xFFFFu;
+    const bool earlier_big = (bball & lt) != 0;
+    const bool firstbig = big && !earlier_big;
+    const unsigned g2ball = (__ballot_sync(0xffffffffu, firstbig && mag > 2) >> sh) & 0xFFFFu;
+    const int anybig = bball != 0;
+    const int n2 = n1 + (nz < 8 ? nz : 8), n3 = n2 + anybig;
+    const bool escape = nz > 8 || __popc(bball) > 1 || g2ball != 0;
+    // sign bits, first coded level in the most significant position
+    int signs = (nzf && v < 0) ? 1 << (nz - 1 - nzidx) : 0;
+#pragma unroll
+    for (int d = 1; d < 16; d <<= 1) signs |= __shfl_xor_sync(0xffffffffu, signs, d, 16);
+    const int n4 = n3 + (nz > 8 ? 2 : nz > 0 ? 1 : 0);
+
+    // remaining absolute levels: Rice parameter and base level evolve along the group (:1252-1263)
+    int my_rice = 0, my_base = 3;
+    if (__any_sync(0xffffffffu, escape && has)) {
+        int rice = 0, base = 3, seen = 0;
+#pragma unroll 4
+        for (int q = 0; q < 16; q++) {
+            const int mq = __shfl_sync(0xffffffffu, mag, q, 16);
+            if (q == hl) { my_rice = rice; my_base = base; }
+            if (mq > 0) {
+                const int ev = mq - (seen < 8 ? base : 1);
+                if (ev >= 0 && mq > (3 << rice)) rice = rice < 4 ? rice + 1 : 4;
+                if (mq >= 2) base = 2;
+                seen++;
+            }
+        }
+    }
+    int lenA = 0, valA = 0, lenB = 0, valB = 0;
+    if (escape && nzf) {
+        const int ev = mag - (nzidx < 8 ? my_base : 1);
+        if (ev >= 0) {                                                          // putRemainExGolomb :1153-1168
+            if (ev < (3 << my_rice)) {
+                const int len = ev >> my_rice;
+                lenA = len + 1; valA = (1 << (len + 1)) - 2;
+                lenB = my_rice; valB = ev & ((1 << my_rice) - 1);
+            } else {
+                int len = my_rice, w = ev - (3 << my_rice);
+                for (; w >= (1 << len); len++) w -= 1 << len;
+                lenA = 4 + len - my_rice; valA = (1 << lenA) - 2;
+                lenB = len; valB = w;
+            }
+        }
+    }
+    const int mine = chunks_of(lenA) + chunks_of(lenB);
+    int incl = mine;
+#pragma unroll
+    for (int d = 1; d < 16; d <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, d, 16); if (hl >= d) incl += t; }
+    const int total = n4 + __shfl_sync(0xffffffffu, incl, 15, 16);
+
+    if (!has) return;
+    unsigned short *slot = lists + (size_t)D.lid * CAND_LIST_U16 + (size_t)(D.slot0 + cg) * SLOT;
+    if (sig_coded) slot[__popc(sball & lt)] = ent_ctx(0, CX_SIG + sig_ctx_index(sz, st, y, x, nb), nzf);
+    if (nzf && nzidx < 8) {
+        const int c1 = earlier_big ? 0 : (nzidx < 2 ? 1 + nzidx : 3);
+        slot[n1 + nzidx] = ent_ctx(1, CX_ONE + (first_cg ? 0 : 8) + c1, mag > 1);
+    }
+    if (firstbig) slot[n2] = ent_ctx(2, CX_ABS + (first_cg ? 0 : 2), mag > 2);
+    if (nzf && nzidx == 0) {
+        if (nz > 8) { slot[n3] = ent_byp((signs >> (nz - 8)) & 0xFF, 8); slot[n3 + 1] = ent_byp(signs & ((1 << (nz - 8)) - 1), nz - 8); }
+        else slot[n3] = ent_byp(signs, nz);
+    }
+    if (mine) {
+        int o = n4 + incl - mine;
+        emit_bypass(slot, o, valA, lenA);
+        emit_bypass(slot, o, valB, lenB);
+    }
+    if (hl == 0) lists[(size_t)D.lid * CAND_LIST_U16 + 64 * SLOT + D.slot0 + cg] = (unsigned short)(total | (nz > 0 ? 0x80 : 0) | (anybig ? 0x100 : 0));
+}
+
+// Binarises the transform units a warp has just quantised (descriptors in sm.bdesc[warp][0..G-1], levels in sm.lev).
+// Tasks are the significant coefficient groups plus group 0 of every unit; each half-warp takes its share.
+template <int TS>
+__device__ __forceinline__ void binarize_warp(Smem &sm, int warp, int lane, unsigned short *lists)
+{
+    constexpr int G = 32 / TS;
+    const int half = lane >> 4, hl = lane & 15;
+    int gi = G == 1 ? 0 : half * (G / 2);
+    const int gend = G == 1 ? 1 : gi + G / 2;
+    unsigned m0 = 0, m1 = 0;
+    BinDesc D = sm.bdesc[warp][gi];
+    auto load_masks = [&]() {
+        m0 = 0; m1 = 0;
+        if (D.active) {
+            m0 = D.sg0 | 1u; m1 = D.sg1;
+            if (G == 1) { const unsigned alt = half ? 0xAAAAAAAAu : 0x55555555u; m0 &= alt; m1 &= alt; }
+        }
+    };
+    load_masks();
+    for (;;) {
+        while ((m0 | m1) == 0 && gi + 1 < gend) { gi++; D = sm.bdesc[warp][gi]; load_masks(); }
+        const bool has = (m0 | m1) != 0;
+        if (!__any_sync(0xffffffffu, has)) break;
+        int cg = 0;
+        if (has) {
+            if (m0) { cg = __ffs((int)m0) - 1; m0 &= m0 - 1; }
+            else    { cg = 32 + __ffs((int)m1) - 1; m1 &= m1 - 1; }
+        }
+        // position-order group mask of this unit (for the neighbour-group context)
+        const int blk = D.slot0 / ((TS / 4) * (TS / 4));
+        const int cand = D.lid;
+        const unsigned cgp0 = has ? sm.ccg[cand][blk][0] : 0u, cgp1 = has ? sm.ccg[cand][blk][1] : 0u;
+        binarize_cg(has, D, TS, cg, hl, half, sm.scan, &sm.lev[0][0], cgp0, cgp1, lists);
+    }
+}
+
+// Arithmetic coding of one transform unit from its bin lists (one lane).  slots / hdrs point at the unit's group 0.
+__device__ __forceinline__ void code_block(Coder &c, int sz, int mode, int last, unsigned cgp0, unsigned cgp1, unsigned sg0, unsigned sg1,
+                                           const unsigned short *slots, const unsigned short *hdrs, const uint8_t (*scan_all)[2])
 {
     const int st = scan_type_for(sz, mode), ncg = sz >> 2;
     const uint8_t (*scan)[2] = scan_all + scan_base(st, size_class(sz));
-    const int last = L.last;
-    int nz = 0, signs = 0, nb = 0, c1 = 1, cgs = 0;
-
     put_last_pos(c, sz, st, scan[last][0], scan[last][1]);
-
-    for (int i = last; i >= 0; i--) {
-        const int y = scan[i][0], x = scan[i][1], yc = y >> 2, xc = x >> 2;
-        const bool is_last = i == last, first_cg = (yc | xc) == 0;
-        const bool cg_begin = (i & 15) == 15 || is_last, cg_end = (i & 15) == 0;
-        if (cg_begin) {
-            const int b = yc * 8 + xc;
-            cgs = (int)(((b < 32 ? L.cg0 >> b : L.cg1 >> (b - 32))) & 1u);
-            const int br = b + 1, bb = b + 8;
-            const int right = xc < ncg - 1 && (((br < 32 ? L.cg0 >> br : L.cg1 >> (br - 32))) & 1u);
-            const int below = yc < ncg - 1 && (((bb < 32 ? L.cg0 >> bb : L.cg1 >> (bb - 32))) & 1u);
-            nb = (below << 1) | right;
-            nz = 0; signs = 0;
-            if (!first_cg && !is_last) {
-                c.bin(cgs, CX_SIGCG + (nb != 0));
-                if (!cgs) { i &= ~15; continue; }               // nothing else is coded for an all-zero group
-            }
+    int cg = last >> 4, prevbig = 0, add = 0, k = 0;
+    unsigned h = hdrs[cg];
+    int cnt = (int)(h & 0x7Fu);
+    const unsigned short *sp = slots + cg * SLOT;
+    for (;;) {
+        int isb = 0, a = 0, b = 0;
+        bool emit = false;
+        if (k < cnt) {
+            const unsigned e = sp[k++];
+            const int type = (int)(e >> 14);
+            if (type == 3) { isb = 1; a = (int)(e & 0xFFu); b = (int)((e >> 8) & 15u); }
+            else { a = (int)(e & 0xFFu) + (type == 1 ? 4 * add : type == 2 ? add : 0); b = (int)((e >> 8) & 1u); }
+            emit = true;
+        } else {
+            if (h & 0x80u) prevbig = (int)((h >> 8) & 1u);
+            if (--cg < 0) break;
+            const int yc = scan[cg * 16][0] >> 2, xc = scan[cg * 16][1] >> 2;
+            const int bpos = yc * 8 + xc, br = bpos + 1, bb = bpos + 8;
+            const int cgs = (int)((cg < 32 ? sg0 >> cg : sg1 >> (cg - 32)) & 1u);
+            const int right = xc < ncg - 1 && ((br < 32 ? cgp0 >> br : cgp1 >> (br - 32)) & 1u);
+            const int below = yc < ncg - 1 && ((bb < 32 ? cgp0 >> bb : cgp1 >> (bb - 32)) & 1u);
+            if (cg > 0) { a = CX_SIGCG + ((right | below) != 0); b = cgs; emit = true; }      // coded_sub_block_flag
+            if (cgs || cg == 0) { h = hdrs[cg]; cnt = (int)(h & 0x7Fu); sp = slots + cg * SLOT; add = prevbig; }
+            else { h = 0; cnt = 0; }
+            k = 0;
         }
-        const int v = L.p[y * L.pitch + x];
-        if (!is_last && (first_cg || (cgs && (!cg_end || nz > 0))))
-            c.bin(v != 0, CX_SIG + sig_ctx_index(sz, st, y, x, nb));
-        if (v != 0) { mag[nz++] = (short)iabs(v); signs = (signs << 1) | (v < 0); }
-
-        if (cg_end && nz > 0) {
-            const int set = (first_cg ? 0 : 2) + (c1 == 0);
-            int escape = nz > 8, g2 = -1;
-            c1 = 1;
-            for (int j = 0; j < 8 && j < nz; j++) {
-                const int big = mag[j] > 1;
-                c.bin(big, CX_ONE + 4 * set + c1);
-                if (big) {
-                    c1 = 0;
-                    if (g2 < 0) g2 = mag[j] > 2; else escape = 1;
-                } else if (c1 > 0 && c1 < 3) c1++;
-            }
-            if (c1 == 0 && g2 >= 0) { c.bin(g2, CX_ABS + set); escape |= g2; }
-            c.bypass(signs, nz);
-            if (escape) {
-                int base = 3, rice = 0;
-                for (int j = 0; j < nz; j++) {
-                    const int m = mag[j];
-                    const int ev = m - (j < 8 ? base : 1);
-                    if (ev >= 0) {
-                        put_remaining(c, ev, rice);
-                        if (m > (3 << rice)) rice = rice < 4 ? rice + 1 : 4;
-                    }
-                    if (m >= 2) base = 2;
-                }
-            }
-        }
+        if (emit) { if (isb) c.bypass_chunk(a, b); else c.bin(b, a); }
     }
 }
 
-// everything of a coding unit after split_cu_flag.
-// kind 0: 2Nx2N one TU (:1271-1290)   kind 1: 2Nx2N four TUs (:1293-1315)   kind 2: NxN (:1318-1339)
-__device__ inline void put_cu(Coder &c, int sz, int kind, const int *modes, const int *left, const int *above,
-                              const LevBlock *blk, const uint8_t (*scan_all)[2], short *mag)
+// coding-unit syntax before the residual (putCU_* :1271-1339 up to the cbf flags)
+__device__ __forceinline__ void put_cu_head(Coder &c, int sz, int kind, const int *modes, const int *left, const int *above)
 {
     if (sz == 8) c.bin(kind != 2, CX_PART);                                            // putPartSize :951-954
     put_luma_modes(c, kind == 2 ? 4 : 1, modes, left, above);
@@ -445,17 +583,6 @@ __device__ inline void put_cu(Coder &c, int sz, int kind, const int *modes, cons
     if (kind != 2) c.bin(kind == 1, CX_SPLIT_TU + (sz == 32 ? 0 : sz == 16 ? 1 : 2));  // :1025-1032
     c.bin(0, CX_UVCBF + 0);                                                            // cbf_cb, cbf_cr at depth 0
     c.bin(0, CX_UVCBF + 0);
-    if (kind == 0) {
-        const int cbf = (blk[0].cg0 | blk[0].cg1) != 0;
-        c.bin(cbf, CX_YCBF + 1);                                                       // depth 0 (:1039)
-        if (cbf) put_coefs(c, sz, modes[0], blk[0], scan_all, mag);
-    } else {
-        for (int i = 0; i < 4; i++) {
-            const int cbf = (blk[i].cg0 | blk[i].cg1) != 0;
-            c.bin(cbf, CX_YCBF + 0);
-            if (cbf) put_coefs(c, sz >> 1, modes[kind == 2 ? i : 0], blk[i], scan_all, mag);
-        }
-    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -559,14 +686,14 @@ template <int TS> __device__ __forceinline__ unsigned group_or(unsigned v)
     return v;
 }
 
-struct TuResult { int sse, last; unsigned cg0, cg1; };
+struct TuResult { int sse, last; unsigned cg0, cg1, sg0, sg1; };    // cg: groups by position (bit yc*8+xc), sg: by scan index
 
 // Must be called by all 32 lanes of a warp (it contains warp-level exchanges); `active` masks the stores of idle
 // groups.  (y0, x0): position of the TU inside the CTU.  avail: bit0 left, bit1 below-left, bit2 above, bit3 above-right.
 // lev: TS x TS levels with pitch TS+2.  rec: TS x TS tile (pitch rec_pitch) that receives the reconstruction.
 template <int TS>
 __device__ __forceinline__ TuResult tu_pipeline(Smem &sm, int warp, int lane, bool active, const Src &src, int y0, int x0,
-                                                int avail, int mode, int qpd6, short *lev, uint8_t *rec, int rec_pitch)
+                                                int avail, int mode, int qpd6, const RdK &rd, short *lev, uint8_t *rec, int rec_pitch)
 {
     constexpr int LOG = TS == 4 ? 2 : TS == 8 ? 3 : TS == 16 ? 4 : 5;
     constexpr int SC = LOG - 2;
@@ -701,10 +828,11 @@ __device__ __forceinline__ TuResult tu_pipeline(Smem &sm, int warp, int lane, bo
             int level = clip16((d + add) >> sft);
             const int lo = level - 2 > 0 ? level - 2 : 0;
             int best = I32MAX, pick = 0;
+            if (level == 0) level = -1;                     // a lone level-0 candidate can only confirm pick = 0
             for (; level >= lo; level--) {
                 const int d1 = iabs(d - (level << sft)) >> dist_sft;
                 const int dist = (d1 < 46340 ? d1 * d1 : I32MAX) >> 7;
-                const int cost = rd_cost(qpd6, dist, level_rate(level));
+                const int cost = rd.cost(dist, level_rate(level));
                 if (cost < best) { best = cost; pick = level; }
             }
             t[n] = coef < 0 ? -pick : pick;
@@ -732,19 +860,22 @@ __device__ __forceinline__ TuResult tu_pipeline(Smem &sm, int warp, int lane, bo
     {
         const uint8_t (*scan)[2] = sm.scan + scan_base(scan_type_for(TS, mode), SC);
         int last = 0;
-        unsigned cg0 = 0, cg1 = 0;
+        unsigned cg0 = 0, cg1 = 0, sg0 = 0, sg1 = 0;
 #pragma unroll 4
         for (int i = l; i < TS * TS; i += TS) {
             const int y = scan[i][0], x = scan[i][1];
             if (lv[y * LP + x] != 0) {
                 last = i;
-                const int b = (y >> 2) * 8 + (x >> 2);
+                const int b = (y >> 2) * 8 + (x >> 2), g4 = i >> 4;
                 if (b < 32) cg0 |= 1u << b; else cg1 |= 1u << (b - 32);
+                if (g4 < 32) sg0 |= 1u << g4; else sg1 |= 1u << (g4 - 32);
             }
         }
         res.last = group_max<TS>(last);
         res.cg0 = group_or<TS>(cg0);
         res.cg1 = TS == 32 ? group_or<TS>(cg1) : 0u;
+        res.sg0 = group_or<TS>(sg0);
+        res.sg1 = TS == 32 ? group_or<TS>(sg1) : 0u;
     }
 
     // ---- de-quantise (:599-614) + inverse transform: columns, then rows ----
@@ -802,27 +933,44 @@ __device__ __forceinline__ void copy_words(void *dst, const void *src, int nword
     for (int i = tid; i < nwords; i += nthreads) d[i] = s[i];
 }
 
-// candidate c is coded by lane c / NW of warp c % NW, so that concurrent trial encodes sit in different warps
-__device__ __forceinline__ int candidate_of_thread(int tid)
+// Trial encodes run on warps 0..3 (one per SM sub-partition): candidates [0,35) = one-TU trials on warps 0,1,
+// candidates [35,70) = four-TU trials on warps 2,3, so that the lanes of a warp walk the same syntax.
+__device__ __forceinline__ int candidate_of_thread(int tid, int ncand)
 {
     const int lane = tid & 31, warp = tid >> 5;
-    const int c = lane * NW + warp;
-    return (lane < (NMODE + NW - 1) / NW && c < NMODE) ? c : -1;
+    if (warp >= 4 || lane >= 18) return -1;
+    const int c = (warp >> 1) * NMODE + (warp & 1) * 18 + lane;
+    return (c < (warp >> 1) * NMODE + NMODE && c < ncand) ? c : -1;
+}
+// the 35 stand-alone 4x4 trials of step 4: 9 per warp
+__device__ __forceinline__ int candidate4_of_thread(int tid)
+{
+    const int lane = tid & 31, warp = tid >> 5;
+    if (warp >= 4 || lane >= 9) return -1;
+    const int c = warp * 9 + lane;
+    return c < NMODE ? c : -1;
 }
 
 struct Ctx {
     Smem *sm;
     const Params *P;
     uint8_t *out;               // this frame's output slot
-    uint8_t *scratch;           // this CTA's [NMODE][SCR_BYTES]
+    uint8_t *scratch;           // this CTA's [NCAND][SCR_BYTES]
+    unsigned short *lists;      // this CTA's [NCAND][CAND_LIST_U16]
     int qpd6;
+    RdK rd;
 };
 
 template <int SZ> struct Level { static constexpr int v = SZ == 32 ? 0 : SZ == 16 ? 1 : 2; static constexpr int best_off = SZ == 32 ? 0 : SZ == 16 ? 1024 : 1280; };
 
-// the winner of a step becomes the current state: coder, bytes, reconstruction, maps (:1439-1446)
+__device__ __forceinline__ void attach(Coder &c, Smem &sm, uint8_t *ctx, uint8_t *out, unsigned cap)
+{
+    c.ctx = ctx; c.out = out; c.cap = cap; c.lps = sm.lpsw; c.nlps = sm.next_lps;
+}
+
+// the winner of a step becomes the current state: coder, bytes, reconstruction (:1439-1446)
 template <int SZ>
-__device__ __forceinline__ void commit_candidate(Ctx &K, int win, int y0, int x0)
+__device__ __forceinline__ void commit_candidate(Ctx &K, int win)
 {
     Smem &sm = *K.sm;
     constexpr int LV = Level<SZ>::v;
@@ -835,7 +983,6 @@ __device__ __forceinline__ void commit_candidate(Ctx &K, int win, int y0, int x0
     if (tid == 0) { sm.cur = sm.ccoder[win]; sm.cur.nout = base + n; }
     uint8_t *best = sm.best_rec + Level<SZ>::best_off;
     for (int i = tid; i < SZ * SZ / 4; i += NT) ((unsigned *)best)[i] = ((const unsigned *)sm.rec[win])[i];
-    (void)y0; (void)x0;
 }
 
 template <int SZ>
@@ -850,6 +997,18 @@ __device__ __forceinline__ void fill_maps(Smem &sm, int y0, int x0, int mode)
     }
 }
 
+// group leaders publish what binarize_warp needs about the unit they just quantised
+__device__ __forceinline__ void publish_tu(Smem &sm, int warp, int g, bool active, int cand, int blk, int ncg, int mode, int lev_off, const TuResult &r)
+{
+    BinDesc &D = sm.bdesc[warp][g];
+    D.active = active; D.lid = cand; D.slot0 = blk * ncg; D.mode = mode; D.lev_off = lev_off; D.last = r.last; D.sg0 = r.sg0; D.sg1 = r.sg1;
+    if (active) {
+        sm.clast[cand][blk] = r.last;
+        sm.ccg[cand][blk][0] = r.cg0; sm.ccg[cand][blk][1] = r.cg1;
+        sm.csg[cand][blk][0] = r.sg0; sm.csg[cand][blk][1] = r.sg1;
+    }
+}
+
 // RD search of one coding unit (processCURecurs :1349-1559).  Executed by the whole CTA in uniform control flow.
 template <int SZ>
 __device__ void search_cu(Ctx &K, int y0, int x0, int avail)
@@ -859,9 +1018,11 @@ __device__ void search_cu(Ctx &K, int y0, int x0, int avail)
     constexpr int H = SZ / 2;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int qpd6 = K.qpd6;
+    const RdK rd = K.rd;
     const int cy = y0 / 4, cx = x0 / 4;
     const bool hl = avail & 1, hbl = avail & 2, ha = avail & 4, har = avail & 8;
     uint8_t *best = sm.best_rec + Level<SZ>::best_off;
+    const unsigned out_cap = (unsigned)K.P->out_stride;
 
     __syncthreads();
     // ---- entry state (:1363-1372) ----
@@ -884,7 +1045,7 @@ __device__ void search_cu(Ctx &K, int y0, int x0, int avail)
     // ---- 1: four smaller CUs (:1402-1412) ----
     if constexpr (SZ > 8) {
         if (tid == 0) {
-            Coder c; c.load(sm.cur); c.ctx = sm.cur_ctx; c.out = K.out; c.cap = (unsigned)K.P->out_stride; c.lps = sm.lps; c.nlps = sm.next_lps;
+            Coder c; c.load(sm.cur); attach(c, sm, sm.cur_ctx, K.out, out_cap);
             c.bin(1, CX_SPLIT_CU + split_ctx);
             c.store(sm.cur);
         }
@@ -901,86 +1062,99 @@ __device__ void search_cu(Ctx &K, int y0, int x0, int avail)
         sse = block_sum(sm, sse);
         if (tid == 0) {
             const int bits = 8 * ((int)sm.cur.nout + sm.cur.pending) + 23 - sm.cur.nbits;
-            sm.best_cost[LV] = rd_cost(qpd6, sse, bits - entry_bits_abs);
+            sm.best_cost[LV] = rd.cost(sse, bits - entry_bits_abs);
         }
         __syncthreads();
     }
 
     Src src; src.rc = &sm.rc[0][0]; src.priv = nullptr; src.py0 = y0; src.px0 = x0; src.psz = SZ; src.ppitch = SZ;
 
-    // ---- 2 and 3: one CU, 35 modes; one TU (kind 0, :1419-1447), then four TUs (kind 1, :1454-1483) ----
-    for (int kind = 0; kind < 2; kind++) {
-        // phase A
-        if (kind == 0) {
-            constexpr int G = 32 / SZ, NG = NW * G;
-            for (int base = 0; base < NMODE; base += NG) {
-                if (base + warp * G >= NMODE) break;                        // warp-uniform
-                const int item = base + warp * G + lane / SZ;
-                const bool active = item < NMODE;
-                const int m = active ? item : 0;
-                TuResult r = tu_pipeline<SZ>(sm, warp, lane, active, src, y0, x0, avail, m, qpd6, sm.lev[m], sm.rec[m], SZ);
-                if (active && lane % SZ == 0) { sm.csse[m] = r.sse; sm.clast[m][0] = r.last; sm.ccg[m][0][0] = r.cg0; sm.ccg[m][0][1] = r.cg1; }
+    // ---- 2 and 3, phase A: 35 modes as one TU (candidates 0..34, :1419-1447) and as four TUs (35..69, :1454-1483);
+    //      every warp binarises the units it has just quantised ----
+    {
+        constexpr int G = 32 / SZ, NG = NW * G;
+        for (int base = 0; base < NMODE; base += NG) {
+            if (base + warp * G >= NMODE) break;                            // warp-uniform
+            const int item = base + warp * G + lane / SZ;
+            const bool active = item < NMODE;
+            const int m = active ? item : 0;
+            TuResult r = tu_pipeline<SZ>(sm, warp, lane, active, src, y0, x0, avail, m, qpd6, rd, sm.lev[m], sm.rec[m], SZ);
+            if (lane % SZ == 0) {
+                publish_tu(sm, warp, lane / SZ, active, m, 0, (SZ / 4) * (SZ / 4), m, m * LEV_STRIDE, r);
+                if (active) sm.csse[m] = r.sse;
             }
-        } else {
-            constexpr int G = 32 / H, NG = NW * G;
-            for (int base = 0; base < NMODE; base += NG) {
-                if (base + warp * G >= NMODE) break;
-                const int item = base + warp * G + lane / H;
-                const bool active = item < NMODE;
-                const int m = active ? item : 0;
-                Src ps = src; ps.priv = sm.rec[m];                           // earlier sub-TUs of the same trial
-                int sse = 0;
-                for (int i = 0; i < 4; i++) {
-                    TuResult r = tu_pipeline<H>(sm, warp, lane, active, ps, sub_y[i], sub_x[i], sub_avail[i], m, qpd6,
-                                                sm.lev[m] + i * H * (H + 2), sm.rec[m] + (sub_y[i] - y0) * SZ + (sub_x[i] - x0), SZ);
-                    sse += r.sse;
-                    if (active && lane % H == 0) { sm.clast[m][i] = r.last; sm.ccg[m][i][0] = r.cg0; sm.ccg[m][i][1] = r.cg1; }
-                }
-                if (active && lane % H == 0) sm.csse[m] = sse;
-            }
+            __syncwarp();
+            binarize_warp<SZ>(sm, warp, lane, K.lists);
+            __syncwarp();
         }
-        __syncthreads();
-        // phase B: trial encodes from the entry state
-        for (int i = tid; i < NMODE * (CXP / 4); i += NT)
-            ((unsigned *)sm.cctx)[i] = ((const unsigned *)sm.entry_ctx[LV])[i % (CXP / 4)];
-        __syncthreads();
-        {
-            const int c = candidate_of_thread(tid);
-            if (c >= 0) {
-                Coder cd; cd.load(entry); cd.nout = 0;
-                cd.ctx = sm.cctx[c]; cd.out = K.scratch + (size_t)c * SCR_BYTES; cd.cap = SCR_BYTES; cd.lps = sm.lps; cd.nlps = sm.next_lps;
-                if (SZ >= 16) cd.bin(0, CX_SPLIT_CU + split_ctx);          // putSplitCUflag :942-946
-                LevBlock blk[4];
-                const int tsz = kind == 0 ? SZ : H;
-                for (int i = 0; i < (kind == 0 ? 1 : 4); i++) {
-                    blk[i].p = sm.lev[c] + i * H * (H + 2); blk[i].pitch = tsz + 2;
-                    blk[i].last = sm.clast[c][i]; blk[i].cg0 = sm.ccg[c][i][0]; blk[i].cg1 = sm.ccg[c][i][1];
-                }
-                const int mode = c;
-                put_cu(cd, SZ, kind, &mode, &mode_l, &mode_a, blk, sm.scan, sm.cmag[c]);
-                cd.store(sm.ccoder[c]);
-                sm.cbits[c] = cd.bits() - entry_bits_rel;
+    }
+    __syncthreads();                                                        // sm.lev is reused by the four-TU trials
+    {
+        constexpr int G = 32 / H, NG = NW * G;
+        for (int base = 0; base < NMODE; base += NG) {
+            if (base + warp * G >= NMODE) break;
+            const int item = base + warp * G + lane / H;
+            const bool active = item < NMODE;
+            const int m = active ? item : 0, cand = NMODE + m;
+            Src ps = src; ps.priv = sm.rec[cand];                            // earlier sub-TUs of the same trial
+            int sse = 0;
+            for (int i = 0; i < 4; i++) {
+                TuResult r = tu_pipeline<H>(sm, warp, lane, active, ps, sub_y[i], sub_x[i], sub_avail[i], m, qpd6, rd,
+                                            sm.lev[m] + i * H * (H + 2), sm.rec[cand] + (sub_y[i] - y0) * SZ + (sub_x[i] - x0), SZ);
+                sse += r.sse;
+                if (lane % H == 0) publish_tu(sm, warp, lane / H, active, cand, i, (H / 4) * (H / 4), m, m * LEV_STRIDE + i * H * (H + 2), r);
+                __syncwarp();
+                binarize_warp<H>(sm, warp, lane, K.lists);
+                __syncwarp();
             }
+            if (active && lane % H == 0) sm.csse[cand] = sse;
         }
-        __syncthreads();
-        // decide (:1437-1446): candidates in mode order, a later candidate wins ties
-        if (tid == 0) {
-            int bc = sm.best_cost[LV], win = -1;
-            for (int m = 0; m < NMODE; m++) {
-                const int cost = rd_cost(qpd6, sm.csse[m], sm.cbits[m]);
-                if (bc >= cost) { bc = cost; win = m; }
+    }
+    // ---- phase B: 70 trial encodes from the entry state, one lane each ----
+    for (int i = tid; i < NCAND * (CXP / 4); i += NT)
+        ((unsigned *)sm.cctx)[i] = ((const unsigned *)sm.entry_ctx[LV])[i % (CXP / 4)];
+    __syncthreads();
+    {
+        const int c = candidate_of_thread(tid, NCAND);
+        if (c >= 0) {
+            const int kind = c >= NMODE, mode = c - kind * NMODE;
+            Coder cd; cd.load(entry); cd.nout = 0;
+            attach(cd, sm, sm.cctx[c], K.scratch + (size_t)c * SCR_BYTES, SCR_BYTES);
+            if (SZ >= 16) cd.bin(0, CX_SPLIT_CU + split_ctx);                // putSplitCUflag :942-946
+            put_cu_head(cd, SZ, kind, &mode, &mode_l, &mode_a);
+            const unsigned short *lst = K.lists + (size_t)c * CAND_LIST_U16;
+            const int tsz = kind ? H : SZ, ncg = (tsz / 4) * (tsz / 4);
+            for (int i = 0; i < (kind ? 4 : 1); i++) {
+                const unsigned g0 = sm.ccg[c][i][0], g1 = sm.ccg[c][i][1];
+                const int cbf = (g0 | g1) != 0;
+                cd.bin(cbf, CX_YCBF + (kind ? 0 : 1));                       // :1039
+                if (cbf) code_block(cd, tsz, mode, sm.clast[c][i], g0, g1, sm.csg[c][i][0], sm.csg[c][i][1],
+                                    lst + (size_t)i * ncg * SLOT, lst + 64 * SLOT + i * ncg, sm.scan);
             }
-            sm.best_cost[LV] = bc;
-            sm.win = win;
+            cd.store(sm.ccoder[c]);
+            sm.cbits[c] = cd.bits() - entry_bits_rel;
         }
-        __syncthreads();
+    }
+    __syncthreads();
+    // decide (:1437-1446, :1473-1482): candidates in the reference order, a later candidate wins ties
+    if (tid == 0) {
+        int bc = sm.best_cost[LV], win = -1;
+        for (int c = 0; c < NCAND; c++) {
+            const int cost = rd.cost(sm.csse[c], sm.cbits[c]);
+            if (bc >= cost) { bc = cost; win = c; }
+        }
+        sm.best_cost[LV] = bc;
+        sm.win = win;
+    }
+    __syncthreads();
+    {
         const int win = sm.win;
         if (win >= 0) {
-            commit_candidate<SZ>(K, win, y0, x0);
-            fill_maps<SZ>(sm, y0, x0, win);
+            commit_candidate<SZ>(K, win);
+            fill_maps<SZ>(sm, y0, x0, win >= NMODE ? win - NMODE : win);
         }
-        __syncthreads();
     }
+    __syncthreads();
 
     // ---- 4: 8x8 only: four 4x4 PUs, each mode chosen by a stand-alone cost on a fresh coder (:1490-1556) ----
     if constexpr (SZ == 8) {
@@ -992,19 +1166,25 @@ __device__ void search_cu(Ctx &K, int y0, int x0, int avail)
                 const int item = base + warp * G + lane / 4;
                 const bool active = item < NMODE;
                 const int m = active ? item : 0;
-                TuResult r = tu_pipeline<4>(sm, warp, lane, active, ps, sub_y[i], sub_x[i], sub_avail[i], m, qpd6, sm.lev[m], sm.rec[m], 4);
-                if (active && lane % 4 == 0) { sm.csse[m] = r.sse; sm.clast[m][0] = r.last; sm.ccg[m][0][0] = r.cg0; sm.ccg[m][0][1] = r.cg1; }
+                TuResult r = tu_pipeline<4>(sm, warp, lane, active, ps, sub_y[i], sub_x[i], sub_avail[i], m, qpd6, rd, sm.lev[m], sm.rec[m], 4);
+                if (lane % 4 == 0) {
+                    publish_tu(sm, warp, lane / 4, active, m, 0, 1, m, m * LEV_STRIDE, r);
+                    if (active) sm.csse[m] = r.sse;
+                }
+                __syncwarp();
+                binarize_warp<4>(sm, warp, lane, K.lists);
+                __syncwarp();
             }
             for (int k = tid; k < NMODE * (CXP / 4); k += NT)
                 ((unsigned *)sm.cctx)[k] = ((const unsigned *)sm.init_ctx)[k % (CXP / 4)];
             __syncthreads();
             {
-                const int c = candidate_of_thread(tid);
+                const int c = candidate4_of_thread(tid);
                 if (c >= 0) {
                     Coder cd; cd.fresh();
-                    cd.ctx = sm.cctx[c]; cd.out = K.scratch + (size_t)c * SCR_BYTES; cd.cap = SCR_BYTES; cd.lps = sm.lps; cd.nlps = sm.next_lps;
-                    LevBlock blk; blk.p = sm.lev[c]; blk.pitch = 6; blk.last = sm.clast[c][0]; blk.cg0 = sm.ccg[c][0][0]; blk.cg1 = 0;
-                    put_coefs(cd, 4, c, blk, sm.scan, sm.cmag[c]);
+                    attach(cd, sm, sm.cctx[c], K.scratch + (size_t)c * SCR_BYTES, SCR_BYTES);
+                    const unsigned short *lst = K.lists + (size_t)c * CAND_LIST_U16;
+                    code_block(cd, 4, c, sm.clast[c][0], sm.ccg[c][0][0], 0u, sm.csg[c][0][0], 0u, lst, lst + 64 * SLOT, sm.scan);
                     sm.cbits[c] = cd.bits();
                 }
             }
@@ -1012,17 +1192,22 @@ __device__ void search_cu(Ctx &K, int y0, int x0, int avail)
             if (tid == 0) {
                 int bc = I32MAX, win = -1;
                 for (int m = 0; m < NMODE; m++) {
-                    const int cost = rd_cost(qpd6, sm.csse[m], sm.cbits[m]);
+                    const int cost = rd.cost(sm.csse[m], sm.cbits[m]);
                     if (bc >= cost) { bc = cost; win = m; }
                 }
                 sm.win = win;
                 sm.nxn_mode[i] = win; sm.nxn_last[i] = sm.clast[win][0]; sm.nxn_cg[i] = sm.ccg[win][0][0];
             }
             __syncthreads();
-            if (tid < 16) {
-                const int w = sm.win, y = tid >> 2, x = tid & 3;
-                sm.nxn_lev[i][y * 6 + x] = sm.lev[w][y * 6 + x];
-                sm.nxn_rec[(sub_y[i] - y0 + y) * 8 + (sub_x[i] - x0 + x)] = sm.rec[w][y * 4 + x];
+            {
+                const int w = sm.win;
+                const unsigned short *lst = K.lists + (size_t)w * CAND_LIST_U16;
+                if (tid < SLOT) sm.nxn_list[i][tid] = lst[tid];               // keep the winner's bins for the NxN trial
+                if (tid == SLOT) sm.nxn_hdr[i] = lst[64 * SLOT];
+                if (tid >= 128 && tid < 144) {
+                    const int y = (tid - 128) >> 2, x = (tid - 128) & 3;
+                    sm.nxn_rec[(sub_y[i] - y0 + y) * 8 + (sub_x[i] - x0 + x)] = sm.rec[w][y * 4 + x];
+                }
             }
             __syncthreads();
         }
@@ -1033,27 +1218,28 @@ __device__ void search_cu(Ctx &K, int y0, int x0, int avail)
         sse = block_sum(sm, sse);                                           // contains the barriers the copy above needs
         if (tid == 0) {
             Coder cd; cd.load(entry); cd.nout = 0;
-            cd.ctx = sm.cctx[0]; cd.out = K.scratch; cd.cap = SCR_BYTES; cd.lps = sm.lps; cd.nlps = sm.next_lps;
+            attach(cd, sm, sm.cctx[0], K.scratch, SCR_BYTES);
             int modes[4], left[4], above[4];
-            LevBlock blk[4];
-            for (int i = 0; i < 4; i++) {
-                modes[i] = sm.nxn_mode[i];
-                blk[i].p = sm.nxn_lev[i]; blk[i].pitch = 6; blk[i].last = sm.nxn_last[i]; blk[i].cg0 = sm.nxn_cg[i]; blk[i].cg1 = 0;
-            }
+            for (int i = 0; i < 4; i++) modes[i] = sm.nxn_mode[i];
             left[0] = mode_l;                  above[0] = mode_a;                               // :1530-1537
             left[1] = modes[0];                above[1] = sm.mmd[cy][1 + cx + 1];
             left[2] = sm.mmd[1 + cy + 1][cx];  above[2] = modes[0];
             left[3] = modes[2];                above[3] = modes[1];
-            put_cu(cd, 8, 2, modes, left, above, blk, sm.scan, sm.cmag[0]);
+            put_cu_head(cd, 8, 2, modes, left, above);
+            for (int i = 0; i < 4; i++) {
+                const int cbf = sm.nxn_cg[i] != 0;
+                cd.bin(cbf, CX_YCBF + 0);
+                if (cbf) code_block(cd, 4, modes[i], sm.nxn_last[i], sm.nxn_cg[i], 0u, 1u, 0u, sm.nxn_list[i], &sm.nxn_hdr[i], sm.scan);
+            }
             cd.store(sm.ccoder[0]);
-            const int cost = rd_cost(qpd6, sse, cd.bits() - entry_bits_rel);
+            const int cost = rd.cost(sse, cd.bits() - entry_bits_rel);
             sm.win = (sm.best_cost[LV] >= cost) ? 1 : 0;
         }
         __syncthreads();
         if (sm.win) {
             // commit: coder, bytes, maps; the reconstruction is the four kept 4x4 tiles (:1546-1554)
-            const unsigned base = entry.nout, n = sm.ccoder[0].nout, cap = (unsigned)K.P->out_stride;
-            for (unsigned i = tid; i < n && i < SCR_BYTES; i += NT) if (base + i < cap) K.out[base + i] = K.scratch[i];
+            const unsigned base = entry.nout, n = sm.ccoder[0].nout;
+            for (unsigned i = tid; i < n && i < SCR_BYTES; i += NT) if (base + i < out_cap) K.out[base + i] = K.scratch[i];
             copy_words(sm.cur_ctx, sm.cctx[0], CXP / 4, tid, NT);
             if (tid == 0) { sm.cur = sm.ccoder[0]; sm.cur.nout = base + n; }
             if (tid < 4) {
@@ -1116,7 +1302,7 @@ __device__ inline unsigned put_headers(uint8_t *out, int qpd6, int hp, int wp)
 __device__ inline void build_tables(Smem &sm, int qpd6)
 {
     const int tid = threadIdx.x;
-    for (int i = tid; i < 256; i += NT) sm.lps[i] = c_lps[i >> 2][i & 3];
+    for (int i = tid; i < 64; i += NT) sm.lpsw[i] = (unsigned)c_lps[i][0] | ((unsigned)c_lps[i][1] << 8) | ((unsigned)c_lps[i][2] << 16) | ((unsigned)c_lps[i][3] << 24);
     for (int i = tid; i < 128; i += NT) sm.next_lps[i] = c_next_lps[i];
     if (tid < CXP) {                                                        // initContextValue :726-734
         int s = 0;
@@ -1202,7 +1388,7 @@ __device__ inline void encode_frame(Ctx &K, int f)
             }
             if (tid < 8) { sm.left_sz[tid] = sm.msz[1 + tid][8]; sm.left_md[tid] = sm.mmd[1 + tid][8]; sm.above_sz[x / 4 + tid] = sm.msz[8][1 + tid]; }
             if (tid == 0) {
-                Coder c; c.load(sm.cur); c.ctx = sm.cur_ctx; c.out = K.out; c.cap = (unsigned)P.out_stride; c.lps = sm.lps; c.nlps = sm.next_lps;
+                Coder c; c.load(sm.cur); attach(c, sm, sm.cur_ctx, K.out, (unsigned)P.out_stride);
                 c.terminate(y + CTU >= hp && x + CTU >= wp);                     // :1629
                 c.store(sm.cur);
             }
@@ -1210,7 +1396,7 @@ __device__ inline void encode_frame(Ctx &K, int f)
         }
     }
     if (tid == 0) {
-        Coder c; c.load(sm.cur); c.ctx = sm.cur_ctx; c.out = K.out; c.cap = (unsigned)P.out_stride; c.lps = sm.lps; c.nlps = sm.next_lps;
+        Coder c; c.load(sm.cur); attach(c, sm, sm.cur_ctx, K.out, (unsigned)P.out_stride);
         c.finish();                                                             // :1639-1640
         const bool fits = c.nout <= (unsigned)P.out_stride;
         P.out_len[f] = fits ? c.nout : 0;
@@ -1223,8 +1409,9 @@ __global__ void __launch_bounds__(NT, 1) hevc_frame_kernel(Params P)
 {
     Smem &sm = *reinterpret_cast<Smem *>(IMCVT_DYN_SMEM());
     Ctx K;
-    K.sm = &sm; K.P = &P; K.qpd6 = P.qpd6;
-    K.scratch = P.scratch + (size_t)blockIdx.x * NMODE * SCR_BYTES;
+    K.sm = &sm; K.P = &P; K.qpd6 = P.qpd6; K.rd.init(P.qpd6);
+    K.scratch = P.scratch + (size_t)blockIdx.x * NCAND * SCR_BYTES;
+    K.lists = P.lists + (size_t)blockIdx.x * NCAND * CAND_LIST_U16;
     K.out = nullptr;
     build_tables(sm, P.qpd6);
     for (;;) {                                                                  // frames vary 2-3x in cost: dynamic queue

@@ -2,7 +2,7 @@
 //
 // A minimal CPU SIMT emulator: runs the *source* of a CUDA kernel on the host so that the kernel's logic can be
 // checked bit-for-bit against the oracle in the CPU test tier (and debugged without a GPU).  Every CUDA thread
-// of a block is a fiber (ucontext); __syncthreads / __syncwarp / shuffles / ballots are cooperative yield
+// of a block is a fiber (own stack, hand-rolled context switch); __syncthreads / __syncwarp / shuffles / ballots are cooperative yield
 // points resolved by a round-robin scheduler.  A barrier that can never complete (divergent __syncthreads,
 // a shuffle executed by part of a warp only) is reported as a deadlock instead of hanging -- which is exactly
 // the class of bug that would hang or corrupt a real GPU run.
@@ -10,7 +10,6 @@
 // Blocks run one after the other, so there is no inter-block concurrency (kernels that need it cannot be
 // emulated).  Dynamic shared memory is filled with 0xCD to surface reads of uninitialised shared memory.
 #pragma once
-#include <ucontext.h>
 #include <stdint.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -34,8 +33,21 @@ struct Dim3 { unsigned x = 1, y = 1, z = 1; };
 
 enum { RUNNABLE = 0, AT_BLOCK_BARRIER = 1, AT_WARP_BARRIER = 2, DONE = 3 };
 
+// Hand-rolled x86-64 context switch (callee-saved registers + stack pointer): ~50x cheaper than swapcontext,
+// which makes a system call per switch.
+extern "C" void emu_switch(void **save_sp, void *new_sp);
+#if defined(__x86_64__)
+asm(".text\n.globl emu_switch\n.type emu_switch,@function\nemu_switch:\n"
+    "  pushq %rbp\n  pushq %rbx\n  pushq %r12\n  pushq %r13\n  pushq %r14\n  pushq %r15\n"
+    "  movq %rsp, (%rdi)\n  movq %rsi, %rsp\n"
+    "  popq %r15\n  popq %r14\n  popq %r13\n  popq %r12\n  popq %rbx\n  popq %rbp\n  ret\n"
+    ".size emu_switch,.-emu_switch\n");
+#else
+#error "cuda_emu.h: only x86-64 hosts are supported"
+#endif
+
 struct Fiber {
-    ucontext_t ctx;
+    void *sp = nullptr;
     char *stack = nullptr;
     int state = RUNNABLE;
 };
@@ -43,7 +55,7 @@ struct Fiber {
 struct State {
     Dim3 blockIdx, blockDim, gridDim;
     int tid = 0, nthreads = 0;
-    ucontext_t sched;
+    void *sched_sp = nullptr;
     std::vector<Fiber> fibers;
     std::vector<uint64_t> slots;            // [warp][32] exchange slots for shuffles / ballots
     unsigned char *smem = nullptr;
@@ -58,7 +70,7 @@ inline void yield_as(int st)
     State &s = S();
     Fiber &f = s.fibers[s.tid];
     f.state = st;
-    swapcontext(&f.ctx, &s.sched);
+    emu_switch(&f.sp, s.sched_sp);
 }
 
 inline void trampoline()
@@ -66,7 +78,8 @@ inline void trampoline()
     State &s = S();
     s.body();
     s.fibers[s.tid].state = DONE;
-    swapcontext(&s.fibers[s.tid].ctx, &s.sched);
+    emu_switch(&s.fibers[s.tid].sp, s.sched_sp);
+    abort();
 }
 
 constexpr size_t STACK_BYTES = 512 * 1024;
@@ -87,11 +100,11 @@ inline void launch(unsigned grid_x, unsigned block_x, size_t smem_bytes, std::fu
         memset(s.smem, 0xCD, smem_bytes + 64);
         for (unsigned t = 0; t < block_x; t++) {
             Fiber &f = s.fibers[t];
-            getcontext(&f.ctx);
-            f.ctx.uc_stack.ss_sp = f.stack;
-            f.ctx.uc_stack.ss_size = STACK_BYTES;
-            f.ctx.uc_link = nullptr;
-            makecontext(&f.ctx, (void (*)())trampoline, 0);
+            void **top = (void **)(((uintptr_t)f.stack + STACK_BYTES) & ~(uintptr_t)15);
+            *--top = nullptr;                       // fake return address: keeps the ABI stack alignment at entry
+            *--top = (void *)trampoline;            // `ret` of the first switch lands here
+            for (int k = 0; k < 6; k++) *--top = nullptr;
+            f.sp = top;
             f.state = RUNNABLE;
         }
         const int nwarps = (int)(block_x + 31) / 32;
@@ -100,7 +113,7 @@ inline void launch(unsigned grid_x, unsigned block_x, size_t smem_bytes, std::fu
             for (int t = 0; t < s.nthreads; t++)
                 if (s.fibers[t].state == RUNNABLE) {
                     s.tid = t;
-                    swapcontext(&s.sched, &s.fibers[t].ctx);
+                    emu_switch(&s.sched_sp, s.fibers[t].sp);
                     ran = true;
                 }
             bool released = false;

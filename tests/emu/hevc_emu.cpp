@@ -14,14 +14,16 @@ extern "C" long emu_hevc_encode(uint8_t *stream, size_t cap, const uint8_t *img,
     Params P;
     unsigned long long len = 0;
     int overflow = 0, next = 0;
-    std::vector<uint8_t> scratch((size_t)NMODE * SCR_BYTES);
+    std::vector<uint8_t> scratch((size_t)NCAND * SCR_BYTES);
+    std::vector<unsigned short> lists((size_t)NCAND * CAND_LIST_U16, 0xDEAD);
     P.frames = img; P.frame_stride = (size_t)H * W; P.n = 1; P.H = H; P.W = W; P.hp = hp; P.wp = wp; P.qpd6 = qpd6;
     P.out = stream; P.out_stride = cap; P.out_len = &len;
     P.rcon = img_rcon; P.rcon_stride = (size_t)hp * wp;
-    P.scratch = scratch.data(); P.overflow = &overflow; P.next_frame = &next;
+    P.scratch = scratch.data(); P.lists = lists.data(); P.overflow = &overflow; P.next_frame = &next;
     emu::launch(1, NT, sizeof(Smem), [&] { hevc_frame_kernel(P); });
     *ysz = hp; *xsz = wp;
     return overflow ? 0 : (long)len;
 }
 
+extern "C" long emu_smem_bytes(void) { return (long)sizeof(Smem); }
 extern "C" long emu_barrier_count(int which) { return which ? emu::S().n_warp_barriers : emu::S().n_block_barriers; }
