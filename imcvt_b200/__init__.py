@@ -31,7 +31,7 @@ EXPORTED_SYMBOLS = [
     "imcvtEncodeBatchJLS", "imcvtEncodeBatchJLSDevice",
     "imcvtEncodeBatchHEVC", "imcvtEncodeBatchHEVCDevice",
     "imcvtProfileEnable", "imcvtProfileReset", "imcvtProfileGet", "imcvtProfileList", "imcvtLaunchCount",
-    "imcvtDebugJLSForceSerial",
+    "imcvtDebugJLSForceSerial", "imcvtDebugJLSPath",
     "writeJLSImageFile", "writeHEVCImageFile", "HEVCImageEncoder",
 ]
 
@@ -69,6 +69,7 @@ def lib():
     L.imcvtProfileList.argtypes = [C.c_char_p, sz]; L.imcvtProfileList.restype = i32
     L.imcvtLaunchCount.argtypes = []; L.imcvtLaunchCount.restype = C.c_long
     L.imcvtDebugJLSForceSerial.argtypes = [i32]; L.imcvtDebugJLSForceSerial.restype = None
+    L.imcvtDebugJLSPath.argtypes = [i32]; L.imcvtDebugJLSPath.restype = None
     L.writeJLSImageFile.argtypes = [C.c_char_p, vp, i32, u32, u32, i32]; L.writeJLSImageFile.restype = i32
     L.writeHEVCImageFile.argtypes = [C.c_char_p, vp, i32, u32, u32, i32]; L.writeHEVCImageFile.restype = i32
     L.HEVCImageEncoder.argtypes = [vp, vp, vp, C.POINTER(i32), C.POINTER(i32), i32]; L.HEVCImageEncoder.restype = i32
@@ -225,3 +226,8 @@ def launch_count():
 
 def debug_jls_force_serial(on):
     lib().imcvtDebugJLSForceSerial(int(bool(on)))
+
+
+def debug_jls_path(path):
+    """0 = default NEAR=0 path (tile kernel), 1 = force the multi-kernel pipeline (used for planes wider than 6144)."""
+    lib().imcvtDebugJLSPath(int(path))

@@ -53,6 +53,7 @@ struct Engine {
     std::vector<Pending> pending;
     std::vector<cudaEvent_t> event_pool;
     bool jls_force_serial = false;
+    int jls_path = 0;       // 0 = default (tile kernel when the plane fits), 1 = force the multi-kernel pipeline
     int sm_count = 148;
 };
 

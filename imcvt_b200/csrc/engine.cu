@@ -193,5 +193,6 @@ int imcvtProfileList(char *buf, size_t cap)
 long imcvtLaunchCount(void) { return engine().launches; }
 
 void imcvtDebugJLSForceSerial(int on) { engine().jls_force_serial = on != 0; }
+void imcvtDebugJLSPath(int path) { engine().jls_path = path; }
 
 }  // extern "C"

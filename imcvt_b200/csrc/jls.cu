@@ -23,56 +23,17 @@
 #include "common.cuh"
 #include "../../include/imcvt_b200.h"
 
+#include "jls_tile_kernel.cuh"
+
 namespace imcvt {
 namespace jls {
 
-constexpr int NCTX      = 364;       // regular contexts (:241-244)
-constexpr int NBUCKET   = 365;       // + one bucket holding the run events of a plane
-constexpr int HSLOTS    = 366;       // + a dummy slot for samples that produce no record
 constexpr int ROWS_PER_TILE = 8;     // classify / multisplit tile = 8 image rows handled by one warp
 constexpr int CLS_WARPS = 4;
 constexpr int PK_THREADS = 256;      // bit packer: 256 threads x 8 samples
 constexpr int PK_PER     = 8;
 constexpr int PK_TILE    = PK_THREADS * PK_PER;
 constexpr int ST_CHUNK_WORDS = 2048; // stuffing kernel: shared-memory window over the unstuffed stream
-
-__constant__ uint8_t c_J[32] = {0,0,0,0,1,1,1,1,2,2,2,2,3,3,3,3,4,4,5,5,6,6,7,7,8,9,10,11,12,13,14,15};   // :15
-
-// ------------------------------------------------------------------------------------------------
-// small device helpers
-// ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ int grad_q_lossless(int g)          // gradientQuantize :68-76 with T1,T2,T3 = 3,7,21, NEAR = 0
-{
-    int m = abs(g);
-    int q = (m > 0) + (m >= 3) + (m >= 7) + (m >= 21);
-    return g < 0 ? -q : q;
-}
-
-__device__ __forceinline__ int med3(int a, int b, int c)        // predict :87-94
-{
-    int mx = max(a, b), mn = min(a, b);
-    return c >= mx ? mn : (c <= mn ? mx : a + b - c);
-}
-
-__device__ __forceinline__ int golomb_k(int A, int N)           // getK :114-121, closed form
-{
-    int k = max(0, __clz(N) - __clz(A));                        // bitlen(A) - bitlen(N)
-    if ((N << k) < A) k++;
-    return k;
-}
-
-// Golomb code of GolombCoding :187-197 as (value, length): `hi` zeros, a one, k low bits -- or the escape.
-__device__ __forceinline__ void golomb_code(int me, int k, int limit, int qbpp, uint32_t &code, int &len)
-{
-    int hi = me >> k;
-    if (hi < limit) {
-        len  = hi + 1 + k;
-        code = (1u << k) | ((uint32_t)me & ((1u << k) - 1u));
-    } else {
-        len  = limit + 1 + qbpp;
-        code = (1u << qbpp) | ((uint32_t)(me - 1) & ((1u << qbpp) - 1u));
-    }
-}
 
 __device__ __forceinline__ uint32_t warp_incl_scan(uint32_t v, int lane)
 {
@@ -513,27 +474,6 @@ pack_kernel(const uint32_t *__restrict__ codes_all, const uint8_t *__restrict__ 
 // dst of plane p: component 0 of a frame goes straight to its place in the frame's output slot,
 // components 1,2 (RGB) go to scratch and are moved by assemble_kernel once the sizes are known.
 // ------------------------------------------------------------------------------------------------
-struct FrameLayout {
-    int ncomp;              // 1 gray, 3 RGB
-    int hdr_len;            // SOI + SOF55 : 15 gray / 21 RGB   (:211-232)
-    uint8_t *out;           // device output slots
-    size_t out_stride;
-    uint8_t *scratch;       // [P][scratch_stride]
-    size_t scratch_stride;
-};
-
-__device__ __forceinline__ uint8_t *plane_dst(const FrameLayout &L, int p, size_t &cap)
-{
-    const int f = p / L.ncomp, c = p - f * L.ncomp;
-    if (c == 0) {
-        const size_t o = (size_t)L.hdr_len + 10;
-        cap = L.out_stride > o ? L.out_stride - o : 0;
-        return L.out + (size_t)f * L.out_stride + o;
-    }
-    cap = L.scratch_stride;
-    return L.scratch + (size_t)p * L.scratch_stride;
-}
-
 __global__ void __launch_bounds__(32)
 stuff_kernel(const uint32_t *__restrict__ ubits, size_t uw_stride, const uint64_t *__restrict__ plane_bits,
              FrameLayout L, uint64_t *__restrict__ plane_bytes)
@@ -833,6 +773,8 @@ int encode_device(const uint8_t *d_frames, size_t frame_stride, int n, int is_rg
     const size_t npix = (size_t)H * W;
     const size_t slot_stride = round_up(npix, 16);
     const bool lossless = (near_ == 0) && !E.jls_force_serial;
+    // planes up to tile::WMAX wide stream through shared memory (jls_tile_kernel.cuh); wider ones take the multi-kernel path
+    const bool use_tile = lossless && (int)W <= tile::WMAX && E.jls_path != 1;
 
     // ---- workspace layout ----
     const int T  = (int)((H + ROWS_PER_TILE - 1) / ROWS_PER_TILE);             // classify tiles per plane
@@ -843,7 +785,9 @@ int encode_device(const uint8_t *d_frames, size_t frame_stride, int n, int is_rg
     size_t bytes = 4096;
     auto add = [&](size_t b) { bytes += round_up(b, 256); };
     if (need_planes) add((size_t)P * slot_stride);
-    if (lossless) {
+    if (use_tile) {
+        add(256);                                  // plane queue counter
+    } else if (lossless) {
         add((size_t)P * NBUCKET * T * 4);          // hist
         add((size_t)P * NBUCKET * 4 * 2);          // bucket_total, bucket_start
         add((size_t)P * slot_stride * 4);          // rec_pos
@@ -882,7 +826,23 @@ int encode_device(const uint8_t *d_frames, size_t frame_stride, int n, int is_rg
 
     uint64_t *plane_bytes = nullptr;
 
-    if (lossless) {
+    if (use_tile) {
+        int *next = E.ws.take<int>(1);
+        plane_bytes = E.ws.take<uint64_t>((size_t)P);
+        if (ncomp > 1) Lay.scratch = E.ws.take<uint8_t>((size_t)P * scratch_stride);
+        if (!next || !plane_bytes || (ncomp > 1 && !Lay.scratch)) { set_error("workspace carve failed"); return 1; }
+        static bool attr_set = false;
+        if (!attr_set) {
+            IMCVT_CUDA(cudaFuncSetAttribute(tile::jls_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(tile::Smem)));
+            attr_set = true;
+        }
+        IMCVT_CUDA(cudaMemsetAsync(next, 0, sizeof(int), st));
+        tile::Params TP;
+        TP.pix = planes; TP.plane_stride = plane_stride; TP.P = P; TP.W = (int)W; TP.H = (int)H;
+        TP.L = Lay; TP.plane_bytes = (unsigned long long *)plane_bytes; TP.next_plane = next;
+        LaunchScope ls("jls_tile", st);
+        tile::jls_tile_kernel<<<P < E.sm_count ? P : E.sm_count, tile::NTHREADS, sizeof(tile::Smem), st>>>(TP);
+    } else if (lossless) {
         uint32_t *hist         = E.ws.take<uint32_t>((size_t)P * NBUCKET * T);
         uint32_t *bucket_total = E.ws.take<uint32_t>((size_t)P * NBUCKET);
         uint32_t *bucket_start = E.ws.take<uint32_t>((size_t)P * NBUCKET);

@@ -1,0 +1,556 @@
+// jls_tile_kernel.cuh -- lossless (NEAR = 0) JPEG-LS scan encoder for sm_100a: one CTA per plane, the plane streams
+// through shared memory in row tiles and never touches HBM in between (device code only).
+//
+// Replaces JLSencodeScan + the bit writer (reference: src/imageio_jls.c:240-399, :124-197) for NEAR = 0.
+// With NEAR = 0 the reconstruction equals the input, so the causal template, the context, the MED prediction and
+// the run / regular classification of every sample depend on the input only; what is serial is
+// one chain per context (A,B,C,N, :376-393), the run_index chain (:291-344) and the bit position.
+//
+// A CTA is a three-stage software pipeline over tiles of <= 6144 samples (whole rows); each `tick` (one
+// __syncthreads) the three warp groups work on three consecutive tiles:
+//   producers (6 warps)  tile k   : classify every sample (carry-lookahead run state over warp ballots), counting-sort
+//                                   the samples by context into shared memory, stage the rows of tile k+1
+//   chains   (12 warps)  tile k-1 : thread b owns context b for the whole plane (state in registers) and walks its
+//                                   slice of the sorted tile; thread 364 walks the run events; each sample's Golomb
+//                                   code + length go to the tile's raster-order slots
+//   packer    (1 warp)   tile k-2 : prefix sum of the code lengths, MSB-first packing, marker-avoidance bit stuffing
+//                                   (:156-169) straight into the plane's output stream
+// HBM traffic = the pixels once + the stream once (the algorithmic minimum); the tile never leaves the SM.
+//
+// Also compiled for the host by tests/emu (fiber SIMT emulator, test infrastructure only).
+#pragma once
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef IMCVT_HOST_EMU
+#define JLS_DYN_SMEM() (emu::S().smem)
+#define JLS_NAMED_BARRIER(id, count) emu_named_barrier(id, count)
+#define JLS_CONSTANT static const
+#else
+extern __shared__ __align__(16) unsigned char jls_dyn_smem[];
+#define JLS_DYN_SMEM() (jls_dyn_smem)
+#define JLS_NAMED_BARRIER(id, count) asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory")
+#define JLS_CONSTANT __constant__ const
+#endif
+
+namespace imcvt {
+namespace jls {
+
+constexpr int NCTX    = 364;       // regular contexts (:241-244)
+constexpr int NBUCKET = 365;       // + one bucket holding the run events
+constexpr int HSLOTS  = 366;       // + a dummy slot for samples that produce no record
+
+JLS_CONSTANT uint8_t c_J[32] = {0,0,0,0,1,1,1,1,2,2,2,2,3,3,3,3,4,4,5,5,6,6,7,7,8,9,10,11,12,13,14,15};   // :15
+
+// ---- small device helpers (shared with jls.cu) ----------------------------------------------------
+__device__ __forceinline__ int grad_q_lossless(int g)          // gradientQuantize :68-76 with T1,T2,T3 = 3,7,21, NEAR = 0
+{
+    const int m = g < 0 ? -g : g;
+    const int q = (m > 0) + (m >= 3) + (m >= 7) + (m >= 21);
+    return g < 0 ? -q : q;
+}
+__device__ __forceinline__ int med3(int a, int b, int c)        // predict :87-94
+{
+    const int mx = max(a, b), mn = min(a, b);
+    return c >= mx ? mn : (c <= mn ? mx : a + b - c);
+}
+__device__ __forceinline__ int golomb_k(int A, int N)           // getK :114-121, closed form
+{
+    int k = max(0, __clz(N) - __clz(A));                        // bitlen(A) - bitlen(N)
+    if ((N << k) < A) k++;
+    return k;
+}
+// Golomb code of GolombCoding :187-197 as (value, length): `hi` zeros, a one, k low bits -- or the escape.
+__device__ __forceinline__ void golomb_code(int me, int k, int limit, int qbpp, uint32_t &code, int &len)
+{
+    const int hi = me >> k;
+    if (hi < limit) {
+        len  = hi + 1 + k;
+        code = (1u << k) | ((uint32_t)me & ((1u << k) - 1u));
+    } else {
+        len  = limit + 1 + qbpp;
+        code = (1u << qbpp) | ((uint32_t)(me - 1) & ((1u << qbpp) - 1u));
+    }
+}
+
+// where the scan of plane p goes: component 0 of a frame straight into the frame's output slot, components 1,2
+// (RGB) into scratch, moved by assemble_kernel once the sizes are known
+struct FrameLayout {
+    int ncomp;              // 1 gray, 3 RGB
+    int hdr_len;            // SOI + SOF55 : 15 gray / 21 RGB   (:211-232)
+    uint8_t *out;           // device output slots
+    size_t out_stride;
+    uint8_t *scratch;       // [P][scratch_stride]
+    size_t scratch_stride;
+};
+__device__ __forceinline__ uint8_t *plane_dst(const FrameLayout &L, int p, size_t &cap)
+{
+    const int f = p / L.ncomp, c = p - f * L.ncomp;
+    if (c == 0) {
+        const size_t o = (size_t)L.hdr_len + 10;
+        cap = L.out_stride > o ? L.out_stride - o : 0;
+        return L.out + (size_t)f * L.out_stride + o;
+    }
+    cap = L.scratch_stride;
+    return L.scratch + (size_t)p * L.scratch_stride;
+}
+
+// ------------------------------------------------------------------------------------------------
+// the tile kernel
+// ------------------------------------------------------------------------------------------------
+namespace tile {
+
+constexpr int TSMAX = 6144;         // samples per tile (whole rows)
+constexpr int WMAX  = 6144;         // widest plane this kernel takes (wider ones use the multi-kernel path)
+constexpr int CHAIN_WARPS = 12, PROD_WARPS = 6, PACK_WARPS = 1;
+constexpr int NWARPS = CHAIN_WARPS + PROD_WARPS + PACK_WARPS;
+constexpr int NTHREADS = NWARPS * 32;
+constexpr int PROD_THREADS = PROD_WARPS * 32;
+constexpr int PIXBUF = 16 + TSMAX + WMAX + 16;
+constexpr int CHUNK = 1024;         // samples per packer chunk (32 per lane)
+constexpr int CHUNK_WORDS = CHUNK + 8;
+
+struct Params {
+    const uint8_t *pix; size_t plane_stride;   // P planes, H x W u8
+    int P, W, H;
+    FrameLayout L;
+    unsigned long long *plane_bytes;           // [P] stuffed scan length
+    int *next_plane;                           // plane queue
+};
+
+struct Smem {
+    uint32_t sorted[2][TSMAX];      // records of a tile, grouped by context, raster order inside a context
+    uint32_t codes[2][TSMAX];       // Golomb code per sample, raster order
+    uint32_t temp_rec[TSMAX];       // producers: record per sample, raster order (pass 1 -> pass 2)
+    uint16_t temp_bkt[TSMAX];       // producers: bucket per sample
+    uint16_t bstart[2][HSLOTS + 2]; // start of every context's slice inside sorted[]
+    uint16_t cursor[PROD_WARPS][HSLOTS + 2];   // producers: per-warp histogram, then scatter cursor
+    uint32_t chunk[CHUNK_WORDS];    // packer: un-stuffed bits of one chunk
+    uint8_t  lens[2][TSMAX];        // code length per sample (0 = nothing), raster order
+    uint8_t  pix[3][PIXBUF];        // rows of a tile (+ the row above, + the sample two rows above column 0)
+    int plane;
+};
+
+// records: regular sample  pos | x << 13 | med << 21 | sign << 29
+//          run event       pos | run length << 13 | row-end flag << 28
+__device__ __forceinline__ uint8_t *pix_row(uint8_t *buf, int local_row, int W) { return buf + 16 + (local_row + 1) * W; }
+
+// stages the rows of tile t (and the row above it) into a pix buffer; executed by `nthr` threads
+__device__ __forceinline__ void stage_tile(uint8_t *buf, const uint8_t *img, int W, int H, int rows_per_tile, int t, int tid, int nthr)
+{
+    const int r0 = t * rows_per_tile;
+    if (r0 >= H) return;
+    const int r1 = min(H, r0 + rows_per_tile);
+    const int first = r0 > 0 ? r0 - 1 : 0;
+    const uint8_t *src = img + (size_t)first * W;
+    uint8_t *dst = buf + 16 + (first - (r0 - 1)) * W;
+    const int n = (r1 - first) * W;
+    // 4-byte words where source and destination agree on alignment, bytes otherwise
+    const int mis = (int)((size_t)src & 3);
+    if (((size_t)dst & 3) == (size_t)mis) {
+        const int head = min(n, (4 - mis) & 3);
+        if (tid < head) dst[tid] = src[tid];
+        const int words = (n - head) >> 2;
+        const uint32_t *s4 = reinterpret_cast<const uint32_t *>(src + head);
+        uint32_t *d4 = reinterpret_cast<uint32_t *>(dst + head);
+        for (int i = tid; i < words; i += nthr) d4[i] = s4[i];
+        const int done = head + words * 4;
+        if (tid < n - done) dst[done + tid] = src[done + tid];
+    } else {
+        for (int i = tid; i < n; i += nthr) dst[i] = src[i];
+    }
+    if (tid == 0) buf[0] = r0 >= 2 ? img[(size_t)(r0 - 2) * W] : 0;
+}
+
+// ---- producers ------------------------------------------------------------------------------------
+// Classifies one row for one warp.  PASS 1: record + bucket per sample into temp_*, histogram into hist[].
+// (samplePixels :46-65, getQ :79-84, run state :270, :284-289 resolved 32 samples at a time by one 64-bit addition)
+__device__ __forceinline__ void classify_row(Smem &sm, uint8_t *pb, int W, int i_global, int i_local, int lane, uint16_t *hist)
+{
+    const uint8_t *cur = pix_row(pb, i_local, W);
+    const uint8_t *up = cur - W;
+    const uint32_t lane_le = 0xFFFFFFFFu >> (31 - lane), lane_lt = lane_le >> 1;
+    uint32_t cin = 0;
+    int run_start = 0;
+    for (int j0 = 0; j0 < W; j0 += 32) {
+        const int j = j0 + lane;
+        const bool active = j < W;
+        int x = 0, a = 0, b = 0, c = 0, d = 0;
+        if (active) {
+            x = cur[j];
+            if (i_global > 0) { b = up[j]; d = (j + 1 < W) ? up[j + 1] : b; }
+            if (j == 0) { a = b; c = (i_global > 1) ? (i_local >= 1 ? (int)up[-W] : (int)pb[0]) : 0; }
+            else        { a = cur[j - 1]; c = (i_global > 0) ? up[j - 1] : 0; }
+        }
+        const int Q = 81 * grad_q_lossless(d - b) + 9 * grad_q_lossless(b - c) + grad_q_lossless(c - a);
+        const bool q0 = active && Q == 0;
+        const bool eq = active && x == a;
+        const uint32_t act = __ballot_sync(0xffffffffu, active);
+        const uint32_t Pm  = __ballot_sync(0xffffffffu, eq);
+        const uint32_t Gm  = __ballot_sync(0xffffffffu, q0 && eq);
+        const uint32_t Q0m = __ballot_sync(0xffffffffu, q0);
+        const uint64_t cv  = ((uint64_t)Pm + Gm + cin) ^ Pm ^ Gm;   // bit j = carry into j = running_{j-1}
+        const uint32_t prevrun = (uint32_t)cv;
+        const uint32_t R   = (uint32_t)(cv >> 1) & act;             // running_j
+        const uint32_t INM = (Q0m | prevrun) & act;                 // sample is coded in run mode (hit or interruption)
+        const uint32_t S   = Q0m & ~prevrun;                        // a run-mode stretch starts here
+        const bool inm = (INM >> lane) & 1u, run = (R >> lane) & 1u;
+        const bool is_int = inm && !run;
+        const bool is_eol = run && (j == W - 1);
+
+        int bucket = NBUCKET;                                       // dummy: plain run sample / inactive lane
+        uint32_t rec = 0;
+        const uint32_t lp = (uint32_t)(i_local * W + j);
+        if (active) {
+            if (!inm) {
+                bucket = (Q < 0 ? -Q : Q) - 1;
+                rec = lp | ((uint32_t)x << 13) | ((uint32_t)med3(a, b, c) << 21) | ((uint32_t)(Q < 0) << 29);
+            } else if (is_int || is_eol) {
+                bucket = NCTX;
+                const uint32_t sm_ = S & lane_le;
+                const int start_col = sm_ ? (j0 + 31 - __clz((int)sm_)) : run_start;
+                rec = lp | ((uint32_t)(j - start_col + (is_eol ? 1 : 0)) << 13) | ((uint32_t)is_eol << 28);
+            }
+            sm.temp_rec[lp] = rec;
+            sm.temp_bkt[lp] = (uint16_t)bucket;
+        }
+        const uint32_t peers = __match_any_sync(0xffffffffu, bucket);
+        if ((peers & lane_lt) == 0) hist[bucket] = (uint16_t)(hist[bucket] + __popc(peers));
+        __syncwarp();
+        cin = (uint32_t)(cv >> 32) & 1u;
+        if (S) run_start = j0 + 31 - __clz((int)S);
+    }
+}
+
+// PASS 2: scatter the records of one row into sorted[] (cursor[] = next free slot per bucket for this warp)
+__device__ __forceinline__ void scatter_row(Smem &sm, uint32_t *sorted, int W, int i_local, int lane, uint16_t *cursor)
+{
+    const uint32_t lane_lt = (0xFFFFFFFFu >> (31 - lane)) >> 1;
+    for (int j0 = 0; j0 < W; j0 += 32) {
+        const int j = j0 + lane;
+        int bucket = NBUCKET;
+        uint32_t rec = 0;
+        if (j < W) { const int lp = i_local * W + j; bucket = sm.temp_bkt[lp]; rec = sm.temp_rec[lp]; }
+        const uint32_t peers = __match_any_sync(0xffffffffu, bucket);
+        const int rank = __popc(peers & lane_lt);
+        const int base = cursor[bucket];
+        __syncwarp();
+        if (rank == 0) cursor[bucket] = (uint16_t)(base + __popc(peers));
+        if (bucket < NBUCKET) sorted[base + rank] = rec;
+        __syncwarp();
+    }
+}
+
+__device__ __forceinline__ void producer_tick(Smem &sm, const Params &P, const uint8_t *img, int rows_per_tile, int t, int ntiles, int pw, int lane)
+{
+    const int W = P.W, H = P.H;
+    const int ptid = pw * 32 + lane;
+    if (t < ntiles) {
+        const int buf = t & 1;
+        uint8_t *pb = sm.pix[t % 3];
+        const int r0 = t * rows_per_tile, R = min(H, r0 + rows_per_tile) - r0;
+        const int per = (R + PROD_WARPS - 1) / PROD_WARPS;           // contiguous rows per warp keep raster order
+        const int a = min(R, pw * per), b = min(R, a + per);
+        uint16_t *h = sm.cursor[pw];
+        for (int k = lane; k < HSLOTS; k += 32) h[k] = 0;
+        __syncwarp();
+        for (int r = a; r < b; r++) classify_row(sm, pb, W, r0 + r, r, lane, h);
+        JLS_NAMED_BARRIER(1, PROD_THREADS);
+        if (pw == 0) {
+            // exclusive scan over the buckets of (sum over warps); per-warp histograms become scatter cursors
+            uint32_t carry = 0;
+            for (int k0 = 0; k0 < NBUCKET + 1; k0 += 32) {
+                const int k = k0 + lane;
+                uint32_t cnt[PROD_WARPS], tot = 0;
+#pragma unroll
+                for (int w = 0; w < PROD_WARPS; w++) { cnt[w] = k < NBUCKET ? sm.cursor[w][k] : 0; tot += cnt[w]; }
+                uint32_t inc = tot;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) { const uint32_t v = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += v; }
+                uint32_t start = carry + inc - tot;
+                if (k <= NBUCKET) sm.bstart[buf][k] = (uint16_t)start;
+                if (k < NBUCKET) {
+#pragma unroll
+                    for (int w = 0; w < PROD_WARPS; w++) { sm.cursor[w][k] = (uint16_t)start; start += cnt[w]; }
+                }
+                carry += __shfl_sync(0xffffffffu, inc, 31);
+            }
+        }
+        JLS_NAMED_BARRIER(1, PROD_THREADS);
+        for (int r = a; r < b; r++) scatter_row(sm, sm.sorted[buf], W, r, lane, h);
+    }
+    // rows of the next tile
+    if (t + 1 < ntiles) stage_tile(sm.pix[(t + 1) % 3], img, W, H, rows_per_tile, t + 1, ptid, PROD_THREADS);
+}
+
+// ---- chains ---------------------------------------------------------------------------------------
+struct RegularState { int A, B, C, N; };
+struct RunState { int run_index, A0, B0, N0, A1, B1, N1; };
+
+__device__ __forceinline__ void regular_step(uint32_t rec, RegularState &s, uint32_t *codes, uint8_t *lens)
+{
+    const int lp = rec & 0x1FFF, x = (rec >> 13) & 0xFF, med = (rec >> 21) & 0xFF;
+    const bool neg = (rec >> 29) & 1u;
+    int px = med + (neg ? -s.C : s.C);                  // :349
+    px = min(max(px, 0), 255);
+    int e = x - px;
+    if (neg) e = -e;
+    e = (int)(int8_t)e;                                 // modRange :105-111 with RANGE = 256
+    const int k = golomb_k(s.A, s.N);
+    const int ae = e < 0 ? -e : e;
+    const int map = (k == 0) && (2 * s.B <= -s.N);      // :367
+    const int me = 2 * ae + (e < 0 ? -(map + 1) : map);
+    uint32_t code; int len;
+    golomb_code(me, k, 23, 8, code, len);
+    codes[lp] = code;
+    lens[lp]  = (uint8_t)len;
+    s.B += e;                                           // :376-393
+    s.A += ae;
+    if (s.N >= 64) { s.A >>= 1; s.B >>= 1; s.N >>= 1; }
+    s.N++;
+    if (s.B <= -s.N) {
+        s.B += s.N; if (s.B <= -s.N) s.B = -s.N + 1;
+        s.C = max(s.C - 1, -128);
+    } else if (s.B > 0) {
+        s.B -= s.N; if (s.B > 0) s.B = 0;
+        s.C = min(s.C + 1, 127);
+    }
+}
+
+// one run event (:291-344): completed 2^J blocks -> ones in the slot of the run's last sample; interruption sample:
+// run remainder in J+1 bits + Golomb code of the interruption error
+__device__ __forceinline__ void run_step(uint32_t rec, RunState &s, uint8_t *pb, int W, int r0_global, uint32_t *codes, uint8_t *lens)
+{
+    const int lp = rec & 0x1FFF, L = (rec >> 13) & 0x7FFF;
+    const bool eol = (rec >> 28) & 1u;
+    int cnt = L, ones = 0;
+    while (cnt >= (1 << c_J[s.run_index])) {            // :295-300, whole blocks at once
+        cnt -= 1 << c_J[s.run_index];
+        ones++;
+        if (s.run_index < 31) s.run_index++;
+    }
+    if (eol) {                                          // :302-303
+        if (cnt > 0) ones++;
+        codes[lp] = (uint32_t)((1ull << ones) - 1ull);
+        lens[lp]  = (uint8_t)ones;
+        return;
+    }
+    if (ones > 0) {
+        codes[lp - 1] = (uint32_t)((1ull << ones) - 1ull);
+        lens[lp - 1]  = (uint8_t)ones;
+    }
+    const int jj = c_J[s.run_index];
+    const int glimit = 23 - 1 - jj;                     // :306
+    if (s.run_index > 0) s.run_index--;                 // :310-311
+    const int row = lp / W, col = lp - row * W;
+    const uint8_t *cur = pix_row(pb, row, W);
+    const int x = cur[col];
+    const int b = (r0_global + row) > 0 ? cur[col - W] : 0;
+    const int a = col > 0 ? cur[col - 1] : b;
+    const int t = (a == b);                             // RItype :313
+    const bool neg = a > b;                             // :314
+    const int px = t ? a : b;
+    int e = x - px;
+    if (neg) e = -e;
+    e = (int)(int8_t)e;
+    const int At = t ? s.A1 : s.A0, Bt = t ? s.B1 : s.B0, Nt = t ? s.N1 : s.N0;
+    const int k = golomb_k(At + (t ? (Nt >> 1) : 0), Nt);               // :329
+    const int map = (e != 0) && ((e > 0) == (k == 0 && 2 * Bt < Nt));   // :331
+    const int me = 2 * (e < 0 ? -e : e) - t - map;
+    uint32_t gcode; int glen;
+    golomb_code(me, k, glimit, 8, gcode, glen);
+    codes[lp] = ((uint32_t)cnt << glen) | gcode;        // run remainder in J+1 bits, then the Golomb code (<= 32 bits)
+    lens[lp]  = (uint8_t)(jj + 1 + glen);
+    int An = At + ((me + 1 - t) >> 1), Bn = Bt + (e < 0), Nn = Nt;      // :336-344
+    if (Nn >= 64) { An >>= 1; Bn >>= 1; Nn >>= 1; }
+    Nn++;
+    if (t) { s.A1 = An; s.B1 = Bn; s.N1 = Nn; } else { s.A0 = An; s.B0 = Bn; s.N0 = Nn; }
+}
+
+// ---- packer ---------------------------------------------------------------------------------------
+struct PackState {
+    uint8_t *dst; size_t cap; size_t out_pos;
+    uint32_t carry_bits;        // un-stuffed bits waiting at the front of chunk[] (< 8)
+    uint32_t pz;                // 1: the next byte starts with a stuffed 0 bit (previous byte was 0xFF)
+};
+
+// Turns the first `T` bits of chunk[] (MSB first) into stuffed bytes.  Only whole bytes are produced unless `flush`;
+// the left-over bits move to the front of chunk[].  One warp.
+__device__ __forceinline__ void stuff_chunk(Smem &sm, PackState &ps, uint32_t T, bool flush, int lane)
+{
+    uint32_t *buf = sm.chunk;
+    uint32_t in_pos = 0;
+    for (;;) {
+        const uint32_t s = in_pos - ps.pz;              // stream bit that lands on the MSB of this window's first byte (may wrap to -1)
+        const int32_t avail = (int32_t)T - (int32_t)s;  // bits from s to the end
+        uint32_t whole = avail > 0 ? (uint32_t)avail >> 3 : 0u;
+        if (whole == 0) break;
+        const int32_t w0 = (int32_t)s >> 5;             // -1 when s == -1
+        const uint32_t sh = s & 31u;
+        const int32_t wi = w0 + lane;
+        const uint32_t hi = (wi >= 0 && wi < CHUNK_WORDS) ? buf[wi] : 0u, lo = (wi + 1 < CHUNK_WORDS) ? buf[wi + 1] : 0u;
+        uint32_t v = __funnelshift_l(lo, hi, sh);
+        if (ps.pz && lane == 0) v &= 0x7FFFFFFFu;
+        int fb = 4;
+        if      ((v >> 24) == 0xFFu)           fb = 0;
+        else if (((v >> 16) & 0xFFu) == 0xFFu) fb = 1;
+        else if (((v >> 8) & 0xFFu) == 0xFFu)  fb = 2;
+        else if ((v & 0xFFu) == 0xFFu)         fb = 3;
+        // bytes past `whole` are not complete yet and must not end the window
+        const uint32_t ball = __ballot_sync(0xffffffffu, fb < 4 && (uint32_t)(4 * lane + fb) < whole);
+        uint32_t nbytes = whole < 128u ? whole : 128u;
+        bool ends_ff = false;
+        if (ball) {
+            const int f = __ffs((int)ball) - 1;
+            const uint32_t cut = 4u * f + (uint32_t)__shfl_sync(0xffffffffu, fb, f) + 1u;
+            if (cut <= nbytes) { nbytes = cut; ends_ff = true; }
+        }
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const uint32_t bi = 4u * lane + k;
+            if (bi < nbytes && ps.out_pos + bi < ps.cap) ps.dst[ps.out_pos + bi] = (uint8_t)(v >> (24 - 8 * k));
+        }
+        ps.out_pos += nbytes;
+        in_pos = s + 8u * nbytes;
+        ps.pz = ends_ff ? 1u : 0u;
+    }
+    const uint32_t left = T - in_pos;                   // < 8 (no whole byte can be formed)
+    if (flush) {
+        if (lane == 0) {
+            if (left > 0) {                             // flushBits :177-184: pad the last byte with zeros
+                const uint32_t w = in_pos >> 5, sh = in_pos & 31u;
+                uint32_t v = __funnelshift_l(buf[w + 1], buf[w], sh) & ~(0xFFFFFFFFu >> left);
+                uint32_t byte = ps.pz ? (v >> 25) : (v >> 24);
+                if (ps.out_pos < ps.cap) ps.dst[ps.out_pos] = (uint8_t)byte;
+            }
+        }
+        if (left > 0) { ps.out_pos++; ps.pz = 0; }
+        if (ps.pz) { if (lane == 0 && ps.out_pos < ps.cap) ps.dst[ps.out_pos] = 0; ps.out_pos++; ps.pz = 0; }   // a 0x00 after a trailing 0xFF (:178)
+        ps.carry_bits = 0;
+        return;
+    }
+    // move the left-over bits to the front
+    uint32_t keep = 0;
+    if (left > 0) {
+        const uint32_t w = in_pos >> 5, sh = in_pos & 31u;
+        keep = __funnelshift_l(buf[w + 1], buf[w], sh) & ~(0xFFFFFFFFu >> left);
+    }
+    __syncwarp();
+    if (lane == 0) buf[0] = keep;
+    ps.carry_bits = left;
+    __syncwarp();
+}
+
+// packs tile samples [0, n) (codes/lens in raster order) chunk by chunk and appends the stuffed bytes
+__device__ __forceinline__ void packer_tile(Smem &sm, PackState &ps, uint32_t *codes, uint8_t *lens, int n, bool last_tile, int lane)
+{
+    uint32_t *buf = sm.chunk;
+    for (int c0 = 0; c0 < n; c0 += CHUNK) {
+        const int cn = min(CHUNK, n - c0);
+        // zero the words this chunk may touch (word 0 holds the carried bits)
+        for (int w = 1 + lane; w < CHUNK_WORDS; w += 32) buf[w] = 0;
+        if (ps.carry_bits == 0 && lane == 0) buf[0] = 0;
+        __syncwarp();
+        // lane owns 32 consecutive samples
+        const int s0 = c0 + lane * 32;
+        uint32_t mylen = 0;
+        uint32_t l4[8];
+#pragma unroll
+        for (int q = 0; q < 8; q++) {
+            uint32_t v = 0;
+            if (s0 + 4 * q < c0 + cn) v = *reinterpret_cast<const uint32_t *>(lens + s0 + 4 * q);   // tile arrays are padded: reads past n see zeros
+            l4[q] = v;
+            mylen += (v & 0xFF) + ((v >> 8) & 0xFF) + ((v >> 16) & 0xFF) + (v >> 24);
+        }
+        uint32_t inc = mylen;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { const uint32_t v = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += v; }
+        const uint32_t total = __shfl_sync(0xffffffffu, inc, 31);
+        uint32_t bit = ps.carry_bits + inc - mylen;
+        if (mylen) {
+#pragma unroll
+            for (int q = 0; q < 8; q++) {
+#pragma unroll
+                for (int r = 0; r < 4; r++) {
+                    const uint32_t len = (l4[q] >> (8 * r)) & 0xFF;
+                    if (len) {
+                        const uint32_t code = codes[s0 + 4 * q + r];
+                        const uint32_t w = bit >> 5, sh = bit & 31u;
+                        const uint64_t v = (uint64_t)code << (64 - len - sh);      // left-align the code at stream bit `bit`
+                        atomicOr(&buf[w], (uint32_t)(v >> 32));
+                        if ((uint32_t)v) atomicOr(&buf[w + 1], (uint32_t)v);
+                        bit += len;
+                    }
+                }
+            }
+        }
+        // the slots are consumed: the chains of a later tile expect zero lengths
+#pragma unroll
+        for (int q = 0; q < 8; q++)
+            if (s0 + 4 * q < c0 + cn && l4[q]) *reinterpret_cast<uint32_t *>(lens + s0 + 4 * q) = 0;
+        __syncwarp();
+        stuff_chunk(sm, ps, ps.carry_bits + total, last_tile && c0 + CHUNK >= n, lane);
+    }
+}
+
+// ---- the kernel -----------------------------------------------------------------------------------
+__global__ void __launch_bounds__(NTHREADS, 1) jls_tile_kernel(Params P)
+{
+    Smem &sm = *reinterpret_cast<Smem *>(JLS_DYN_SMEM());
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int W = P.W, H = P.H;
+    const int rows_per_tile = max(1, TSMAX / W);
+    const int ntiles = (H + rows_per_tile - 1) / rows_per_tile;
+    // chain thread -> bucket: consecutive buckets sit in different warps (the busy low-gradient contexts are neighbours)
+    const int bucket = warp < CHAIN_WARPS ? (lane * CHAIN_WARPS + warp) : -1;
+    const bool is_chain = bucket >= 0 && bucket < NBUCKET;
+
+    for (int i = tid; i < 2 * TSMAX / 4; i += NTHREADS) reinterpret_cast<uint32_t *>(&sm.lens[0][0])[i] = 0;
+
+    for (;;) {
+        __syncthreads();
+        if (tid == 0) sm.plane = atomicAdd(P.next_plane, 1);
+        __syncthreads();
+        const int p = sm.plane;
+        if (p >= P.P) break;
+        const uint8_t *img = P.pix + (size_t)p * P.plane_stride;
+
+        RegularState rs; rs.A = 4; rs.B = 0; rs.C = 0; rs.N = 1;                       // :256-261 (a_init = 4 for RANGE 256)
+        RunState us; us.run_index = 0; us.A0 = 4; us.B0 = 0; us.N0 = 1; us.A1 = 4; us.B1 = 0; us.N1 = 1;     // :250, :263-267
+        PackState ps; ps.out_pos = 0; ps.carry_bits = 0; ps.pz = 0;
+        ps.dst = plane_dst(P.L, p, ps.cap);
+
+        stage_tile(sm.pix[0], img, W, H, rows_per_tile, 0, tid, NTHREADS);
+        __syncthreads();
+
+        for (int tick = 0; tick < ntiles + 2; tick++) {
+            if (warp >= CHAIN_WARPS && warp < CHAIN_WARPS + PROD_WARPS) {
+                producer_tick(sm, P, img, rows_per_tile, tick, ntiles, warp - CHAIN_WARPS, lane);
+            } else if (warp < CHAIN_WARPS) {
+                const int t = tick - 1;
+                if (t >= 0 && t < ntiles && is_chain) {
+                    const int buf = t & 1;
+                    const uint32_t *rec = sm.sorted[buf];
+                    const int b0 = sm.bstart[buf][bucket], b1 = sm.bstart[buf][bucket + 1];
+                    if (bucket < NCTX) {
+                        for (int i = b0; i < b1; i++) regular_step(rec[i], rs, sm.codes[buf], sm.lens[buf]);
+                    } else {
+                        for (int i = b0; i < b1; i++) run_step(rec[i], us, sm.pix[t % 3], W, t * rows_per_tile, sm.codes[buf], sm.lens[buf]);
+                    }
+                }
+            } else {
+                const int t = tick - 2;
+                if (t >= 0 && t < ntiles) {
+                    const int r0 = t * rows_per_tile, n = (min(H, r0 + rows_per_tile) - r0) * W;
+                    packer_tile(sm, ps, sm.codes[t & 1], sm.lens[t & 1], n, t == ntiles - 1, lane);
+                }
+            }
+            __syncthreads();
+        }
+        if (warp == NWARPS - 1 && lane == 0) P.plane_bytes[p] = ps.out_pos;
+    }
+}
+
+}  // namespace tile
+}  // namespace jls
+}  // namespace imcvt

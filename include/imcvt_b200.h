@@ -81,6 +81,9 @@ long imcvtLaunchCount(void);                         /* total kernels launched s
 
 /* Debug / cross-check: force the fully serial JPEG-LS scan kernel also for NEAR=0 (default 0). */
 void imcvtDebugJLSForceSerial(int on);
+/* Debug / cross-check: 0 = default NEAR=0 path (shared-memory tile kernel for planes up to 6144 wide),
+ * 1 = force the multi-kernel pipeline that wider planes use. */
+void imcvtDebugJLSPath(int path);
 
 #ifdef __cplusplus
 }

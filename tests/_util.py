@@ -167,7 +167,7 @@ def emu_hevc(img, qpd6):
     """The SOURCE of the CUDA HEVC kernel run under the CPU SIMT emulator (tests/emu, test infrastructure)."""
     if "emu" not in _libs:
         d = os.path.join(ROOT, "tests", "emu")
-        subprocess.run(["make", "-C", d, "-s"], check=True, capture_output=True)
+        subprocess.run(["make", "-C", d, "-s", "libhevc_emu.so"], check=True, capture_output=True)
         lib = C.CDLL(os.path.join(d, "libhevc_emu.so"))
         lib.emu_hevc_encode.restype = C.c_long
         lib.emu_hevc_encode.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int), C.c_int]
@@ -181,3 +181,20 @@ def emu_hevc(img, qpd6):
     n = _libs["emu"].emu_hevc_encode(out.ctypes.data, out.size, img.ctypes.data, rcon.ctypes.data, C.byref(ch), C.byref(cw), qpd6)
     assert n > 0 and ch.value == hp and cw.value == wp
     return out[:n].tobytes(), rcon.reshape(hp, wp).copy()
+
+
+def emu_jls(img):
+    """The SOURCE of the CUDA JPEG-LS tile kernel (NEAR = 0, gray) run under the CPU SIMT emulator (tests/emu)."""
+    if "emu_jls" not in _libs:
+        d = os.path.join(ROOT, "tests", "emu")
+        subprocess.run(["make", "-C", d, "-s", "libjls_emu.so"], check=True, capture_output=True)
+        lib = C.CDLL(os.path.join(d, "libjls_emu.so"))
+        lib.emu_jls_encode.restype = C.c_size_t
+        lib.emu_jls_encode.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_size_t]
+        _libs["emu_jls"] = lib
+    img = np.ascontiguousarray(img, dtype=np.uint8)
+    h, w = img.shape
+    out = np.zeros(8 * h * w + 65536, dtype=np.uint8)
+    n = _libs["emu_jls"].emu_jls_encode(img.ctypes.data, h, w, out.ctypes.data, out.size)
+    assert n > 0
+    return out[:n].tobytes()

@@ -31,7 +31,7 @@ namespace emu {
 
 struct Dim3 { unsigned x = 1, y = 1, z = 1; };
 
-enum { RUNNABLE = 0, AT_BLOCK_BARRIER = 1, AT_WARP_BARRIER = 2, DONE = 3 };
+enum { RUNNABLE = 0, AT_BLOCK_BARRIER = 1, AT_WARP_BARRIER = 2, DONE = 3, AT_NAMED_BARRIER = 4 };
 
 // Hand-rolled x86-64 context switch (callee-saved registers + stack pointer): ~50x cheaper than swapcontext,
 // which makes a system call per switch.
@@ -50,6 +50,7 @@ struct Fiber {
     void *sp = nullptr;
     char *stack = nullptr;
     int state = RUNNABLE;
+    int bar_id = 0, bar_count = 0;          // named barrier (bar.sync id, count) this fiber waits at
 };
 
 struct State {
@@ -132,6 +133,17 @@ inline void launch(unsigned grid_x, unsigned block_x, size_t smem_bytes, std::fu
                     released = true;
                 }
             }
+            // named barriers: `count` threads wait at the same id
+            for (int id = 1; id < 16; id++) {
+                int waiting_n = 0, want = 0;
+                for (int t = 0; t < s.nthreads; t++)
+                    if (s.fibers[t].state == AT_NAMED_BARRIER && s.fibers[t].bar_id == id) { waiting_n++; want = s.fibers[t].bar_count; }
+                if (waiting_n > 0 && waiting_n >= want) {
+                    for (int t = 0; t < s.nthreads; t++)
+                        if (s.fibers[t].state == AT_NAMED_BARRIER && s.fibers[t].bar_id == id) s.fibers[t].state = RUNNABLE;
+                    released = true;
+                }
+            }
             // block barrier
             int live = 0, waiting = 0;
             for (int t = 0; t < s.nthreads; t++) {
@@ -184,6 +196,13 @@ template <class T> inline T exchange(T v, int src_lane)
 #define gridDim   (emu::S().gridDim)
 
 inline void __syncthreads() { emu::yield_as(emu::AT_BLOCK_BARRIER); }
+// bar.sync id, count  (count = number of THREADS that meet at barrier `id`, 1 <= id <= 15)
+inline void emu_named_barrier(int id, int count)
+{
+    emu::Fiber &f = emu::S().fibers[emu::S().tid];
+    f.bar_id = id; f.bar_count = count;
+    emu::yield_as(emu::AT_NAMED_BARRIER);
+}
 inline void __syncwarp(unsigned = 0xffffffffu) { emu::yield_as(emu::AT_WARP_BARRIER); }
 inline void __threadfence_block() {}
 inline void __threadfence() {}
@@ -224,6 +243,18 @@ inline unsigned __ballot_sync(unsigned, int pred)
     return r;
 }
 inline int __any_sync(unsigned m, int p) { return __ballot_sync(m, p) != 0; }
+template <class T> inline unsigned __match_any_sync(unsigned, T v)
+{
+    uint64_t *sl = emu::warp_slots();
+    sl[emu::lane_id()] = emu::to_bits(v);
+    emu::yield_as(emu::AT_WARP_BARRIER);
+    unsigned r = 0;
+    int base = emu::S().tid & ~31;
+    for (int l = 0; l < 32 && base + l < emu::S().nthreads; l++)
+        if (emu::S().fibers[base + l].state != emu::DONE && sl[l] == emu::to_bits(v)) r |= 1u << l;
+    emu::yield_as(emu::AT_WARP_BARRIER);
+    return r;
+}
 
 inline int __clz(int v) { return v == 0 ? 32 : __builtin_clz((unsigned)v); }
 inline int __clzll(long long v) { return v == 0 ? 64 : __builtin_clzll((unsigned long long)v); }

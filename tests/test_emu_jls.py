@@ -1,0 +1,34 @@
+"""CPU: the SOURCE of the CUDA JPEG-LS tile kernel (imcvt_b200/csrc/jls_tile_kernel.cuh: producers / chains / packer
+software pipeline over shared-memory tiles), compiled for the host and run under the fiber SIMT emulator of
+tests/emu, must match the oracle and the golden fixtures bit for bit."""
+import os
+
+import numpy as np
+
+from imcvt_b200 import synth
+from tests._util import GOLDEN, emu_jls, golden_table, load_pnm, oracle_jls, sha256
+from tests.test_oracle_jls import edge_images
+
+
+def test_known_answer_p5():
+    img, _ = load_pnm(os.path.join(GOLDEN, "P5.pnm"))
+    entry = [e for e in golden_table() if e["codec"] == "jls" and e["fixture"] == "P5" and e["setting"] == 0][0]
+    s = emu_jls(img)
+    assert len(s) == entry["length"] and sha256(s) == entry["sha256"]
+
+
+def test_edge_cases_match_oracle():
+    for name, img in edge_images():
+        if img.ndim == 2:
+            assert emu_jls(img) == oracle_jls(img, 0), name
+
+
+def test_multi_tile_planes_match_oracle():
+    rng = np.random.default_rng(8)
+    cases = [(kind, synth.frame(kind, 3, 200, 480)) for kind in ["natural", "texture", "noise", "constant"]]
+    cases.append(("binary", (rng.integers(0, 2, (90, 700)) * 255).astype(np.uint8)))          # 0xFF stuffing across chunks
+    cases.append(("few-levels", (rng.integers(0, 4, (120, 333)) * 85).astype(np.uint8)))      # runs + interruptions
+    cases.append(("widest", rng.integers(0, 256, (5, 6144), dtype=np.uint8)))                  # one row per tile
+    cases.append(("steps", np.repeat(rng.integers(0, 256, (30, 375), dtype=np.uint8), 16, axis=1)))
+    for name, img in cases:
+        assert emu_jls(img) == oracle_jls(img, 0), name

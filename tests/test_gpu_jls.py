@@ -27,10 +27,21 @@ def check(img, near):
     assert got == want, first_diff(got, want)
 
 
+@pytest.fixture(params=[0, 1], ids=["tile-kernel", "multi-kernel"], autouse=True)
+def lossless_path(request):
+    """Every test runs on both NEAR=0 device paths: the shared-memory tile kernel (default) and the multi-kernel
+    pipeline that planes wider than 6144 use."""
+    imcvt_b200.debug_jls_path(request.param)
+    yield request.param
+    imcvt_b200.debug_jls_path(0)
+
+
 @pytest.mark.parametrize("serial", [False, True], ids=["pipeline", "serial"])
 @pytest.mark.parametrize("entry", [e for e in golden_table() if e["codec"] == "jls"],
                          ids=lambda e: f"{e['fixture']}-near{e['setting']}")
-def test_known_answers(entry, serial):
+def test_known_answers(entry, serial, lossless_path):
+    if serial and lossless_path == 1:
+        pytest.skip("the serial kernel does not depend on the lossless path")
     img, _ = load_pnm(os.path.join(GOLDEN, entry["fixture"] + ".pnm"))
     imcvt_b200.debug_jls_force_serial(serial)
     try:
@@ -113,6 +124,19 @@ def test_write_jls_image_file_is_a_drop_in():
         assert not os.path.exists(bad)
         # unwritable path -> 1 (imageio_jls.c:467-472)
         assert imcvt_b200.write_jls_image_file(os.path.join(d, "no/such/dir.jls"), img, 0, img.shape[0], img.shape[1], 0) == 1
+
+
+def test_planes_wider_than_the_tile_kernel_take_the_multi_kernel_path():
+    rng = np.random.default_rng(4)
+    img = np.repeat(rng.integers(0, 256, (6, 2100), dtype=np.uint8), 4, axis=1)[:, :8200].copy()
+    check(img, 0)
+
+
+def test_more_planes_than_sms_use_the_plane_queue():
+    frames = synth.batch("natural", 70, 40, 96, rgb=True)                  # 210 planes
+    got = imcvt_b200.encode_jls_batch(frames, 0)
+    for i in (0, 33, 69):
+        assert got[i] == oracle_jls(frames[i], 0), i
 
 
 def test_small_output_slot_is_an_error_not_a_crash():
