@@ -128,11 +128,15 @@ struct Smem {
     uint32_t chunk[CHUNK_WORDS];    // packer: un-stuffed bits of one chunk
     uint8_t  lens[2][TSMAX];        // code length per sample (0 = nothing), raster order
     uint8_t  pix[3][PIXBUF];        // rows of a tile (+ the row above, + the sample two rows above column 0)
+    int ctx[NCTX][4];               // (A, B, C, N) of every regular context of the plane in flight
+    int run_state[8];               // run_index, A/B/N of the two run-interruption contexts, pending run length
+    uint16_t order[2][CHAIN_WARPS * 32];   // chain thread -> bucket for a tile: buckets sorted by slice size (big slices share warps)
+    int cls_cnt[16], cls_pos[16];
     int plane;
 };
 
-// records: regular sample  pos | x << 13 | med << 21 | sign << 29
-//          run event       pos | run length << 13 | row-end flag << 28
+// records: regular sample  pos | x << 13 | med << 21 | sign << 29     (rewritten by its chain as pos | (e+128) << 13 | k << 21 | map << 25)
+//          run event       pos | run length << 13 | row-end flag << 28 | partial flag << 29 (the run goes on in the next segment)
 __device__ __forceinline__ uint8_t *pix_row(uint8_t *buf, int local_row, int W) { return buf + 16 + (local_row + 1) * W; }
 
 // stages the rows of tile t (and the row above it) into a pix buffer; executed by `nthr` threads
@@ -163,40 +167,61 @@ __device__ __forceinline__ void stage_tile(uint8_t *buf, const uint8_t *img, int
 }
 
 // ---- producers ------------------------------------------------------------------------------------
-// Classifies one row for one warp.  PASS 1: record + bucket per sample into temp_*, histogram into hist[].
-// (samplePixels :46-65, getQ :79-84, run state :270, :284-289 resolved 32 samples at a time by one 64-bit addition)
-__device__ __forceinline__ void classify_row(Smem &sm, uint8_t *pb, int W, int i_global, int i_local, int lane, uint16_t *hist)
+// Per-sample classification inputs of 32 consecutive samples of a row (samplePixels :46-65, getQ :79-84)
+struct Cls { int x, a, b, c, Q; bool active; };
+__device__ __forceinline__ Cls classify_sample(const uint8_t *pb, const uint8_t *cur, int W, int i_global, int i_local, int j)
+{
+    Cls s; s.x = 0; s.a = 0; s.b = 0; s.c = 0; s.Q = 1;
+    s.active = j >= 0 && j < W;
+    if (s.active) {
+        const uint8_t *up = cur - W;
+        int d = 0;
+        s.x = cur[j];
+        if (i_global > 0) { s.b = up[j]; d = (j + 1 < W) ? up[j + 1] : s.b; }
+        if (j == 0) { s.a = s.b; s.c = (i_global > 1) ? (i_local >= 1 ? (int)up[-W] : (int)pb[0]) : 0; }
+        else        { s.a = cur[j - 1]; s.c = (i_global > 0) ? up[j - 1] : 0; }
+        s.Q = 81 * grad_q_lossless(d - s.b) + 9 * grad_q_lossless(s.b - s.c) + grad_q_lossless(s.c - s.a);
+    }
+    return s;
+}
+
+// Classifies the samples [c0, c1) of one row (c0 a multiple of 32) for one warp.  PASS 1: record + bucket per sample
+// into temp_*, histogram into hist[].  Run state (:270, :284-289): running_j = (q0_j | running_{j-1}) & eq_j, a carry
+// chain resolved 32 samples at a time by one 64-bit addition of the two ballot masks.  A segment that does not start
+// the row finds its carry-in by looking back: the closest earlier sample with !eq (carry 0) or q0 & eq (carry 1) decides.
+__device__ __forceinline__ void classify_segment(Smem &sm, uint8_t *pb, int W, int i_global, int i_local, int c0, int c1, int lane, uint16_t *hist)
 {
     const uint8_t *cur = pix_row(pb, i_local, W);
-    const uint8_t *up = cur - W;
     const uint32_t lane_le = 0xFFFFFFFFu >> (31 - lane), lane_lt = lane_le >> 1;
     uint32_t cin = 0;
-    int run_start = 0;
-    for (int j0 = 0; j0 < W; j0 += 32) {
+    for (int jb = c0 - 32; jb >= 0; jb -= 32) {
+        const Cls s = classify_sample(pb, cur, W, i_global, i_local, jb + lane);
+        const uint32_t eqm = __ballot_sync(0xffffffffu, s.x == s.a);
+        const uint32_t q0m = __ballot_sync(0xffffffffu, s.Q == 0);
+        const uint32_t dec = ~eqm | q0m;
+        if (dec) { const int top = 31 - __clz((int)dec); cin = (eqm >> top) & (q0m >> top) & 1u; break; }
+    }
+    int run_start = c0;
+    for (int j0 = c0; j0 < c1; j0 += 32) {
         const int j = j0 + lane;
-        const bool active = j < W;
-        int x = 0, a = 0, b = 0, c = 0, d = 0;
-        if (active) {
-            x = cur[j];
-            if (i_global > 0) { b = up[j]; d = (j + 1 < W) ? up[j + 1] : b; }
-            if (j == 0) { a = b; c = (i_global > 1) ? (i_local >= 1 ? (int)up[-W] : (int)pb[0]) : 0; }
-            else        { a = cur[j - 1]; c = (i_global > 0) ? up[j - 1] : 0; }
-        }
-        const int Q = 81 * grad_q_lossless(d - b) + 9 * grad_q_lossless(b - c) + grad_q_lossless(c - a);
+        const Cls s = classify_sample(pb, cur, W, i_global, i_local, j < c1 ? j : -1);
+        const bool active = s.active;
+        const int Q = s.Q;
         const bool q0 = active && Q == 0;
-        const bool eq = active && x == a;
+        const bool eq = active && s.x == s.a;
         const uint32_t act = __ballot_sync(0xffffffffu, active);
         const uint32_t Pm  = __ballot_sync(0xffffffffu, eq);
         const uint32_t Gm  = __ballot_sync(0xffffffffu, q0 && eq);
         const uint32_t Q0m = __ballot_sync(0xffffffffu, q0);
         const uint64_t cv  = ((uint64_t)Pm + Gm + cin) ^ Pm ^ Gm;   // bit j = carry into j = running_{j-1}
         const uint32_t prevrun = (uint32_t)cv;
-        const uint32_t R   = (uint32_t)(cv >> 1) & act;             // running_j
+        const uint32_t Rm  = (uint32_t)(cv >> 1) & act;             // running_j
         const uint32_t INM = (Q0m | prevrun) & act;                 // sample is coded in run mode (hit or interruption)
         const uint32_t S   = Q0m & ~prevrun;                        // a run-mode stretch starts here
-        const bool inm = (INM >> lane) & 1u, run = (R >> lane) & 1u;
+        const bool inm = (INM >> lane) & 1u, run = (Rm >> lane) & 1u;
         const bool is_int = inm && !run;
         const bool is_eol = run && (j == W - 1);
+        const bool is_part = run && !is_eol && (j == c1 - 1);       // the run goes on in the next segment of the row
 
         int bucket = NBUCKET;                                       // dummy: plain run sample / inactive lane
         uint32_t rec = 0;
@@ -204,12 +229,12 @@ __device__ __forceinline__ void classify_row(Smem &sm, uint8_t *pb, int W, int i
         if (active) {
             if (!inm) {
                 bucket = (Q < 0 ? -Q : Q) - 1;
-                rec = lp | ((uint32_t)x << 13) | ((uint32_t)med3(a, b, c) << 21) | ((uint32_t)(Q < 0) << 29);
-            } else if (is_int || is_eol) {
+                rec = lp | ((uint32_t)s.x << 13) | ((uint32_t)med3(s.a, s.b, s.c) << 21) | ((uint32_t)(Q < 0) << 29);
+            } else if (is_int || is_eol || is_part) {
                 bucket = NCTX;
                 const uint32_t sm_ = S & lane_le;
                 const int start_col = sm_ ? (j0 + 31 - __clz((int)sm_)) : run_start;
-                rec = lp | ((uint32_t)(j - start_col + (is_eol ? 1 : 0)) << 13) | ((uint32_t)is_eol << 28);
+                rec = lp | ((uint32_t)(j - start_col + (is_int ? 0 : 1)) << 13) | ((uint32_t)is_eol << 28) | ((uint32_t)is_part << 29);
             }
             sm.temp_rec[lp] = rec;
             sm.temp_bkt[lp] = (uint16_t)bucket;
@@ -222,15 +247,15 @@ __device__ __forceinline__ void classify_row(Smem &sm, uint8_t *pb, int W, int i
     }
 }
 
-// PASS 2: scatter the records of one row into sorted[] (cursor[] = next free slot per bucket for this warp)
-__device__ __forceinline__ void scatter_row(Smem &sm, uint32_t *sorted, int W, int i_local, int lane, uint16_t *cursor)
+// PASS 2: scatter the records of one row segment into sorted[] (cursor[] = next free slot per bucket for this warp)
+__device__ __forceinline__ void scatter_segment(Smem &sm, uint32_t *sorted, int W, int i_local, int c0, int c1, int lane, uint16_t *cursor)
 {
     const uint32_t lane_lt = (0xFFFFFFFFu >> (31 - lane)) >> 1;
-    for (int j0 = 0; j0 < W; j0 += 32) {
+    for (int j0 = c0; j0 < c1; j0 += 32) {
         const int j = j0 + lane;
         int bucket = NBUCKET;
         uint32_t rec = 0;
-        if (j < W) { const int lp = i_local * W + j; bucket = sm.temp_bkt[lp]; rec = sm.temp_rec[lp]; }
+        if (j < c1) { const int lp = i_local * W + j; bucket = sm.temp_bkt[lp]; rec = sm.temp_rec[lp]; }
         const uint32_t peers = __match_any_sync(0xffffffffu, bucket);
         const int rank = __popc(peers & lane_lt);
         const int base = cursor[bucket];
@@ -249,15 +274,26 @@ __device__ __forceinline__ void producer_tick(Smem &sm, const Params &P, const u
         const int buf = t & 1;
         uint8_t *pb = sm.pix[t % 3];
         const int r0 = t * rows_per_tile, R = min(H, r0 + rows_per_tile) - r0;
-        const int per = (R + PROD_WARPS - 1) / PROD_WARPS;           // contiguous rows per warp keep raster order
-        const int a = min(R, pw * per), b = min(R, a + per);
+        // tasks = row segments in raster order; every warp takes a contiguous block of them (keeps raster order per bucket)
+        const int chunks = (W + 31) >> 5;
+        const int nseg = max(1, min(chunks, (PROD_WARPS + R - 1) / R));    // segments per row: about one task per producer warp
+        const int seg_chunks = (chunks + nseg - 1) / nseg;
+        const int ntask = R * nseg;
+        const int per = (ntask + PROD_WARPS - 1) / PROD_WARPS;
+        const int ta = min(ntask, pw * per), tb = min(ntask, ta + per);
         uint16_t *h = sm.cursor[pw];
         for (int k = lane; k < HSLOTS; k += 32) h[k] = 0;
         __syncwarp();
-        for (int r = a; r < b; r++) classify_row(sm, pb, W, r0 + r, r, lane, h);
+        for (int task = ta; task < tb; task++) {
+            const int r = task / nseg, sg = task - r * nseg;
+            const int c0 = min(W, sg * seg_chunks * 32), c1 = min(W, c0 + seg_chunks * 32);
+            if (c0 < c1) classify_segment(sm, pb, W, r0 + r, r, c0, c1, lane, h);
+        }
         JLS_NAMED_BARRIER(1, PROD_THREADS);
         if (pw == 0) {
             // exclusive scan over the buckets of (sum over warps); per-warp histograms become scatter cursors
+            if (lane < 16) { sm.cls_cnt[lane] = 0; }
+            __syncwarp();
             uint32_t carry = 0;
             for (int k0 = 0; k0 < NBUCKET + 1; k0 += 32) {
                 const int k = k0 + lane;
@@ -272,12 +308,26 @@ __device__ __forceinline__ void producer_tick(Smem &sm, const Params &P, const u
                 if (k < NBUCKET) {
 #pragma unroll
                     for (int w = 0; w < PROD_WARPS; w++) { sm.cursor[w][k] = (uint16_t)start; start += cnt[w]; }
+                    atomicAdd(&sm.cls_cnt[32 - __clz((int)tot)], 1);                 // size class = bit length of the slice size
                 }
                 carry += __shfl_sync(0xffffffffu, inc, 31);
             }
+            __syncwarp();
+            // chain thread i of the tile takes the i-th biggest slice (by size class): similar slices share a warp
+            if (lane == 0) { int pos = 0; for (int c = 15; c >= 0; c--) { sm.cls_pos[c] = pos; pos += sm.cls_cnt[c]; } }
+            __syncwarp();
+            for (int k = lane; k < NBUCKET; k += 32) {
+                const int size = (int)sm.bstart[buf][k + 1] - (int)sm.bstart[buf][k];
+                const int slot = atomicAdd(&sm.cls_pos[32 - __clz(size)], 1);
+                sm.order[buf][slot] = (uint16_t)k;
+            }
         }
         JLS_NAMED_BARRIER(1, PROD_THREADS);
-        for (int r = a; r < b; r++) scatter_row(sm, sm.sorted[buf], W, r, lane, h);
+        for (int task = ta; task < tb; task++) {
+            const int r = task / nseg, sg = task - r * nseg;
+            const int c0 = min(W, sg * seg_chunks * 32), c1 = min(W, c0 + seg_chunks * 32);
+            if (c0 < c1) scatter_segment(sm, sm.sorted[buf], W, r, c0, c1, lane, h);
+        }
     }
     // rows of the next tile
     if (t + 1 < ntiles) stage_tile(sm.pix[(t + 1) % 3], img, W, H, rows_per_tile, t + 1, ptid, PROD_THREADS);
@@ -285,11 +335,13 @@ __device__ __forceinline__ void producer_tick(Smem &sm, const Params &P, const u
 
 // ---- chains ---------------------------------------------------------------------------------------
 struct RegularState { int A, B, C, N; };
-struct RunState { int run_index, A0, B0, N0, A1, B1, N1; };
+struct RunState { int run_index, A0, B0, N0, A1, B1, N1, pending; };
 
-__device__ __forceinline__ void regular_step(uint32_t rec, RegularState &s, uint32_t *codes, uint8_t *lens)
+// The serial part of a regular sample (:346-393): prediction correction, error, context update.  What the code needs
+// (error, Golomb parameter, mapping flag) replaces the record; the code itself is generated later by all threads.
+__device__ __forceinline__ uint32_t regular_step(uint32_t rec, RegularState &s)
 {
-    const int lp = rec & 0x1FFF, x = (rec >> 13) & 0xFF, med = (rec >> 21) & 0xFF;
+    const int x = (rec >> 13) & 0xFF, med = (rec >> 21) & 0xFF;
     const bool neg = (rec >> 29) & 1u;
     int px = med + (neg ? -s.C : s.C);                  // :349
     px = min(max(px, 0), 255);
@@ -297,15 +349,10 @@ __device__ __forceinline__ void regular_step(uint32_t rec, RegularState &s, uint
     if (neg) e = -e;
     e = (int)(int8_t)e;                                 // modRange :105-111 with RANGE = 256
     const int k = golomb_k(s.A, s.N);
-    const int ae = e < 0 ? -e : e;
     const int map = (k == 0) && (2 * s.B <= -s.N);      // :367
-    const int me = 2 * ae + (e < 0 ? -(map + 1) : map);
-    uint32_t code; int len;
-    golomb_code(me, k, 23, 8, code, len);
-    codes[lp] = code;
-    lens[lp]  = (uint8_t)len;
+    const uint32_t out = (rec & 0x1FFFu) | ((uint32_t)(e + 128) << 13) | ((uint32_t)k << 21) | ((uint32_t)map << 25);
     s.B += e;                                           // :376-393
-    s.A += ae;
+    s.A += e < 0 ? -e : e;
     if (s.N >= 64) { s.A >>= 1; s.B >>= 1; s.N >>= 1; }
     s.N++;
     if (s.B <= -s.N) {
@@ -315,14 +362,31 @@ __device__ __forceinline__ void regular_step(uint32_t rec, RegularState &s, uint
         s.B -= s.N; if (s.B > 0) s.B = 0;
         s.C = min(s.C + 1, 127);
     }
+    return out;
+}
+
+// Golomb code of a regular sample from what its chain left in the record (:364-373)
+__device__ __forceinline__ void regular_code(uint32_t w, uint32_t *codes, uint8_t *lens)
+{
+    const int lp = w & 0x1FFF, e = (int)((w >> 13) & 0xFF) - 128, k = (w >> 21) & 15, map = (w >> 25) & 1;
+    const int ae = e < 0 ? -e : e;
+    const int me = 2 * ae + (e < 0 ? -(map + 1) : map);
+    uint32_t code; int len;
+    golomb_code(me, k, 23, 8, code, len);
+    codes[lp] = code;
+    lens[lp]  = (uint8_t)len;
 }
 
 // one run event (:291-344): completed 2^J blocks -> ones in the slot of the run's last sample; interruption sample:
 // run remainder in J+1 bits + Golomb code of the interruption error
 __device__ __forceinline__ void run_step(uint32_t rec, RunState &s, uint8_t *pb, int W, int r0_global, uint32_t *codes, uint8_t *lens)
 {
-    const int lp = rec & 0x1FFF, L = (rec >> 13) & 0x7FFF;
+    const int lp = rec & 0x1FFF;
+    int L = (rec >> 13) & 0x7FFF;
     const bool eol = (rec >> 28) & 1u;
+    if ((rec >> 29) & 1u) { s.pending += L; return; }   // the run goes on in the next segment of the row
+    L += s.pending;
+    s.pending = 0;
     int cnt = L, ones = 0;
     while (cnt >= (1 << c_J[s.run_index])) {            // :295-300, whole blocks at once
         cnt -= 1 << c_J[s.run_index];
@@ -501,9 +565,6 @@ __global__ void __launch_bounds__(NTHREADS, 1) jls_tile_kernel(Params P)
     const int W = P.W, H = P.H;
     const int rows_per_tile = max(1, TSMAX / W);
     const int ntiles = (H + rows_per_tile - 1) / rows_per_tile;
-    // chain thread -> bucket: consecutive buckets sit in different warps (the busy low-gradient contexts are neighbours)
-    const int bucket = warp < CHAIN_WARPS ? (lane * CHAIN_WARPS + warp) : -1;
-    const bool is_chain = bucket >= 0 && bucket < NBUCKET;
 
     for (int i = tid; i < 2 * TSMAX / 4; i += NTHREADS) reinterpret_cast<uint32_t *>(&sm.lens[0][0])[i] = 0;
 
@@ -515,8 +576,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) jls_tile_kernel(Params P)
         if (p >= P.P) break;
         const uint8_t *img = P.pix + (size_t)p * P.plane_stride;
 
-        RegularState rs; rs.A = 4; rs.B = 0; rs.C = 0; rs.N = 1;                       // :256-261 (a_init = 4 for RANGE 256)
-        RunState us; us.run_index = 0; us.A0 = 4; us.B0 = 0; us.N0 = 1; us.A1 = 4; us.B1 = 0; us.N1 = 1;     // :250, :263-267
+        // :256-261 (a_init = 4 for RANGE 256), :250, :263-267
+        for (int i = tid; i < NCTX; i += NTHREADS) { sm.ctx[i][0] = 4; sm.ctx[i][1] = 0; sm.ctx[i][2] = 0; sm.ctx[i][3] = 1; }
+        if (tid < 8) sm.run_state[tid] = (tid == 1 || tid == 4) ? 4 : (tid == 3 || tid == 6) ? 1 : 0;
         PackState ps; ps.out_pos = 0; ps.carry_bits = 0; ps.pz = 0;
         ps.dst = plane_dst(P.L, p, ps.cap);
 
@@ -528,15 +590,36 @@ __global__ void __launch_bounds__(NTHREADS, 1) jls_tile_kernel(Params P)
                 producer_tick(sm, P, img, rows_per_tile, tick, ntiles, warp - CHAIN_WARPS, lane);
             } else if (warp < CHAIN_WARPS) {
                 const int t = tick - 1;
-                if (t >= 0 && t < ntiles && is_chain) {
+                if (t >= 0 && t < ntiles) {
                     const int buf = t & 1;
-                    const uint32_t *rec = sm.sorted[buf];
-                    const int b0 = sm.bstart[buf][bucket], b1 = sm.bstart[buf][bucket + 1];
-                    if (bucket < NCTX) {
-                        for (int i = b0; i < b1; i++) regular_step(rec[i], rs, sm.codes[buf], sm.lens[buf]);
-                    } else {
-                        for (int i = b0; i < b1; i++) run_step(rec[i], us, sm.pix[t % 3], W, t * rows_per_tile, sm.codes[buf], sm.lens[buf]);
+                    uint32_t *rec = sm.sorted[buf];
+                    const int bucket = tid < NBUCKET ? (int)sm.order[buf][tid] : -1;
+                    if (bucket >= 0) {
+                        const int b0 = sm.bstart[buf][bucket], b1 = sm.bstart[buf][bucket + 1];
+                        if (bucket < NCTX) {
+                            if (b1 > b0) {
+                                RegularState rs; rs.A = sm.ctx[bucket][0]; rs.B = sm.ctx[bucket][1]; rs.C = sm.ctx[bucket][2]; rs.N = sm.ctx[bucket][3];
+                                uint32_t r = rec[b0];
+                                for (int i = b0; i < b1; i++) {
+                                    const uint32_t cur = r;
+                                    if (i + 1 < b1) r = rec[i + 1];
+                                    rec[i] = regular_step(cur, rs);
+                                }
+                                sm.ctx[bucket][0] = rs.A; sm.ctx[bucket][1] = rs.B; sm.ctx[bucket][2] = rs.C; sm.ctx[bucket][3] = rs.N;
+                            }
+                        } else if (b1 > b0) {
+                            RunState us;
+                            us.run_index = sm.run_state[0]; us.A0 = sm.run_state[1]; us.B0 = sm.run_state[2]; us.N0 = sm.run_state[3];
+                            us.A1 = sm.run_state[4]; us.B1 = sm.run_state[5]; us.N1 = sm.run_state[6]; us.pending = sm.run_state[7];
+                            for (int i = b0; i < b1; i++) run_step(rec[i], us, sm.pix[t % 3], W, t * rows_per_tile, sm.codes[buf], sm.lens[buf]);
+                            sm.run_state[0] = us.run_index; sm.run_state[1] = us.A0; sm.run_state[2] = us.B0; sm.run_state[3] = us.N0;
+                            sm.run_state[4] = us.A1; sm.run_state[5] = us.B1; sm.run_state[6] = us.N1; sm.run_state[7] = us.pending;
+                        }
                     }
+                    JLS_NAMED_BARRIER(2, CHAIN_WARPS * 32);
+                    // all chain threads: Golomb codes of the tile's regular samples into their raster slots
+                    const int nreg = sm.bstart[buf][NCTX];
+                    for (int i = tid; i < nreg; i += CHAIN_WARPS * 32) regular_code(rec[i], sm.codes[buf], sm.lens[buf]);
                 }
             } else {
                 const int t = tick - 2;

@@ -30,5 +30,12 @@ def test_multi_tile_planes_match_oracle():
     cases.append(("few-levels", (rng.integers(0, 4, (120, 333)) * 85).astype(np.uint8)))      # runs + interruptions
     cases.append(("widest", rng.integers(0, 256, (5, 6144), dtype=np.uint8)))                  # one row per tile
     cases.append(("steps", np.repeat(rng.integers(0, 256, (30, 375), dtype=np.uint8), 16, axis=1)))
+    # rows split into segments across producer warps: runs that cross segment boundaries
+    cases.append(("const-wide", np.full((4, 5000), 77, np.uint8)))
+    row = np.repeat(rng.integers(0, 256, 200), rng.integers(1, 400, 200))[:6000].astype(np.uint8)
+    cases.append(("random-runs", np.stack([np.roll(row, 37 * i) for i in range(6)])))
+    img = np.repeat(rng.integers(0, 3, (7, 40), dtype=np.uint8) * 100, 50, axis=1)[:, :1999].copy()
+    img[rng.integers(0, 7, 30), rng.integers(0, 1999, 30)] += 1
+    cases.append(("runs+interrupts", img))
     for name, img in cases:
         assert emu_jls(img) == oracle_jls(img, 0), name
