@@ -22,7 +22,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libimcvt_b200.so")
+# IMCVT_B200_LIB selects a development build of the same library (e.g. libimcvt_b200_prof.so, `make PROF=1`)
+LIB_PATH = os.path.join(_HERE, os.environ.get("IMCVT_B200_LIB", "libimcvt_b200.so"))
 
 # every symbol include/imcvt_b200.h and include/imcvt_imageio.h declare
 EXPORTED_SYMBOLS = [

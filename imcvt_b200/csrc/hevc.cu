@@ -8,6 +8,9 @@
 namespace imcvt {
 namespace hevc {
 
+#ifdef IMCVT_HEVC_PROF
+static unsigned long long *g_prof = nullptr;
+#endif
 static inline int pad32(uint32_t v) { uint32_t c = v > 8192 ? 8192 : v; return (int)((c + 31) / 32 * 32); }   // HEVCe.c:1580-1581
 
 // d_frames: device, n gray8 images.  d_out / d_out_len / d_rcon (optional): device.  Queues everything on `st`.
@@ -47,6 +50,15 @@ int encode_device(const uint8_t *d_frames, size_t frame_stride, int n, uint32_t 
     P.out_len = (unsigned long long *)d_out_len;
     P.rcon = rc; P.rcon_stride = rcs;
     P.scratch = scratch; P.lists = lists; P.overflow = d_overflow; P.next_frame = next;
+    P.prof = nullptr;
+#ifdef IMCVT_HEVC_PROF
+    {
+        static unsigned long long *d_prof = nullptr;
+        if (!d_prof) { IMCVT_CUDA(cudaMalloc(&d_prof, 64 * 8)); IMCVT_CUDA(cudaMemset(d_prof, 0, 64 * 8)); }
+        P.prof = d_prof;
+        g_prof = d_prof;
+    }
+#endif
     {
         LaunchScope ls("hevc_frame", st);
         hevc_frame_kernel<<<grid, NT, sizeof(Smem), st>>>(P);
@@ -57,3 +69,15 @@ int encode_device(const uint8_t *d_frames, size_t frame_stride, int n, uint32_t 
 
 }  // namespace hevc
 }  // namespace imcvt
+
+#ifdef IMCVT_HEVC_PROF
+// development build only (make PROF=1): reads and clears the 64 phase counters of hevc_frame_kernel
+extern "C" int imcvtDebugHevcProf(unsigned long long *out64)
+{
+    if (!imcvt::hevc::g_prof) return 1;
+    cudaDeviceSynchronize();
+    cudaMemcpy(out64, imcvt::hevc::g_prof, 64 * 8, cudaMemcpyDeviceToHost);
+    cudaMemset(imcvt::hevc::g_prof, 0, 64 * 8);
+    return 0;
+}
+#endif

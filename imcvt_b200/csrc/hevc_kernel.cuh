@@ -34,6 +34,19 @@ extern __shared__ __align__(16) unsigned char imcvt_dyn_smem[];
 namespace imcvt {
 namespace hevc {
 
+// development aid: cycles of thread 0 between phase marks, accumulated per (CU level, phase) in Params::prof
+#if defined(IMCVT_HEVC_PROF) && !defined(IMCVT_HOST_EMU)
+#define HPROF(K, id) do { if (threadIdx.x == 0) { const long long t__ = clock64(); atomicAdd(&(K).P->prof[(id)], (unsigned long long)(t__ - (K).prof_t)); (K).prof_t = t__; } } while (0)
+#else
+#define HPROF(K, id) do { } while (0)
+#endif
+
+#if defined(IMCVT_HEVC_NOINLINE) && !defined(IMCVT_HOST_EMU)
+#define HEVC_BIGFN __device__ __noinline__
+#else
+#define HEVC_BIGFN __device__ __forceinline__
+#endif
+
 #include "hevc_tables.h"
 
 constexpr int NW = 12;                  // warps per CTA
@@ -102,6 +115,7 @@ struct Params {
     unsigned short *lists;                           // [gridDim.x][NCAND][CAND_LIST_U16] bin lists of the trials
     int *overflow;                                   // set to 1 when a stream did not fit its slot
     int *next_frame;                                 // dynamic frame queue
+    unsigned long long *prof;                        // phase cycle counters (only with IMCVT_HEVC_PROF; else unused)
 };
 
 struct CoderRegs { int range, low, nbits, pending, held, zeros; unsigned nout; int pad_; };
@@ -504,7 +518,7 @@ __device__ __forceinline__ void binarize_cg(bool has, const BinDesc &D, int sz, 
 // Binarises the transform units a warp has just quantised (descriptors in sm.bdesc[warp][0..G-1], levels in sm.lev).
 // Tasks are the significant coefficient groups plus group 0 of every unit; each half-warp takes its share.
 template <int TS>
-__device__ __forceinline__ void binarize_warp(Smem &sm, int warp, int lane, unsigned short *lists)
+HEVC_BIGFN void binarize_warp(Smem &sm, int warp, int lane, unsigned short *lists)
 {
     constexpr int G = 32 / TS;
     const int half = lane >> 4, hl = lane & 15;
@@ -538,7 +552,7 @@ __device__ __forceinline__ void binarize_warp(Smem &sm, int warp, int lane, unsi
 }
 
 // Arithmetic coding of one transform unit from its bin lists (one lane).  slots / hdrs point at the unit's group 0.
-__device__ __forceinline__ void code_block(Coder &c, int sz, int mode, int last, unsigned cgp0, unsigned cgp1, unsigned sg0, unsigned sg1,
+HEVC_BIGFN void code_block(Coder &c, int sz, int mode, int last, unsigned cgp0, unsigned cgp1, unsigned sg0, unsigned sg1,
                                            const unsigned short *slots, const unsigned short *hdrs, const uint8_t (*scan_all)[2])
 {
     const int st = scan_type_for(sz, mode), ncg = sz >> 2;
@@ -692,7 +706,7 @@ struct TuResult { int sse, last; unsigned cg0, cg1, sg0, sg1; };    // cg: group
 // groups.  (y0, x0): position of the TU inside the CTU.  avail: bit0 left, bit1 below-left, bit2 above, bit3 above-right.
 // lev: TS x TS levels with pitch TS+2.  rec: TS x TS tile (pitch rec_pitch) that receives the reconstruction.
 template <int TS>
-__device__ __forceinline__ TuResult tu_pipeline(Smem &sm, int warp, int lane, bool active, const Src &src, int y0, int x0,
+HEVC_BIGFN TuResult tu_pipeline(Smem &sm, int warp, int lane, bool active, const Src &src, int y0, int x0,
                                                 int avail, int mode, int qpd6, const RdK &rd, short *lev, uint8_t *rec, int rec_pitch)
 {
     constexpr int LOG = TS == 4 ? 2 : TS == 8 ? 3 : TS == 16 ? 4 : 5;
@@ -959,6 +973,7 @@ struct Ctx {
     unsigned short *lists;      // this CTA's [NCAND][CAND_LIST_U16]
     int qpd6;
     RdK rd;
+    long long prof_t;
 };
 
 template <int SZ> struct Level { static constexpr int v = SZ == 32 ? 0 : SZ == 16 ? 1 : 2; static constexpr int best_off = SZ == 32 ? 0 : SZ == 16 ? 1024 : 1280; };
@@ -1032,6 +1047,7 @@ __device__ void search_cu(Ctx &K, int y0, int x0, int avail)
     const int mode_l = sm.mmd[1 + cy][cx], mode_a = sm.mmd[cy][1 + cx];
     __syncthreads();
     const CoderRegs entry = sm.entry[LV];
+    HPROF(K, LV * 16 + 0);
     const int entry_bits_abs = 8 * ((int)entry.nout + entry.pending) + 23 - entry.nbits;
     const int entry_bits_rel = 8 * entry.pending + 23 - entry.nbits;
 
@@ -1065,6 +1081,7 @@ __device__ void search_cu(Ctx &K, int y0, int x0, int avail)
             sm.best_cost[LV] = rd.cost(sse, bits - entry_bits_abs);
         }
         __syncthreads();
+        HPROF(K, LV * 16 + 1);
     }
 
     Src src; src.rc = &sm.rc[0][0]; src.priv = nullptr; src.py0 = y0; src.px0 = x0; src.psz = SZ; src.ppitch = SZ;
@@ -1089,6 +1106,7 @@ __device__ void search_cu(Ctx &K, int y0, int x0, int avail)
         }
     }
     __syncthreads();                                                        // sm.lev is reused by the four-TU trials
+    HPROF(K, LV * 16 + 2);
     {
         constexpr int G = 32 / H, NG = NW * G;
         for (int base = 0; base < NMODE; base += NG) {
@@ -1111,9 +1129,12 @@ __device__ void search_cu(Ctx &K, int y0, int x0, int avail)
         }
     }
     // ---- phase B: 70 trial encodes from the entry state, one lane each ----
+    __syncthreads();
+    HPROF(K, LV * 16 + 3);
     for (int i = tid; i < NCAND * (CXP / 4); i += NT)
         ((unsigned *)sm.cctx)[i] = ((const unsigned *)sm.entry_ctx[LV])[i % (CXP / 4)];
     __syncthreads();
+    HPROF(K, LV * 16 + 4);
     {
         const int c = candidate_of_thread(tid, NCAND);
         if (c >= 0) {
@@ -1136,6 +1157,7 @@ __device__ void search_cu(Ctx &K, int y0, int x0, int avail)
         }
     }
     __syncthreads();
+    HPROF(K, LV * 16 + 5);
     // decide (:1437-1446, :1473-1482): candidates in the reference order, a later candidate wins ties
     if (tid == 0) {
         int bc = sm.best_cost[LV], win = -1;
@@ -1147,6 +1169,7 @@ __device__ void search_cu(Ctx &K, int y0, int x0, int avail)
         sm.win = win;
     }
     __syncthreads();
+    HPROF(K, LV * 16 + 6);
     {
         const int win = sm.win;
         if (win >= 0) {
@@ -1155,6 +1178,7 @@ __device__ void search_cu(Ctx &K, int y0, int x0, int avail)
         }
     }
     __syncthreads();
+    HPROF(K, LV * 16 + 7);
 
     // ---- 4: 8x8 only: four 4x4 PUs, each mode chosen by a stand-alone cost on a fresh coder (:1490-1556) ----
     if constexpr (SZ == 8) {
@@ -1175,9 +1199,12 @@ __device__ void search_cu(Ctx &K, int y0, int x0, int avail)
                 binarize_warp<4>(sm, warp, lane, K.lists);
                 __syncwarp();
             }
+            __syncthreads();
+            HPROF(K, LV * 16 + 8);
             for (int k = tid; k < NMODE * (CXP / 4); k += NT)
                 ((unsigned *)sm.cctx)[k] = ((const unsigned *)sm.init_ctx)[k % (CXP / 4)];
             __syncthreads();
+            HPROF(K, LV * 16 + 9);
             {
                 const int c = candidate4_of_thread(tid);
                 if (c >= 0) {
@@ -1189,6 +1216,7 @@ __device__ void search_cu(Ctx &K, int y0, int x0, int avail)
                 }
             }
             __syncthreads();
+            HPROF(K, LV * 16 + 10);
             if (tid == 0) {
                 int bc = I32MAX, win = -1;
                 for (int m = 0; m < NMODE; m++) {
@@ -1210,6 +1238,7 @@ __device__ void search_cu(Ctx &K, int y0, int x0, int avail)
                 }
             }
             __syncthreads();
+            HPROF(K, LV * 16 + 11);
         }
         // the NxN coding unit from the entry state (:1528-1545)
         copy_words(sm.cctx[0], sm.entry_ctx[LV], CXP / 4, tid, NT);
@@ -1236,6 +1265,7 @@ __device__ void search_cu(Ctx &K, int y0, int x0, int avail)
             sm.win = (sm.best_cost[LV] >= cost) ? 1 : 0;
         }
         __syncthreads();
+        HPROF(K, LV * 16 + 12);
         if (sm.win) {
             // commit: coder, bytes, maps; the reconstruction is the four kept 4x4 tiles (:1546-1554)
             const unsigned base = entry.nout, n = sm.ccoder[0].nout;
@@ -1249,6 +1279,7 @@ __device__ void search_cu(Ctx &K, int y0, int x0, int avail)
             }
             if (tid < 64) sm.rc[1 + y0 + (tid >> 3)][1 + x0 + (tid & 7)] = sm.nxn_rec[tid];
             __syncthreads();
+            HPROF(K, LV * 16 + 13);
             return;
         }
     }
@@ -1256,6 +1287,7 @@ __device__ void search_cu(Ctx &K, int y0, int x0, int avail)
     // ---- the best reconstruction becomes the CU's reconstruction (:1558) ----
     for (int i = tid; i < SZ * SZ; i += NT) sm.rc[1 + y0 + i / SZ][1 + x0 + i % SZ] = best[i];
     __syncthreads();
+    HPROF(K, LV * 16 + 13);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1379,6 +1411,7 @@ __device__ inline void encode_frame(Ctx &K, int f)
                 else if (c == 0) { if (hl) { s = sm.left_sz[r - 1]; m = sm.left_md[r - 1]; } }
                 if (r == 0 || c == 0) { sm.msz[r][c] = s; sm.mmd[r][c] = m; }
             }
+            HPROF(K, 48);
             search_cu<CTU>(K, 0, 0, (hl ? 1 : 0) | (ha ? 4 : 0) | (har ? 8 : 0));
 
             for (int i = tid; i < CTU * CTU / 4; i += NT) {                      // :1625-1627
@@ -1393,6 +1426,7 @@ __device__ inline void encode_frame(Ctx &K, int f)
                 c.store(sm.cur);
             }
             __syncthreads();
+            HPROF(K, 49);
         }
     }
     if (tid == 0) {
@@ -1414,6 +1448,9 @@ __global__ void __launch_bounds__(NT, 1) hevc_frame_kernel(Params P)
     K.lists = P.lists + (size_t)blockIdx.x * NCAND * CAND_LIST_U16;
     K.out = nullptr;
     build_tables(sm, P.qpd6);
+#if defined(IMCVT_HEVC_PROF) && !defined(IMCVT_HOST_EMU)
+    K.prof_t = clock64();
+#endif
     for (;;) {                                                                  // frames vary 2-3x in cost: dynamic queue
         __syncthreads();
         if (threadIdx.x == 0) sm.win = atomicAdd(P.next_frame, 1);

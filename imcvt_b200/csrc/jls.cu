@@ -762,6 +762,9 @@ static SerialParams make_params(int near_)               // setParameters :26-38
     return P;
 }
 
+#ifdef IMCVT_JLS_PROF
+static unsigned long long *g_jls_prof = nullptr;
+#endif
 // d_frames: device, interleaved.  d_out / d_out_len: device.  Queues everything on `st`.
 // d_overflow: device int set to 1 when a slot was too small.
 int encode_device(const uint8_t *d_frames, size_t frame_stride, int n, int is_rgb, uint32_t H, uint32_t W, int near_,
@@ -840,6 +843,13 @@ int encode_device(const uint8_t *d_frames, size_t frame_stride, int n, int is_rg
         tile::Params TP;
         TP.pix = planes; TP.plane_stride = plane_stride; TP.P = P; TP.W = (int)W; TP.H = (int)H;
         TP.L = Lay; TP.plane_bytes = (unsigned long long *)plane_bytes; TP.next_plane = next;
+        TP.prof = nullptr;
+#ifdef IMCVT_JLS_PROF
+        {
+            if (!g_jls_prof) { IMCVT_CUDA(cudaMalloc(&g_jls_prof, 16 * 8)); IMCVT_CUDA(cudaMemset(g_jls_prof, 0, 16 * 8)); }
+            TP.prof = g_jls_prof;
+        }
+#endif
         LaunchScope ls("jls_tile", st);
         tile::jls_tile_kernel<<<P < E.sm_count ? P : E.sm_count, tile::NTHREADS, sizeof(tile::Smem), st>>>(TP);
     } else if (lossless) {
@@ -923,3 +933,15 @@ int encode_device(const uint8_t *d_frames, size_t frame_stride, int n, int is_rg
 
 }  // namespace jls
 }  // namespace imcvt
+
+#ifdef IMCVT_JLS_PROF
+// development build only (make PROF=1): reads and clears the role cycle counters of jls_tile_kernel
+extern "C" int imcvtDebugJlsProf(unsigned long long *out16)
+{
+    if (!imcvt::jls::g_jls_prof) return 1;
+    cudaDeviceSynchronize();
+    cudaMemcpy(out16, imcvt::jls::g_jls_prof, 16 * 8, cudaMemcpyDeviceToHost);
+    cudaMemset(imcvt::jls::g_jls_prof, 0, 16 * 8);
+    return 0;
+}
+#endif

@@ -102,13 +102,18 @@ namespace tile {
 
 constexpr int TSMAX = 6144;         // samples per tile (whole rows)
 constexpr int WMAX  = 6144;         // widest plane this kernel takes (wider ones use the multi-kernel path)
-constexpr int CHAIN_WARPS = 12, PROD_WARPS = 6, PACK_WARPS = 1;
+constexpr int CHAIN_WARPS = 12, PROD_WARPS = 10, PACK_WARPS = 1;
 constexpr int NWARPS = CHAIN_WARPS + PROD_WARPS + PACK_WARPS;
 constexpr int NTHREADS = NWARPS * 32;
 constexpr int PROD_THREADS = PROD_WARPS * 32;
 constexpr int PIXBUF = 16 + TSMAX + WMAX + 16;
 constexpr int CHUNK = 1024;         // samples per packer chunk (32 per lane)
 constexpr int CHUNK_WORDS = CHUNK + 8;
+// codes / lens of a tile are indexed with one pad word per 32 samples: the packer's lanes read 32 consecutive samples
+// each, and the pad spreads them over the shared-memory banks
+constexpr int CODE_SLOTS = TSMAX + TSMAX / 32, LEN_SLOTS = TSMAX + TSMAX / 8;
+__device__ __forceinline__ int code_idx(int lp) { return lp + (lp >> 5); }
+__device__ __forceinline__ int len_idx(int lp) { return lp + ((lp >> 5) << 2); }
 
 struct Params {
     const uint8_t *pix; size_t plane_stride;   // P planes, H x W u8
@@ -116,26 +121,37 @@ struct Params {
     FrameLayout L;
     unsigned long long *plane_bytes;           // [P] stuffed scan length
     int *next_plane;                           // plane queue
+    unsigned long long *prof;                  // role cycle counters (development build IMCVT_JLS_PROF only)
 };
+
+#if defined(IMCVT_JLS_PROF) && !defined(IMCVT_HOST_EMU)
+#define JPROF_T0() const long long jp_t0 = clock64()
+#define JPROF(id, cond) do { if (cond) atomicAdd(&P.prof[(id)], (unsigned long long)(clock64() - jp_t0)); } while (0)
+#else
+#define JPROF_T0() do { } while (0)
+#define JPROF(id, cond) do { } while (0)
+#endif
 
 struct Smem {
     uint32_t sorted[2][TSMAX];      // records of a tile, grouped by context, raster order inside a context
-    uint32_t codes[2][TSMAX];       // Golomb code per sample, raster order
+    uint32_t codes[2][CODE_SLOTS];  // Golomb code per sample, raster order (code_idx)
     uint32_t temp_rec[TSMAX];       // producers: record per sample, raster order (pass 1 -> pass 2)
     uint16_t temp_bkt[TSMAX];       // producers: bucket per sample
     uint16_t bstart[2][HSLOTS + 2]; // start of every context's slice inside sorted[]
-    uint16_t cursor[PROD_WARPS][HSLOTS + 2];   // producers: per-warp histogram, then scatter cursor
+    alignas(4) uint16_t cursor[PROD_WARPS][HSLOTS + 2];   // producers: per-warp histogram, then scatter cursor
     uint32_t chunk[CHUNK_WORDS];    // packer: un-stuffed bits of one chunk
-    uint8_t  lens[2][TSMAX];        // code length per sample (0 = nothing), raster order
+    uint8_t  lens[2][LEN_SLOTS];    // code length per sample (0 = nothing), raster order (len_idx)
     uint8_t  pix[3][PIXBUF];        // rows of a tile (+ the row above, + the sample two rows above column 0)
     int ctx[NCTX][4];               // (A, B, C, N) of every regular context of the plane in flight
     int run_state[8];               // run_index, A/B/N of the two run-interruption contexts, pending run length
     uint16_t order[2][CHAIN_WARPS * 32];   // chain thread -> bucket for a tile: buckets sorted by slice size (big slices share warps)
     int cls_cnt[16], cls_pos[16];
+    uint32_t blk_tot[32];           // producers: histogram totals per block of 32 buckets
+    int8_t qlut[512];               // quantised gradient of g at [g + 255]
     int plane;
 };
 
-// records: regular sample  pos | x << 13 | med << 21 | sign << 29     (rewritten by its chain as pos | (e+128) << 13 | k << 21 | map << 25)
+// records: regular sample  pos | (sign*(x-MED) + 255) << 13 | clamp window << 22     (rewritten by its chain as pos | (e & 255) << 13 | k << 21 | map << 25)
 //          run event       pos | run length << 13 | row-end flag << 28 | partial flag << 29 (the run goes on in the next segment)
 __device__ __forceinline__ uint8_t *pix_row(uint8_t *buf, int local_row, int W) { return buf + 16 + (local_row + 1) * W; }
 
@@ -145,6 +161,7 @@ __device__ __forceinline__ void stage_tile(uint8_t *buf, const uint8_t *img, int
     const int r0 = t * rows_per_tile;
     if (r0 >= H) return;
     const int r1 = min(H, r0 + rows_per_tile);
+    if (r0 == 0) for (int i = tid; i < W; i += nthr) buf[16 + i] = 0;     // the row above the picture reads as zeros (:47-49)
     const int first = r0 > 0 ? r0 - 1 : 0;
     const uint8_t *src = img + (size_t)first * W;
     uint8_t *dst = buf + 16 + (first - (r0 - 1)) * W;
@@ -167,52 +184,65 @@ __device__ __forceinline__ void stage_tile(uint8_t *buf, const uint8_t *img, int
 }
 
 // ---- producers ------------------------------------------------------------------------------------
-// Per-sample classification inputs of 32 consecutive samples of a row (samplePixels :46-65, getQ :79-84)
-struct Cls { int x, a, b, c, Q; bool active; };
-__device__ __forceinline__ Cls classify_sample(const uint8_t *pb, const uint8_t *cur, int W, int i_global, int i_local, int j)
+// Gradient quantisation (gradientQuantize :68-76 with T1,T2,T3 = 3,7,21, NEAR = 0) from a table in shared memory:
+// qlut[g + 255] = quantised gradient of g in [-255, 255]; the three terms of getQ :79-84 are 81*q1 + 9*q2 + q3.
+__device__ __forceinline__ void build_qlut(int8_t *qlut, int tid, int nthr)
 {
-    Cls s; s.x = 0; s.a = 0; s.b = 0; s.c = 0; s.Q = 1;
+    for (int i = tid; i < 511; i += nthr) qlut[i] = (int8_t)grad_q_lossless(i - 255);
+}
+
+// Per-sample classification inputs of 32 consecutive samples of a row (samplePixels :46-65, getQ :79-84).  The row above
+// the picture is staged as zeros, so only column 0 and the last column need care.
+struct Cls { int x, a, b, c, Q; bool active; };
+__device__ __forceinline__ Cls classify_sample(const int8_t *qlut, const uint8_t *pb, const uint8_t *cur, int W, int i_local, int j)
+{
+    Cls s;
     s.active = j >= 0 && j < W;
-    if (s.active) {
-        const uint8_t *up = cur - W;
-        int d = 0;
-        s.x = cur[j];
-        if (i_global > 0) { s.b = up[j]; d = (j + 1 < W) ? up[j + 1] : s.b; }
-        if (j == 0) { s.a = s.b; s.c = (i_global > 1) ? (i_local >= 1 ? (int)up[-W] : (int)pb[0]) : 0; }
-        else        { s.a = cur[j - 1]; s.c = (i_global > 0) ? up[j - 1] : 0; }
-        s.Q = 81 * grad_q_lossless(d - s.b) + 9 * grad_q_lossless(s.b - s.c) + grad_q_lossless(s.c - s.a);
-    }
+    const int jc = s.active ? j : 0;
+    const uint8_t *up = cur - W;
+    const int jm = jc > 0 ? jc - 1 : 0, jp = jc + 1 < W ? jc + 1 : jc;
+    s.x = cur[jc];
+    s.b = up[jc];
+    const int d = up[jp];
+    int a = cur[jm], c = up[jm];
+    if (jc == 0) { a = s.b; c = i_local >= 1 ? (int)up[-W] : (int)pb[0]; }
+    s.a = a; s.c = c;
+    s.Q = 81 * (int)qlut[d - s.b + 255] + 9 * (int)qlut[s.b - c + 255] + (int)qlut[c - a + 255];
     return s;
 }
 
 // Classifies the samples [c0, c1) of one row (c0 a multiple of 32) for one warp.  PASS 1: record + bucket per sample
-// into temp_*, histogram into hist[].  Run state (:270, :284-289): running_j = (q0_j | running_{j-1}) & eq_j, a carry
-// chain resolved 32 samples at a time by one 64-bit addition of the two ballot masks.  A segment that does not start
-// the row finds its carry-in by looking back: the closest earlier sample with !eq (carry 0) or q0 & eq (carry 1) decides.
-__device__ __forceinline__ void classify_segment(Smem &sm, uint8_t *pb, int W, int i_global, int i_local, int c0, int c1, int lane, uint16_t *hist)
+// into temp_*, histogram into hist[] (16-bit counters, incremented two to a word by shared-memory atomics so that
+// successive iterations do not depend on each other).  Run state (:270, :284-289): running_j = (q0_j | running_{j-1})
+// & eq_j, a carry chain resolved 32 samples at a time by one 64-bit addition of the two ballot masks.  A segment that
+// does not start the row finds its carry-in by looking back: the closest earlier sample with !eq (carry 0) or
+// q0 & eq (carry 1) decides.
+__device__ __forceinline__ void classify_segment(Smem &sm, uint8_t *pb, int W, int i_local, int c0, int c1, int lane, uint16_t *hist)
 {
     const uint8_t *cur = pix_row(pb, i_local, W);
-    const uint32_t lane_le = 0xFFFFFFFFu >> (31 - lane), lane_lt = lane_le >> 1;
+    const int8_t *qlut = sm.qlut;
+    const uint32_t lane_le = 0xFFFFFFFFu >> (31 - lane);
     uint32_t cin = 0;
     for (int jb = c0 - 32; jb >= 0; jb -= 32) {
-        const Cls s = classify_sample(pb, cur, W, i_global, i_local, jb + lane);
+        const Cls s = classify_sample(qlut, pb, cur, W, i_local, jb + lane);
         const uint32_t eqm = __ballot_sync(0xffffffffu, s.x == s.a);
         const uint32_t q0m = __ballot_sync(0xffffffffu, s.Q == 0);
         const uint32_t dec = ~eqm | q0m;
         if (dec) { const int top = 31 - __clz((int)dec); cin = (eqm >> top) & (q0m >> top) & 1u; break; }
     }
     int run_start = c0;
+    uint32_t *hist32 = reinterpret_cast<uint32_t *>(hist);
     for (int j0 = c0; j0 < c1; j0 += 32) {
         const int j = j0 + lane;
-        const Cls s = classify_sample(pb, cur, W, i_global, i_local, j < c1 ? j : -1);
+        const Cls s = classify_sample(qlut, pb, cur, W, i_local, j < c1 ? j : -1);
         const bool active = s.active;
         const int Q = s.Q;
         const bool q0 = active && Q == 0;
         const bool eq = active && s.x == s.a;
         const uint32_t act = __ballot_sync(0xffffffffu, active);
         const uint32_t Pm  = __ballot_sync(0xffffffffu, eq);
-        const uint32_t Gm  = __ballot_sync(0xffffffffu, q0 && eq);
         const uint32_t Q0m = __ballot_sync(0xffffffffu, q0);
+        const uint32_t Gm  = Pm & Q0m;
         const uint64_t cv  = ((uint64_t)Pm + Gm + cin) ^ Pm ^ Gm;   // bit j = carry into j = running_{j-1}
         const uint32_t prevrun = (uint32_t)cv;
         const uint32_t Rm  = (uint32_t)(cv >> 1) & act;             // running_j
@@ -223,13 +253,18 @@ __device__ __forceinline__ void classify_segment(Smem &sm, uint8_t *pb, int W, i
         const bool is_eol = run && (j == W - 1);
         const bool is_part = run && !is_eol && (j == c1 - 1);       // the run goes on in the next segment of the row
 
-        int bucket = NBUCKET;                                       // dummy: plain run sample / inactive lane
-        uint32_t rec = 0;
-        const uint32_t lp = (uint32_t)(i_local * W + j);
         if (active) {
+            int bucket = NBUCKET;                                   // dummy: plain run sample
+            uint32_t rec = 0;
+            const uint32_t lp = (uint32_t)(i_local * W + j);
             if (!inm) {
-                bucket = (Q < 0 ? -Q : Q) - 1;
-                rec = lp | ((uint32_t)s.x << 13) | ((uint32_t)med3(s.a, s.b, s.c) << 21) | ((uint32_t)(Q < 0) << 29);
+                // regular sample: what its chain needs -- sign * (x - MED) and the clamp window of the bias (regular_step)
+                const bool neg = Q < 0;
+                const int med = med3(s.a, s.b, s.c);
+                bucket = (neg ? -Q : Q) - 1;
+                const int d0 = neg ? med - s.x : s.x - med;
+                const int nlo = neg ? 255 - med : med;
+                rec = lp | ((uint32_t)(d0 + 255) << 13) | ((uint32_t)nlo << 22);
             } else if (is_int || is_eol || is_part) {
                 bucket = NCTX;
                 const uint32_t sm_ = S & lane_le;
@@ -238,10 +273,8 @@ __device__ __forceinline__ void classify_segment(Smem &sm, uint8_t *pb, int W, i
             }
             sm.temp_rec[lp] = rec;
             sm.temp_bkt[lp] = (uint16_t)bucket;
+            if (bucket < NBUCKET) atomicAdd(&hist32[bucket >> 1], 1u << ((bucket & 1) * 16));
         }
-        const uint32_t peers = __match_any_sync(0xffffffffu, bucket);
-        if ((peers & lane_lt) == 0) hist[bucket] = (uint16_t)(hist[bucket] + __popc(peers));
-        __syncwarp();
         cin = (uint32_t)(cv >> 32) & 1u;
         if (S) run_start = j0 + 31 - __clz((int)S);
     }
@@ -266,10 +299,13 @@ __device__ __forceinline__ void scatter_segment(Smem &sm, uint32_t *sorted, int 
     }
 }
 
+constexpr int NBLK = (NBUCKET + 1 + 31) / 32;      // blocks of 32 histogram slots (the extra slot closes the last slice)
+
 __device__ __forceinline__ void producer_tick(Smem &sm, const Params &P, const uint8_t *img, int rows_per_tile, int t, int ntiles, int pw, int lane)
 {
     const int W = P.W, H = P.H;
     const int ptid = pw * 32 + lane;
+    JPROF_T0();
     if (t < ntiles) {
         const int buf = t & 1;
         uint8_t *pb = sm.pix[t % 3];
@@ -282,51 +318,72 @@ __device__ __forceinline__ void producer_tick(Smem &sm, const Params &P, const u
         const int per = (ntask + PROD_WARPS - 1) / PROD_WARPS;
         const int ta = min(ntask, pw * per), tb = min(ntask, ta + per);
         uint16_t *h = sm.cursor[pw];
-        for (int k = lane; k < HSLOTS; k += 32) h[k] = 0;
+        for (int k = lane; k < (HSLOTS + 2) / 2; k += 32) reinterpret_cast<uint32_t *>(h)[k] = 0;
+        if (ptid < 16) { sm.cls_cnt[ptid] = 0; sm.cls_pos[ptid] = 0; }
         __syncwarp();
         for (int task = ta; task < tb; task++) {
             const int r = task / nseg, sg = task - r * nseg;
             const int c0 = min(W, sg * seg_chunks * 32), c1 = min(W, c0 + seg_chunks * 32);
-            if (c0 < c1) classify_segment(sm, pb, W, r0 + r, r, c0, c1, lane, h);
+            if (c0 < c1) classify_segment(sm, pb, W, r, c0, c1, lane, h);
+        }
+        JPROF(8, ptid == 0);
+        JLS_NAMED_BARRIER(1, PROD_THREADS);
+        JPROF(9, ptid == 0);
+        // exclusive scan over the buckets of (sum over warps), blocks of 32 buckets spread over the producer warps;
+        // the per-warp histograms become scatter cursors
+        for (int kb = pw; kb < NBLK; kb += PROD_WARPS) {
+            const int k = kb * 32 + lane;
+            uint32_t tot = 0;
+#pragma unroll
+            for (int w = 0; w < PROD_WARPS; w++) tot += k < NBUCKET ? sm.cursor[w][k] : 0;
+            uint32_t inc = tot;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) { const uint32_t v = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += v; }
+            if (lane == 31) sm.blk_tot[kb] = inc;
         }
         JLS_NAMED_BARRIER(1, PROD_THREADS);
-        if (pw == 0) {
-            // exclusive scan over the buckets of (sum over warps); per-warp histograms become scatter cursors
-            if (lane < 16) { sm.cls_cnt[lane] = 0; }
-            __syncwarp();
-            uint32_t carry = 0;
-            for (int k0 = 0; k0 < NBUCKET + 1; k0 += 32) {
-                const int k = k0 + lane;
-                uint32_t cnt[PROD_WARPS], tot = 0;
+        for (int kb = pw; kb < NBLK; kb += PROD_WARPS) {
+            const int k = kb * 32 + lane;
+            uint32_t bt = lane < kb ? sm.blk_tot[lane] : 0;                 // NBLK <= 32
 #pragma unroll
-                for (int w = 0; w < PROD_WARPS; w++) { cnt[w] = k < NBUCKET ? sm.cursor[w][k] : 0; tot += cnt[w]; }
-                uint32_t inc = tot;
+            for (int d = 16; d >= 1; d >>= 1) bt += __shfl_xor_sync(0xffffffffu, bt, d);
+            uint32_t cnt[PROD_WARPS], tot = 0;
 #pragma unroll
-                for (int d = 1; d < 32; d <<= 1) { const uint32_t v = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += v; }
-                uint32_t start = carry + inc - tot;
-                if (k <= NBUCKET) sm.bstart[buf][k] = (uint16_t)start;
-                if (k < NBUCKET) {
+            for (int w = 0; w < PROD_WARPS; w++) { cnt[w] = k < NBUCKET ? sm.cursor[w][k] : 0; tot += cnt[w]; }
+            uint32_t inc = tot;
 #pragma unroll
-                    for (int w = 0; w < PROD_WARPS; w++) { sm.cursor[w][k] = (uint16_t)start; start += cnt[w]; }
-                    atomicAdd(&sm.cls_cnt[32 - __clz((int)tot)], 1);                 // size class = bit length of the slice size
-                }
-                carry += __shfl_sync(0xffffffffu, inc, 31);
-            }
-            __syncwarp();
-            // chain thread i of the tile takes the i-th biggest slice (by size class): similar slices share a warp
-            if (lane == 0) { int pos = 0; for (int c = 15; c >= 0; c--) { sm.cls_pos[c] = pos; pos += sm.cls_cnt[c]; } }
-            __syncwarp();
-            for (int k = lane; k < NBUCKET; k += 32) {
-                const int size = (int)sm.bstart[buf][k + 1] - (int)sm.bstart[buf][k];
-                const int slot = atomicAdd(&sm.cls_pos[32 - __clz(size)], 1);
-                sm.order[buf][slot] = (uint16_t)k;
+            for (int d = 1; d < 32; d <<= 1) { const uint32_t v = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += v; }
+            uint32_t start = bt + inc - tot;
+            if (k <= NBUCKET) sm.bstart[buf][k] = (uint16_t)start;
+            if (k < NBUCKET) {
+#pragma unroll
+                for (int w = 0; w < PROD_WARPS; w++) { sm.cursor[w][k] = (uint16_t)start; start += cnt[w]; }
+                if (k < NCTX) atomicAdd(&sm.cls_cnt[32 - __clz((int)tot)], 1);   // size class = bit length of the slice size
             }
         }
+        JPROF(10, ptid == 0);
         JLS_NAMED_BARRIER(1, PROD_THREADS);
         for (int task = ta; task < tb; task++) {
             const int r = task / nseg, sg = task - r * nseg;
             const int c0 = min(W, sg * seg_chunks * 32), c1 = min(W, c0 + seg_chunks * 32);
             if (c0 < c1) scatter_segment(sm, sm.sorted[buf], W, r, c0, c1, lane, h);
+        }
+        JPROF(11, ptid == 0);
+        // chain thread i of the tile takes the i-th biggest slice (by size class): similar slices share a warp; the run
+        // events have a thread of their own in the last chain warp (next to the smallest slices)
+        {
+            int below = lane < 16 ? sm.cls_cnt[lane] : 0;                   // lane c: number of slices of class c
+            int pos = below;                                                // -> number of slices of a bigger class
+#pragma unroll
+            for (int d = 1; d < 16; d <<= 1) { const int v = __shfl_down_sync(0xffffffffu, pos, d); if (lane + d < 16) pos += v; }
+            pos -= below;
+            for (int kb = pw; kb < NBLK; kb += PROD_WARPS) {
+                const int k = kb * 32 + lane;
+                int cls = 0;
+                if (k < NCTX) cls = 32 - __clz((int)sm.bstart[buf][k + 1] - (int)sm.bstart[buf][k]);
+                const int first = __shfl_sync(0xffffffffu, pos, cls);
+                if (k < NCTX) sm.order[buf][first + atomicAdd(&sm.cls_pos[cls], 1)] = (uint16_t)k;
+            }
         }
     }
     // rows of the next tile
@@ -339,42 +396,43 @@ struct RunState { int run_index, A0, B0, N0, A1, B1, N1, pending; };
 
 // The serial part of a regular sample (:346-393): prediction correction, error, context update.  What the code needs
 // (error, Golomb parameter, mapping flag) replaces the record; the code itself is generated later by all threads.
+//
+// The loop-carried dependency is C -> prediction -> error -> B -> bias test -> C; everything else is kept off it:
+// with s = +-1 the sample's sign, sign * (Px - MED) = clamp(C, lo, hi) where lo/hi depend on MED only, so the error is
+// sext8(sign * (x - MED) - clamp(C, lo, hi)); N and the halving flag form their own short chain; k and the mapping
+// flag are outputs.  No branches: a warp's chain threads run different contexts in lock step.
 __device__ __forceinline__ uint32_t regular_step(uint32_t rec, RegularState &s)
 {
-    const int x = (rec >> 13) & 0xFF, med = (rec >> 21) & 0xFF;
-    const bool neg = (rec >> 29) & 1u;
-    int px = med + (neg ? -s.C : s.C);                  // :349
-    px = min(max(px, 0), 255);
-    int e = x - px;
-    if (neg) e = -e;
-    e = (int)(int8_t)e;                                 // modRange :105-111 with RANGE = 256
+    const int d0 = (int)((rec >> 13) & 0x1FFu) - 255;   // sign * (x - MED)
+    const int nlo = (int)((rec >> 22) & 0xFFu);         // sign * (Px - MED) = clamp(C, lo, hi), lo = -nlo, hi = 255 - nlo  (:349 + the [0,255] clip)
+    const int dlo = d0 + nlo, dhi = dlo - 255;          // d0 - lo, d0 - hi
     const int k = golomb_k(s.A, s.N);
     const int map = (k == 0) && (2 * s.B <= -s.N);      // :367
-    const uint32_t out = (rec & 0x1FFFu) | ((uint32_t)(e + 128) << 13) | ((uint32_t)k << 21) | ((uint32_t)map << 25);
-    s.B += e;                                           // :376-393
-    s.A += e < 0 ? -e : e;
-    if (s.N >= 64) { s.A >>= 1; s.B >>= 1; s.N >>= 1; }
-    s.N++;
-    if (s.B <= -s.N) {
-        s.B += s.N; if (s.B <= -s.N) s.B = -s.N + 1;
-        s.C = max(s.C - 1, -128);
-    } else if (s.B > 0) {
-        s.B -= s.N; if (s.B > 0) s.B = 0;
-        s.C = min(s.C + 1, 127);
-    }
+    const int rs = s.N >= 64;                           // :378-383: halve, then N++
+    const int N1 = (s.N >> rs) + 1;
+    const int e = (int)(int8_t)max(min(d0 - s.C, dlo), dhi);    // d0 - clamp(C, lo, hi), then modRange :105-111 with RANGE = 256
+    const uint32_t out = (rec & 0x1FFFu) | ((uint32_t)(e & 0xFF) << 13) | ((uint32_t)k << 21) | ((uint32_t)map << 25);
+    const int B1 = (s.B + e) >> rs;                     // :376-383
+    s.A = (s.A + (e < 0 ? -e : e)) >> rs;
+    s.N = N1;
+    // bias update :384-393 without branches: dn = (B1 <= -N1), up = (B1 > 0) as sign masks
+    const int sdn = (B1 + N1 - 1) >> 31, sup = (-B1) >> 31;
+    const int dC = sdn - sup;                           // -1 / 0 / +1
+    s.B = min(max(B1 - N1 * dC, 1 - N1), 0);
+    s.C = min(max(s.C + dC, -128), 127);
     return out;
 }
 
 // Golomb code of a regular sample from what its chain left in the record (:364-373)
 __device__ __forceinline__ void regular_code(uint32_t w, uint32_t *codes, uint8_t *lens)
 {
-    const int lp = w & 0x1FFF, e = (int)((w >> 13) & 0xFF) - 128, k = (w >> 21) & 15, map = (w >> 25) & 1;
+    const int lp = w & 0x1FFF, e = (int)(int8_t)(w >> 13), k = (w >> 21) & 15, map = (w >> 25) & 1;
     const int ae = e < 0 ? -e : e;
     const int me = 2 * ae + (e < 0 ? -(map + 1) : map);
     uint32_t code; int len;
     golomb_code(me, k, 23, 8, code, len);
-    codes[lp] = code;
-    lens[lp]  = (uint8_t)len;
+    codes[code_idx(lp)] = code;
+    lens[len_idx(lp)]  = (uint8_t)len;
 }
 
 // one run event (:291-344): completed 2^J blocks -> ones in the slot of the run's last sample; interruption sample:
@@ -395,13 +453,13 @@ __device__ __forceinline__ void run_step(uint32_t rec, RunState &s, uint8_t *pb,
     }
     if (eol) {                                          // :302-303
         if (cnt > 0) ones++;
-        codes[lp] = (uint32_t)((1ull << ones) - 1ull);
-        lens[lp]  = (uint8_t)ones;
+        codes[code_idx(lp)] = (uint32_t)((1ull << ones) - 1ull);
+        lens[len_idx(lp)]  = (uint8_t)ones;
         return;
     }
     if (ones > 0) {
-        codes[lp - 1] = (uint32_t)((1ull << ones) - 1ull);
-        lens[lp - 1]  = (uint8_t)ones;
+        codes[code_idx(lp - 1)] = (uint32_t)((1ull << ones) - 1ull);
+        lens[len_idx(lp - 1)]  = (uint8_t)ones;
     }
     const int jj = c_J[s.run_index];
     const int glimit = 23 - 1 - jj;                     // :306
@@ -423,8 +481,8 @@ __device__ __forceinline__ void run_step(uint32_t rec, RunState &s, uint8_t *pb,
     const int me = 2 * (e < 0 ? -e : e) - t - map;
     uint32_t gcode; int glen;
     golomb_code(me, k, glimit, 8, gcode, glen);
-    codes[lp] = ((uint32_t)cnt << glen) | gcode;        // run remainder in J+1 bits, then the Golomb code (<= 32 bits)
-    lens[lp]  = (uint8_t)(jj + 1 + glen);
+    codes[code_idx(lp)] = ((uint32_t)cnt << glen) | gcode;        // run remainder in J+1 bits, then the Golomb code (<= 32 bits)
+    lens[len_idx(lp)]  = (uint8_t)(jj + 1 + glen);
     int An = At + ((me + 1 - t) >> 1), Bn = Bt + (e < 0), Nn = Nt;      // :336-344
     if (Nn >= 64) { An >>= 1; Bn >>= 1; Nn >>= 1; }
     Nn++;
@@ -506,23 +564,25 @@ __device__ __forceinline__ void stuff_chunk(Smem &sm, PackState &ps, uint32_t T,
 }
 
 // packs tile samples [0, n) (codes/lens in raster order) chunk by chunk and appends the stuffed bytes
-__device__ __forceinline__ void packer_tile(Smem &sm, PackState &ps, uint32_t *codes, uint8_t *lens, int n, bool last_tile, int lane)
+__device__ __forceinline__ void packer_tile(Smem &sm, const Params &P, PackState &ps, uint32_t *codes, uint8_t *lens, int n, bool last_tile, int lane)
 {
     uint32_t *buf = sm.chunk;
     for (int c0 = 0; c0 < n; c0 += CHUNK) {
+        JPROF_T0();
         const int cn = min(CHUNK, n - c0);
         // zero the words this chunk may touch (word 0 holds the carried bits)
         for (int w = 1 + lane; w < CHUNK_WORDS; w += 32) buf[w] = 0;
         if (ps.carry_bits == 0 && lane == 0) buf[0] = 0;
         __syncwarp();
-        // lane owns 32 consecutive samples
+        // lane owns 32 consecutive samples: their codes are concatenated in a register window and leave as whole words;
+        // only the first and the last word of a lane can be shared with its neighbours (atomicOr)
         const int s0 = c0 + lane * 32;
         uint32_t mylen = 0;
         uint32_t l4[8];
 #pragma unroll
         for (int q = 0; q < 8; q++) {
             uint32_t v = 0;
-            if (s0 + 4 * q < c0 + cn) v = *reinterpret_cast<const uint32_t *>(lens + s0 + 4 * q);   // tile arrays are padded: reads past n see zeros
+            if (s0 + 4 * q < c0 + cn) v = *reinterpret_cast<const uint32_t *>(lens + len_idx(s0) + 4 * q);   // reads past n see zeros
             l4[q] = v;
             mylen += (v & 0xFF) + ((v >> 8) & 0xFF) + ((v >> 16) & 0xFF) + (v >> 24);
         }
@@ -530,30 +590,40 @@ __device__ __forceinline__ void packer_tile(Smem &sm, PackState &ps, uint32_t *c
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) { const uint32_t v = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += v; }
         const uint32_t total = __shfl_sync(0xffffffffu, inc, 31);
-        uint32_t bit = ps.carry_bits + inc - mylen;
+        const uint32_t bit = ps.carry_bits + inc - mylen;
+        JPROF(12, lane == 0);
         if (mylen) {
+            uint32_t w = bit >> 5;
+            uint32_t nacc = bit & 31u;                  // bits in the window (the first `bit & 31` are a neighbour's: zeros here)
+            uint64_t acc = 0;
 #pragma unroll
             for (int q = 0; q < 8; q++) {
+                uint32_t cd[4];
+#pragma unroll
+                for (int r = 0; r < 4; r++) cd[r] = codes[code_idx(s0) + 4 * q + r];     // stale codes of empty slots are masked by len = 0
 #pragma unroll
                 for (int r = 0; r < 4; r++) {
                     const uint32_t len = (l4[q] >> (8 * r)) & 0xFF;
-                    if (len) {
-                        const uint32_t code = codes[s0 + 4 * q + r];
-                        const uint32_t w = bit >> 5, sh = bit & 31u;
-                        const uint64_t v = (uint64_t)code << (64 - len - sh);      // left-align the code at stream bit `bit`
-                        atomicOr(&buf[w], (uint32_t)(v >> 32));
-                        if ((uint32_t)v) atomicOr(&buf[w + 1], (uint32_t)v);
-                        bit += len;
+                    acc = (acc << len) | (len ? (uint64_t)cd[r] : 0ull);
+                    nacc += len;
+                    if (nacc >= 32) {
+                        nacc -= 32;
+                        const uint32_t word = (uint32_t)(acc >> nacc);
+                        atomicOr(&buf[w], word);
+                        w++;
                     }
                 }
             }
+            if (nacc) atomicOr(&buf[w], (uint32_t)(acc << (32 - nacc)));
         }
         // the slots are consumed: the chains of a later tile expect zero lengths
 #pragma unroll
         for (int q = 0; q < 8; q++)
-            if (s0 + 4 * q < c0 + cn && l4[q]) *reinterpret_cast<uint32_t *>(lens + s0 + 4 * q) = 0;
+            if (s0 + 4 * q < c0 + cn && l4[q]) *reinterpret_cast<uint32_t *>(lens + len_idx(s0) + 4 * q) = 0;
         __syncwarp();
+        JPROF(13, lane == 0);
         stuff_chunk(sm, ps, ps.carry_bits + total, last_tile && c0 + CHUNK >= n, lane);
+        JPROF(14, lane == 0);
     }
 }
 
@@ -566,7 +636,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) jls_tile_kernel(Params P)
     const int rows_per_tile = max(1, TSMAX / W);
     const int ntiles = (H + rows_per_tile - 1) / rows_per_tile;
 
-    for (int i = tid; i < 2 * TSMAX / 4; i += NTHREADS) reinterpret_cast<uint32_t *>(&sm.lens[0][0])[i] = 0;
+    for (int i = tid; i < 2 * LEN_SLOTS / 4; i += NTHREADS) reinterpret_cast<uint32_t *>(&sm.lens[0][0])[i] = 0;
+    build_qlut(sm.qlut, tid, NTHREADS);
 
     for (;;) {
         __syncthreads();
@@ -586,14 +657,17 @@ __global__ void __launch_bounds__(NTHREADS, 1) jls_tile_kernel(Params P)
         __syncthreads();
 
         for (int tick = 0; tick < ntiles + 2; tick++) {
+            JPROF_T0();
             if (warp >= CHAIN_WARPS && warp < CHAIN_WARPS + PROD_WARPS) {
                 producer_tick(sm, P, img, rows_per_tile, tick, ntiles, warp - CHAIN_WARPS, lane);
+                JPROF(1, warp == CHAIN_WARPS && lane == 0);
+                JPROF(5, warp == CHAIN_WARPS + PROD_WARPS - 1 && lane == 0);
             } else if (warp < CHAIN_WARPS) {
                 const int t = tick - 1;
                 if (t >= 0 && t < ntiles) {
                     const int buf = t & 1;
                     uint32_t *rec = sm.sorted[buf];
-                    const int bucket = tid < NBUCKET ? (int)sm.order[buf][tid] : -1;
+                    const int bucket = tid < NCTX ? (int)sm.order[buf][tid] : (tid == CHAIN_WARPS * 32 - 1 ? NCTX : -1);
                     if (bucket >= 0) {
                         const int b0 = sm.bstart[buf][bucket], b1 = sm.bstart[buf][bucket + 1];
                         if (bucket < NCTX) {
@@ -616,19 +690,25 @@ __global__ void __launch_bounds__(NTHREADS, 1) jls_tile_kernel(Params P)
                             sm.run_state[4] = us.A1; sm.run_state[5] = us.B1; sm.run_state[6] = us.N1; sm.run_state[7] = us.pending;
                         }
                     }
+                    JPROF(0, tid == 0);
+                    JPROF(6, tid == CHAIN_WARPS * 32 - 1);
                     JLS_NAMED_BARRIER(2, CHAIN_WARPS * 32);
+                    JPROF(7, tid == 0);
                     // all chain threads: Golomb codes of the tile's regular samples into their raster slots
                     const int nreg = sm.bstart[buf][NCTX];
                     for (int i = tid; i < nreg; i += CHAIN_WARPS * 32) regular_code(rec[i], sm.codes[buf], sm.lens[buf]);
+                    JPROF(4, tid == 0);
                 }
             } else {
                 const int t = tick - 2;
                 if (t >= 0 && t < ntiles) {
                     const int r0 = t * rows_per_tile, n = (min(H, r0 + rows_per_tile) - r0) * W;
-                    packer_tile(sm, ps, sm.codes[t & 1], sm.lens[t & 1], n, t == ntiles - 1, lane);
+                    packer_tile(sm, P, ps, sm.codes[t & 1], sm.lens[t & 1], n, t == ntiles - 1, lane);
                 }
+                JPROF(2, lane == 0);
             }
             __syncthreads();
+            JPROF(3, tid == 0);
         }
         if (warp == NWARPS - 1 && lane == 0) P.plane_bytes[p] = ps.out_pos;
     }

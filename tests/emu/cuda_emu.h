@@ -271,3 +271,4 @@ using std::max;
 inline unsigned atomicOr(unsigned *p, unsigned v) { unsigned o = *p; *p |= v; return o; }
 inline int atomicExch(int *p, int v) { int o = *p; *p = v; return o; }
 inline int atomicAdd(int *p, int v) { int o = *p; *p += v; return o; }
+inline unsigned atomicAdd(unsigned *p, unsigned v) { unsigned o = *p; *p += v; return o; }
