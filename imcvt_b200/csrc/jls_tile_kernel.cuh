@@ -102,13 +102,13 @@ namespace tile {
 
 constexpr int TSMAX = 6144;         // samples per tile (whole rows)
 constexpr int WMAX  = 6144;         // widest plane this kernel takes (wider ones use the multi-kernel path)
-constexpr int CHAIN_WARPS = 12, PROD_WARPS = 10, PACK_WARPS = 1;
+constexpr int CHAIN_WARPS = 12, PROD_WARPS = 10, PACK_WARPS = 4;
 constexpr int NWARPS = CHAIN_WARPS + PROD_WARPS + PACK_WARPS;
 constexpr int NTHREADS = NWARPS * 32;
 constexpr int PROD_THREADS = PROD_WARPS * 32;
 constexpr int PIXBUF = 16 + TSMAX + WMAX + 16;
 constexpr int CHUNK = 1024;         // samples per packer chunk (32 per lane)
-constexpr int CHUNK_WORDS = CHUNK + 8;
+constexpr int UBITS_WORDS = TSMAX + 8;   // un-stuffed bits of one tile: <= 32 per sample
 // codes / lens of a tile are indexed with one pad word per 32 samples: the packer's lanes read 32 consecutive samples
 // each, and the pad spreads them over the shared-memory banks
 constexpr int CODE_SLOTS = TSMAX + TSMAX / 32, LEN_SLOTS = TSMAX + TSMAX / 8;
@@ -135,11 +135,11 @@ struct Params {
 struct Smem {
     uint32_t sorted[2][TSMAX];      // records of a tile, grouped by context, raster order inside a context
     uint32_t codes[2][CODE_SLOTS];  // Golomb code per sample, raster order (code_idx)
-    uint32_t temp_rec[TSMAX];       // producers: record per sample, raster order (pass 1 -> pass 2)
-    uint16_t temp_bkt[TSMAX];       // producers: bucket per sample
+    uint32_t temp_rec[TSMAX];       // producers: bucket | record payload << 9 per sample, raster order (pass 1 -> pass 2)
     uint16_t bstart[2][HSLOTS + 2]; // start of every context's slice inside sorted[]
     alignas(4) uint16_t cursor[PROD_WARPS][HSLOTS + 2];   // producers: per-warp histogram, then scatter cursor
-    uint32_t chunk[CHUNK_WORDS];    // packer: un-stuffed bits of one chunk
+    uint32_t ubits[UBITS_WORDS];    // packer: un-stuffed bits of one tile
+    uint32_t chunk_bits[8];         // packer: code bits per chunk
     uint8_t  lens[2][LEN_SLOTS];    // code length per sample (0 = nothing), raster order (len_idx)
     uint8_t  pix[3][PIXBUF];        // rows of a tile (+ the row above, + the sample two rows above column 0)
     int ctx[NCTX][4];               // (A, B, C, N) of every regular context of the plane in flight
@@ -152,7 +152,7 @@ struct Smem {
 };
 
 // records: regular sample  pos | (sign*(x-MED) + 255) << 13 | clamp window << 22     (rewritten by its chain as pos | (e & 255) << 13 | k << 21 | map << 25)
-//          run event       pos | run length << 13 | row-end flag << 28 | partial flag << 29 (the run goes on in the next segment)
+//          run event       pos | run length << 13 | row-end flag << 28 | partial flag << 29 (the run goes on in the next segment) | first column << 30
 __device__ __forceinline__ uint8_t *pix_row(uint8_t *buf, int local_row, int W) { return buf + 16 + (local_row + 1) * W; }
 
 // stages the rows of tile t (and the row above it) into a pix buffer; executed by `nthr` threads
@@ -255,7 +255,7 @@ __device__ __forceinline__ void classify_segment(Smem &sm, uint8_t *pb, int W, i
 
         if (active) {
             int bucket = NBUCKET;                                   // dummy: plain run sample
-            uint32_t rec = 0;
+            uint32_t rec = 0;                                       // payload: the record without its position
             const uint32_t lp = (uint32_t)(i_local * W + j);
             if (!inm) {
                 // regular sample: what its chain needs -- sign * (x - MED) and the clamp window of the bias (regular_step)
@@ -264,15 +264,14 @@ __device__ __forceinline__ void classify_segment(Smem &sm, uint8_t *pb, int W, i
                 bucket = (neg ? -Q : Q) - 1;
                 const int d0 = neg ? med - s.x : s.x - med;
                 const int nlo = neg ? 255 - med : med;
-                rec = lp | ((uint32_t)(d0 + 255) << 13) | ((uint32_t)nlo << 22);
+                rec = (uint32_t)(d0 + 255) | ((uint32_t)nlo << 9);
             } else if (is_int || is_eol || is_part) {
                 bucket = NCTX;
                 const uint32_t sm_ = S & lane_le;
                 const int start_col = sm_ ? (j0 + 31 - __clz((int)sm_)) : run_start;
-                rec = lp | ((uint32_t)(j - start_col + (is_int ? 0 : 1)) << 13) | ((uint32_t)is_eol << 28) | ((uint32_t)is_part << 29);
+                rec = (uint32_t)(j - start_col + (is_int ? 0 : 1)) | ((uint32_t)is_eol << 15) | ((uint32_t)is_part << 16) | ((uint32_t)(j == 0) << 17);
             }
-            sm.temp_rec[lp] = rec;
-            sm.temp_bkt[lp] = (uint16_t)bucket;
+            sm.temp_rec[lp] = (uint32_t)bucket | (rec << 9);
             if (bucket < NBUCKET) atomicAdd(&hist32[bucket >> 1], 1u << ((bucket & 1) * 16));
         }
         cin = (uint32_t)(cv >> 32) & 1u;
@@ -288,7 +287,7 @@ __device__ __forceinline__ void scatter_segment(Smem &sm, uint32_t *sorted, int 
         const int j = j0 + lane;
         int bucket = NBUCKET;
         uint32_t rec = 0;
-        if (j < c1) { const int lp = i_local * W + j; bucket = sm.temp_bkt[lp]; rec = sm.temp_rec[lp]; }
+        if (j < c1) { const int lp = i_local * W + j; const uint32_t t = sm.temp_rec[lp]; bucket = (int)(t & 0x1FFu); rec = (uint32_t)lp | ((t >> 9) << 13); }
         const uint32_t peers = __match_any_sync(0xffffffffu, bucket);
         const int rank = __popc(peers & lane_lt);
         const int base = cursor[bucket];
@@ -310,21 +309,20 @@ __device__ __forceinline__ void producer_tick(Smem &sm, const Params &P, const u
         const int buf = t & 1;
         uint8_t *pb = sm.pix[t % 3];
         const int r0 = t * rows_per_tile, R = min(H, r0 + rows_per_tile) - r0;
-        // tasks = row segments in raster order; every warp takes a contiguous block of them (keeps raster order per bucket)
+        // work units = 32-sample chunks of the tile's rows in raster order; every warp takes an equal contiguous range of
+        // them (keeps raster order per bucket), i.e. one row segment per row it touches
         const int chunks = (W + 31) >> 5;
-        const int nseg = max(1, min(chunks, (PROD_WARPS + R - 1) / R));    // segments per row: about one task per producer warp
-        const int seg_chunks = (chunks + nseg - 1) / nseg;
-        const int ntask = R * nseg;
-        const int per = (ntask + PROD_WARPS - 1) / PROD_WARPS;
-        const int ta = min(ntask, pw * per), tb = min(ntask, ta + per);
+        const int nunits = R * chunks;
+        const int per = (nunits + PROD_WARPS - 1) / PROD_WARPS;
+        const int ua = min(nunits, pw * per), ub = min(nunits, ua + per);
+        const int ra = ua / chunks, rb = ub > ua ? (ub - 1) / chunks : ra - 1;       // rows [ra, rb]
         uint16_t *h = sm.cursor[pw];
         for (int k = lane; k < (HSLOTS + 2) / 2; k += 32) reinterpret_cast<uint32_t *>(h)[k] = 0;
         if (ptid < 16) { sm.cls_cnt[ptid] = 0; sm.cls_pos[ptid] = 0; }
         __syncwarp();
-        for (int task = ta; task < tb; task++) {
-            const int r = task / nseg, sg = task - r * nseg;
-            const int c0 = min(W, sg * seg_chunks * 32), c1 = min(W, c0 + seg_chunks * 32);
-            if (c0 < c1) classify_segment(sm, pb, W, r, c0, c1, lane, h);
+        for (int r = ra; r <= rb; r++) {
+            const int c0 = max(ua - r * chunks, 0) * 32, c1 = min(W, min(ub - r * chunks, chunks) * 32);
+            classify_segment(sm, pb, W, r, c0, c1, lane, h);
         }
         JPROF(8, ptid == 0);
         JLS_NAMED_BARRIER(1, PROD_THREADS);
@@ -363,10 +361,9 @@ __device__ __forceinline__ void producer_tick(Smem &sm, const Params &P, const u
         }
         JPROF(10, ptid == 0);
         JLS_NAMED_BARRIER(1, PROD_THREADS);
-        for (int task = ta; task < tb; task++) {
-            const int r = task / nseg, sg = task - r * nseg;
-            const int c0 = min(W, sg * seg_chunks * 32), c1 = min(W, c0 + seg_chunks * 32);
-            if (c0 < c1) scatter_segment(sm, sm.sorted[buf], W, r, c0, c1, lane, h);
+        for (int r = ra; r <= rb; r++) {
+            const int c0 = max(ua - r * chunks, 0) * 32, c1 = min(W, min(ub - r * chunks, chunks) * 32);
+            scatter_segment(sm, sm.sorted[buf], W, r, c0, c1, lane, h);
         }
         JPROF(11, ptid == 0);
         // chain thread i of the tile takes the i-th biggest slice (by size class): similar slices share a warp; the run
@@ -437,7 +434,13 @@ __device__ __forceinline__ void regular_code(uint32_t w, uint32_t *codes, uint8_
 
 // one run event (:291-344): completed 2^J blocks -> ones in the slot of the run's last sample; interruption sample:
 // run remainder in J+1 bits + Golomb code of the interruption error
-__device__ __forceinline__ void run_step(uint32_t rec, RunState &s, uint8_t *pb, int W, int r0_global, uint32_t *codes, uint8_t *lens)
+// J[] (:15) from two packed constants, four bits per entry
+__device__ __forceinline__ int run_order(int i)
+{
+    const unsigned long long t = i < 16 ? 0x3333222211110000ull : 0xFEDCBA9877665544ull;
+    return (int)((t >> ((i & 15) * 4)) & 15ull);
+}
+__device__ __forceinline__ void run_step(uint32_t rec, RunState &s, const uint8_t *pb, int W, uint32_t *codes, uint8_t *lens)
 {
     const int lp = rec & 0x1FFF;
     int L = (rec >> 13) & 0x7FFF;
@@ -446,10 +449,11 @@ __device__ __forceinline__ void run_step(uint32_t rec, RunState &s, uint8_t *pb,
     L += s.pending;
     s.pending = 0;
     int cnt = L, ones = 0;
-    while (cnt >= (1 << c_J[s.run_index])) {            // :295-300, whole blocks at once
-        cnt -= 1 << c_J[s.run_index];
+    int jj = run_order(s.run_index);
+    while (cnt >= (1 << jj)) {                          // :295-300, whole blocks at once
+        cnt -= 1 << jj;
         ones++;
-        if (s.run_index < 31) s.run_index++;
+        if (s.run_index < 31) { s.run_index++; jj = run_order(s.run_index); }
     }
     if (eol) {                                          // :302-303
         if (cnt > 0) ones++;
@@ -461,14 +465,12 @@ __device__ __forceinline__ void run_step(uint32_t rec, RunState &s, uint8_t *pb,
         codes[code_idx(lp - 1)] = (uint32_t)((1ull << ones) - 1ull);
         lens[len_idx(lp - 1)]  = (uint8_t)ones;
     }
-    const int jj = c_J[s.run_index];
     const int glimit = 23 - 1 - jj;                     // :306
     if (s.run_index > 0) s.run_index--;                 // :310-311
-    const int row = lp / W, col = lp - row * W;
-    const uint8_t *cur = pix_row(pb, row, W);
-    const int x = cur[col];
-    const int b = (r0_global + row) > 0 ? cur[col - W] : 0;
-    const int a = col > 0 ? cur[col - 1] : b;
+    const uint8_t *px_ = pb + 16 + W + lp;              // the sample; the row above the picture is staged as zeros
+    const int x = px_[0];
+    const int b = px_[-W];
+    const int a = ((rec >> 30) & 1u) ? b : (int)px_[-1];    // first column: a = b (:55)
     const int t = (a == b);                             // RItype :313
     const bool neg = a > b;                             // :314
     const int px = t ? a : b;
@@ -490,27 +492,36 @@ __device__ __forceinline__ void run_step(uint32_t rec, RunState &s, uint8_t *pb,
 }
 
 // ---- packer ---------------------------------------------------------------------------------------
+// PACK_WARPS warps share a tile: (1) code-length totals per chunk of 1024 samples, (2) every chunk's codes are
+// concatenated MSB-first at its bit offset in the tile-wide buffer ubits[], (3) one warp turns the bits into stuffed
+// bytes.  Bits that do not fill a byte at the end of a tile wait in a register (`carry`) and read as word -1.
 struct PackState {
     uint8_t *dst; size_t cap; size_t out_pos;
-    uint32_t carry_bits;        // un-stuffed bits waiting at the front of chunk[] (< 8)
+    uint32_t carry_bits;        // un-stuffed bits of earlier tiles still to be written (< 8)
+    uint32_t carry;             // ... right-aligned
     uint32_t pz;                // 1: the next byte starts with a stuffed 0 bit (previous byte was 0xFF)
 };
 
-// Turns the first `T` bits of chunk[] (MSB first) into stuffed bytes.  Only whole bytes are produced unless `flush`;
-// the left-over bits move to the front of chunk[].  One warp.
-__device__ __forceinline__ void stuff_chunk(Smem &sm, PackState &ps, uint32_t T, bool flush, int lane)
+__device__ __forceinline__ uint32_t ubits_word(const uint32_t *buf, int32_t w, uint32_t carry)
 {
-    uint32_t *buf = sm.chunk;
-    uint32_t in_pos = 0;
+    return w >= 0 ? (w < UBITS_WORDS ? buf[w] : 0u) : (w == -1 ? carry : 0u);
+}
+
+// Turns the carried bits followed by the first `T` bits of ubits[] into stuffed bytes (writeBit :156-169).  Only whole
+// bytes are produced unless `flush`; the left-over bits become the new carry.  One warp.
+__device__ __forceinline__ void stuff_bits(const uint32_t *buf, PackState &ps, uint32_t T, bool flush, int lane)
+{
+    int32_t in_pos = -(int32_t)ps.carry_bits;
+    const uint32_t carry = ps.carry;
     for (;;) {
-        const uint32_t s = in_pos - ps.pz;              // stream bit that lands on the MSB of this window's first byte (may wrap to -1)
-        const int32_t avail = (int32_t)T - (int32_t)s;  // bits from s to the end
+        const int32_t s = in_pos - (int32_t)ps.pz;      // stream bit that lands on the MSB of this window's first byte
+        const int32_t avail = (int32_t)T - s;           // bits from s to the end
         uint32_t whole = avail > 0 ? (uint32_t)avail >> 3 : 0u;
         if (whole == 0) break;
-        const int32_t w0 = (int32_t)s >> 5;             // -1 when s == -1
-        const uint32_t sh = s & 31u;
+        const int32_t w0 = s >> 5;                      // >= -1
+        const uint32_t sh = (uint32_t)s & 31u;
         const int32_t wi = w0 + lane;
-        const uint32_t hi = (wi >= 0 && wi < CHUNK_WORDS) ? buf[wi] : 0u, lo = (wi + 1 < CHUNK_WORDS) ? buf[wi + 1] : 0u;
+        const uint32_t hi = ubits_word(buf, wi, carry), lo = ubits_word(buf, wi + 1, carry);
         uint32_t v = __funnelshift_l(lo, hi, sh);
         if (ps.pz && lane == 0) v &= 0x7FFFFFFFu;
         int fb = 4;
@@ -533,68 +544,77 @@ __device__ __forceinline__ void stuff_chunk(Smem &sm, PackState &ps, uint32_t T,
             if (bi < nbytes && ps.out_pos + bi < ps.cap) ps.dst[ps.out_pos + bi] = (uint8_t)(v >> (24 - 8 * k));
         }
         ps.out_pos += nbytes;
-        in_pos = s + 8u * nbytes;
+        in_pos = s + (int32_t)(8u * nbytes);
         ps.pz = ends_ff ? 1u : 0u;
     }
-    const uint32_t left = T - in_pos;                   // < 8 (no whole byte can be formed)
+    const uint32_t left = (uint32_t)((int32_t)T - in_pos);      // < 8 (no whole byte can be formed)
+    uint32_t rest = 0;                                          // the left-over bits, left-aligned
+    if (left > 0) {
+        const int32_t w = in_pos >> 5;
+        rest = __funnelshift_l(ubits_word(buf, w + 1, carry), ubits_word(buf, w, carry), (uint32_t)in_pos & 31u) & ~(0xFFFFFFFFu >> left);
+    }
     if (flush) {
-        if (lane == 0) {
-            if (left > 0) {                             // flushBits :177-184: pad the last byte with zeros
-                const uint32_t w = in_pos >> 5, sh = in_pos & 31u;
-                uint32_t v = __funnelshift_l(buf[w + 1], buf[w], sh) & ~(0xFFFFFFFFu >> left);
-                uint32_t byte = ps.pz ? (v >> 25) : (v >> 24);
-                if (ps.out_pos < ps.cap) ps.dst[ps.out_pos] = (uint8_t)byte;
-            }
+        if (left > 0) {                                 // flushBits :177-184: pad the last byte with zeros
+            if (lane == 0 && ps.out_pos < ps.cap) ps.dst[ps.out_pos] = (uint8_t)(ps.pz ? (rest >> 25) : (rest >> 24));
+            ps.out_pos++; ps.pz = 0;
         }
-        if (left > 0) { ps.out_pos++; ps.pz = 0; }
         if (ps.pz) { if (lane == 0 && ps.out_pos < ps.cap) ps.dst[ps.out_pos] = 0; ps.out_pos++; ps.pz = 0; }   // a 0x00 after a trailing 0xFF (:178)
-        ps.carry_bits = 0;
+        ps.carry_bits = 0; ps.carry = 0;
         return;
     }
-    // move the left-over bits to the front
-    uint32_t keep = 0;
-    if (left > 0) {
-        const uint32_t w = in_pos >> 5, sh = in_pos & 31u;
-        keep = __funnelshift_l(buf[w + 1], buf[w], sh) & ~(0xFFFFFFFFu >> left);
-    }
-    __syncwarp();
-    if (lane == 0) buf[0] = keep;
     ps.carry_bits = left;
-    __syncwarp();
+    ps.carry = left ? rest >> (32 - left) : 0u;
 }
 
-// packs tile samples [0, n) (codes/lens in raster order) chunk by chunk and appends the stuffed bytes
-__device__ __forceinline__ void packer_tile(Smem &sm, const Params &P, PackState &ps, uint32_t *codes, uint8_t *lens, int n, bool last_tile, int lane)
+// the packer warps' share of one tick: tile samples [0, n) (codes/lens in raster order) -> stuffed bytes
+__device__ __forceinline__ void packer_tile(Smem &sm, const Params &P, PackState &ps, uint32_t *codes, uint8_t *lens, int n, bool last_tile, int pw, int lane)
 {
-    uint32_t *buf = sm.chunk;
-    for (int c0 = 0; c0 < n; c0 += CHUNK) {
-        JPROF_T0();
-        const int cn = min(CHUNK, n - c0);
-        // zero the words this chunk may touch (word 0 holds the carried bits)
-        for (int w = 1 + lane; w < CHUNK_WORDS; w += 32) buf[w] = 0;
-        if (ps.carry_bits == 0 && lane == 0) buf[0] = 0;
-        __syncwarp();
-        // lane owns 32 consecutive samples: their codes are concatenated in a register window and leave as whole words;
-        // only the first and the last word of a lane can be shared with its neighbours (atomicOr)
-        const int s0 = c0 + lane * 32;
-        uint32_t mylen = 0;
-        uint32_t l4[8];
+    constexpr int MAXC = (TSMAX / CHUNK + PACK_WARPS - 1) / PACK_WARPS;     // chunks per warp
+    uint32_t *buf = sm.ubits;
+    const int nchunk = (n + CHUNK - 1) / CHUNK;
+    JPROF_T0();
+    // (1) lane owns 32 consecutive samples of each of its warp's chunks
+    uint32_t l4[MAXC][8], mylen[MAXC];
+#pragma unroll
+    for (int m = 0; m < MAXC; m++) {
+        const int c = pw + m * PACK_WARPS;
+        const int s0 = c * CHUNK + lane * 32;
+        mylen[m] = 0;
 #pragma unroll
         for (int q = 0; q < 8; q++) {
             uint32_t v = 0;
-            if (s0 + 4 * q < c0 + cn) v = *reinterpret_cast<const uint32_t *>(lens + len_idx(s0) + 4 * q);   // reads past n see zeros
-            l4[q] = v;
-            mylen += (v & 0xFF) + ((v >> 8) & 0xFF) + ((v >> 16) & 0xFF) + (v >> 24);
+            if (c < nchunk && s0 + 4 * q < n) v = *reinterpret_cast<const uint32_t *>(lens + len_idx(s0) + 4 * q);   // slots past n hold zeros
+            l4[m][q] = v;
+            mylen[m] += (v & 0xFF) + ((v >> 8) & 0xFF) + ((v >> 16) & 0xFF) + (v >> 24);
         }
-        uint32_t inc = mylen;
+        uint32_t tot = mylen[m];
+#pragma unroll
+        for (int d = 16; d >= 1; d >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, d);
+        if (lane == 0 && c < nchunk) sm.chunk_bits[c] = tot;
+    }
+    JLS_NAMED_BARRIER(3, PACK_WARPS * 32);
+    // chunk offsets; zero the words the tile's bits will be OR-ed into
+    uint32_t cb = lane < nchunk ? sm.chunk_bits[lane] : 0u, cinc = cb;
+#pragma unroll
+    for (int d = 1; d < 8; d <<= 1) { const uint32_t v = __shfl_up_sync(0xffffffffu, cinc, d); if (lane >= d) cinc += v; }
+    const uint32_t T = __shfl_sync(0xffffffffu, cinc, 7);                   // TSMAX / CHUNK <= 8 chunks
+    const uint32_t cex = cinc - cb;
+    for (uint32_t w = pw * 32 + lane; w < (T >> 5) + 2; w += PACK_WARPS * 32) buf[w] = 0;
+    JLS_NAMED_BARRIER(3, PACK_WARPS * 32);
+    JPROF(12, pw == 0 && lane == 0);
+    // (2) the codes of a lane's samples are concatenated in a register window and leave as whole words
+#pragma unroll
+    for (int m = 0; m < MAXC; m++) {
+        const int c = pw + m * PACK_WARPS;
+        const uint32_t coff = __shfl_sync(0xffffffffu, cex, c & 7);
+        uint32_t inc = mylen[m];
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) { const uint32_t v = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += v; }
-        const uint32_t total = __shfl_sync(0xffffffffu, inc, 31);
-        const uint32_t bit = ps.carry_bits + inc - mylen;
-        JPROF(12, lane == 0);
-        if (mylen) {
+        if (mylen[m]) {
+            const int s0 = c * CHUNK + lane * 32;
+            const uint32_t bit = coff + inc - mylen[m];
             uint32_t w = bit >> 5;
-            uint32_t nacc = bit & 31u;                  // bits in the window (the first `bit & 31` are a neighbour's: zeros here)
+            uint32_t nacc = bit & 31u;                  // bits in the window (the first `bit & 31` belong to a neighbour: zeros here)
             uint64_t acc = 0;
 #pragma unroll
             for (int q = 0; q < 8; q++) {
@@ -603,28 +623,26 @@ __device__ __forceinline__ void packer_tile(Smem &sm, const Params &P, PackState
                 for (int r = 0; r < 4; r++) cd[r] = codes[code_idx(s0) + 4 * q + r];     // stale codes of empty slots are masked by len = 0
 #pragma unroll
                 for (int r = 0; r < 4; r++) {
-                    const uint32_t len = (l4[q] >> (8 * r)) & 0xFF;
+                    const uint32_t len = (l4[m][q] >> (8 * r)) & 0xFF;
                     acc = (acc << len) | (len ? (uint64_t)cd[r] : 0ull);
                     nacc += len;
                     if (nacc >= 32) {
                         nacc -= 32;
-                        const uint32_t word = (uint32_t)(acc >> nacc);
-                        atomicOr(&buf[w], word);
+                        atomicOr(&buf[w], (uint32_t)(acc >> nacc));
                         w++;
                     }
                 }
+                // the slots are consumed: the chains of a later tile expect zero lengths
+                if (l4[m][q]) *reinterpret_cast<uint32_t *>(lens + len_idx(s0) + 4 * q) = 0;
             }
             if (nacc) atomicOr(&buf[w], (uint32_t)(acc << (32 - nacc)));
         }
-        // the slots are consumed: the chains of a later tile expect zero lengths
-#pragma unroll
-        for (int q = 0; q < 8; q++)
-            if (s0 + 4 * q < c0 + cn && l4[q]) *reinterpret_cast<uint32_t *>(lens + len_idx(s0) + 4 * q) = 0;
-        __syncwarp();
-        JPROF(13, lane == 0);
-        stuff_chunk(sm, ps, ps.carry_bits + total, last_tile && c0 + CHUNK >= n, lane);
-        JPROF(14, lane == 0);
     }
+    JLS_NAMED_BARRIER(3, PACK_WARPS * 32);
+    JPROF(13, pw == 0 && lane == 0);
+    // (3)
+    if (pw == 0) stuff_bits(buf, ps, T, last_tile, lane);
+    JPROF(14, pw == 0 && lane == 0);
 }
 
 // ---- the kernel -----------------------------------------------------------------------------------
@@ -650,7 +668,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) jls_tile_kernel(Params P)
         // :256-261 (a_init = 4 for RANGE 256), :250, :263-267
         for (int i = tid; i < NCTX; i += NTHREADS) { sm.ctx[i][0] = 4; sm.ctx[i][1] = 0; sm.ctx[i][2] = 0; sm.ctx[i][3] = 1; }
         if (tid < 8) sm.run_state[tid] = (tid == 1 || tid == 4) ? 4 : (tid == 3 || tid == 6) ? 1 : 0;
-        PackState ps; ps.out_pos = 0; ps.carry_bits = 0; ps.pz = 0;
+        PackState ps; ps.out_pos = 0; ps.carry_bits = 0; ps.carry = 0; ps.pz = 0;
         ps.dst = plane_dst(P.L, p, ps.cap);
 
         stage_tile(sm.pix[0], img, W, H, rows_per_tile, 0, tid, NTHREADS);
@@ -685,7 +703,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) jls_tile_kernel(Params P)
                             RunState us;
                             us.run_index = sm.run_state[0]; us.A0 = sm.run_state[1]; us.B0 = sm.run_state[2]; us.N0 = sm.run_state[3];
                             us.A1 = sm.run_state[4]; us.B1 = sm.run_state[5]; us.N1 = sm.run_state[6]; us.pending = sm.run_state[7];
-                            for (int i = b0; i < b1; i++) run_step(rec[i], us, sm.pix[t % 3], W, t * rows_per_tile, sm.codes[buf], sm.lens[buf]);
+                            for (int i = b0; i < b1; i++) run_step(rec[i], us, sm.pix[t % 3], W, sm.codes[buf], sm.lens[buf]);
                             sm.run_state[0] = us.run_index; sm.run_state[1] = us.A0; sm.run_state[2] = us.B0; sm.run_state[3] = us.N0;
                             sm.run_state[4] = us.A1; sm.run_state[5] = us.B1; sm.run_state[6] = us.N1; sm.run_state[7] = us.pending;
                         }
@@ -703,14 +721,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) jls_tile_kernel(Params P)
                 const int t = tick - 2;
                 if (t >= 0 && t < ntiles) {
                     const int r0 = t * rows_per_tile, n = (min(H, r0 + rows_per_tile) - r0) * W;
-                    packer_tile(sm, P, ps, sm.codes[t & 1], sm.lens[t & 1], n, t == ntiles - 1, lane);
+                    packer_tile(sm, P, ps, sm.codes[t & 1], sm.lens[t & 1], n, t == ntiles - 1, warp - CHAIN_WARPS - PROD_WARPS, lane);
                 }
-                JPROF(2, lane == 0);
+                JPROF(2, warp == CHAIN_WARPS + PROD_WARPS && lane == 0);
             }
             __syncthreads();
             JPROF(3, tid == 0);
         }
-        if (warp == NWARPS - 1 && lane == 0) P.plane_bytes[p] = ps.out_pos;
+        if (warp == CHAIN_WARPS + PROD_WARPS && lane == 0) P.plane_bytes[p] = ps.out_pos;
     }
 }
 
