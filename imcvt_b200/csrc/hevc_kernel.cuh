@@ -37,10 +37,19 @@ namespace hevc {
 // development aid: cycles of thread 0 between phase marks, accumulated per (CU level, phase) in Params::prof
 #if defined(IMCVT_HEVC_PROF) && !defined(IMCVT_HOST_EMU)
 #define HPROF(K, id) do { if (threadIdx.x == 0) { const long long t__ = clock64(); atomicAdd(&(K).P->prof[(id)], (unsigned long long)(t__ - (K).prof_t)); (K).prof_t = t__; } } while (0)
+#define TPROF(sm, id) do { if (threadIdx.x == 0) { const long long t__ = clock64(); atomicAdd(&(sm).prof[(id)], (unsigned long long)(t__ - (sm).prof_t)); (sm).prof_t = t__; } } while (0)
+#define TPROF_START(sm) do { if (threadIdx.x == 0) (sm).prof_t = clock64(); } while (0)
 #else
 #define HPROF(K, id) do { } while (0)
+#define TPROF(sm, id) do { } while (0)
+#define TPROF_START(sm) do { } while (0)
 #endif
 
+#ifdef IMCVT_HOST_EMU
+#define HEVC_NAMED_BARRIER(id, count) emu_named_barrier(id, count)
+#else
+#define HEVC_NAMED_BARRIER(id, count) asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory")
+#endif
 #if defined(IMCVT_HEVC_NOINLINE) && !defined(IMCVT_HOST_EMU)
 #define HEVC_BIGFN __device__ __noinline__
 #else
@@ -63,6 +72,8 @@ constexpr int SCR_BYTES = 8192;         // private trial stream per candidate (r
 constexpr int I32MAX = 0x7fffffff;
 constexpr int NSCAN = 1520;
 constexpr int NCAND = 2 * NMODE;        // candidates coded together: 35 one-TU trials + 35 four-TU trials
+constexpr int NXN = NCAND + NMODE;      // 8x8 CUs: slots NCAND..NXN-1 = stand-alone 4x4 trials of the round in flight, slot NXN = the NxN trial
+constexpr int NALL = NXN + 1;
 constexpr int SLOT = 112;               // bin-list entries per coefficient group (worst case 107)
 constexpr int CAND_LIST_U16 = 64 * SLOT + 64;   // 64 group slots + 64 group headers per candidate
 
@@ -111,8 +122,8 @@ struct Params {
     uint8_t *out; size_t out_stride;                 // output slots
     unsigned long long *out_len;                     // [n]
     uint8_t *rcon; size_t rcon_stride;               // [n][hp*wp] reconstruction (also the line buffer between CTU rows)
-    uint8_t *scratch;                                // [gridDim.x][NCAND][SCR_BYTES] private trial streams
-    unsigned short *lists;                           // [gridDim.x][NCAND][CAND_LIST_U16] bin lists of the trials
+    uint8_t *scratch;                                // [gridDim.x][NALL][SCR_BYTES] private trial streams
+    unsigned short *lists;                           // [gridDim.x][NALL][CAND_LIST_U16] bin lists of the trials
     int *overflow;                                   // set to 1 when a stream did not fit its slot
     int *next_frame;                                 // dynamic frame queue
     unsigned long long *prof;                        // phase cycle counters (only with IMCVT_HEVC_PROF; else unused)
@@ -128,12 +139,13 @@ struct Smem {
     uint8_t rec[NCAND][REC_STRIDE];                 // candidate prediction -> reconstruction tiles
     uint8_t refs[NW][REFS_BYTES];
     BinDesc bdesc[NW][8];
-    uint8_t cctx[NCAND][CXP];                       // candidate context sets
-    CoderRegs ccoder[NCAND];
-    int cbits[NCAND], csse[NCAND];
-    int clast[NCAND][4];
-    unsigned ccg[NCAND][4][2];                      // significant groups by position: bit yc*8+xc
-    unsigned csg[NCAND][4][2];                      // significant groups by scan index
+    uint8_t cctx[NALL][CXP];                        // candidate context sets
+    CoderRegs ccoder[NALL];
+    int cbits[NALL], csse[NALL];
+    int clast[NALL][4];
+    unsigned ccg[NALL][4][2];                       // significant groups by position: bit yc*8+xc
+    unsigned csg[NALL][4][2];                       // significant groups by scan index
+    int sse0[NMODE];                                // 8x8 CUs: squared error of the first 4x4 block per mode
     // CTU state
     uint8_t orig[CTU][CTU];
     uint8_t rc[CTU + 1][RCP];                       // reconstruction window: row 0 / column 0 are the neighbours (:1588-1589)
@@ -153,6 +165,9 @@ struct Smem {
     uint8_t scan[NSCAN][2];                         // coefficient scans (y, x): see scan_base()
     uint8_t dord[4][64][2];                         // up-right diagonal orders of 1, 2x2, 4x4, 8x8 grids
     uint8_t above_sz[2048];                         // CU sizes along the bottom of the CTU row above (4x4 cells)
+#if defined(IMCVT_HEVC_PROF) && !defined(IMCVT_HOST_EMU)
+    unsigned long long *prof; long long prof_t;     // development build: stage counters of thread 0
+#endif
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -521,6 +536,7 @@ template <int TS>
 HEVC_BIGFN void binarize_warp(Smem &sm, int warp, int lane, unsigned short *lists)
 {
     constexpr int G = 32 / TS;
+    TPROF_START(sm);
     const int half = lane >> 4, hl = lane & 15;
     int gi = G == 1 ? 0 : half * (G / 2);
     const int gend = G == 1 ? 1 : gi + G / 2;
@@ -528,7 +544,7 @@ HEVC_BIGFN void binarize_warp(Smem &sm, int warp, int lane, unsigned short *list
     BinDesc D = sm.bdesc[warp][gi];
     auto load_masks = [&]() {
         m0 = 0; m1 = 0;
-        if (D.active) {
+        if (D.active && (D.sg0 | D.sg1) != 0) {             // an all-zero unit has no bins: publish_tu wrote its empty group 0
             m0 = D.sg0 | 1u; m1 = D.sg1;
             if (G == 1) { const unsigned alt = half ? 0xAAAAAAAAu : 0x55555555u; m0 &= alt; m1 &= alt; }
         }
@@ -549,6 +565,7 @@ HEVC_BIGFN void binarize_warp(Smem &sm, int warp, int lane, unsigned short *list
         const unsigned cgp0 = has ? sm.ccg[cand][blk][0] : 0u, cgp1 = has ? sm.ccg[cand][blk][1] : 0u;
         binarize_cg(has, D, TS, cg, hl, half, sm.scan, &sm.lev[0][0], cgp0, cgp1, lists);
     }
+    TPROF(sm, 64 + SizeClass<TS>::v * 8 + 7);
 }
 
 // Arithmetic coding of one transform unit from its bin lists (one lane).  slots / hdrs point at the unit's group 0.
@@ -718,6 +735,7 @@ HEVC_BIGFN TuResult tu_pipeline(Smem &sm, int warp, int lane, bool active, const
     uint8_t *left = R + 4, *top = left + 2 * TS, *fleft = top + 2 * TS, *ftop = fleft + 2 * TS, *line = ftop + 2 * TS;
     short *ws = sm.ws[warp] + g * TS * LP;
     const bool hl = avail & 1, hbl = avail & 2, ha = avail & 4, har = avail & 8;
+    TPROF_START(sm);
 
     // ---- reference samples with substitution (getBorder :212-243) ----
     const int corner = (hl && ha) ? src.at(y0 - 1, x0 - 1) : hl ? src.at(y0, x0 - 1) : ha ? src.at(y0 - 1, x0) : 128;
@@ -748,6 +766,7 @@ HEVC_BIGFN TuResult tu_pipeline(Smem &sm, int warp, int lane, bool active, const
     if (l == 0) R[1] = (uint8_t)((2 + left[0] + top[0] + 2 * corner) >> 2);
     __syncwarp();
 
+    TPROF(sm, 64 + SC * 8 + 0);
     // ---- prediction (predict :262-381), this lane owns column l ----
     const bool smo = uses_smoothed(TS, mode);
     const uint8_t *Lr = smo ? fleft : left, *Tr = smo ? ftop : top;
@@ -817,6 +836,7 @@ HEVC_BIGFN TuResult tu_pipeline(Smem &sm, int warp, int lane, bool active, const
         }
     }
 
+    TPROF(sm, 64 + SC * 8 + 1);
     // ---- forward transform (:497-516, inverse = 0): columns, then rows ----
     int t[TS];
     fwd1d<TS>(v, t);
@@ -828,7 +848,9 @@ HEVC_BIGFN TuResult tu_pipeline(Smem &sm, int warp, int lane, bool active, const
     fwd1d<TS>(v, t);
     __syncwarp();
 
+    TPROF(sm, 64 + SC * 8 + 2);
     // ---- RDOQ-lite (quantize :540-594): this lane owns row l of the coefficient block ----
+    bool warp_nz;                                       // some unit of this warp has a non-zero level
     {
         const int dist_sft = 8 - SC, sft = 19 - SC + qpd6;
         const int add = 1 << sft >> 1, max_d = I32MAX - add, thr = 9 << sft >> 2;
@@ -858,20 +880,28 @@ HEVC_BIGFN TuResult tu_pipeline(Smem &sm, int warp, int lane, bool active, const
                 cgsum = 0;
             }
         }
-        if (active) {
+        int nzrow = 0;
 #pragma unroll
-            for (int n = 0; n < TS; n++) lev[l * LP + n] = (short)t[n];
-        } else {
+        for (int n = 0; n < TS; n++) nzrow |= t[n];
+        warp_nz = __any_sync(0xffffffffu, nzrow != 0);
+        if (warp_nz) {
+            if (active) {
 #pragma unroll
-            for (int n = 0; n < TS; n++) ws[l * LP + n] = (short)t[n];     // idle group: keep its data private
+                for (int n = 0; n < TS; n++) lev[l * LP + n] = (short)t[n];
+            } else {
+#pragma unroll
+                for (int n = 0; n < TS; n++) ws[l * LP + n] = (short)t[n];     // idle group: keep its data private
+            }
         }
     }
     __syncwarp();
     const short *lv = active ? lev : ws;
 
+    TPROF(sm, 64 + SC * 8 + 3);
     // ---- last significant position and coefficient-group mask (first pass of putCoef :1196-1203) ----
     TuResult res;
-    {
+    res.last = 0; res.cg0 = 0; res.cg1 = 0; res.sg0 = 0; res.sg1 = 0;
+    if (warp_nz) {
         const uint8_t (*scan)[2] = sm.scan + scan_base(scan_type_for(TS, mode), SC);
         int last = 0;
         unsigned cg0 = 0, cg1 = 0, sg0 = 0, sg1 = 0;
@@ -892,22 +922,29 @@ HEVC_BIGFN TuResult tu_pipeline(Smem &sm, int warp, int lane, bool active, const
         res.sg1 = TS == 32 ? group_or<TS>(sg1) : 0u;
     }
 
-    // ---- de-quantise (:599-614) + inverse transform: columns, then rows ----
-    {
-        const int s = 5 - SC + qpd6;
+    TPROF(sm, 64 + SC * 8 + 4);
+    // ---- de-quantise (:599-614) + inverse transform: columns, then rows (all-zero levels reconstruct the prediction) ----
+    if (warp_nz) {
+        {
+            const int s = 5 - SC + qpd6;
 #pragma unroll
-        for (int k = 0; k < TS; k++) v[k] = clip16((int)lv[k * LP + l] * (1 << s));
+            for (int k = 0; k < TS; k++) v[k] = clip16((int)lv[k * LP + l] * (1 << s));
+        }
+        __syncwarp();                                   // idle groups keep their levels in ws: all reads done before it is reused
+        inv1d<TS>(v, t);
+#pragma unroll
+        for (int i = 0; i < TS; i++) ws[i * LP + l] = (short)clip16((t[i] + 64) >> 7);
+        __syncwarp();
+#pragma unroll
+        for (int k = 0; k < TS; k++) v[k] = ws[l * LP + k];
+        inv1d<TS>(v, t);
+        __syncwarp();
+    } else {
+#pragma unroll
+        for (int j = 0; j < TS; j++) t[j] = 0;
     }
-    __syncwarp();                                       // idle groups keep their levels in ws: all reads done before it is reused
-    inv1d<TS>(v, t);
-#pragma unroll
-    for (int i = 0; i < TS; i++) ws[i * LP + l] = (short)clip16((t[i] + 64) >> 7);
-    __syncwarp();
-#pragma unroll
-    for (int k = 0; k < TS; k++) v[k] = ws[l * LP + k];
-    inv1d<TS>(v, t);
-    __syncwarp();
 
+    TPROF(sm, 64 + SC * 8 + 5);
     // ---- reconstruction of row l and its squared error ----
     int sse = 0;
     if (active) {
@@ -921,6 +958,7 @@ HEVC_BIGFN TuResult tu_pipeline(Smem &sm, int warp, int lane, bool active, const
     }
     res.sse = group_sum<TS>(sse);
     __syncwarp();
+    TPROF(sm, 64 + SC * 8 + 6);
     return res;
 }
 
@@ -969,8 +1007,8 @@ struct Ctx {
     Smem *sm;
     const Params *P;
     uint8_t *out;               // this frame's output slot
-    uint8_t *scratch;           // this CTA's [NCAND][SCR_BYTES]
-    unsigned short *lists;      // this CTA's [NCAND][CAND_LIST_U16]
+    uint8_t *scratch;           // this CTA's [NALL][SCR_BYTES]
+    unsigned short *lists;      // this CTA's [NALL][CAND_LIST_U16]
     int qpd6;
     RdK rd;
     long long prof_t;
@@ -1013,22 +1051,50 @@ __device__ __forceinline__ void fill_maps(Smem &sm, int y0, int x0, int mode)
 }
 
 // group leaders publish what binarize_warp needs about the unit they just quantised
-__device__ __forceinline__ void publish_tu(Smem &sm, int warp, int g, bool active, int cand, int blk, int ncg, int mode, int lev_off, const TuResult &r)
+__device__ __forceinline__ void publish_tu(Smem &sm, unsigned short *lists, int warp, int g, bool active, int cand, int blk, int ncg, int mode, int lev_off, const TuResult &r)
 {
     BinDesc &D = sm.bdesc[warp][g];
     D.active = active; D.lid = cand; D.slot0 = blk * ncg; D.mode = mode; D.lev_off = lev_off; D.last = r.last; D.sg0 = r.sg0; D.sg1 = r.sg1;
     if (active) {
+        if ((r.sg0 | r.sg1) == 0) lists[(size_t)cand * CAND_LIST_U16 + 64 * SLOT + blk * ncg] = 0;      // empty group 0 (stand-alone 4x4 trials read it)
         sm.clast[cand][blk] = r.last;
         sm.ccg[cand][blk][0] = r.cg0; sm.ccg[cand][blk][1] = r.cg1;
         sm.csg[cand][blk][0] = r.sg0; sm.csg[cand][blk][1] = r.sg1;
     }
 }
 
-// RD search of one coding unit (processCURecurs :1349-1559).  Executed by the whole CTA in uniform control flow.
+// CABAC trial encode of candidate c of a coding unit from the unit's entry state (:1422-1437, :1455-1473): c < 35 one
+// transform unit, c >= 35 four.  One lane.
+__device__ __forceinline__ void trial_cu(Ctx &K, int SZ, int c, const CoderRegs &entry, int entry_bits_rel, int split_ctx, int mode_l, int mode_a)
+{
+    Smem &sm = *K.sm;
+    const int H = SZ / 2;
+    const int kind = c >= NMODE, mode = c - kind * NMODE;
+    Coder cd; cd.load(entry); cd.nout = 0;
+    attach(cd, sm, sm.cctx[c], K.scratch + (size_t)c * SCR_BYTES, SCR_BYTES);
+    if (SZ >= 16) cd.bin(0, CX_SPLIT_CU + split_ctx);                // putSplitCUflag :942-946
+    put_cu_head(cd, SZ, kind, &mode, &mode_l, &mode_a);
+    const unsigned short *lst = K.lists + (size_t)c * CAND_LIST_U16;
+    const int tsz = kind ? H : SZ, ncg = (tsz / 4) * (tsz / 4);
+    for (int i = 0; i < (kind ? 4 : 1); i++) {
+        const unsigned g0 = sm.ccg[c][i][0], g1 = sm.ccg[c][i][1];
+        const int cbf = (g0 | g1) != 0;
+        cd.bin(cbf, CX_YCBF + (kind ? 0 : 1));                       // :1039
+        if (cbf) code_block(cd, tsz, mode, sm.clast[c][i], g0, g1, sm.csg[c][i][0], sm.csg[c][i][1],
+                            lst + (size_t)i * ncg * SLOT, lst + 64 * SLOT + i * ncg, sm.scan);
+    }
+    cd.store(sm.ccoder[c]);
+    sm.cbits[c] = cd.bits() - entry_bits_rel;
+}
+
+__device__ void search_cu8(Ctx &K, int y0, int x0, int avail);
+
+// RD search of a 32x32 or 16x16 coding unit (processCURecurs :1349-1559).  Executed by the whole CTA in uniform control flow.
 template <int SZ>
 __device__ void search_cu(Ctx &K, int y0, int x0, int avail)
 {
     Smem &sm = *K.sm;
+    static_assert(SZ == 32 || SZ == 16, "8x8 coding units: search_cu8");
     constexpr int LV = Level<SZ>::v;
     constexpr int H = SZ / 2;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -1065,7 +1131,10 @@ __device__ void search_cu(Ctx &K, int y0, int x0, int avail)
             c.bin(1, CX_SPLIT_CU + split_ctx);
             c.store(sm.cur);
         }
-        for (int i = 0; i < 4; i++) search_cu<H>(K, sub_y[i], sub_x[i], sub_avail[i]);
+        for (int i = 0; i < 4; i++) {
+            if constexpr (H == 8) search_cu8(K, sub_y[i], sub_x[i], sub_avail[i]);
+            else search_cu<H>(K, sub_y[i], sub_x[i], sub_avail[i]);
+        }
         __syncthreads();
         int sse = 0;
         for (int i = tid; i < SZ * SZ; i += NT) {
@@ -1097,7 +1166,7 @@ __device__ void search_cu(Ctx &K, int y0, int x0, int avail)
             const int m = active ? item : 0;
             TuResult r = tu_pipeline<SZ>(sm, warp, lane, active, src, y0, x0, avail, m, qpd6, rd, sm.lev[m], sm.rec[m], SZ);
             if (lane % SZ == 0) {
-                publish_tu(sm, warp, lane / SZ, active, m, 0, (SZ / 4) * (SZ / 4), m, m * LEV_STRIDE, r);
+                publish_tu(sm, K.lists, warp, lane / SZ, active, m, 0, (SZ / 4) * (SZ / 4), m, m * LEV_STRIDE, r);
                 if (active) sm.csse[m] = r.sse;
             }
             __syncwarp();
@@ -1120,7 +1189,7 @@ __device__ void search_cu(Ctx &K, int y0, int x0, int avail)
                 TuResult r = tu_pipeline<H>(sm, warp, lane, active, ps, sub_y[i], sub_x[i], sub_avail[i], m, qpd6, rd,
                                             sm.lev[m] + i * H * (H + 2), sm.rec[cand] + (sub_y[i] - y0) * SZ + (sub_x[i] - x0), SZ);
                 sse += r.sse;
-                if (lane % H == 0) publish_tu(sm, warp, lane / H, active, cand, i, (H / 4) * (H / 4), m, m * LEV_STRIDE + i * H * (H + 2), r);
+                if (lane % H == 0) publish_tu(sm, K.lists, warp, lane / H, active, cand, i, (H / 4) * (H / 4), m, m * LEV_STRIDE + i * H * (H + 2), r);
                 __syncwarp();
                 binarize_warp<H>(sm, warp, lane, K.lists);
                 __syncwarp();
@@ -1137,24 +1206,7 @@ __device__ void search_cu(Ctx &K, int y0, int x0, int avail)
     HPROF(K, LV * 16 + 4);
     {
         const int c = candidate_of_thread(tid, NCAND);
-        if (c >= 0) {
-            const int kind = c >= NMODE, mode = c - kind * NMODE;
-            Coder cd; cd.load(entry); cd.nout = 0;
-            attach(cd, sm, sm.cctx[c], K.scratch + (size_t)c * SCR_BYTES, SCR_BYTES);
-            if (SZ >= 16) cd.bin(0, CX_SPLIT_CU + split_ctx);                // putSplitCUflag :942-946
-            put_cu_head(cd, SZ, kind, &mode, &mode_l, &mode_a);
-            const unsigned short *lst = K.lists + (size_t)c * CAND_LIST_U16;
-            const int tsz = kind ? H : SZ, ncg = (tsz / 4) * (tsz / 4);
-            for (int i = 0; i < (kind ? 4 : 1); i++) {
-                const unsigned g0 = sm.ccg[c][i][0], g1 = sm.ccg[c][i][1];
-                const int cbf = (g0 | g1) != 0;
-                cd.bin(cbf, CX_YCBF + (kind ? 0 : 1));                       // :1039
-                if (cbf) code_block(cd, tsz, mode, sm.clast[c][i], g0, g1, sm.csg[c][i][0], sm.csg[c][i][1],
-                                    lst + (size_t)i * ncg * SLOT, lst + 64 * SLOT + i * ncg, sm.scan);
-            }
-            cd.store(sm.ccoder[c]);
-            sm.cbits[c] = cd.bits() - entry_bits_rel;
-        }
+        if (c >= 0) trial_cu(K, SZ, c, entry, entry_bits_rel, split_ctx, mode_l, mode_a);
     }
     __syncthreads();
     HPROF(K, LV * 16 + 5);
@@ -1180,74 +1232,175 @@ __device__ void search_cu(Ctx &K, int y0, int x0, int avail)
     __syncthreads();
     HPROF(K, LV * 16 + 7);
 
-    // ---- 4: 8x8 only: four 4x4 PUs, each mode chosen by a stand-alone cost on a fresh coder (:1490-1556) ----
-    if constexpr (SZ == 8) {
-        Src ps = src; ps.priv = sm.nxn_rec; ps.ppitch = 8;
+    // ---- the best reconstruction becomes the CU's reconstruction (:1558) ----
+    for (int i = tid; i < SZ * SZ; i += NT) sm.rc[1 + y0 + i / SZ][1 + x0 + i % SZ] = best[i];
+    __syncthreads();
+    HPROF(K, LV * 16 + 13);
+}
+
+// RD search of an 8x8 coding unit (processCURecurs :1349-1559 with sz == 8: no split; one 8x8 TU, four 4x4 TUs, or
+// four 4x4 PUs).  The reference's steps 2, 3 and 4 all start from the unit's entry state, so they run side by side:
+//   all warps     one-TU candidates (35 x TU8): phase A
+//   warps 10,11   CABAC trials of the one-TU candidates                                 } concurrently, the ten
+//   warps 0..9    four rounds, one per 4x4 block i: warps 0-4 block i of the 35 four-TU  } warps synchronise on a
+//                 candidates (:1454-1467), warps 5-9 the 35 stand-alone modes of PU i     } named barrier
+//                 (:1498-1527; for i = 0 these are the same transform units as the four-TU candidates' first block),
+//                 then the stand-alone trials on fresh coders, the choice and the kept 4x4 reconstruction
+//   warps 2,3     CABAC trials of the four-TU candidates;  warp 0: the NxN trial (:1528-1545)
+// and the decision follows the reference order: one-TU modes, four-TU modes, NxN, a later candidate wins ties.
+__device__ void search_cu8(Ctx &K, int y0, int x0, int avail)
+{
+    Smem &sm = *K.sm;
+    constexpr int SZ = 8, LV = 2, H = 4, RT = 320;                            // RT: threads of the round warps
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int qpd6 = K.qpd6;
+    const RdK rd = K.rd;
+    const int cy = y0 / 4, cx = x0 / 4;
+    const bool hl = avail & 1, hbl = avail & 2, ha = avail & 4, har = avail & 8;
+    const unsigned out_cap = (unsigned)K.P->out_stride;
+
+    __syncthreads();
+    // ---- entry state (:1363-1372) ----
+    copy_words(sm.entry_ctx[LV], sm.cur_ctx, CXP / 4, tid, NT);
+    if (tid == 0) sm.entry[LV] = sm.cur;
+    const int mode_l = sm.mmd[1 + cy][cx], mode_a = sm.mmd[cy][1 + cx];
+    // candidate contexts: the trials of the whole unit start from the entry state, the stand-alone 4x4 trials are fresh
+    for (int i = tid; i < NALL * (CXP / 4); i += NT) {
+        const int c = i / (CXP / 4), w = i % (CXP / 4);
+        ((unsigned *)sm.cctx[c])[w] = (c >= NCAND && c < NXN) ? ((const unsigned *)sm.init_ctx)[w] : ((const unsigned *)sm.cur_ctx)[w];
+    }
+    __syncthreads();
+    const CoderRegs entry = sm.entry[LV];
+    const int entry_bits_rel = 8 * entry.pending + 23 - entry.nbits;
+    HPROF(K, LV * 16 + 0);
+
+    const int sub_y[4] = {y0, y0, y0 + H, y0 + H}, sub_x[4] = {x0, x0 + H, x0, x0 + H};
+    const int sub_avail[4] = {                                                        // :1375-1378
+        (hl ? 1 : 0) | (hl ? 2 : 0) | (ha ? 4 : 0) | (ha ? 8 : 0),
+        1 | 0 | (ha ? 4 : 0) | (har ? 8 : 0),
+        (hl ? 1 : 0) | (hbl ? 2 : 0) | 4 | 8,
+        1 | 0 | 4 | 0 };
+    Src src; src.rc = &sm.rc[0][0]; src.priv = nullptr; src.py0 = y0; src.px0 = x0; src.psz = SZ; src.ppitch = SZ;
+
+    // ---- one-TU candidates 0..34 (:1419-1447), phase A: four transform units per warp ----
+    {
+        constexpr int G = 4;
+        if (warp * G < NMODE) {
+            const int item = warp * G + lane / SZ;
+            const bool active = item < NMODE;
+            const int m = active ? item : 0;
+            TuResult r = tu_pipeline<SZ>(sm, warp, lane, active, src, y0, x0, avail, m, qpd6, rd, sm.lev[m], sm.rec[m], SZ);
+            if (lane % SZ == 0) {
+                publish_tu(sm, K.lists, warp, lane / SZ, active, m, 0, 4, m, m * LEV_STRIDE, r);
+                if (active) sm.csse[m] = r.sse;
+            }
+            __syncwarp();
+            binarize_warp<SZ>(sm, warp, lane, K.lists);
+            __syncwarp();
+        }
+    }
+    __syncthreads();
+    HPROF(K, LV * 16 + 2);
+
+    if (warp >= 10) {
+        // ---- CABAC trials of the one-TU candidates ----
+        const int c = (warp - 10) * 18 + lane;
+        if (lane < 18 && c < NMODE) trial_cu(K, SZ, c, entry, entry_bits_rel, 0, mode_l, mode_a);
+    } else {
+        // ---- four rounds over the 4x4 blocks ----
+        const bool grp3 = warp < 5;                                         // four-TU candidates; else stand-alone PUs
+        const int item = (grp3 ? warp : warp - 5) * 8 + lane / H;
+        const bool active = item < NMODE;
+        const int m = active ? item : 0;
+        int sse3 = 0;
         for (int i = 0; i < 4; i++) {
-            constexpr int G = 8, NG = NW * G;
-            for (int base = 0; base < NMODE; base += NG) {
-                if (base + warp * G >= NMODE) break;
-                const int item = base + warp * G + lane / 4;
-                const bool active = item < NMODE;
-                const int m = active ? item : 0;
-                TuResult r = tu_pipeline<4>(sm, warp, lane, active, ps, sub_y[i], sub_x[i], sub_avail[i], m, qpd6, rd, sm.lev[m], sm.rec[m], 4);
-                if (lane % 4 == 0) {
-                    publish_tu(sm, warp, lane / 4, active, m, 0, 1, m, m * LEV_STRIDE, r);
-                    if (active) sm.csse[m] = r.sse;
+            if (grp3) {
+                const int cand = NMODE + m;
+                Src ps = src; ps.priv = sm.rec[cand];                        // earlier blocks of the same trial
+                TuResult r = tu_pipeline<H>(sm, warp, lane, active, ps, sub_y[i], sub_x[i], sub_avail[i], m, qpd6, rd,
+                                            sm.lev[m] + i * H * (H + 2), sm.rec[cand] + (sub_y[i] - y0) * SZ + (sub_x[i] - x0), SZ);
+                sse3 += r.sse;
+                if (lane % H == 0) {
+                    publish_tu(sm, K.lists, warp, lane / H, active, cand, i, 1, m, m * LEV_STRIDE + i * H * (H + 2), r);
+                    if (active && i == 0) sm.sse0[m] = r.sse;
                 }
                 __syncwarp();
-                binarize_warp<4>(sm, warp, lane, K.lists);
+                binarize_warp<H>(sm, warp, lane, K.lists);
+                __syncwarp();
+            } else if (i > 0) {
+                const int cand = NCAND + m;
+                Src ps = src; ps.priv = sm.nxn_rec; ps.ppitch = 8;          // the kept blocks of the earlier PUs
+                TuResult r = tu_pipeline<H>(sm, warp, lane, active, ps, sub_y[i], sub_x[i], sub_avail[i], m, qpd6, rd,
+                                            sm.lev[m] + 128, sm.rec[m] + 512, H);
+                if (lane % H == 0) {
+                    publish_tu(sm, K.lists, warp, lane / H, active, cand, 0, 1, m, m * LEV_STRIDE + 128, r);
+                    if (active) sm.csse[cand] = r.sse;
+                }
+                __syncwarp();
+                binarize_warp<H>(sm, warp, lane, K.lists);
                 __syncwarp();
             }
-            __syncthreads();
+            HEVC_NAMED_BARRIER(4, RT);
             HPROF(K, LV * 16 + 8);
-            for (int k = tid; k < NMODE * (CXP / 4); k += NT)
-                ((unsigned *)sm.cctx)[k] = ((const unsigned *)sm.init_ctx)[k % (CXP / 4)];
-            __syncthreads();
-            HPROF(K, LV * 16 + 9);
+            // stand-alone trial of every mode on a fresh coder: cost = absolute length of the block's residual (:1504-1518)
             {
                 const int c = candidate4_of_thread(tid);
                 if (c >= 0) {
+                    const int from = i == 0 ? NMODE + c : NCAND + c;
                     Coder cd; cd.fresh();
-                    attach(cd, sm, sm.cctx[c], K.scratch + (size_t)c * SCR_BYTES, SCR_BYTES);
-                    const unsigned short *lst = K.lists + (size_t)c * CAND_LIST_U16;
-                    code_block(cd, 4, c, sm.clast[c][0], sm.ccg[c][0][0], 0u, sm.csg[c][0][0], 0u, lst, lst + 64 * SLOT, sm.scan);
-                    sm.cbits[c] = cd.bits();
+                    attach(cd, sm, sm.cctx[NCAND + c], K.scratch + (size_t)(NCAND + c) * SCR_BYTES, SCR_BYTES);
+                    const unsigned short *lst = K.lists + (size_t)from * CAND_LIST_U16;
+                    code_block(cd, 4, c, sm.clast[from][0], sm.ccg[from][0][0], 0u, sm.csg[from][0][0], 0u, lst, lst + 64 * SLOT, sm.scan);
+                    sm.cbits[NCAND + c] = cd.bits();
+                    if (i == 0) sm.csse[NCAND + c] = sm.sse0[c];
                 }
             }
-            __syncthreads();
+            HEVC_NAMED_BARRIER(4, RT);
             HPROF(K, LV * 16 + 10);
             if (tid == 0) {
                 int bc = I32MAX, win = -1;
-                for (int m = 0; m < NMODE; m++) {
-                    const int cost = rd.cost(sm.csse[m], sm.cbits[m]);
-                    if (bc >= cost) { bc = cost; win = m; }
+                for (int q = 0; q < NMODE; q++) {
+                    const int cost = rd.cost(sm.csse[NCAND + q], sm.cbits[NCAND + q]);
+                    if (bc >= cost) { bc = cost; win = q; }
                 }
+                const int from = i == 0 ? NMODE + win : NCAND + win;
                 sm.win = win;
-                sm.nxn_mode[i] = win; sm.nxn_last[i] = sm.clast[win][0]; sm.nxn_cg[i] = sm.ccg[win][0][0];
+                sm.nxn_mode[i] = win; sm.nxn_last[i] = sm.clast[from][0]; sm.nxn_cg[i] = sm.ccg[from][0][0];
             }
-            __syncthreads();
+            // fresh contexts for the next round's trials
+            for (int k = tid; k < NMODE * (CXP / 4); k += RT)
+                ((unsigned *)sm.cctx[NCAND])[k] = ((const unsigned *)sm.init_ctx)[k % (CXP / 4)];
+            HEVC_NAMED_BARRIER(4, RT);
             {
                 const int w = sm.win;
-                const unsigned short *lst = K.lists + (size_t)w * CAND_LIST_U16;
+                const int from = i == 0 ? NMODE + w : NCAND + w;
+                const unsigned short *lst = K.lists + (size_t)from * CAND_LIST_U16;
                 if (tid < SLOT) sm.nxn_list[i][tid] = lst[tid];               // keep the winner's bins for the NxN trial
                 if (tid == SLOT) sm.nxn_hdr[i] = lst[64 * SLOT];
                 if (tid >= 128 && tid < 144) {
                     const int y = (tid - 128) >> 2, x = (tid - 128) & 3;
-                    sm.nxn_rec[(sub_y[i] - y0 + y) * 8 + (sub_x[i] - x0 + x)] = sm.rec[w][y * 4 + x];
+                    sm.nxn_rec[(sub_y[i] - y0 + y) * 8 + (sub_x[i] - x0 + x)] = i == 0 ? sm.rec[NMODE + w][y * 8 + x] : sm.rec[w][512 + y * 4 + x];
                 }
             }
-            __syncthreads();
+            HEVC_NAMED_BARRIER(4, RT);
             HPROF(K, LV * 16 + 11);
         }
-        // the NxN coding unit from the entry state (:1528-1545)
-        copy_words(sm.cctx[0], sm.entry_ctx[LV], CXP / 4, tid, NT);
+        if (grp3 && active && lane % H == 0) sm.csse[NMODE + m] = sse3;
+    }
+    __syncthreads();
+    HPROF(K, LV * 16 + 3);
+
+    // ---- CABAC trials of the four-TU candidates 35..69 (warps 2, 3) and of the NxN coding unit (warp 0) ----
+    if (warp == 2 || warp == 3) {
+        const int c = NMODE + (warp - 2) * 18 + lane;
+        if (lane < 18 && c < NCAND) trial_cu(K, SZ, c, entry, entry_bits_rel, 0, mode_l, mode_a);
+    } else if (warp == 0) {
         int sse = 0;
-        if (tid < 64) { const int d = (int)sm.orig[y0 + (tid >> 3)][x0 + (tid & 7)] - (int)sm.nxn_rec[tid]; sse = d * d; }
-        sse = block_sum(sm, sse);                                           // contains the barriers the copy above needs
-        if (tid == 0) {
+        for (int q = lane; q < 64; q += 32) { const int d = (int)sm.orig[y0 + (q >> 3)][x0 + (q & 7)] - (int)sm.nxn_rec[q]; sse += d * d; }
+        sse = group_sum<32>(sse);
+        if (lane == 0) {
             Coder cd; cd.load(entry); cd.nout = 0;
-            attach(cd, sm, sm.cctx[0], K.scratch, SCR_BYTES);
+            attach(cd, sm, sm.cctx[NXN], K.scratch + (size_t)NXN * SCR_BYTES, SCR_BYTES);
             int modes[4], left[4], above[4];
             for (int i = 0; i < 4; i++) modes[i] = sm.nxn_mode[i];
             left[0] = mode_l;                  above[0] = mode_a;                               // :1530-1537
@@ -1260,34 +1413,47 @@ __device__ void search_cu(Ctx &K, int y0, int x0, int avail)
                 cd.bin(cbf, CX_YCBF + 0);
                 if (cbf) code_block(cd, 4, modes[i], sm.nxn_last[i], sm.nxn_cg[i], 0u, 1u, 0u, sm.nxn_list[i], &sm.nxn_hdr[i], sm.scan);
             }
-            cd.store(sm.ccoder[0]);
-            const int cost = rd.cost(sse, cd.bits() - entry_bits_rel);
-            sm.win = (sm.best_cost[LV] >= cost) ? 1 : 0;
+            cd.store(sm.ccoder[NXN]);
+            sm.cbits[NXN] = cd.bits() - entry_bits_rel;
+            sm.csse[NXN] = sse;
         }
-        __syncthreads();
-        HPROF(K, LV * 16 + 12);
-        if (sm.win) {
-            // commit: coder, bytes, maps; the reconstruction is the four kept 4x4 tiles (:1546-1554)
-            const unsigned base = entry.nout, n = sm.ccoder[0].nout;
-            for (unsigned i = tid; i < n && i < SCR_BYTES; i += NT) if (base + i < out_cap) K.out[base + i] = K.scratch[i];
-            copy_words(sm.cur_ctx, sm.cctx[0], CXP / 4, tid, NT);
-            if (tid == 0) { sm.cur = sm.ccoder[0]; sm.cur.nout = base + n; }
+    }
+    __syncthreads();
+    HPROF(K, LV * 16 + 5);
+    // decide (:1437-1446, :1473-1482, :1543-1545)
+    if (tid == 0) {
+        int bc = I32MAX, win = -1;
+        for (int c = 0; c < NCAND; c++) {
+            const int cost = rd.cost(sm.csse[c], sm.cbits[c]);
+            if (bc >= cost) { bc = cost; win = c; }
+        }
+        if (bc >= rd.cost(sm.csse[NXN], sm.cbits[NXN])) win = NXN;
+        sm.win = win;
+    }
+    __syncthreads();
+    HPROF(K, LV * 16 + 6);
+    {
+        // commit: coder, bytes, maps, reconstruction (:1439-1446, :1546-1554)
+        const int win = sm.win;
+        const unsigned base = entry.nout, n = sm.ccoder[win].nout;
+        const uint8_t *bytes = K.scratch + (size_t)win * SCR_BYTES;
+        for (unsigned i = tid; i < n && i < SCR_BYTES; i += NT) if (base + i < out_cap) K.out[base + i] = bytes[i];
+        copy_words(sm.cur_ctx, sm.cctx[win], CXP / 4, tid, NT);
+        if (tid == 0) { sm.cur = sm.ccoder[win]; sm.cur.nout = base + n; }
+        if (win == NXN) {
             if (tid < 4) {
                 const int r = 1 + cy + (tid >> 1), c = 1 + cx + (tid & 1);
                 sm.msz[r][c] = 8;
                 sm.mmd[r][c] = (uint8_t)sm.nxn_mode[tid];
             }
-            if (tid < 64) sm.rc[1 + y0 + (tid >> 3)][1 + x0 + (tid & 7)] = sm.nxn_rec[tid];
-            __syncthreads();
-            HPROF(K, LV * 16 + 13);
-            return;
+            if (tid >= 64 && tid < 128) sm.rc[1 + y0 + ((tid - 64) >> 3)][1 + x0 + (tid & 7)] = sm.nxn_rec[tid - 64];
+        } else {
+            fill_maps<SZ>(sm, y0, x0, win >= NMODE ? win - NMODE : win);
+            if (tid >= 64 && tid < 128) sm.rc[1 + y0 + ((tid - 64) >> 3)][1 + x0 + (tid & 7)] = sm.rec[win][tid - 64];
         }
     }
-
-    // ---- the best reconstruction becomes the CU's reconstruction (:1558) ----
-    for (int i = tid; i < SZ * SZ; i += NT) sm.rc[1 + y0 + i / SZ][1 + x0 + i % SZ] = best[i];
     __syncthreads();
-    HPROF(K, LV * 16 + 13);
+    HPROF(K, LV * 16 + 7);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1444,12 +1610,14 @@ __global__ void __launch_bounds__(NT, 1) hevc_frame_kernel(Params P)
     Smem &sm = *reinterpret_cast<Smem *>(IMCVT_DYN_SMEM());
     Ctx K;
     K.sm = &sm; K.P = &P; K.qpd6 = P.qpd6; K.rd.init(P.qpd6);
-    K.scratch = P.scratch + (size_t)blockIdx.x * NCAND * SCR_BYTES;
-    K.lists = P.lists + (size_t)blockIdx.x * NCAND * CAND_LIST_U16;
+    K.scratch = P.scratch + (size_t)blockIdx.x * NALL * SCR_BYTES;
+    K.lists = P.lists + (size_t)blockIdx.x * NALL * CAND_LIST_U16;
     K.out = nullptr;
     build_tables(sm, P.qpd6);
 #if defined(IMCVT_HEVC_PROF) && !defined(IMCVT_HOST_EMU)
     K.prof_t = clock64();
+    if (threadIdx.x == 0) sm.prof = P.prof;
+    __syncthreads();
 #endif
     for (;;) {                                                                  // frames vary 2-3x in cost: dynamic queue
         __syncthreads();

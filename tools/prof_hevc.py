@@ -18,7 +18,7 @@ d = torch.from_numpy(frames).cuda()
 out = torch.empty((n, imcvt_b200.hevc_bound(h, w)), dtype=torch.uint8, device="cuda")
 lens = torch.zeros(n, dtype=torch.int64, device="cuda")
 L = imcvt_b200.lib()
-buf = (C.c_ulonglong * 64)()
+buf = (C.c_ulonglong * 128)()
 for it in range(2):
     imcvt_b200.encode_hevc_device(d, q, out, lens)
     torch.cuda.synchronize()
@@ -35,3 +35,8 @@ for lv, nm in enumerate(["CU32", "CU16", "CU8"]):
         if c > 0:
             print(f"  {nm} {pn:20s} {c/nctu:10.0f} cyc/CTU  {100*c/tot:5.1f}%")
 print(f"  CTU load {v[48]/nctu:10.0f}  {100*v[48]/tot:5.1f}%   CTU store+terminate {v[49]/nctu:10.0f}  {100*v[49]/tot:5.1f}%")
+stages = ["refs+smooth", "predict", "fwd transform", "rdoq", "last/cg scan", "dequant+inverse", "recon+sse", "binarize"]
+for sc, nm in enumerate(["TU4", "TU8", "TU16", "TU32"]):
+    row = v[64 + sc * 8: 64 + sc * 8 + 8]
+    if row.sum() > 0:
+        print(f"  {nm} (thread 0, cyc/CTU): " + "  ".join(f"{a} {b/nctu:.0f}" for a, b in zip(stages, row)) + f"   total {row.sum()/nctu:.0f}")
