@@ -837,8 +837,13 @@ int encode_device(const uint8_t *d_frames, size_t frame_stride, int n, int is_rg
         static bool attr_set = false;
         if (!attr_set) {
             IMCVT_CUDA(cudaFuncSetAttribute(tile::jls_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(tile::Smem)));
+            IMCVT_CUDA(cudaFuncSetAttribute(tile::jls_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(tile::Smem)));
             attr_set = true;
         }
+        // Two SMs per plane (cluster of two CTAs: producers | chains + packers) only on request: measured on B200 it is
+        // not faster than one CTA per plane (7.2 vs 6.9 ms for 64 x 1080p) because a tile's tick is bounded by its
+        // longest context chain, which runs on one warp either way.  See DESIGN.md section 3.
+        const bool pair = E.jls_path == 3;
         IMCVT_CUDA(cudaMemsetAsync(next, 0, sizeof(int), st));
         tile::Params TP;
         TP.pix = planes; TP.plane_stride = plane_stride; TP.P = P; TP.W = (int)W; TP.H = (int)H;
@@ -850,8 +855,14 @@ int encode_device(const uint8_t *d_frames, size_t frame_stride, int n, int is_rg
             TP.prof = g_jls_prof;
         }
 #endif
-        LaunchScope ls("jls_tile", st);
-        tile::jls_tile_kernel<<<P < E.sm_count ? P : E.sm_count, tile::NTHREADS, sizeof(tile::Smem), st>>>(TP);
+        if (pair) {
+            LaunchScope ls("jls_pair", st);
+            const int pairs = P < E.sm_count / 2 ? P : E.sm_count / 2;
+            tile::jls_pair_kernel<<<2 * pairs, tile::NTHREADS, sizeof(tile::Smem), st>>>(TP);
+        } else {
+            LaunchScope ls("jls_tile", st);
+            tile::jls_tile_kernel<<<P < E.sm_count ? P : E.sm_count, tile::NTHREADS, sizeof(tile::Smem), st>>>(TP);
+        }
     } else if (lossless) {
         uint32_t *hist         = E.ws.take<uint32_t>((size_t)P * NBUCKET * T);
         uint32_t *bucket_total = E.ws.take<uint32_t>((size_t)P * NBUCKET);

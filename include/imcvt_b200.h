@@ -81,8 +81,9 @@ long imcvtLaunchCount(void);                         /* total kernels launched s
 
 /* Debug / cross-check: force the fully serial JPEG-LS scan kernel also for NEAR=0 (default 0). */
 void imcvtDebugJLSForceSerial(int on);
-/* Debug / cross-check: 0 = default NEAR=0 path (shared-memory tile kernel for planes up to 6144 wide),
- * 1 = force the multi-kernel pipeline that wider planes use. */
+/* Debug / cross-check of the NEAR=0 paths: 0 = default (planes up to 6144 wide: shared-memory tile kernel, one CTA
+ * per plane), 1 = force the multi-kernel pipeline that wider planes use, 2 = same as 0, 3 = the tile kernel on a
+ * cluster of two CTAs per plane (rank 0 produces sorted tiles into the shared memory of rank 1). */
 void imcvtDebugJLSPath(int path);
 
 #ifdef __cplusplus

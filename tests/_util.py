@@ -183,18 +183,21 @@ def emu_hevc(img, qpd6):
     return out[:n].tobytes(), rcon.reshape(hp, wp).copy()
 
 
-def emu_jls(img):
-    """The SOURCE of the CUDA JPEG-LS tile kernel (NEAR = 0, gray) run under the CPU SIMT emulator (tests/emu)."""
+def emu_jls(img, pair=False):
+    """The SOURCE of the CUDA JPEG-LS tile kernel (NEAR = 0, gray) run under the CPU SIMT emulator (tests/emu);
+    pair=True: the two-CTA cluster variant (rank 0 producers, rank 1 chains + packers)."""
     if "emu_jls" not in _libs:
         d = os.path.join(ROOT, "tests", "emu")
         subprocess.run(["make", "-C", d, "-s", "libjls_emu.so"], check=True, capture_output=True)
         lib = C.CDLL(os.path.join(d, "libjls_emu.so"))
         lib.emu_jls_encode.restype = C.c_size_t
         lib.emu_jls_encode.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_size_t]
+        lib.emu_jls_encode_mode.restype = C.c_size_t
+        lib.emu_jls_encode_mode.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_size_t, C.c_int]
         _libs["emu_jls"] = lib
     img = np.ascontiguousarray(img, dtype=np.uint8)
     h, w = img.shape
     out = np.zeros(8 * h * w + 65536, dtype=np.uint8)
-    n = _libs["emu_jls"].emu_jls_encode(img.ctypes.data, h, w, out.ctypes.data, out.size)
+    n = _libs["emu_jls"].emu_jls_encode_mode(img.ctypes.data, h, w, out.ctypes.data, out.size, 1 if pair else 0)
     assert n > 0
     return out[:n].tobytes()

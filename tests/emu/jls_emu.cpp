@@ -7,7 +7,10 @@
 using namespace imcvt::jls;
 
 // gray8 image H x W -> complete .jls stream (NEAR = 0); returns its length, 0 when it did not fit
-extern "C" size_t emu_jls_encode(const uint8_t *img, int H, int W, uint8_t *out, size_t cap)
+extern "C" size_t emu_jls_encode_mode(const uint8_t *img, int H, int W, uint8_t *out, size_t cap, int pair);
+extern "C" size_t emu_jls_encode(const uint8_t *img, int H, int W, uint8_t *out, size_t cap) { return emu_jls_encode_mode(img, H, W, out, cap, 0); }
+// pair = 1: the two-CTA cluster kernel, emulated as one block of 2 x NTHREADS fibers with two shared-memory images
+extern "C" size_t emu_jls_encode_mode(const uint8_t *img, int H, int W, uint8_t *out, size_t cap, int pair)
 {
     if (W > tile::WMAX || cap < 64) return 0;
     tile::Params P;
@@ -16,7 +19,9 @@ extern "C" size_t emu_jls_encode(const uint8_t *img, int H, int W, uint8_t *out,
     P.pix = img; P.plane_stride = (size_t)H * W; P.P = 1; P.W = W; P.H = H;
     P.L.ncomp = 1; P.L.hdr_len = 15; P.L.out = out; P.L.out_stride = cap - 2; P.L.scratch = nullptr; P.L.scratch_stride = 0;
     P.plane_bytes = &bytes; P.next_plane = &next;
-    emu::launch(1, tile::NTHREADS, sizeof(tile::Smem), [&] { tile::jls_tile_kernel(P); });
+    P.prof = nullptr;
+    if (pair) emu::launch(1, 2 * tile::NTHREADS, 2 * tile::SMEM_STRIDE, [&] { tile::jls_pair_kernel(P); });
+    else emu::launch(1, tile::NTHREADS, sizeof(tile::Smem), [&] { tile::jls_tile_kernel(P); });
     const size_t total = 25 + (size_t)bytes + 2;
     if (total > cap) return 0;
     const uint8_t hdr[25] = {0xFF, 0xD8, 0xFF, 0xF7, 0x00, 0x0B, 8, (uint8_t)(H >> 8), (uint8_t)H, (uint8_t)(W >> 8), (uint8_t)W, 1, 1, 0x11, 0,

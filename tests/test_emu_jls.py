@@ -10,20 +10,26 @@ from tests._util import GOLDEN, emu_jls, golden_table, load_pnm, oracle_jls, sha
 from tests.test_oracle_jls import edge_images
 
 
-def test_known_answer_p5():
+import pytest
+
+
+@pytest.mark.parametrize("pair", [False, True], ids=["one-cta", "cluster-pair"])
+def test_known_answer_p5(pair):
     img, _ = load_pnm(os.path.join(GOLDEN, "P5.pnm"))
     entry = [e for e in golden_table() if e["codec"] == "jls" and e["fixture"] == "P5" and e["setting"] == 0][0]
-    s = emu_jls(img)
+    s = emu_jls(img, pair)
     assert len(s) == entry["length"] and sha256(s) == entry["sha256"]
 
 
-def test_edge_cases_match_oracle():
+@pytest.mark.parametrize("pair", [False, True], ids=["one-cta", "cluster-pair"])
+def test_edge_cases_match_oracle(pair):
     for name, img in edge_images():
         if img.ndim == 2:
-            assert emu_jls(img) == oracle_jls(img, 0), name
+            assert emu_jls(img, pair) == oracle_jls(img, 0), name
 
 
-def test_multi_tile_planes_match_oracle():
+@pytest.mark.parametrize("pair", [False, True], ids=["one-cta", "cluster-pair"])
+def test_multi_tile_planes_match_oracle(pair):
     rng = np.random.default_rng(8)
     cases = [(kind, synth.frame(kind, 3, 200, 480)) for kind in ["natural", "texture", "noise", "constant"]]
     cases.append(("binary", (rng.integers(0, 2, (90, 700)) * 255).astype(np.uint8)))          # 0xFF stuffing across chunks
@@ -38,4 +44,4 @@ def test_multi_tile_planes_match_oracle():
     img[rng.integers(0, 7, 30), rng.integers(0, 1999, 30)] += 1
     cases.append(("runs+interrupts", img))
     for name, img in cases:
-        assert emu_jls(img) == oracle_jls(img, 0), name
+        assert emu_jls(img, pair) == oracle_jls(img, 0), name

@@ -27,10 +27,11 @@ def check(img, near):
     assert got == want, first_diff(got, want)
 
 
-@pytest.fixture(params=[0, 1], ids=["tile-kernel", "multi-kernel"], autouse=True)
+@pytest.fixture(params=[2, 3, 1], ids=["tile-kernel", "cluster-pair", "multi-kernel"], autouse=True)
 def lossless_path(request):
-    """Every test runs on both NEAR=0 device paths: the shared-memory tile kernel (default) and the multi-kernel
-    pipeline that planes wider than 6144 use."""
+    """Every test runs on all NEAR=0 device paths: the shared-memory tile kernel with one CTA per plane, the same on a
+    cluster of two CTAs per plane (the default for small batches), and the multi-kernel pipeline that planes wider
+    than 6144 use."""
     imcvt_b200.debug_jls_path(request.param)
     yield request.param
     imcvt_b200.debug_jls_path(0)
@@ -40,7 +41,7 @@ def lossless_path(request):
 @pytest.mark.parametrize("entry", [e for e in golden_table() if e["codec"] == "jls"],
                          ids=lambda e: f"{e['fixture']}-near{e['setting']}")
 def test_known_answers(entry, serial, lossless_path):
-    if serial and lossless_path == 1:
+    if serial and lossless_path != 2:
         pytest.skip("the serial kernel does not depend on the lossless path")
     img, _ = load_pnm(os.path.join(GOLDEN, entry["fixture"] + ".pnm"))
     imcvt_b200.debug_jls_force_serial(serial)

@@ -8,10 +8,12 @@ from imcvt_b200 import synth
 kind = sys.argv[1] if len(sys.argv) > 1 else "natural"
 n = int(sys.argv[2]) if len(sys.argv) > 2 else 64
 near = int(sys.argv[3]) if len(sys.argv) > 3 else 0
+path = int(sys.argv[4]) if len(sys.argv) > 4 else 0
 h, w = 1080, 1920
 base = synth.batch(kind, min(n, 8), h, w)
 frames = np.concatenate([base] * ((n + len(base) - 1) // len(base)))[:n]
 imcvt_b200.init(0)
+imcvt_b200.debug_jls_path(path)
 d = torch.from_numpy(frames).cuda()
 stride = 2 * h * w + 4096
 out = torch.empty((n, stride), dtype=torch.uint8, device="cuda")
