@@ -31,11 +31,11 @@ int encode_device(const uint8_t *d_frames, size_t frame_stride, int n, uint32_t 
     }
     const int grid = n < E.sm_count ? n : E.sm_count;                       // one CTA per SM; frames come from a queue
     const size_t rstride = (rbytes + 255) & ~(size_t)255;
-    size_t bytes = 4096 + (size_t)grid * NALL * SCR_BYTES + 256 + (size_t)grid * NALL * CAND_LIST_U16 * 2 + 256;
+    size_t bytes = 4096 + (size_t)grid * 2 * NALL * SCR_BYTES + 256 + (size_t)grid * 2 * NALL * CAND_LIST_U16 * 2 + 256;
     if (!d_rcon) bytes += (size_t)n * rstride + 256;
     if (E.ws.reserve(bytes)) return 1;
-    uint8_t *scratch = E.ws.take<uint8_t>((size_t)grid * NALL * SCR_BYTES);
-    unsigned short *lists = E.ws.take<unsigned short>((size_t)grid * NALL * CAND_LIST_U16);
+    uint8_t *scratch = E.ws.take<uint8_t>((size_t)grid * 2 * NALL * SCR_BYTES);
+    unsigned short *lists = E.ws.take<unsigned short>((size_t)grid * 2 * NALL * CAND_LIST_U16);
     int *next = E.ws.take<int>(1);
     uint8_t *rc = d_rcon;
     size_t rcs = rcon_stride;

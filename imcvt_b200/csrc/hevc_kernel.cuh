@@ -122,8 +122,8 @@ struct Params {
     uint8_t *out; size_t out_stride;                 // output slots
     unsigned long long *out_len;                     // [n]
     uint8_t *rcon; size_t rcon_stride;               // [n][hp*wp] reconstruction (also the line buffer between CTU rows)
-    uint8_t *scratch;                                // [gridDim.x][NALL][SCR_BYTES] private trial streams
-    unsigned short *lists;                           // [gridDim.x][NALL][CAND_LIST_U16] bin lists of the trials
+    uint8_t *scratch;                                // [gridDim.x][2][NALL][SCR_BYTES] private trial streams (per candidate set)
+    unsigned short *lists;                           // [gridDim.x][2][NALL][CAND_LIST_U16] bin lists of the trials
     int *overflow;                                   // set to 1 when a stream did not fit its slot
     int *next_frame;                                 // dynamic frame queue
     unsigned long long *prof;                        // phase cycle counters (only with IMCVT_HEVC_PROF; else unused)
@@ -131,20 +131,24 @@ struct Params {
 
 struct CoderRegs { int range, low, nbits, pending, held, zeros; unsigned nout; int pad_; };
 
-struct BinDesc { int active, lid, slot0, mode, lev_off, last; unsigned sg0, sg1; };   // one transform unit to binarise
+struct BinDesc { int active, lid, slot0, mode, lev_off, last; unsigned sg0, sg1; int set, pad_; };   // one transform unit to binarise
 
 struct Smem {
-    short lev[NMODE][LEV_STRIDE];                   // quantised levels of the candidates of the step in flight
+    short lev[NW][LEV_STRIDE];                      // quantised levels of the units a warp has in flight (binarised at once)
     short ws[NW][WS_STRIDE];                        // per-warp transpose scratch
-    uint8_t rec[NCAND][REC_STRIDE];                 // candidate prediction -> reconstruction tiles
+    // Candidate state exists twice: set 0 belongs to the 32x32 level, set 1 to the 16x16 and 8x8 levels.  One CTA walks
+    // the levels one after the other; in the two-CTA kernel the upper CTA keeps a 32x32 and a 16x16 evaluation in flight.
+    uint8_t rec0[NCAND][REC_STRIDE];                // candidate prediction -> reconstruction tiles, set 0
+    uint8_t rec1[NCAND][REC_STRIDE / 4];            // ... set 1 (16x16 and smaller)
+    uint8_t rec4[NMODE][16];                        // 8x8 CUs: stand-alone 4x4 trials of the round in flight
     uint8_t refs[NW][REFS_BYTES];
     BinDesc bdesc[NW][8];
-    uint8_t cctx[NALL][CXP];                        // candidate context sets
-    CoderRegs ccoder[NALL];
-    int cbits[NALL], csse[NALL];
-    int clast[NALL][4];
-    unsigned ccg[NALL][4][2];                       // significant groups by position: bit yc*8+xc
-    unsigned csg[NALL][4][2];                       // significant groups by scan index
+    uint8_t cctx[2][NALL][CXP];                     // candidate context sets
+    CoderRegs ccoder[2][NALL];
+    int cbits[2][NALL], csse[2][NALL];
+    int clast[2][NALL][4];
+    unsigned ccg[2][NALL][4][2];                    // significant groups by position: bit yc*8+xc
+    unsigned csg[2][NALL][4][2];                    // significant groups by scan index
     int sse0[NMODE];                                // 8x8 CUs: squared error of the first 4x4 block per mode
     // CTU state
     uint8_t orig[CTU][CTU];
@@ -562,7 +566,7 @@ HEVC_BIGFN void binarize_warp(Smem &sm, int warp, int lane, unsigned short *list
         // position-order group mask of this unit (for the neighbour-group context)
         const int blk = D.slot0 / ((TS / 4) * (TS / 4));
         const int cand = D.lid;
-        const unsigned cgp0 = has ? sm.ccg[cand][blk][0] : 0u, cgp1 = has ? sm.ccg[cand][blk][1] : 0u;
+        const unsigned cgp0 = has ? sm.ccg[D.set][cand][blk][0] : 0u, cgp1 = has ? sm.ccg[D.set][cand][blk][1] : 0u;
         binarize_cg(has, D, TS, cg, hl, half, sm.scan, &sm.lev[0][0], cgp0, cgp1, lists);
     }
     TPROF(sm, 64 + SizeClass<TS>::v * 8 + 7);
@@ -1007,14 +1011,16 @@ struct Ctx {
     Smem *sm;
     const Params *P;
     uint8_t *out;               // this frame's output slot
-    uint8_t *scratch;           // this CTA's [NALL][SCR_BYTES]
-    unsigned short *lists;      // this CTA's [NALL][CAND_LIST_U16]
+    uint8_t *scratch[2];        // this CTA's [NALL][SCR_BYTES] per candidate set
+    unsigned short *lists[2];   // this CTA's [NALL][CAND_LIST_U16] per candidate set
     int qpd6;
     RdK rd;
     long long prof_t;
 };
 
-template <int SZ> struct Level { static constexpr int v = SZ == 32 ? 0 : SZ == 16 ? 1 : 2; static constexpr int best_off = SZ == 32 ? 0 : SZ == 16 ? 1024 : 1280; };
+template <int SZ> struct Level { static constexpr int v = SZ == 32 ? 0 : SZ == 16 ? 1 : 2; static constexpr int best_off = SZ == 32 ? 0 : SZ == 16 ? 1024 : 1280;
+                                 static constexpr int set = SZ == 32 ? 0 : 1; };
+template <int SET> __device__ __forceinline__ uint8_t *rec_tile(Smem &sm, int c) { return SET == 0 ? sm.rec0[c] : sm.rec1[c]; }
 
 __device__ __forceinline__ void attach(Coder &c, Smem &sm, uint8_t *ctx, uint8_t *out, unsigned cap)
 {
@@ -1026,16 +1032,16 @@ template <int SZ>
 __device__ __forceinline__ void commit_candidate(Ctx &K, int win)
 {
     Smem &sm = *K.sm;
-    constexpr int LV = Level<SZ>::v;
+    constexpr int LV = Level<SZ>::v, SET = Level<SZ>::set;
     const int tid = threadIdx.x;
-    const unsigned base = sm.entry[LV].nout, n = sm.ccoder[win].nout;
-    const uint8_t *src = K.scratch + (size_t)win * SCR_BYTES;
+    const unsigned base = sm.entry[LV].nout, n = sm.ccoder[SET][win].nout;
+    const uint8_t *src = K.scratch[SET] + (size_t)win * SCR_BYTES;
     const unsigned cap = (unsigned)K.P->out_stride;
     for (unsigned i = tid; i < n && i < SCR_BYTES; i += NT) if (base + i < cap) K.out[base + i] = src[i];
-    copy_words(sm.cur_ctx, sm.cctx[win], CXP / 4, tid, NT);
-    if (tid == 0) { sm.cur = sm.ccoder[win]; sm.cur.nout = base + n; }
+    copy_words(sm.cur_ctx, sm.cctx[SET][win], CXP / 4, tid, NT);
+    if (tid == 0) { sm.cur = sm.ccoder[SET][win]; sm.cur.nout = base + n; }
     uint8_t *best = sm.best_rec + Level<SZ>::best_off;
-    for (int i = tid; i < SZ * SZ / 4; i += NT) ((unsigned *)best)[i] = ((const unsigned *)sm.rec[win])[i];
+    for (int i = tid; i < SZ * SZ / 4; i += NT) ((unsigned *)best)[i] = ((const unsigned *)rec_tile<SET>(sm, win))[i];
 }
 
 template <int SZ>
@@ -1051,40 +1057,43 @@ __device__ __forceinline__ void fill_maps(Smem &sm, int y0, int x0, int mode)
 }
 
 // group leaders publish what binarize_warp needs about the unit they just quantised
+template <int SET>
 __device__ __forceinline__ void publish_tu(Smem &sm, unsigned short *lists, int warp, int g, bool active, int cand, int blk, int ncg, int mode, int lev_off, const TuResult &r)
 {
     BinDesc &D = sm.bdesc[warp][g];
+    D.set = SET;
     D.active = active; D.lid = cand; D.slot0 = blk * ncg; D.mode = mode; D.lev_off = lev_off; D.last = r.last; D.sg0 = r.sg0; D.sg1 = r.sg1;
     if (active) {
         if ((r.sg0 | r.sg1) == 0) lists[(size_t)cand * CAND_LIST_U16 + 64 * SLOT + blk * ncg] = 0;      // empty group 0 (stand-alone 4x4 trials read it)
-        sm.clast[cand][blk] = r.last;
-        sm.ccg[cand][blk][0] = r.cg0; sm.ccg[cand][blk][1] = r.cg1;
-        sm.csg[cand][blk][0] = r.sg0; sm.csg[cand][blk][1] = r.sg1;
+        sm.clast[SET][cand][blk] = r.last;
+        sm.ccg[SET][cand][blk][0] = r.cg0; sm.ccg[SET][cand][blk][1] = r.cg1;
+        sm.csg[SET][cand][blk][0] = r.sg0; sm.csg[SET][cand][blk][1] = r.sg1;
     }
 }
 
 // CABAC trial encode of candidate c of a coding unit from the unit's entry state (:1422-1437, :1455-1473): c < 35 one
 // transform unit, c >= 35 four.  One lane.
-__device__ __forceinline__ void trial_cu(Ctx &K, int SZ, int c, const CoderRegs &entry, int entry_bits_rel, int split_ctx, int mode_l, int mode_a)
+template <int SZ>
+__device__ __forceinline__ void trial_cu(Ctx &K, int c, const CoderRegs &entry, int entry_bits_rel, int split_ctx, int mode_l, int mode_a)
 {
     Smem &sm = *K.sm;
-    const int H = SZ / 2;
+    constexpr int H = SZ / 2, SET = Level<SZ>::set;
     const int kind = c >= NMODE, mode = c - kind * NMODE;
     Coder cd; cd.load(entry); cd.nout = 0;
-    attach(cd, sm, sm.cctx[c], K.scratch + (size_t)c * SCR_BYTES, SCR_BYTES);
+    attach(cd, sm, sm.cctx[SET][c], K.scratch[SET] + (size_t)c * SCR_BYTES, SCR_BYTES);
     if (SZ >= 16) cd.bin(0, CX_SPLIT_CU + split_ctx);                // putSplitCUflag :942-946
     put_cu_head(cd, SZ, kind, &mode, &mode_l, &mode_a);
-    const unsigned short *lst = K.lists + (size_t)c * CAND_LIST_U16;
+    const unsigned short *lst = K.lists[SET] + (size_t)c * CAND_LIST_U16;
     const int tsz = kind ? H : SZ, ncg = (tsz / 4) * (tsz / 4);
     for (int i = 0; i < (kind ? 4 : 1); i++) {
-        const unsigned g0 = sm.ccg[c][i][0], g1 = sm.ccg[c][i][1];
+        const unsigned g0 = sm.ccg[SET][c][i][0], g1 = sm.ccg[SET][c][i][1];
         const int cbf = (g0 | g1) != 0;
         cd.bin(cbf, CX_YCBF + (kind ? 0 : 1));                       // :1039
-        if (cbf) code_block(cd, tsz, mode, sm.clast[c][i], g0, g1, sm.csg[c][i][0], sm.csg[c][i][1],
+        if (cbf) code_block(cd, tsz, mode, sm.clast[SET][c][i], g0, g1, sm.csg[SET][c][i][0], sm.csg[SET][c][i][1],
                             lst + (size_t)i * ncg * SLOT, lst + 64 * SLOT + i * ncg, sm.scan);
     }
-    cd.store(sm.ccoder[c]);
-    sm.cbits[c] = cd.bits() - entry_bits_rel;
+    cd.store(sm.ccoder[SET][c]);
+    sm.cbits[SET][c] = cd.bits() - entry_bits_rel;
 }
 
 __device__ void search_cu8(Ctx &K, int y0, int x0, int avail);
@@ -1095,7 +1104,7 @@ __device__ void search_cu(Ctx &K, int y0, int x0, int avail)
 {
     Smem &sm = *K.sm;
     static_assert(SZ == 32 || SZ == 16, "8x8 coding units: search_cu8");
-    constexpr int LV = Level<SZ>::v;
+    constexpr int LV = Level<SZ>::v, SET = Level<SZ>::set;
     constexpr int H = SZ / 2;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int qpd6 = K.qpd6;
@@ -1164,13 +1173,14 @@ __device__ void search_cu(Ctx &K, int y0, int x0, int avail)
             const int item = base + warp * G + lane / SZ;
             const bool active = item < NMODE;
             const int m = active ? item : 0;
-            TuResult r = tu_pipeline<SZ>(sm, warp, lane, active, src, y0, x0, avail, m, qpd6, rd, sm.lev[m], sm.rec[m], SZ);
+            const int loff = (lane / SZ) * SZ * (SZ + 2);
+            TuResult r = tu_pipeline<SZ>(sm, warp, lane, active, src, y0, x0, avail, m, qpd6, rd, sm.lev[warp] + loff, rec_tile<SET>(sm, m), SZ);
             if (lane % SZ == 0) {
-                publish_tu(sm, K.lists, warp, lane / SZ, active, m, 0, (SZ / 4) * (SZ / 4), m, m * LEV_STRIDE, r);
-                if (active) sm.csse[m] = r.sse;
+                publish_tu<SET>(sm, K.lists[SET], warp, lane / SZ, active, m, 0, (SZ / 4) * (SZ / 4), m, warp * LEV_STRIDE + loff, r);
+                if (active) sm.csse[SET][m] = r.sse;
             }
             __syncwarp();
-            binarize_warp<SZ>(sm, warp, lane, K.lists);
+            binarize_warp<SZ>(sm, warp, lane, K.lists[SET]);
             __syncwarp();
         }
     }
@@ -1183,30 +1193,31 @@ __device__ void search_cu(Ctx &K, int y0, int x0, int avail)
             const int item = base + warp * G + lane / H;
             const bool active = item < NMODE;
             const int m = active ? item : 0, cand = NMODE + m;
-            Src ps = src; ps.priv = sm.rec[cand];                            // earlier sub-TUs of the same trial
+            Src ps = src; ps.priv = rec_tile<SET>(sm, cand);                 // earlier sub-TUs of the same trial
+            const int loff = (lane / H) * H * (H + 2);
             int sse = 0;
             for (int i = 0; i < 4; i++) {
                 TuResult r = tu_pipeline<H>(sm, warp, lane, active, ps, sub_y[i], sub_x[i], sub_avail[i], m, qpd6, rd,
-                                            sm.lev[m] + i * H * (H + 2), sm.rec[cand] + (sub_y[i] - y0) * SZ + (sub_x[i] - x0), SZ);
+                                            sm.lev[warp] + loff, rec_tile<SET>(sm, cand) + (sub_y[i] - y0) * SZ + (sub_x[i] - x0), SZ);
                 sse += r.sse;
-                if (lane % H == 0) publish_tu(sm, K.lists, warp, lane / H, active, cand, i, (H / 4) * (H / 4), m, m * LEV_STRIDE + i * H * (H + 2), r);
+                if (lane % H == 0) publish_tu<SET>(sm, K.lists[SET], warp, lane / H, active, cand, i, (H / 4) * (H / 4), m, warp * LEV_STRIDE + loff, r);
                 __syncwarp();
-                binarize_warp<H>(sm, warp, lane, K.lists);
+                binarize_warp<H>(sm, warp, lane, K.lists[SET]);
                 __syncwarp();
             }
-            if (active && lane % H == 0) sm.csse[cand] = sse;
+            if (active && lane % H == 0) sm.csse[SET][cand] = sse;
         }
     }
     // ---- phase B: 70 trial encodes from the entry state, one lane each ----
     __syncthreads();
     HPROF(K, LV * 16 + 3);
     for (int i = tid; i < NCAND * (CXP / 4); i += NT)
-        ((unsigned *)sm.cctx)[i] = ((const unsigned *)sm.entry_ctx[LV])[i % (CXP / 4)];
+        ((unsigned *)sm.cctx[SET])[i] = ((const unsigned *)sm.entry_ctx[LV])[i % (CXP / 4)];
     __syncthreads();
     HPROF(K, LV * 16 + 4);
     {
         const int c = candidate_of_thread(tid, NCAND);
-        if (c >= 0) trial_cu(K, SZ, c, entry, entry_bits_rel, split_ctx, mode_l, mode_a);
+        if (c >= 0) trial_cu<SZ>(K, c, entry, entry_bits_rel, split_ctx, mode_l, mode_a);
     }
     __syncthreads();
     HPROF(K, LV * 16 + 5);
@@ -1214,7 +1225,7 @@ __device__ void search_cu(Ctx &K, int y0, int x0, int avail)
     if (tid == 0) {
         int bc = sm.best_cost[LV], win = -1;
         for (int c = 0; c < NCAND; c++) {
-            const int cost = rd.cost(sm.csse[c], sm.cbits[c]);
+            const int cost = rd.cost(sm.csse[SET][c], sm.cbits[SET][c]);
             if (bc >= cost) { bc = cost; win = c; }
         }
         sm.best_cost[LV] = bc;
@@ -1251,7 +1262,7 @@ __device__ void search_cu(Ctx &K, int y0, int x0, int avail)
 __device__ void search_cu8(Ctx &K, int y0, int x0, int avail)
 {
     Smem &sm = *K.sm;
-    constexpr int SZ = 8, LV = 2, H = 4, RT = 320;                            // RT: threads of the round warps
+    constexpr int SZ = 8, LV = 2, H = 4, SET = 1, RT = 320;                   // RT: threads of the round warps
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int qpd6 = K.qpd6;
     const RdK rd = K.rd;
@@ -1267,7 +1278,7 @@ __device__ void search_cu8(Ctx &K, int y0, int x0, int avail)
     // candidate contexts: the trials of the whole unit start from the entry state, the stand-alone 4x4 trials are fresh
     for (int i = tid; i < NALL * (CXP / 4); i += NT) {
         const int c = i / (CXP / 4), w = i % (CXP / 4);
-        ((unsigned *)sm.cctx[c])[w] = (c >= NCAND && c < NXN) ? ((const unsigned *)sm.init_ctx)[w] : ((const unsigned *)sm.cur_ctx)[w];
+        ((unsigned *)sm.cctx[SET][c])[w] = (c >= NCAND && c < NXN) ? ((const unsigned *)sm.init_ctx)[w] : ((const unsigned *)sm.cur_ctx)[w];
     }
     __syncthreads();
     const CoderRegs entry = sm.entry[LV];
@@ -1289,13 +1300,14 @@ __device__ void search_cu8(Ctx &K, int y0, int x0, int avail)
             const int item = warp * G + lane / SZ;
             const bool active = item < NMODE;
             const int m = active ? item : 0;
-            TuResult r = tu_pipeline<SZ>(sm, warp, lane, active, src, y0, x0, avail, m, qpd6, rd, sm.lev[m], sm.rec[m], SZ);
+            const int loff = (lane / SZ) * SZ * (SZ + 2);
+            TuResult r = tu_pipeline<SZ>(sm, warp, lane, active, src, y0, x0, avail, m, qpd6, rd, sm.lev[warp] + loff, sm.rec1[m], SZ);
             if (lane % SZ == 0) {
-                publish_tu(sm, K.lists, warp, lane / SZ, active, m, 0, 4, m, m * LEV_STRIDE, r);
-                if (active) sm.csse[m] = r.sse;
+                publish_tu<SET>(sm, K.lists[SET], warp, lane / SZ, active, m, 0, 4, m, warp * LEV_STRIDE + loff, r);
+                if (active) sm.csse[SET][m] = r.sse;
             }
             __syncwarp();
-            binarize_warp<SZ>(sm, warp, lane, K.lists);
+            binarize_warp<SZ>(sm, warp, lane, K.lists[SET]);
             __syncwarp();
         }
     }
@@ -1305,39 +1317,40 @@ __device__ void search_cu8(Ctx &K, int y0, int x0, int avail)
     if (warp >= 10) {
         // ---- CABAC trials of the one-TU candidates ----
         const int c = (warp - 10) * 18 + lane;
-        if (lane < 18 && c < NMODE) trial_cu(K, SZ, c, entry, entry_bits_rel, 0, mode_l, mode_a);
+        if (lane < 18 && c < NMODE) trial_cu<SZ>(K, c, entry, entry_bits_rel, 0, mode_l, mode_a);
     } else {
         // ---- four rounds over the 4x4 blocks ----
         const bool grp3 = warp < 5;                                         // four-TU candidates; else stand-alone PUs
         const int item = (grp3 ? warp : warp - 5) * 8 + lane / H;
         const bool active = item < NMODE;
         const int m = active ? item : 0;
+        const int loff = (lane / H) * H * (H + 2);
         int sse3 = 0;
         for (int i = 0; i < 4; i++) {
             if (grp3) {
                 const int cand = NMODE + m;
-                Src ps = src; ps.priv = sm.rec[cand];                        // earlier blocks of the same trial
+                Src ps = src; ps.priv = sm.rec1[cand];                       // earlier blocks of the same trial
                 TuResult r = tu_pipeline<H>(sm, warp, lane, active, ps, sub_y[i], sub_x[i], sub_avail[i], m, qpd6, rd,
-                                            sm.lev[m] + i * H * (H + 2), sm.rec[cand] + (sub_y[i] - y0) * SZ + (sub_x[i] - x0), SZ);
+                                            sm.lev[warp] + loff, sm.rec1[cand] + (sub_y[i] - y0) * SZ + (sub_x[i] - x0), SZ);
                 sse3 += r.sse;
                 if (lane % H == 0) {
-                    publish_tu(sm, K.lists, warp, lane / H, active, cand, i, 1, m, m * LEV_STRIDE + i * H * (H + 2), r);
+                    publish_tu<SET>(sm, K.lists[SET], warp, lane / H, active, cand, i, 1, m, warp * LEV_STRIDE + loff, r);
                     if (active && i == 0) sm.sse0[m] = r.sse;
                 }
                 __syncwarp();
-                binarize_warp<H>(sm, warp, lane, K.lists);
+                binarize_warp<H>(sm, warp, lane, K.lists[SET]);
                 __syncwarp();
             } else if (i > 0) {
                 const int cand = NCAND + m;
                 Src ps = src; ps.priv = sm.nxn_rec; ps.ppitch = 8;          // the kept blocks of the earlier PUs
                 TuResult r = tu_pipeline<H>(sm, warp, lane, active, ps, sub_y[i], sub_x[i], sub_avail[i], m, qpd6, rd,
-                                            sm.lev[m] + 128, sm.rec[m] + 512, H);
+                                            sm.lev[warp] + loff, sm.rec4[m], H);
                 if (lane % H == 0) {
-                    publish_tu(sm, K.lists, warp, lane / H, active, cand, 0, 1, m, m * LEV_STRIDE + 128, r);
-                    if (active) sm.csse[cand] = r.sse;
+                    publish_tu<SET>(sm, K.lists[SET], warp, lane / H, active, cand, 0, 1, m, warp * LEV_STRIDE + loff, r);
+                    if (active) sm.csse[SET][cand] = r.sse;
                 }
                 __syncwarp();
-                binarize_warp<H>(sm, warp, lane, K.lists);
+                binarize_warp<H>(sm, warp, lane, K.lists[SET]);
                 __syncwarp();
             }
             HEVC_NAMED_BARRIER(4, RT);
@@ -1348,11 +1361,11 @@ __device__ void search_cu8(Ctx &K, int y0, int x0, int avail)
                 if (c >= 0) {
                     const int from = i == 0 ? NMODE + c : NCAND + c;
                     Coder cd; cd.fresh();
-                    attach(cd, sm, sm.cctx[NCAND + c], K.scratch + (size_t)(NCAND + c) * SCR_BYTES, SCR_BYTES);
-                    const unsigned short *lst = K.lists + (size_t)from * CAND_LIST_U16;
-                    code_block(cd, 4, c, sm.clast[from][0], sm.ccg[from][0][0], 0u, sm.csg[from][0][0], 0u, lst, lst + 64 * SLOT, sm.scan);
-                    sm.cbits[NCAND + c] = cd.bits();
-                    if (i == 0) sm.csse[NCAND + c] = sm.sse0[c];
+                    attach(cd, sm, sm.cctx[SET][NCAND + c], K.scratch[SET] + (size_t)(NCAND + c) * SCR_BYTES, SCR_BYTES);
+                    const unsigned short *lst = K.lists[SET] + (size_t)from * CAND_LIST_U16;
+                    code_block(cd, 4, c, sm.clast[SET][from][0], sm.ccg[SET][from][0][0], 0u, sm.csg[SET][from][0][0], 0u, lst, lst + 64 * SLOT, sm.scan);
+                    sm.cbits[SET][NCAND + c] = cd.bits();
+                    if (i == 0) sm.csse[SET][NCAND + c] = sm.sse0[c];
                 }
             }
             HEVC_NAMED_BARRIER(4, RT);
@@ -1360,32 +1373,32 @@ __device__ void search_cu8(Ctx &K, int y0, int x0, int avail)
             if (tid == 0) {
                 int bc = I32MAX, win = -1;
                 for (int q = 0; q < NMODE; q++) {
-                    const int cost = rd.cost(sm.csse[NCAND + q], sm.cbits[NCAND + q]);
+                    const int cost = rd.cost(sm.csse[SET][NCAND + q], sm.cbits[SET][NCAND + q]);
                     if (bc >= cost) { bc = cost; win = q; }
                 }
                 const int from = i == 0 ? NMODE + win : NCAND + win;
                 sm.win = win;
-                sm.nxn_mode[i] = win; sm.nxn_last[i] = sm.clast[from][0]; sm.nxn_cg[i] = sm.ccg[from][0][0];
+                sm.nxn_mode[i] = win; sm.nxn_last[i] = sm.clast[SET][from][0]; sm.nxn_cg[i] = sm.ccg[SET][from][0][0];
             }
             // fresh contexts for the next round's trials
             for (int k = tid; k < NMODE * (CXP / 4); k += RT)
-                ((unsigned *)sm.cctx[NCAND])[k] = ((const unsigned *)sm.init_ctx)[k % (CXP / 4)];
+                ((unsigned *)sm.cctx[SET][NCAND])[k] = ((const unsigned *)sm.init_ctx)[k % (CXP / 4)];
             HEVC_NAMED_BARRIER(4, RT);
             {
                 const int w = sm.win;
                 const int from = i == 0 ? NMODE + w : NCAND + w;
-                const unsigned short *lst = K.lists + (size_t)from * CAND_LIST_U16;
+                const unsigned short *lst = K.lists[SET] + (size_t)from * CAND_LIST_U16;
                 if (tid < SLOT) sm.nxn_list[i][tid] = lst[tid];               // keep the winner's bins for the NxN trial
                 if (tid == SLOT) sm.nxn_hdr[i] = lst[64 * SLOT];
                 if (tid >= 128 && tid < 144) {
                     const int y = (tid - 128) >> 2, x = (tid - 128) & 3;
-                    sm.nxn_rec[(sub_y[i] - y0 + y) * 8 + (sub_x[i] - x0 + x)] = i == 0 ? sm.rec[NMODE + w][y * 8 + x] : sm.rec[w][512 + y * 4 + x];
+                    sm.nxn_rec[(sub_y[i] - y0 + y) * 8 + (sub_x[i] - x0 + x)] = i == 0 ? sm.rec1[NMODE + w][y * 8 + x] : sm.rec4[w][y * 4 + x];
                 }
             }
             HEVC_NAMED_BARRIER(4, RT);
             HPROF(K, LV * 16 + 11);
         }
-        if (grp3 && active && lane % H == 0) sm.csse[NMODE + m] = sse3;
+        if (grp3 && active && lane % H == 0) sm.csse[SET][NMODE + m] = sse3;
     }
     __syncthreads();
     HPROF(K, LV * 16 + 3);
@@ -1393,14 +1406,14 @@ __device__ void search_cu8(Ctx &K, int y0, int x0, int avail)
     // ---- CABAC trials of the four-TU candidates 35..69 (warps 2, 3) and of the NxN coding unit (warp 0) ----
     if (warp == 2 || warp == 3) {
         const int c = NMODE + (warp - 2) * 18 + lane;
-        if (lane < 18 && c < NCAND) trial_cu(K, SZ, c, entry, entry_bits_rel, 0, mode_l, mode_a);
+        if (lane < 18 && c < NCAND) trial_cu<SZ>(K, c, entry, entry_bits_rel, 0, mode_l, mode_a);
     } else if (warp == 0) {
         int sse = 0;
         for (int q = lane; q < 64; q += 32) { const int d = (int)sm.orig[y0 + (q >> 3)][x0 + (q & 7)] - (int)sm.nxn_rec[q]; sse += d * d; }
         sse = group_sum<32>(sse);
         if (lane == 0) {
             Coder cd; cd.load(entry); cd.nout = 0;
-            attach(cd, sm, sm.cctx[NXN], K.scratch + (size_t)NXN * SCR_BYTES, SCR_BYTES);
+            attach(cd, sm, sm.cctx[SET][NXN], K.scratch[SET] + (size_t)NXN * SCR_BYTES, SCR_BYTES);
             int modes[4], left[4], above[4];
             for (int i = 0; i < 4; i++) modes[i] = sm.nxn_mode[i];
             left[0] = mode_l;                  above[0] = mode_a;                               // :1530-1537
@@ -1413,9 +1426,9 @@ __device__ void search_cu8(Ctx &K, int y0, int x0, int avail)
                 cd.bin(cbf, CX_YCBF + 0);
                 if (cbf) code_block(cd, 4, modes[i], sm.nxn_last[i], sm.nxn_cg[i], 0u, 1u, 0u, sm.nxn_list[i], &sm.nxn_hdr[i], sm.scan);
             }
-            cd.store(sm.ccoder[NXN]);
-            sm.cbits[NXN] = cd.bits() - entry_bits_rel;
-            sm.csse[NXN] = sse;
+            cd.store(sm.ccoder[SET][NXN]);
+            sm.cbits[SET][NXN] = cd.bits() - entry_bits_rel;
+            sm.csse[SET][NXN] = sse;
         }
     }
     __syncthreads();
@@ -1424,10 +1437,10 @@ __device__ void search_cu8(Ctx &K, int y0, int x0, int avail)
     if (tid == 0) {
         int bc = I32MAX, win = -1;
         for (int c = 0; c < NCAND; c++) {
-            const int cost = rd.cost(sm.csse[c], sm.cbits[c]);
+            const int cost = rd.cost(sm.csse[SET][c], sm.cbits[SET][c]);
             if (bc >= cost) { bc = cost; win = c; }
         }
-        if (bc >= rd.cost(sm.csse[NXN], sm.cbits[NXN])) win = NXN;
+        if (bc >= rd.cost(sm.csse[SET][NXN], sm.cbits[SET][NXN])) win = NXN;
         sm.win = win;
     }
     __syncthreads();
@@ -1435,11 +1448,11 @@ __device__ void search_cu8(Ctx &K, int y0, int x0, int avail)
     {
         // commit: coder, bytes, maps, reconstruction (:1439-1446, :1546-1554)
         const int win = sm.win;
-        const unsigned base = entry.nout, n = sm.ccoder[win].nout;
-        const uint8_t *bytes = K.scratch + (size_t)win * SCR_BYTES;
+        const unsigned base = entry.nout, n = sm.ccoder[SET][win].nout;
+        const uint8_t *bytes = K.scratch[SET] + (size_t)win * SCR_BYTES;
         for (unsigned i = tid; i < n && i < SCR_BYTES; i += NT) if (base + i < out_cap) K.out[base + i] = bytes[i];
-        copy_words(sm.cur_ctx, sm.cctx[win], CXP / 4, tid, NT);
-        if (tid == 0) { sm.cur = sm.ccoder[win]; sm.cur.nout = base + n; }
+        copy_words(sm.cur_ctx, sm.cctx[SET][win], CXP / 4, tid, NT);
+        if (tid == 0) { sm.cur = sm.ccoder[SET][win]; sm.cur.nout = base + n; }
         if (win == NXN) {
             if (tid < 4) {
                 const int r = 1 + cy + (tid >> 1), c = 1 + cx + (tid & 1);
@@ -1449,7 +1462,7 @@ __device__ void search_cu8(Ctx &K, int y0, int x0, int avail)
             if (tid >= 64 && tid < 128) sm.rc[1 + y0 + ((tid - 64) >> 3)][1 + x0 + (tid & 7)] = sm.nxn_rec[tid - 64];
         } else {
             fill_maps<SZ>(sm, y0, x0, win >= NMODE ? win - NMODE : win);
-            if (tid >= 64 && tid < 128) sm.rc[1 + y0 + ((tid - 64) >> 3)][1 + x0 + (tid & 7)] = sm.rec[win][tid - 64];
+            if (tid >= 64 && tid < 128) sm.rc[1 + y0 + ((tid - 64) >> 3)][1 + x0 + (tid & 7)] = sm.rec1[win][tid - 64];
         }
     }
     __syncthreads();
@@ -1610,8 +1623,10 @@ __global__ void __launch_bounds__(NT, 1) hevc_frame_kernel(Params P)
     Smem &sm = *reinterpret_cast<Smem *>(IMCVT_DYN_SMEM());
     Ctx K;
     K.sm = &sm; K.P = &P; K.qpd6 = P.qpd6; K.rd.init(P.qpd6);
-    K.scratch = P.scratch + (size_t)blockIdx.x * NALL * SCR_BYTES;
-    K.lists = P.lists + (size_t)blockIdx.x * NALL * CAND_LIST_U16;
+    for (int q = 0; q < 2; q++) {
+        K.scratch[q] = P.scratch + ((size_t)blockIdx.x * 2 + q) * NALL * SCR_BYTES;
+        K.lists[q] = P.lists + ((size_t)blockIdx.x * 2 + q) * NALL * CAND_LIST_U16;
+    }
     K.out = nullptr;
     build_tables(sm, P.qpd6);
 #if defined(IMCVT_HEVC_PROF) && !defined(IMCVT_HOST_EMU)

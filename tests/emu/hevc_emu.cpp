@@ -14,8 +14,8 @@ extern "C" long emu_hevc_encode(uint8_t *stream, size_t cap, const uint8_t *img,
     Params P;
     unsigned long long len = 0;
     int overflow = 0, next = 0;
-    std::vector<uint8_t> scratch((size_t)NALL * SCR_BYTES);
-    std::vector<unsigned short> lists((size_t)NALL * CAND_LIST_U16, 0xDEAD);
+    std::vector<uint8_t> scratch((size_t)2 * NALL * SCR_BYTES);
+    std::vector<unsigned short> lists((size_t)2 * NALL * CAND_LIST_U16, 0xDEAD);
     P.frames = img; P.frame_stride = (size_t)H * W; P.n = 1; P.H = H; P.W = W; P.hp = hp; P.wp = wp; P.qpd6 = qpd6;
     P.out = stream; P.out_stride = cap; P.out_len = &len;
     P.rcon = img_rcon; P.rcon_stride = (size_t)hp * wp;
