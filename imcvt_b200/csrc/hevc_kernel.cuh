@@ -22,13 +22,24 @@
 #include <stdint.h>
 #include <stddef.h>
 
+// The pair kernel encodes one frame on a cluster of two CTAs that exchange state through distributed shared memory;
+// the host emulator runs the two CTAs' threads as one set of fibers with two shared-memory images.
 #ifdef IMCVT_HOST_EMU
 #define IMCVT_CONSTANT static const
-#define IMCVT_DYN_SMEM() (emu::S().smem)
+#define IMCVT_DYN_SMEM() (emu::dyn_smem())
+#define HEVC_PAIR_RANK() (emu::cta_rank())
+#define HEVC_PAIR_SMEM(r) (emu::cluster_smem(r))
+#define HEVC_PAIR_SYNC() emu_cluster_sync()
+#define HEVC_CLUSTER_DIMS
 #else
+#include <cooperative_groups.h>
 #define IMCVT_CONSTANT __constant__ const
 extern __shared__ __align__(16) unsigned char imcvt_dyn_smem[];
 #define IMCVT_DYN_SMEM() (imcvt_dyn_smem)
+#define HEVC_PAIR_RANK() ((int)cooperative_groups::this_cluster().block_rank())
+#define HEVC_PAIR_SMEM(r) (cooperative_groups::this_cluster().map_shared_rank(imcvt_dyn_smem, (r)))
+#define HEVC_PAIR_SYNC() cooperative_groups::this_cluster().sync()
+#define HEVC_CLUSTER_DIMS __cluster_dims__(2, 1, 1)
 #endif
 
 namespace imcvt {
@@ -130,6 +141,7 @@ struct Params {
 };
 
 struct CoderRegs { int range, low, nbits, pending, held, zeros; unsigned nout; int pad_; };
+struct CuPar { int y0, x0, avail, split_ctx, mode_l, mode_a; };
 
 struct BinDesc { int active, lid, slot0, mode, lev_off, last; unsigned sg0, sg1; int set, pad_; };   // one transform unit to binarise
 
@@ -164,6 +176,12 @@ struct Smem {
     uint8_t cur_ctx[CXP], entry_ctx[3][CXP], init_ctx[CXP];
     int best_cost[3];
     int win, red[NW];
+    CuPar par[2];                                   // 32x32 / 16x16 unit whose candidates are being evaluated
+    int eval_cost[2], eval_win[2];                  // ... the best of its 70 candidates (reference order, later wins ties)
+    // two-CTA kernel: the winner of the partner's evaluation, written by the partner through distributed shared memory
+    CoderRegs res_coder[2];
+    uint8_t res_ctx[2][CXP];
+    uint8_t res_rec0[REC_STRIDE], res_rec1[REC_STRIDE / 4];
     unsigned lpsw[64];                              // LPS range table, one word per state (4 range classes)
     uint8_t next_lps[128];
     uint8_t scan[NSCAN][2];                         // coefficient scans (y, x): see scan_base()
@@ -1013,6 +1031,8 @@ struct Ctx {
     uint8_t *out;               // this frame's output slot
     uint8_t *scratch[2];        // this CTA's [NALL][SCR_BYTES] per candidate set
     unsigned short *lists[2];   // this CTA's [NALL][CAND_LIST_U16] per candidate set
+    const uint8_t *peer_scratch[2];     // two-CTA kernel: the partner's trial streams
+    Smem *peer;                 // two-CTA kernel: the partner's shared memory
     int qpd6;
     RdK rd;
     long long prof_t;
@@ -1096,157 +1116,227 @@ __device__ __forceinline__ void trial_cu(Ctx &K, int c, const CoderRegs &entry, 
     sm.cbits[SET][c] = cd.bits() - entry_bits_rel;
 }
 
-__device__ void search_cu8(Ctx &K, int y0, int x0, int avail);
 
-// RD search of a 32x32 or 16x16 coding unit (processCURecurs :1349-1559).  Executed by the whole CTA in uniform control flow.
+
+// ------------------------------------------------------------------------------------------------
+// 32x32 and 16x16 coding units (processCURecurs :1349-1559).  The work of a unit comes in pieces that the whole CTA
+// executes in uniform control flow:
+//   cu_enter      entry state (:1363-1372): coder, contexts, neighbour modes -> sm.entry / entry_ctx / par [level]
+//   eval_a1/a4    phase A of the 35 one-TU candidates (:1419-1447) / of the 35 four-TU candidates (:1454-1483)
+//   eval_b        the 70 CABAC trials from the entry state and their best (reference order, a later one wins ties)
+//   cu_split_cost cost of the split alternative once the four smaller units are coded (:1402-1412)
+// The evaluation reads only samples OUTSIDE the unit and the entry state, never the smaller units' results, which is
+// what lets the two-CTA kernel run it on the partner CTA while the smaller units are searched.
+// ------------------------------------------------------------------------------------------------
+template <int SZ> struct SubUnits {
+    int y[4], x[4], avail[4];
+    __device__ __forceinline__ SubUnits(int y0, int x0, int av)
+    {
+        constexpr int H = SZ / 2;
+        const bool hl = av & 1, hbl = av & 2, ha = av & 4, har = av & 8;
+        y[0] = y0; y[1] = y0; y[2] = y0 + H; y[3] = y0 + H;
+        x[0] = x0; x[1] = x0 + H; x[2] = x0; x[3] = x0 + H;
+        avail[0] = (hl ? 1 : 0) | (hl ? 2 : 0) | (ha ? 4 : 0) | (ha ? 8 : 0);          // :1375-1378
+        avail[1] = 1 | 0 | (ha ? 4 : 0) | (har ? 8 : 0);
+        avail[2] = (hl ? 1 : 0) | (hbl ? 2 : 0) | 4 | 8;
+        avail[3] = 1 | 0 | 4 | 0;
+    }
+};
+
 template <int SZ>
-__device__ void search_cu(Ctx &K, int y0, int x0, int avail)
+__device__ __forceinline__ void cu_enter(Ctx &K, int y0, int x0, int avail)
 {
     Smem &sm = *K.sm;
-    static_assert(SZ == 32 || SZ == 16, "8x8 coding units: search_cu8");
-    constexpr int LV = Level<SZ>::v, SET = Level<SZ>::set;
-    constexpr int H = SZ / 2;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int qpd6 = K.qpd6;
-    const RdK rd = K.rd;
-    const int cy = y0 / 4, cx = x0 / 4;
-    const bool hl = avail & 1, hbl = avail & 2, ha = avail & 4, har = avail & 8;
-    uint8_t *best = sm.best_rec + Level<SZ>::best_off;
-    const unsigned out_cap = (unsigned)K.P->out_stride;
-
+    constexpr int LV = Level<SZ>::v;
+    const int tid = threadIdx.x, cy = y0 / 4, cx = x0 / 4;
     __syncthreads();
-    // ---- entry state (:1363-1372) ----
     copy_words(sm.entry_ctx[LV], sm.cur_ctx, CXP / 4, tid, NT);
-    if (tid == 0) { sm.entry[LV] = sm.cur; sm.best_cost[LV] = I32MAX; }
-    const int split_ctx = (SZ > sm.msz[1 + cy][cx]) + (SZ > sm.msz[cy][1 + cx]);
-    const int mode_l = sm.mmd[1 + cy][cx], mode_a = sm.mmd[cy][1 + cx];
+    if (tid == 0) {
+        sm.entry[LV] = sm.cur; sm.best_cost[LV] = I32MAX;
+        CuPar q; q.y0 = y0; q.x0 = x0; q.avail = avail;
+        q.split_ctx = (SZ > sm.msz[1 + cy][cx]) + (SZ > sm.msz[cy][1 + cx]);
+        q.mode_l = sm.mmd[1 + cy][cx]; q.mode_a = sm.mmd[cy][1 + cx];
+        sm.par[LV] = q;
+    }
     __syncthreads();
-    const CoderRegs entry = sm.entry[LV];
-    HPROF(K, LV * 16 + 0);
-    const int entry_bits_abs = 8 * ((int)entry.nout + entry.pending) + 23 - entry.nbits;
-    const int entry_bits_rel = 8 * entry.pending + 23 - entry.nbits;
+}
 
-    const int sub_y[4] = {y0, y0, y0 + H, y0 + H}, sub_x[4] = {x0, x0 + H, x0, x0 + H};
-    const int sub_avail[4] = {                                                        // :1375-1378
-        (hl ? 1 : 0) | (hl ? 2 : 0) | (ha ? 4 : 0) | (ha ? 8 : 0),
-        1 | 0 | (ha ? 4 : 0) | (har ? 8 : 0),
-        (hl ? 1 : 0) | (hbl ? 2 : 0) | 4 | 8,
-        1 | 0 | 4 | 0 };
+// the split flag of a unit that is being split (:1403); one thread, after cu_enter
+template <int SZ>
+__device__ __forceinline__ void put_split_flag(Ctx &K)
+{
+    Smem &sm = *K.sm;
+    if (threadIdx.x == 0) {
+        Coder c; c.load(sm.cur); attach(c, sm, sm.cur_ctx, K.out, (unsigned)K.P->out_stride);
+        c.bin(1, CX_SPLIT_CU + sm.par[Level<SZ>::v].split_ctx);
+        c.store(sm.cur);
+    }
+}
 
-    // ---- 1: four smaller CUs (:1402-1412) ----
-    if constexpr (SZ > 8) {
-        if (tid == 0) {
-            Coder c; c.load(sm.cur); attach(c, sm, sm.cur_ctx, K.out, out_cap);
-            c.bin(1, CX_SPLIT_CU + split_ctx);
-            c.store(sm.cur);
+template <int SZ>
+__device__ __forceinline__ void cu_split_cost(Ctx &K)
+{
+    Smem &sm = *K.sm;
+    constexpr int LV = Level<SZ>::v;
+    const int tid = threadIdx.x, y0 = sm.par[LV].y0, x0 = sm.par[LV].x0;
+    __syncthreads();
+    int sse = 0;
+    for (int i = tid; i < SZ * SZ; i += NT) {
+        const int y = i / SZ, x = i % SZ;
+        const int d = (int)sm.orig[y0 + y][x0 + x] - (int)sm.rc[1 + y0 + y][1 + x0 + x];
+        sse += d * d;
+    }
+    sse = block_sum(sm, sse);
+    if (tid == 0) {
+        const CoderRegs &e = sm.entry[LV];
+        const int bits = 8 * ((int)sm.cur.nout + sm.cur.pending) + 23 - sm.cur.nbits;
+        sm.best_cost[LV] = K.rd.cost(sse, bits - (8 * ((int)e.nout + e.pending) + 23 - e.nbits));
+    }
+    __syncthreads();
+}
+
+template <int SZ>
+__device__ void eval_a1(Ctx &K)
+{
+    Smem &sm = *K.sm;
+    constexpr int LV = Level<SZ>::v, SET = Level<SZ>::set;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const CuPar q = sm.par[LV];
+    Src src; src.rc = &sm.rc[0][0]; src.priv = nullptr; src.py0 = q.y0; src.px0 = q.x0; src.psz = SZ; src.ppitch = SZ;
+    constexpr int G = 32 / SZ, NG = NW * G;
+    for (int base = 0; base < NMODE; base += NG) {
+        if (base + warp * G >= NMODE) break;                                // warp-uniform
+        const int item = base + warp * G + lane / SZ;
+        const bool active = item < NMODE;
+        const int m = active ? item : 0;
+        const int loff = (lane / SZ) * SZ * (SZ + 2);
+        TuResult r = tu_pipeline<SZ>(sm, warp, lane, active, src, q.y0, q.x0, q.avail, m, K.qpd6, K.rd, sm.lev[warp] + loff, rec_tile<SET>(sm, m), SZ);
+        if (lane % SZ == 0) {
+            publish_tu<SET>(sm, K.lists[SET], warp, lane / SZ, active, m, 0, (SZ / 4) * (SZ / 4), m, warp * LEV_STRIDE + loff, r);
+            if (active) sm.csse[SET][m] = r.sse;
         }
-        for (int i = 0; i < 4; i++) {
-            if constexpr (H == 8) search_cu8(K, sub_y[i], sub_x[i], sub_avail[i]);
-            else search_cu<H>(K, sub_y[i], sub_x[i], sub_avail[i]);
-        }
-        __syncthreads();
+        __syncwarp();
+        binarize_warp<SZ>(sm, warp, lane, K.lists[SET]);
+        __syncwarp();
+    }
+    __syncthreads();
+}
+
+template <int SZ>
+__device__ void eval_a4(Ctx &K)
+{
+    Smem &sm = *K.sm;
+    constexpr int LV = Level<SZ>::v, SET = Level<SZ>::set, H = SZ / 2;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const CuPar q = sm.par[LV];
+    const SubUnits<SZ> sub(q.y0, q.x0, q.avail);
+    Src src; src.rc = &sm.rc[0][0]; src.priv = nullptr; src.py0 = q.y0; src.px0 = q.x0; src.psz = SZ; src.ppitch = SZ;
+    constexpr int G = 32 / H, NG = NW * G;
+    for (int base = 0; base < NMODE; base += NG) {
+        if (base + warp * G >= NMODE) break;
+        const int item = base + warp * G + lane / H;
+        const bool active = item < NMODE;
+        const int m = active ? item : 0, cand = NMODE + m;
+        Src ps = src; ps.priv = rec_tile<SET>(sm, cand);                     // earlier sub-TUs of the same trial
+        const int loff = (lane / H) * H * (H + 2);
         int sse = 0;
-        for (int i = tid; i < SZ * SZ; i += NT) {
-            const int y = i / SZ, x = i % SZ;
-            const int r = sm.rc[1 + y0 + y][1 + x0 + x];
-            best[i] = (uint8_t)r;
-            const int d = (int)sm.orig[y0 + y][x0 + x] - r;
-            sse += d * d;
-        }
-        sse = block_sum(sm, sse);
-        if (tid == 0) {
-            const int bits = 8 * ((int)sm.cur.nout + sm.cur.pending) + 23 - sm.cur.nbits;
-            sm.best_cost[LV] = rd.cost(sse, bits - entry_bits_abs);
-        }
-        __syncthreads();
-        HPROF(K, LV * 16 + 1);
-    }
-
-    Src src; src.rc = &sm.rc[0][0]; src.priv = nullptr; src.py0 = y0; src.px0 = x0; src.psz = SZ; src.ppitch = SZ;
-
-    // ---- 2 and 3, phase A: 35 modes as one TU (candidates 0..34, :1419-1447) and as four TUs (35..69, :1454-1483);
-    //      every warp binarises the units it has just quantised ----
-    {
-        constexpr int G = 32 / SZ, NG = NW * G;
-        for (int base = 0; base < NMODE; base += NG) {
-            if (base + warp * G >= NMODE) break;                            // warp-uniform
-            const int item = base + warp * G + lane / SZ;
-            const bool active = item < NMODE;
-            const int m = active ? item : 0;
-            const int loff = (lane / SZ) * SZ * (SZ + 2);
-            TuResult r = tu_pipeline<SZ>(sm, warp, lane, active, src, y0, x0, avail, m, qpd6, rd, sm.lev[warp] + loff, rec_tile<SET>(sm, m), SZ);
-            if (lane % SZ == 0) {
-                publish_tu<SET>(sm, K.lists[SET], warp, lane / SZ, active, m, 0, (SZ / 4) * (SZ / 4), m, warp * LEV_STRIDE + loff, r);
-                if (active) sm.csse[SET][m] = r.sse;
-            }
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            TuResult r = tu_pipeline<H>(sm, warp, lane, active, ps, sub.y[i], sub.x[i], sub.avail[i], m, K.qpd6, K.rd,
+                                        sm.lev[warp] + loff, rec_tile<SET>(sm, cand) + (sub.y[i] - q.y0) * SZ + (sub.x[i] - q.x0), SZ);
+            sse += r.sse;
+            if (lane % H == 0) publish_tu<SET>(sm, K.lists[SET], warp, lane / H, active, cand, i, (H / 4) * (H / 4), m, warp * LEV_STRIDE + loff, r);
             __syncwarp();
-            binarize_warp<SZ>(sm, warp, lane, K.lists[SET]);
+            binarize_warp<H>(sm, warp, lane, K.lists[SET]);
             __syncwarp();
         }
+        if (active && lane % H == 0) sm.csse[SET][cand] = sse;
     }
-    __syncthreads();                                                        // sm.lev is reused by the four-TU trials
-    HPROF(K, LV * 16 + 2);
-    {
-        constexpr int G = 32 / H, NG = NW * G;
-        for (int base = 0; base < NMODE; base += NG) {
-            if (base + warp * G >= NMODE) break;
-            const int item = base + warp * G + lane / H;
-            const bool active = item < NMODE;
-            const int m = active ? item : 0, cand = NMODE + m;
-            Src ps = src; ps.priv = rec_tile<SET>(sm, cand);                 // earlier sub-TUs of the same trial
-            const int loff = (lane / H) * H * (H + 2);
-            int sse = 0;
-            for (int i = 0; i < 4; i++) {
-                TuResult r = tu_pipeline<H>(sm, warp, lane, active, ps, sub_y[i], sub_x[i], sub_avail[i], m, qpd6, rd,
-                                            sm.lev[warp] + loff, rec_tile<SET>(sm, cand) + (sub_y[i] - y0) * SZ + (sub_x[i] - x0), SZ);
-                sse += r.sse;
-                if (lane % H == 0) publish_tu<SET>(sm, K.lists[SET], warp, lane / H, active, cand, i, (H / 4) * (H / 4), m, warp * LEV_STRIDE + loff, r);
-                __syncwarp();
-                binarize_warp<H>(sm, warp, lane, K.lists[SET]);
-                __syncwarp();
-            }
-            if (active && lane % H == 0) sm.csse[SET][cand] = sse;
-        }
-    }
-    // ---- phase B: 70 trial encodes from the entry state, one lane each ----
     __syncthreads();
-    HPROF(K, LV * 16 + 3);
+}
+
+template <int SZ>
+__device__ void eval_b(Ctx &K)
+{
+    Smem &sm = *K.sm;
+    constexpr int LV = Level<SZ>::v, SET = Level<SZ>::set;
+    const int tid = threadIdx.x;
     for (int i = tid; i < NCAND * (CXP / 4); i += NT)
         ((unsigned *)sm.cctx[SET])[i] = ((const unsigned *)sm.entry_ctx[LV])[i % (CXP / 4)];
     __syncthreads();
-    HPROF(K, LV * 16 + 4);
     {
         const int c = candidate_of_thread(tid, NCAND);
-        if (c >= 0) trial_cu<SZ>(K, c, entry, entry_bits_rel, split_ctx, mode_l, mode_a);
+        if (c >= 0) {
+            const CoderRegs entry = sm.entry[LV];
+            const CuPar q = sm.par[LV];
+            trial_cu<SZ>(K, c, entry, 8 * entry.pending + 23 - entry.nbits, q.split_ctx, q.mode_l, q.mode_a);
+        }
     }
     __syncthreads();
-    HPROF(K, LV * 16 + 5);
-    // decide (:1437-1446, :1473-1482): candidates in the reference order, a later candidate wins ties
     if (tid == 0) {
-        int bc = sm.best_cost[LV], win = -1;
+        int bc = I32MAX, win = -1;
         for (int c = 0; c < NCAND; c++) {
-            const int cost = rd.cost(sm.csse[SET][c], sm.cbits[SET][c]);
+            const int cost = K.rd.cost(sm.csse[SET][c], sm.cbits[SET][c]);
             if (bc >= cost) { bc = cost; win = c; }
         }
-        sm.best_cost[LV] = bc;
-        sm.win = win;
+        sm.eval_cost[LV] = bc; sm.eval_win[LV] = win;
     }
     __syncthreads();
-    HPROF(K, LV * 16 + 6);
-    {
-        const int win = sm.win;
-        if (win >= 0) {
-            commit_candidate<SZ>(K, win);
-            fill_maps<SZ>(sm, y0, x0, win >= NMODE ? win - NMODE : win);
-        }
-    }
-    __syncthreads();
-    HPROF(K, LV * 16 + 7);
+}
 
-    // ---- the best reconstruction becomes the CU's reconstruction (:1558) ----
-    for (int i = tid; i < SZ * SZ; i += NT) sm.rc[1 + y0 + i / SZ][1 + x0 + i % SZ] = best[i];
+// decision between the split alternative (cost in best_cost) and the evaluated candidates (:1437-1446, :1473-1482): the
+// candidates come later in the reference order, so they win ties.  When a candidate wins, it becomes the current state.
+//   REMOTE = false: the candidates were evaluated by this CTA;  true: by the partner CTA (two-CTA kernel), which left the
+//   winner's coder, contexts and reconstruction in res_* and its bytes in its own trial stream.
+template <int SZ, bool REMOTE>
+__device__ __forceinline__ void cu_decide_commit(Ctx &K)
+{
+    Smem &sm = *K.sm;
+    constexpr int LV = Level<SZ>::v, SET = Level<SZ>::set;
+    const int tid = threadIdx.x, y0 = sm.par[LV].y0, x0 = sm.par[LV].x0;
+    const int win = sm.eval_win[LV];
+    if (sm.best_cost[LV] >= sm.eval_cost[LV] && win >= 0) {                  // uniform: values were written before a barrier
+        const CoderRegs &wc = REMOTE ? sm.res_coder[LV] : sm.ccoder[SET][win];
+        const unsigned base = sm.entry[LV].nout, n = wc.nout;
+        const uint8_t *bytes = (REMOTE ? K.peer_scratch[SET] : K.scratch[SET]) + (size_t)win * SCR_BYTES;
+        const unsigned cap = (unsigned)K.P->out_stride;
+        for (unsigned i = tid; i < n && i < SCR_BYTES; i += NT) if (base + i < cap) K.out[base + i] = bytes[i];
+        copy_words(sm.cur_ctx, REMOTE ? sm.res_ctx[LV] : sm.cctx[SET][win], CXP / 4, tid, NT);
+        const uint8_t *rec = REMOTE ? (SET == 0 ? sm.res_rec0 : sm.res_rec1) : rec_tile<SET>(sm, win);
+        for (int i = tid; i < SZ * SZ; i += NT) sm.rc[1 + y0 + i / SZ][1 + x0 + i % SZ] = rec[i];
+        fill_maps<SZ>(sm, y0, x0, win >= NMODE ? win - NMODE : win);
+        __syncthreads();                                                    // every thread has read wc.nout
+        if (tid == 0) { CoderRegs c = wc; c.nout = base + n; sm.cur = c; sm.best_cost[LV] = sm.eval_cost[LV]; }
+    }
     __syncthreads();
-    HPROF(K, LV * 16 + 13);
+}
+
+__device__ void search_cu8(Ctx &K, int y0, int x0, int avail);
+
+// one CTA: a unit is searched depth first, the evaluation of its own candidates after its four smaller units
+template <int SZ>
+__device__ void search_cu(Ctx &K, int y0, int x0, int avail)
+{
+    static_assert(SZ == 32 || SZ == 16, "8x8 coding units: search_cu8");
+    constexpr int LV = Level<SZ>::v, H = SZ / 2;
+    cu_enter<SZ>(K, y0, x0, avail);
+    HPROF(K, LV * 16 + 0);
+    put_split_flag<SZ>(K);
+    const SubUnits<SZ> sub(y0, x0, avail);
+    for (int i = 0; i < 4; i++) {
+        if constexpr (H == 8) search_cu8(K, sub.y[i], sub.x[i], sub.avail[i]);
+        else search_cu<H>(K, sub.y[i], sub.x[i], sub.avail[i]);
+    }
+    cu_split_cost<SZ>(K);
+    HPROF(K, LV * 16 + 1);
+    eval_a1<SZ>(K);
+    HPROF(K, LV * 16 + 2);
+    eval_a4<SZ>(K);
+    HPROF(K, LV * 16 + 3);
+    eval_b<SZ>(K);
+    HPROF(K, LV * 16 + 5);
+    cu_decide_commit<SZ, false>(K);
+    HPROF(K, LV * 16 + 7);
 }
 
 // RD search of an 8x8 coding unit (processCURecurs :1349-1559 with sz == 8: no split; one 8x8 TU, four 4x4 TUs, or

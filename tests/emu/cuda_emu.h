@@ -60,6 +60,10 @@ struct State {
     std::vector<Fiber> fibers;
     std::vector<uint64_t> slots;            // [warp][32] exchange slots for shuffles / ballots
     unsigned char *smem = nullptr;
+    int cluster = 1;                        // CTAs per cluster: the fibers of one launch step are cluster x cta_threads
+    int cta_threads = 0;                    // threads of one CTA
+    size_t smem_stride = 0;                 // distance of the CTAs' shared-memory images
+    unsigned cluster_id = 0;
     std::function<void()> body;
     long n_block_barriers = 0, n_warp_barriers = 0;
 };
@@ -85,21 +89,26 @@ inline void trampoline()
 
 constexpr size_t STACK_BYTES = 512 * 1024;
 
-// runs `body` once per CUDA thread for every block of the grid
-inline void launch(unsigned grid_x, unsigned block_x, size_t smem_bytes, std::function<void()> body)
+// runs `body` once per CUDA thread for every block of the grid; cluster > 1: grid_x counts CLUSTERS of `cluster` CTAs
+// whose threads run together (block_x threads and smem_bytes of shared memory per CTA, block_x a multiple of 32)
+inline void launch(unsigned grid_x, unsigned block_x, size_t smem_bytes, std::function<void()> body, int cluster = 1)
 {
     State &s = S();
-    s.gridDim.x = grid_x; s.blockDim.x = block_x;
-    s.nthreads = (int)block_x;
+    s.cluster = cluster; s.cta_threads = (int)block_x;
+    s.smem_stride = (smem_bytes + 127) & ~(size_t)127;
+    s.gridDim.x = grid_x * cluster; s.blockDim.x = block_x;
+    const unsigned nfib = block_x * cluster;
+    s.nthreads = (int)nfib;
     s.body = body;
-    s.fibers.resize(block_x);
-    s.slots.assign((size_t)((block_x + 31) / 32) * 32, 0);
+    s.fibers.resize(nfib);
+    s.slots.assign((size_t)((nfib + 31) / 32) * 32, 0);
     for (auto &f : s.fibers) if (!f.stack) f.stack = (char *)malloc(STACK_BYTES);
-    s.smem = (unsigned char *)malloc(smem_bytes + 64);
+    s.smem = (unsigned char *)malloc(s.smem_stride * cluster + 64);
     for (unsigned b = 0; b < grid_x; b++) {
-        s.blockIdx.x = b;
-        memset(s.smem, 0xCD, smem_bytes + 64);
-        for (unsigned t = 0; t < block_x; t++) {
+        s.blockIdx.x = b * cluster;
+        s.cluster_id = b;
+        memset(s.smem, 0xCD, s.smem_stride * cluster + 64);
+        for (unsigned t = 0; t < nfib; t++) {
             Fiber &f = s.fibers[t];
             void **top = (void **)(((uintptr_t)f.stack + STACK_BYTES) & ~(uintptr_t)15);
             *--top = nullptr;                       // fake return address: keeps the ABI stack alignment at entry
@@ -108,7 +117,7 @@ inline void launch(unsigned grid_x, unsigned block_x, size_t smem_bytes, std::fu
             f.sp = top;
             f.state = RUNNABLE;
         }
-        const int nwarps = (int)(block_x + 31) / 32;
+        const int nwarps = (int)(nfib + 31) / 32;
         for (;;) {
             bool ran = false;
             for (int t = 0; t < s.nthreads; t++)
@@ -134,7 +143,7 @@ inline void launch(unsigned grid_x, unsigned block_x, size_t smem_bytes, std::fu
                 }
             }
             // named barriers: `count` threads wait at the same id
-            for (int id = 1; id < 16; id++) {
+            for (int id = 1; id < 24; id++) {
                 int waiting_n = 0, want = 0;
                 for (int t = 0; t < s.nthreads; t++)
                     if (s.fibers[t].state == AT_NAMED_BARRIER && s.fibers[t].bar_id == id) { waiting_n++; want = s.fibers[t].bar_count; }
@@ -169,7 +178,15 @@ inline void launch(unsigned grid_x, unsigned block_x, size_t smem_bytes, std::fu
     }
     free(s.smem);
     s.smem = nullptr;
+    s.cluster = 1;
 }
+
+// ---- thread-block clusters: rank of the calling thread's CTA, its and its partner's shared memory ----
+inline int cta_rank() { return S().cluster > 1 ? S().tid / S().cta_threads : 0; }
+inline unsigned char *dyn_smem() { return S().smem + (size_t)cta_rank() * S().smem_stride; }
+inline unsigned char *cluster_smem(int rank) { return S().smem + (size_t)rank * S().smem_stride; }
+inline Dim3 thread_idx() { Dim3 d; d.x = (unsigned)(S().cluster > 1 ? S().tid % S().cta_threads : S().tid); return d; }
+inline Dim3 block_idx() { Dim3 d = S().blockIdx; d.x += (unsigned)cta_rank(); return d; }
 
 inline int lane_id() { return S().tid & 31; }
 inline uint64_t *warp_slots() { return &S().slots[(size_t)(S().tid >> 5) * 32]; }
@@ -190,19 +207,25 @@ template <class T> inline T exchange(T v, int src_lane)
 }  // namespace emu
 
 // ---- CUDA surface ------------------------------------------------------------------------------------
-#define threadIdx (emu::Dim3{(unsigned)emu::S().tid, 0, 0})
-#define blockIdx  (emu::S().blockIdx)
+#define threadIdx (emu::thread_idx())
+#define blockIdx  (emu::block_idx())
 #define blockDim  (emu::S().blockDim)
 #define gridDim   (emu::S().gridDim)
 
-inline void __syncthreads() { emu::yield_as(emu::AT_BLOCK_BARRIER); }
-// bar.sync id, count  (count = number of THREADS that meet at barrier `id`, 1 <= id <= 15)
+// bar.sync id, count  (count = number of THREADS that meet at barrier `id`, 1 <= id <= 15; the emulator keeps
+// ids 16.. for the per-CTA __syncthreads of a cluster launch)
 inline void emu_named_barrier(int id, int count)
 {
     emu::Fiber &f = emu::S().fibers[emu::S().tid];
     f.bar_id = id; f.bar_count = count;
     emu::yield_as(emu::AT_NAMED_BARRIER);
 }
+inline void __syncthreads()
+{
+    if (emu::S().cluster > 1) emu_named_barrier(16 + emu::cta_rank(), emu::S().cta_threads);
+    else emu::yield_as(emu::AT_BLOCK_BARRIER);
+}
+inline void emu_cluster_sync() { emu::yield_as(emu::AT_BLOCK_BARRIER); }     // barrier.cluster arrive + wait
 inline void __syncwarp(unsigned = 0xffffffffu) { emu::yield_as(emu::AT_WARP_BARRIER); }
 inline void __threadfence_block() {}
 inline void __threadfence() {}
