@@ -32,7 +32,7 @@ EXPORTED_SYMBOLS = [
     "imcvtEncodeBatchJLS", "imcvtEncodeBatchJLSDevice",
     "imcvtEncodeBatchHEVC", "imcvtEncodeBatchHEVCDevice",
     "imcvtProfileEnable", "imcvtProfileReset", "imcvtProfileGet", "imcvtProfileList", "imcvtLaunchCount",
-    "imcvtDebugJLSForceSerial", "imcvtDebugJLSPath",
+    "imcvtDebugJLSForceSerial", "imcvtDebugJLSPath", "imcvtDebugHEVCPath",
     "writeJLSImageFile", "writeHEVCImageFile", "HEVCImageEncoder",
 ]
 
@@ -71,6 +71,7 @@ def lib():
     L.imcvtLaunchCount.argtypes = []; L.imcvtLaunchCount.restype = C.c_long
     L.imcvtDebugJLSForceSerial.argtypes = [i32]; L.imcvtDebugJLSForceSerial.restype = None
     L.imcvtDebugJLSPath.argtypes = [i32]; L.imcvtDebugJLSPath.restype = None
+    L.imcvtDebugHEVCPath.argtypes = [i32]; L.imcvtDebugHEVCPath.restype = None
     L.writeJLSImageFile.argtypes = [C.c_char_p, vp, i32, u32, u32, i32]; L.writeJLSImageFile.restype = i32
     L.writeHEVCImageFile.argtypes = [C.c_char_p, vp, i32, u32, u32, i32]; L.writeHEVCImageFile.restype = i32
     L.HEVCImageEncoder.argtypes = [vp, vp, vp, C.POINTER(i32), C.POINTER(i32), i32]; L.HEVCImageEncoder.restype = i32
@@ -232,3 +233,8 @@ def debug_jls_force_serial(on):
 def debug_jls_path(path):
     """0 = default NEAR=0 path (tile kernel), 1 = force the multi-kernel pipeline (used for planes wider than 6144)."""
     lib().imcvtDebugJLSPath(int(path))
+
+
+def debug_hevc_path(path):
+    """0 = default, 1 = one CTA per frame, 2 = a cluster of two CTAs per frame (see imcvtDebugHEVCPath)."""
+    lib().imcvtDebugHEVCPath(int(path))

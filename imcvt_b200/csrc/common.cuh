@@ -53,7 +53,8 @@ struct Engine {
     std::vector<Pending> pending;
     std::vector<cudaEvent_t> event_pool;
     bool jls_force_serial = false;
-    int jls_path = 0;       // 0 = default (tile kernel when the plane fits), 1 = force the multi-kernel pipeline
+    int jls_path = 0;       // 0 = default (tile kernel when the plane fits), 1 = force the multi-kernel pipeline, 3 = tile kernel on CTA pairs
+    int hevc_path = 0;      // 0 = default (CTA pair per frame when the batch has at most SMs/2 frames), 1 = one CTA per frame, 2 = CTA pair
     int sm_count = 148;
 };
 

@@ -27,9 +27,14 @@ int encode_device(const uint8_t *d_frames, size_t frame_stride, int n, uint32_t 
     static bool attr_set = false;
     if (!attr_set) {
         IMCVT_CUDA(cudaFuncSetAttribute(hevc_frame_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem)));
+        IMCVT_CUDA(cudaFuncSetAttribute(hevc_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem)));
         attr_set = true;
     }
-    const int grid = n < E.sm_count ? n : E.sm_count;                       // one CTA per SM; frames come from a queue
+    // Few frames: two SMs per frame (a cluster of two CTAs: the spine searches the 8x8 units and decides, the upper CTA
+    // evaluates the 16x16 / 32x32 candidates meanwhile).  Many frames: one CTA per frame keeps every SM on its own frame.
+    const bool pair = E.hevc_path == 2 || (E.hevc_path == 0 && 2 * n <= E.sm_count);
+    const int grid = pair ? 2 * (n < E.sm_count / 2 ? n : E.sm_count / 2)
+                          : (n < E.sm_count ? n : E.sm_count);              // one CTA per SM; frames come from a queue
     const size_t rstride = (rbytes + 255) & ~(size_t)255;
     size_t bytes = 4096 + (size_t)grid * 2 * NALL * SCR_BYTES + 256 + (size_t)grid * 2 * NALL * CAND_LIST_U16 * 2 + 256;
     if (!d_rcon) bytes += (size_t)n * rstride + 256;
@@ -60,8 +65,9 @@ int encode_device(const uint8_t *d_frames, size_t frame_stride, int n, uint32_t 
     }
 #endif
     {
-        LaunchScope ls("hevc_frame", st);
-        hevc_frame_kernel<<<grid, NT, sizeof(Smem), st>>>(P);
+        LaunchScope ls(pair ? "hevc_pair" : "hevc_frame", st);
+        if (pair) hevc_pair_kernel<<<grid, NT, sizeof(Smem), st>>>(P);
+        else hevc_frame_kernel<<<grid, NT, sizeof(Smem), st>>>(P);
     }
     IMCVT_CUDA(cudaGetLastError());
     return 0;

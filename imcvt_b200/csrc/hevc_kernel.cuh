@@ -167,7 +167,6 @@ struct Smem {
     uint8_t rc[CTU + 1][RCP];                       // reconstruction window: row 0 / column 0 are the neighbours (:1588-1589)
     uint8_t msz[9][12], mmd[9][12];                 // CU size / luma mode per 4x4 cell; row 0 / column 0 = above / left CTU
     uint8_t left_sz[8], left_md[8];                 // right-most column of the previous CTU
-    uint8_t best_rec[CTU * CTU + 16 * 16 + 8 * 8];  // best reconstruction so far per CU level
     uint8_t nxn_rec[8 * 8];
     unsigned short nxn_list[4][SLOT], nxn_hdr[4];   // bin lists of the four kept 4x4 blocks
     int nxn_mode[4], nxn_last[4];
@@ -1038,30 +1037,12 @@ struct Ctx {
     long long prof_t;
 };
 
-template <int SZ> struct Level { static constexpr int v = SZ == 32 ? 0 : SZ == 16 ? 1 : 2; static constexpr int best_off = SZ == 32 ? 0 : SZ == 16 ? 1024 : 1280;
-                                 static constexpr int set = SZ == 32 ? 0 : 1; };
+template <int SZ> struct Level { static constexpr int v = SZ == 32 ? 0 : SZ == 16 ? 1 : 2; static constexpr int set = SZ == 32 ? 0 : 1; };
 template <int SET> __device__ __forceinline__ uint8_t *rec_tile(Smem &sm, int c) { return SET == 0 ? sm.rec0[c] : sm.rec1[c]; }
 
 __device__ __forceinline__ void attach(Coder &c, Smem &sm, uint8_t *ctx, uint8_t *out, unsigned cap)
 {
     c.ctx = ctx; c.out = out; c.cap = cap; c.lps = sm.lpsw; c.nlps = sm.next_lps;
-}
-
-// the winner of a step becomes the current state: coder, bytes, reconstruction (:1439-1446)
-template <int SZ>
-__device__ __forceinline__ void commit_candidate(Ctx &K, int win)
-{
-    Smem &sm = *K.sm;
-    constexpr int LV = Level<SZ>::v, SET = Level<SZ>::set;
-    const int tid = threadIdx.x;
-    const unsigned base = sm.entry[LV].nout, n = sm.ccoder[SET][win].nout;
-    const uint8_t *src = K.scratch[SET] + (size_t)win * SCR_BYTES;
-    const unsigned cap = (unsigned)K.P->out_stride;
-    for (unsigned i = tid; i < n && i < SCR_BYTES; i += NT) if (base + i < cap) K.out[base + i] = src[i];
-    copy_words(sm.cur_ctx, sm.cctx[SET][win], CXP / 4, tid, NT);
-    if (tid == 0) { sm.cur = sm.ccoder[SET][win]; sm.cur.nout = base + n; }
-    uint8_t *best = sm.best_rec + Level<SZ>::best_off;
-    for (int i = tid; i < SZ * SZ / 4; i += NT) ((unsigned *)best)[i] = ((const unsigned *)rec_tile<SET>(sm, win))[i];
 }
 
 template <int SZ>
@@ -1639,12 +1620,98 @@ __device__ inline void build_tables(Smem &sm, int qpd6)
     __syncthreads();
 }
 
-__device__ inline void encode_frame(Ctx &K, int f)
+// original block with edge replication, neighbours of the reconstruction (:1613-1621) and, for the CTA that keeps the
+// size / mode maps, their borders
+__device__ __forceinline__ void load_ctu(Ctx &K, const uint8_t *img, const uint8_t *rcon, int y, int x, bool maps)
+{
+    Smem &sm = *K.sm;
+    const Params &P = *K.P;
+    const int tid = threadIdx.x, H = P.H, W = P.W, wp = P.wp;
+    const bool hl = x > 0, ha = y > 0;
+    for (int i = tid; i < CTU * CTU; i += NT) {
+        const int yy = min(y + i / CTU, H - 1), xx = min(x + i % CTU, W - 1);
+        sm.orig[i / CTU][i % CTU] = img[(size_t)yy * W + xx];
+    }
+    if (tid < CTU) sm.rc[1 + tid][0] = hl ? rcon[(size_t)(y + tid) * wp + x - 1] : 0;
+    if (tid >= 64 && tid < 64 + 1 + 2 * CTU) {
+        const int j = tid - 64 - 1;                                     // -1 .. 63
+        const int xx = clampi(x + j, 0, wp - 1);
+        sm.rc[0][1 + j] = ha ? rcon[(size_t)(y - 1) * wp + xx] : 0;
+    }
+    if (maps && tid >= 160 && tid < 160 + 81) {
+        const int r = (tid - 160) / 9, c = (tid - 160) % 9;
+        uint8_t s = 32, m = 1;                                          // outside the picture: size 32, DC
+        if (r == 0) { if (c > 0) s = sm.above_sz[x / 4 + c - 1]; }
+        else if (c == 0) { if (hl) { s = sm.left_sz[r - 1]; m = sm.left_md[r - 1]; } }
+        if (r == 0 || c == 0) { sm.msz[r][c] = s; sm.mmd[r][c] = m; }
+    }
+}
+
+// reconstruction out (:1625-1627), map borders for the next CTUs, end_of_slice_segment_flag (:1629)
+__device__ __forceinline__ void finish_ctu(Ctx &K, uint8_t *rcon, int y, int x)
+{
+    Smem &sm = *K.sm;
+    const Params &P = *K.P;
+    const int tid = threadIdx.x, hp = P.hp, wp = P.wp;
+    for (int i = tid; i < CTU * CTU / 4; i += NT) {
+        const int r = i / 8, c4 = (i % 8) * 4;
+        const uint8_t *s = &sm.rc[1 + r][1 + c4];
+        *(unsigned *)(rcon + (size_t)(y + r) * wp + x + c4) = (unsigned)s[0] | ((unsigned)s[1] << 8) | ((unsigned)s[2] << 16) | ((unsigned)s[3] << 24);
+    }
+    if (tid < 8) { sm.left_sz[tid] = sm.msz[1 + tid][8]; sm.left_md[tid] = sm.mmd[1 + tid][8]; sm.above_sz[x / 4 + tid] = sm.msz[8][1 + tid]; }
+    if (tid == 0) {
+        Coder c; c.load(sm.cur); attach(c, sm, sm.cur_ctx, K.out, (unsigned)P.out_stride);
+        c.terminate(y + CTU >= hp && x + CTU >= wp);
+        c.store(sm.cur);
+    }
+}
+
+// ---- two-CTA kernel: what the CTAs hand each other through distributed shared memory ----
+// spine -> upper: the entry state of the unit whose candidates the upper CTA is to evaluate
+template <int SZ>
+__device__ __forceinline__ void push_entry(Ctx &K)
+{
+    Smem &sm = *K.sm, &pe = *K.peer;
+    constexpr int LV = Level<SZ>::v;
+    const int tid = threadIdx.x;
+    copy_words(pe.entry_ctx[LV], sm.entry_ctx[LV], CXP / 4, tid, NT);
+    if (tid >= 64 && tid < 64 + (int)(sizeof(CoderRegs) / 4)) ((unsigned *)&pe.entry[LV])[tid - 64] = ((const unsigned *)&sm.entry[LV])[tid - 64];
+    if (tid >= 96 && tid < 96 + (int)(sizeof(CuPar) / 4)) ((unsigned *)&pe.par[LV])[tid - 96] = ((const unsigned *)&sm.par[LV])[tid - 96];
+}
+// spine -> upper: the final reconstruction of a 16x16 unit (reference samples of the units that follow)
+__device__ __forceinline__ void push_rc_block(Ctx &K, int y0, int x0)
+{
+    Smem &sm = *K.sm, &pe = *K.peer;
+    const int tid = threadIdx.x;
+    if (tid < 256) pe.rc[1 + y0 + (tid >> 4)][1 + x0 + (tid & 15)] = sm.rc[1 + y0 + (tid >> 4)][1 + x0 + (tid & 15)];
+}
+// upper -> spine: the best candidate of an evaluation: cost, index, coder, contexts, reconstruction (its bytes stay in
+// the upper CTA's trial stream in global memory)
+template <int SZ>
+__device__ __forceinline__ void push_result(Ctx &K)
+{
+    Smem &sm = *K.sm, &pe = *K.peer;
+    constexpr int LV = Level<SZ>::v, SET = Level<SZ>::set;
+    const int tid = threadIdx.x, win = sm.eval_win[LV];
+    copy_words(pe.res_ctx[LV], sm.cctx[SET][win], CXP / 4, tid, NT);
+    copy_words(SET == 0 ? pe.res_rec0 : pe.res_rec1, rec_tile<SET>(sm, win), SZ * SZ / 4, tid, NT);
+    if (tid >= 64 && tid < 64 + (int)(sizeof(CoderRegs) / 4)) ((unsigned *)&pe.res_coder[LV])[tid - 64] = ((const unsigned *)&sm.ccoder[SET][win])[tid - 64];
+    if (tid == 96) { pe.eval_cost[LV] = sm.eval_cost[LV]; pe.eval_win[LV] = win; }
+}
+
+// One frame (HEVCImageEncoder :1569-1646).
+//   PAIR = false: one CTA does everything, depth first.
+//   PAIR = true : a cluster of two CTAs.  Rank 0 ("spine") owns the arithmetic coder, the contexts, the reconstruction
+//     and the maps, searches the 8x8 units and takes every decision; rank 1 ("upper") evaluates the 70 candidates of the
+//     32x32 unit and of each 16x16 unit meanwhile.  Per 16x16 unit the two meet twice at a cluster barrier: once when the
+//     unit's entry state is in the upper CTA's shared memory, once when the upper CTA's result is in the spine's.
+template <bool PAIR>
+__device__ inline void encode_frame(Ctx &K, int f, int rank)
 {
     Smem &sm = *K.sm;
     const Params &P = *K.P;
     const int tid = threadIdx.x;
-    const int H = P.H, W = P.W, hp = P.hp, wp = P.wp, qpd6 = P.qpd6;
+    const int hp = P.hp, wp = P.wp, qpd6 = P.qpd6;
     const uint8_t *img = P.frames + (size_t)f * P.frame_stride;
     uint8_t *rcon = P.rcon + (size_t)f * P.rcon_stride;
     K.out = P.out + (size_t)f * P.out_stride;
@@ -1652,7 +1719,7 @@ __device__ inline void encode_frame(Ctx &K, int f)
     __syncthreads();
     copy_words(sm.cur_ctx, sm.init_ctx, CXP / 4, tid, NT);
     for (int i = tid; i < 2048; i += NT) sm.above_sz[i] = 32;                // :1594-1599
-    if (tid == 0) {
+    if (tid == 0 && rank == 0) {
         Coder c; c.fresh(); c.store(sm.cur);
         sm.cur.nout = P.out_stride >= 128 ? put_headers(K.out, qpd6, hp, wp) : 0;
         if (P.out_stride < 128) atomicExch(P.overflow, 1);
@@ -1662,43 +1729,52 @@ __device__ inline void encode_frame(Ctx &K, int f)
     for (int y = 0; y < hp; y += CTU) {
         for (int x = 0; x < wp; x += CTU) {
             const bool hl = x > 0, ha = y > 0, har = ha && (x + CTU < wp);      // :1605-1608
-            // original block with edge replication, neighbours of the reconstruction (:1613-1621)
-            for (int i = tid; i < CTU * CTU; i += NT) {
-                const int yy = min(y + i / CTU, H - 1), xx = min(x + i % CTU, W - 1);
-                sm.orig[i / CTU][i % CTU] = img[(size_t)yy * W + xx];
-            }
-            if (tid < CTU) sm.rc[1 + tid][0] = hl ? rcon[(size_t)(y + tid) * wp + x - 1] : 0;
-            if (tid >= 64 && tid < 64 + 1 + 2 * CTU) {
-                const int j = tid - 64 - 1;                                     // -1 .. 63
-                const int xx = clampi(x + j, 0, wp - 1);
-                sm.rc[0][1 + j] = ha ? rcon[(size_t)(y - 1) * wp + xx] : 0;
-            }
-            if (tid >= 160 && tid < 160 + 81) {
-                const int r = (tid - 160) / 9, c = (tid - 160) % 9;
-                uint8_t s = 32, m = 1;                                          // outside the picture: size 32, DC
-                if (r == 0) { if (c > 0) s = sm.above_sz[x / 4 + c - 1]; }
-                else if (c == 0) { if (hl) { s = sm.left_sz[r - 1]; m = sm.left_md[r - 1]; } }
-                if (r == 0 || c == 0) { sm.msz[r][c] = s; sm.mmd[r][c] = m; }
-            }
+            const int avail = (hl ? 1 : 0) | (ha ? 4 : 0) | (har ? 8 : 0);
+            load_ctu(K, img, rcon, y, x, rank == 0);
             HPROF(K, 48);
-            search_cu<CTU>(K, 0, 0, (hl ? 1 : 0) | (ha ? 4 : 0) | (har ? 8 : 0));
-
-            for (int i = tid; i < CTU * CTU / 4; i += NT) {                      // :1625-1627
-                const int r = i / 8, c4 = (i % 8) * 4;
-                const uint8_t *s = &sm.rc[1 + r][1 + c4];
-                *(unsigned *)(rcon + (size_t)(y + r) * wp + x + c4) = (unsigned)s[0] | ((unsigned)s[1] << 8) | ((unsigned)s[2] << 16) | ((unsigned)s[3] << 24);
+            if (!PAIR) {
+                search_cu<CTU>(K, 0, 0, avail);
+                finish_ctu(K, rcon, y, x);
+                __syncthreads();
+            } else if (rank == 0) {
+                cu_enter<32>(K, 0, 0, avail);
+                push_entry<32>(K);
+                put_split_flag<32>(K);
+                const SubUnits<32> sub(0, 0, avail);
+                for (int j = 0; j < 4; j++) {
+                    cu_enter<16>(K, sub.y[j], sub.x[j], sub.avail[j]);
+                    push_entry<16>(K);
+                    HEVC_PAIR_SYNC();                                       // the upper CTA may evaluate this unit
+                    put_split_flag<16>(K);
+                    const SubUnits<16> s8(sub.y[j], sub.x[j], sub.avail[j]);
+                    for (int k = 0; k < 4; k++) search_cu8(K, s8.y[k], s8.x[k], s8.avail[k]);
+                    cu_split_cost<16>(K);
+                    HEVC_PAIR_SYNC();                                       // its result is here
+                    cu_decide_commit<16, true>(K);
+                    push_rc_block(K, sub.y[j], sub.x[j]);
+                }
+                cu_split_cost<32>(K);
+                cu_decide_commit<32, true>(K);
+                finish_ctu(K, rcon, y, x);
+                HEVC_PAIR_SYNC();                                           // the reconstruction is in global memory
+            } else {
+                __syncthreads();
+                for (int j = 0; j < 4; j++) {
+                    HEVC_PAIR_SYNC();
+                    eval_a1<16>(K); eval_a4<16>(K); eval_b<16>(K);
+                    push_result<16>(K);
+                    // the 32x32 unit's evaluation, a third per 16x16 unit
+                    if (j == 0) eval_a1<32>(K);
+                    if (j == 1) eval_a4<32>(K);
+                    if (j == 2) { eval_b<32>(K); push_result<32>(K); }
+                    HEVC_PAIR_SYNC();
+                }
+                HEVC_PAIR_SYNC();
             }
-            if (tid < 8) { sm.left_sz[tid] = sm.msz[1 + tid][8]; sm.left_md[tid] = sm.mmd[1 + tid][8]; sm.above_sz[x / 4 + tid] = sm.msz[8][1 + tid]; }
-            if (tid == 0) {
-                Coder c; c.load(sm.cur); attach(c, sm, sm.cur_ctx, K.out, (unsigned)P.out_stride);
-                c.terminate(y + CTU >= hp && x + CTU >= wp);                     // :1629
-                c.store(sm.cur);
-            }
-            __syncthreads();
             HPROF(K, 49);
         }
     }
-    if (tid == 0) {
+    if (tid == 0 && rank == 0) {
         Coder c; c.load(sm.cur); attach(c, sm, sm.cur_ctx, K.out, (unsigned)P.out_stride);
         c.finish();                                                             // :1639-1640
         const bool fits = c.nout <= (unsigned)P.out_stride;
@@ -1708,14 +1784,18 @@ __device__ inline void encode_frame(Ctx &K, int f)
     __syncthreads();
 }
 
-__global__ void __launch_bounds__(NT, 1) hevc_frame_kernel(Params P)
+template <bool PAIR>
+__device__ __forceinline__ void frame_kernel_body(const Params &P)
 {
+    const int rank = PAIR ? HEVC_PAIR_RANK() : 0;
     Smem &sm = *reinterpret_cast<Smem *>(IMCVT_DYN_SMEM());
     Ctx K;
     K.sm = &sm; K.P = &P; K.qpd6 = P.qpd6; K.rd.init(P.qpd6);
+    K.peer = PAIR ? reinterpret_cast<Smem *>(HEVC_PAIR_SMEM(rank ^ 1)) : nullptr;
     for (int q = 0; q < 2; q++) {
         K.scratch[q] = P.scratch + ((size_t)blockIdx.x * 2 + q) * NALL * SCR_BYTES;
         K.lists[q] = P.lists + ((size_t)blockIdx.x * 2 + q) * NALL * CAND_LIST_U16;
+        K.peer_scratch[q] = P.scratch + ((size_t)(blockIdx.x ^ 1) * 2 + q) * NALL * SCR_BYTES;
     }
     K.out = nullptr;
     build_tables(sm, P.qpd6);
@@ -1725,14 +1805,17 @@ __global__ void __launch_bounds__(NT, 1) hevc_frame_kernel(Params P)
     __syncthreads();
 #endif
     for (;;) {                                                                  // frames vary 2-3x in cost: dynamic queue
-        __syncthreads();
-        if (threadIdx.x == 0) sm.win = atomicAdd(P.next_frame, 1);
-        __syncthreads();
+        if (PAIR) HEVC_PAIR_SYNC(); else __syncthreads();
+        if (threadIdx.x == 0 && rank == 0) { const int f = atomicAdd(P.next_frame, 1); sm.win = f; if (PAIR) K.peer->win = f; }
+        if (PAIR) HEVC_PAIR_SYNC(); else __syncthreads();
         const int f = sm.win;
         if (f >= P.n) break;
-        encode_frame(K, f);
+        encode_frame<PAIR>(K, f, rank);
     }
 }
+
+__global__ void __launch_bounds__(NT, 1) hevc_frame_kernel(Params P) { frame_kernel_body<false>(P); }
+__global__ void HEVC_CLUSTER_DIMS __launch_bounds__(NT, 1) hevc_pair_kernel(Params P) { frame_kernel_body<true>(P); }
 
 }  // namespace hevc
 }  // namespace imcvt

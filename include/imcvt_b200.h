@@ -85,6 +85,9 @@ void imcvtDebugJLSForceSerial(int on);
  * per plane), 1 = force the multi-kernel pipeline that wider planes use, 2 = same as 0, 3 = the tile kernel on a
  * cluster of two CTAs per plane (rank 0 produces sorted tiles into the shared memory of rank 1). */
 void imcvtDebugJLSPath(int path);
+/* Debug / cross-check of the H.265 paths: 0 = default (a cluster of two CTAs per frame when the batch has at most SMs/2
+ * frames, else one CTA per frame), 1 = force one CTA per frame, 2 = force the two-CTA cluster. */
+void imcvtDebugHEVCPath(int path);
 
 #ifdef __cplusplus
 }

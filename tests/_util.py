@@ -163,7 +163,7 @@ def ref_hevc(img, qpd6):
     return _hevc_call(ref_lib().HEVCImageEncoder, img, qpd6)
 
 
-def emu_hevc(img, qpd6):
+def emu_hevc(img, qpd6, pair=False):
     """The SOURCE of the CUDA HEVC kernel run under the CPU SIMT emulator (tests/emu, test infrastructure)."""
     if "emu" not in _libs:
         d = os.path.join(ROOT, "tests", "emu")
@@ -171,6 +171,8 @@ def emu_hevc(img, qpd6):
         lib = C.CDLL(os.path.join(d, "libhevc_emu.so"))
         lib.emu_hevc_encode.restype = C.c_long
         lib.emu_hevc_encode.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int), C.c_int]
+        lib.emu_hevc_encode_mode.restype = C.c_long
+        lib.emu_hevc_encode_mode.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int), C.c_int, C.c_int]
         _libs["emu"] = lib
     img = np.ascontiguousarray(img, dtype=np.uint8)
     h, w = img.shape
@@ -178,7 +180,7 @@ def emu_hevc(img, qpd6):
     out = np.zeros(2 * (wp + 32) * (hp + 32) + 65536, dtype=np.uint8)
     rcon = np.zeros(hp * wp, dtype=np.uint8)
     ch, cw = C.c_int(h), C.c_int(w)
-    n = _libs["emu"].emu_hevc_encode(out.ctypes.data, out.size, img.ctypes.data, rcon.ctypes.data, C.byref(ch), C.byref(cw), qpd6)
+    n = _libs["emu"].emu_hevc_encode_mode(out.ctypes.data, out.size, img.ctypes.data, rcon.ctypes.data, C.byref(ch), C.byref(cw), qpd6, 1 if pair else 0)
     assert n > 0 and ch.value == hp and cw.value == wp
     return out[:n].tobytes(), rcon.reshape(hp, wp).copy()
 

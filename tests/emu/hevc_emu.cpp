@@ -7,20 +7,28 @@
 
 using namespace imcvt::hevc;
 
+extern "C" long emu_hevc_encode_mode(uint8_t *stream, size_t cap, const uint8_t *img, uint8_t *img_rcon, int *ysz, int *xsz, int qpd6, int pair);
 extern "C" long emu_hevc_encode(uint8_t *stream, size_t cap, const uint8_t *img, uint8_t *img_rcon, int *ysz, int *xsz, int qpd6)
+{
+    return emu_hevc_encode_mode(stream, cap, img, img_rcon, ysz, xsz, qpd6, 0);
+}
+// pair = 1: the two-CTA cluster kernel (spine + upper), both CTAs' threads as fibers of one emulated cluster
+extern "C" long emu_hevc_encode_mode(uint8_t *stream, size_t cap, const uint8_t *img, uint8_t *img_rcon, int *ysz, int *xsz, int qpd6, int pair)
 {
     const int H = *ysz, W = *xsz;
     const int hp = (std::min(H, 8192) + 31) / 32 * 32, wp = (std::min(W, 8192) + 31) / 32 * 32;
     Params P;
     unsigned long long len = 0;
     int overflow = 0, next = 0;
-    std::vector<uint8_t> scratch((size_t)2 * NALL * SCR_BYTES);
-    std::vector<unsigned short> lists((size_t)2 * NALL * CAND_LIST_U16, 0xDEAD);
+    std::vector<uint8_t> scratch((size_t)2 * 2 * NALL * SCR_BYTES);
+    std::vector<unsigned short> lists((size_t)2 * 2 * NALL * CAND_LIST_U16, 0xDEAD);
     P.frames = img; P.frame_stride = (size_t)H * W; P.n = 1; P.H = H; P.W = W; P.hp = hp; P.wp = wp; P.qpd6 = qpd6;
     P.out = stream; P.out_stride = cap; P.out_len = &len;
     P.rcon = img_rcon; P.rcon_stride = (size_t)hp * wp;
     P.scratch = scratch.data(); P.lists = lists.data(); P.overflow = &overflow; P.next_frame = &next;
-    emu::launch(1, NT, sizeof(Smem), [&] { hevc_frame_kernel(P); });
+    P.prof = nullptr;
+    if (pair) emu::launch(1, NT, sizeof(Smem), [&] { hevc_pair_kernel(P); }, 2);
+    else emu::launch(1, NT, sizeof(Smem), [&] { hevc_frame_kernel(P); });
     *ysz = hp; *xsz = wp;
     return overflow ? 0 : (long)len;
 }

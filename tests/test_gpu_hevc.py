@@ -13,6 +13,15 @@ from tests.test_oracle_hevc import fixture_gray, hevc_edge_images
 pytestmark = pytest.mark.gpu
 
 
+@pytest.fixture(params=[1, 2], ids=["one-cta", "cluster-pair"], autouse=True)
+def hevc_path(request):
+    """Every test runs on both device paths: one CTA per frame, and a cluster of two CTAs per frame (the default for
+    batches of at most SMs/2 frames)."""
+    imcvt_b200.debug_hevc_path(request.param)
+    yield request.param
+    imcvt_b200.debug_hevc_path(0)
+
+
 @pytest.mark.parametrize("entry", [e for e in golden_table() if e["codec"] == "hevc"],
                          ids=lambda e: f"{e['fixture']}-qpd6_{e['setting']}")
 def test_known_answers(entry):

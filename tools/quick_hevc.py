@@ -11,9 +11,11 @@ q = int(sys.argv[3]) if len(sys.argv) > 3 else 4
 h = int(sys.argv[4]) if len(sys.argv) > 4 else 1080
 w = int(sys.argv[5]) if len(sys.argv) > 5 else 1920
 iters = int(sys.argv[6]) if len(sys.argv) > 6 else 2
+path = int(sys.argv[7]) if len(sys.argv) > 7 else 0
 base = synth.batch(kind, min(n, 8), h, w)
 frames = np.concatenate([base] * ((n + len(base) - 1) // len(base)))[:n]
 imcvt_b200.init(0)
+imcvt_b200.debug_hevc_path(path)
 d = torch.from_numpy(frames).cuda()
 stride = imcvt_b200.hevc_bound(h, w)
 out = torch.empty((n, stride), dtype=torch.uint8, device="cuda")
