@@ -44,6 +44,7 @@ def parse():
     ap.add_argument("--codec", default="jls", choices=["jls", "hevc"])
     ap.add_argument("--frames", type=int, default=0, help="frames per GPU (default: the named config's 64)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-hevc", action="store_true", help="default run: skip the H.265 measurement that rides along with the JPEG-LS line")
     return ap.parse_args()
 
 
@@ -127,22 +128,72 @@ def run_reference(args, rank, world):
 # clocks
 # ------------------------------------------------------------------------------------------------
 class ClockSampler:
+    """Samples SM clocks and throttle reasons DURING the timed region: an NVML polling thread (5 ms period; the timed
+    region of the JPEG-LS config is only tens of milliseconds), falling back to `nvidia-smi -lms` when NVML is missing."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
         self.index = index
-        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
-        self.p = None
+        self.samples, self.reasons = [], set()
+        self.max_mhz = None
+        self.thread = self.stop_flag = None
+        self.f = self.p = None
+        self.nvml = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nvml = pynvml
+            # CUDA_VISIBLE_DEVICES may renumber devices: match by PCI bus id of the CUDA device when torch is there
+            try:
+                import torch
+                bus = torch.cuda.get_device_properties(index).pci_bus_id
+                dom = torch.cuda.get_device_properties(index).pci_domain_id
+                dev = torch.cuda.get_device_properties(index).pci_device_id
+                self.h = pynvml.nvmlDeviceGetHandleByPciBusId(f"{dom:08X}:{bus:02X}:{dev:02X}.0")
+            except Exception:
+                self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self.nvml = None
+
+    def _poll(self):
+        nv = self.nvml
+        names = [("hw_slowdown", nv.nvmlClocksThrottleReasonHwSlowdown), ("hw_thermal_slowdown", nv.nvmlClocksThrottleReasonHwThermalSlowdown),
+                 ("sw_thermal_slowdown", nv.nvmlClocksThrottleReasonSwThermalSlowdown), ("sw_power_cap", nv.nvmlClocksThrottleReasonSwPowerCap)]
+        while not self.stop_flag.is_set():
+            try:
+                self.samples.append(float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for nme, bit in names:
+                    if r & bit:
+                        self.reasons.add(nme)
+            except Exception:
+                pass
+            self.stop_flag.wait(0.005)
 
     def start(self):
+        if self.nvml is not None:
+            import threading
+            self.stop_flag = threading.Event()
+            self.thread = threading.Thread(target=self._poll, daemon=True)
+            self.thread.start()
+            return
         try:
+            self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
             self.p = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
                                       stdout=self.f, stderr=subprocess.DEVNULL)
         except OSError:
             self.p = None
 
     def stop(self):
+        if self.thread is not None:
+            self.stop_flag.set()
+            self.thread.join(timeout=2)
+            if not self.samples:
+                return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": ["no samples"]}
+            return {"sm_mhz": statistics.median(self.samples), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                    "samples": len(self.samples), "source": "nvml, 5 ms period"}
         if self.p is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.p.terminate()
@@ -167,7 +218,7 @@ class ClockSampler:
                     reasons.add(nme)
         if not sm:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
-        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm), "source": "nvidia-smi -lms 100"}
 
 
 def measured_peak():
@@ -194,7 +245,25 @@ def run_ours(args, rank, world, local_rank):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     imcvt_b200.init(local_rank)
 
-    codec = args.codec
+    line = measure(args, args.codec, args.steps, max(args.warmup, 3), rank, world, local_rank)
+    if args.codec == "jls" and not args.no_hevc:
+        # the metric names both encoders: the H.265 configuration (configs[2]) rides along, with fewer steps (one step is seconds)
+        sec = measure(args, "hevc", max(1, min(2, args.steps)), 1, rank, world, local_rank)
+        if rank == 0:
+            line["hevc"] = {k: sec[k] for k in ("metric", "value", "unit", "steps", "warmup", "ms_per_step", "config", "e2e", "gpu_launches", "clocks", "roofline", "cpu_baseline") if k in sec}
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def measure(args, codec, steps, warmup, rank, world, local_rank):
+    """One codec's measurement; returns the JSON line's fields on rank 0 (None elsewhere)."""
+    import torch
+    import torch.distributed as dist
+    import imcvt_b200
+    from imcvt_b200 import synth
+
     n = args.frames or (FRAMES_PER_GPU if codec == "jls" else HEVC_FRAMES_PER_GPU)
     first = rank * n                                   # disjoint frames per rank (weak scaling)
     frames = synth.batch(KIND, n, H, W, first=first)   # uint8 [n,H,W]
@@ -248,7 +317,7 @@ def run_ours(args, rank, world, local_rank):
             torch.cuda.synchronize()
 
     # --- warm-up ---
-    for _ in range(max(args.warmup, 3) if args.warmup >= 0 else 3):
+    for _ in range(warmup):
         step_device()
     barrier()
 
@@ -257,7 +326,7 @@ def run_ours(args, rank, world, local_rank):
     sampler.start()
     imcvt_b200.profile_enable(True)
     imcvt_b200.profile_reset()
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
     barrier()
     t_wall = time.perf_counter()
     for a, b in ev:
@@ -278,7 +347,7 @@ def run_ours(args, rank, world, local_rank):
     step_host()
     barrier()
     t_e2e = time.perf_counter()
-    for _ in range(args.steps):
+    for _ in range(steps):
         step_host()
     barrier()
     t_e2e = time.perf_counter() - t_e2e
@@ -308,7 +377,7 @@ def run_ours(args, rank, world, local_rank):
         cpu = {"value": spix / dt / 1e6, "unit": "Mpixels/s", "cores": threads, "kind": kind, "sample": sample}
 
     if rank == 0:
-        K = args.steps
+        K = steps
         value = world * npix * K / (dev_ms / 1e3) / 1e6
         peak, peak_src = measured_peak()
         # dominant kernel = the one with the largest share of the timed region (per-kernel CUDA events in the library)
@@ -331,7 +400,7 @@ def run_ours(args, rank, world, local_rank):
             roof = {"bound": "hbm", "achieved": None, "peak": peak, "unit": "GB/s", "frac": None, "traffic": None}
         line = {
             "metric": f"Mpixels/s encode ({'JLS near=0' if codec == 'jls' else 'H.265-I qpd6=4 (QP 28)'})",
-            "value": value, "unit": "Mpixels/s", "n_gpus": world, "steps": K, "warmup": max(args.warmup, 3),
+            "value": value, "unit": "Mpixels/s", "n_gpus": world, "steps": K, "warmup": warmup,
             "ms_per_step": dev_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u8", "data": "synthetic",
             "config": {
@@ -339,7 +408,7 @@ def run_ours(args, rank, world, local_rank):
                              if codec == "jls" else
                              f"H.265 intra qpd6={HEVC_QPD6} (QP 28; 'QP 27' is not representable), batch {n} synthetic ({KIND}) 1920x1080 gray8 frames per GPU"),
                 "frames_per_gpu": n, "height": H, "width": W, "parallelism": f"frame-sharded x{world}",
-                "l2": "inputs (132.7 MB) plus ~2.8 GB of per-step intermediates exceed the 126 MB L2; no explicit flush",
+                "l2": "the inputs of a step (132.7 MB per GPU) exceed the 126 MB L2 and are read from HBM again every step; no explicit flush",
                 "bytes_out_per_step_rank0": total_bytes,
             },
             "e2e": {"value": world * npix * K / (e2e_ms / 1e3) / 1e6, "unit": "Mpixels/s",
@@ -351,9 +420,8 @@ def run_ours(args, rank, world, local_rank):
         }
         if cpu is not None:
             line["cpu_baseline"] = cpu
-        print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
+        return line
+    return None
 
 
 def main():

@@ -47,7 +47,7 @@ namespace hevc {
 
 // development aid: cycles of thread 0 between phase marks, accumulated per (CU level, phase) in Params::prof
 #if defined(IMCVT_HEVC_PROF) && !defined(IMCVT_HOST_EMU)
-#define HPROF(K, id) do { if (threadIdx.x == 0) { const long long t__ = clock64(); atomicAdd(&(K).P->prof[(id)], (unsigned long long)(t__ - (K).prof_t)); (K).prof_t = t__; } } while (0)
+#define HPROF(K, id) do { if (threadIdx.x == 0 && (K).prof_on) { const long long t__ = clock64(); atomicAdd(&(K).P->prof[(id)], (unsigned long long)(t__ - (K).prof_t)); (K).prof_t = t__; } } while (0)
 #define TPROF(sm, id) do { if (threadIdx.x == 0) { const long long t__ = clock64(); atomicAdd(&(sm).prof[(id)], (unsigned long long)(t__ - (sm).prof_t)); (sm).prof_t = t__; } } while (0)
 #define TPROF_START(sm) do { if (threadIdx.x == 0) (sm).prof_t = clock64(); } while (0)
 #else
@@ -65,6 +65,12 @@ namespace hevc {
 #define HEVC_BIGFN __device__ __noinline__
 #else
 #define HEVC_BIGFN __device__ __forceinline__
+#endif
+// the phases of a coding unit are real functions: one copy of each in the instruction cache however often they are used
+#ifdef IMCVT_HOST_EMU
+#define HEVC_PHASE __device__
+#else
+#define HEVC_PHASE __device__ __noinline__
 #endif
 
 #include "hevc_tables.h"
@@ -212,11 +218,10 @@ struct RdK {
     }
 };
 
+IMCVT_CONSTANT int c_level_rate[6] = {0, 70000, 90000, 92000, 157536, 190304};
 __device__ __forceinline__ int level_rate(int level)                                   // estimateCoeffRate :526-535
 {
-    if (level < 6) {
-        return level == 0 ? 0 : level == 1 ? 70000 : level == 2 ? 90000 : level == 3 ? 92000 : level == 4 ? 157536 : 190304;
-    }
+    if (level < 6) return c_level_rate[level];
     const int i = 31 - __clz(level - 5);                // number of exp-Golomb prefix steps for level - 6
     return 92000 + ((3 + i * 2 + 1) << 15);
 }
@@ -886,7 +891,8 @@ HEVC_BIGFN TuResult tu_pipeline(Smem &sm, int warp, int lane, bool active, const
             const int lo = level - 2 > 0 ? level - 2 : 0;
             int best = I32MAX, pick = 0;
             if (level == 0) level = -1;                     // a lone level-0 candidate can only confirm pick = 0
-            for (; level >= lo; level--) {
+#pragma unroll 1
+            for (; level >= lo; level--) {                  // a real loop: unrolled, this body was 40% of the kernel's code
                 const int d1 = iabs(d - (level << sft)) >> dist_sft;
                 const int dist = (d1 < 46340 ? d1 * d1 : I32MAX) >> 7;
                 const int cost = rd.cost(dist, level_rate(level));
@@ -1035,6 +1041,7 @@ struct Ctx {
     int qpd6;
     RdK rd;
     long long prof_t;
+    bool prof_on;               // development build: this CTA's thread 0 feeds the phase counters (the spine of a pair)
 };
 
 template <int SZ> struct Level { static constexpr int v = SZ == 32 ? 0 : SZ == 16 ? 1 : 2; static constexpr int set = SZ == 32 ? 0 : 1; };
@@ -1177,7 +1184,7 @@ __device__ __forceinline__ void cu_split_cost(Ctx &K)
 }
 
 template <int SZ>
-__device__ void eval_a1(Ctx &K)
+HEVC_PHASE void eval_a1(Ctx &K)
 {
     Smem &sm = *K.sm;
     constexpr int LV = Level<SZ>::v, SET = Level<SZ>::set;
@@ -1204,7 +1211,7 @@ __device__ void eval_a1(Ctx &K)
 }
 
 template <int SZ>
-__device__ void eval_a4(Ctx &K)
+HEVC_PHASE void eval_a4(Ctx &K)
 {
     Smem &sm = *K.sm;
     constexpr int LV = Level<SZ>::v, SET = Level<SZ>::set, H = SZ / 2;
@@ -1237,7 +1244,7 @@ __device__ void eval_a4(Ctx &K)
 }
 
 template <int SZ>
-__device__ void eval_b(Ctx &K)
+HEVC_PHASE void eval_b(Ctx &K)
 {
     Smem &sm = *K.sm;
     constexpr int LV = Level<SZ>::v, SET = Level<SZ>::set;
@@ -1292,7 +1299,7 @@ __device__ __forceinline__ void cu_decide_commit(Ctx &K)
     __syncthreads();
 }
 
-__device__ void search_cu8(Ctx &K, int y0, int x0, int avail);
+HEVC_PHASE void search_cu8(Ctx &K, int y0, int x0, int avail);
 
 // one CTA: a unit is searched depth first, the evaluation of its own candidates after its four smaller units
 template <int SZ>
@@ -1330,7 +1337,7 @@ __device__ void search_cu(Ctx &K, int y0, int x0, int avail)
 //                 then the stand-alone trials on fresh coders, the choice and the kept 4x4 reconstruction
 //   warps 2,3     CABAC trials of the four-TU candidates;  warp 0: the NxN trial (:1528-1545)
 // and the decision follows the reference order: one-TU modes, four-TU modes, NxN, a later candidate wins ties.
-__device__ void search_cu8(Ctx &K, int y0, int x0, int avail)
+HEVC_PHASE void search_cu8(Ctx &K, int y0, int x0, int avail)
 {
     Smem &sm = *K.sm;
     constexpr int SZ = 8, LV = 2, H = 4, SET = 1, RT = 320;                   // RT: threads of the round warps
@@ -1744,19 +1751,25 @@ __device__ inline void encode_frame(Ctx &K, int f, int rank)
                 for (int j = 0; j < 4; j++) {
                     cu_enter<16>(K, sub.y[j], sub.x[j], sub.avail[j]);
                     push_entry<16>(K);
+                    HPROF(K, 50);
                     HEVC_PAIR_SYNC();                                       // the upper CTA may evaluate this unit
+                    HPROF(K, 51);
                     put_split_flag<16>(K);
                     const SubUnits<16> s8(sub.y[j], sub.x[j], sub.avail[j]);
                     for (int k = 0; k < 4; k++) search_cu8(K, s8.y[k], s8.x[k], s8.avail[k]);
                     cu_split_cost<16>(K);
+                    HPROF(K, 52);
                     HEVC_PAIR_SYNC();                                       // its result is here
+                    HPROF(K, 53);
                     cu_decide_commit<16, true>(K);
                     push_rc_block(K, sub.y[j], sub.x[j]);
                 }
                 cu_split_cost<32>(K);
                 cu_decide_commit<32, true>(K);
                 finish_ctu(K, rcon, y, x);
+                HPROF(K, 54);
                 HEVC_PAIR_SYNC();                                           // the reconstruction is in global memory
+                HPROF(K, 55);
             } else {
                 __syncthreads();
                 for (int j = 0; j < 4; j++) {
@@ -1798,6 +1811,7 @@ __device__ __forceinline__ void frame_kernel_body(const Params &P)
         K.peer_scratch[q] = P.scratch + ((size_t)(blockIdx.x ^ 1) * 2 + q) * NALL * SCR_BYTES;
     }
     K.out = nullptr;
+    K.prof_on = rank == 0; K.prof_t = 0;
     build_tables(sm, P.qpd6);
 #if defined(IMCVT_HEVC_PROF) && !defined(IMCVT_HOST_EMU)
     K.prof_t = clock64();

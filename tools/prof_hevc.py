@@ -34,6 +34,7 @@ for lv, nm in enumerate(["CU32", "CU16", "CU8"]):
         c = v[lv * 16 + p]
         if c > 0:
             print(f"  {nm} {pn:20s} {c/nctu:10.0f} cyc/CTU  {100*c/tot:5.1f}%")
+print(f"  pair spine: enter+push {v[50]/nctu:.0f}  wait#1 {v[51]/nctu:.0f}  split-cost {v[52]/nctu:.0f}  wait#2 {v[53]/nctu:.0f}  decide..finish {v[54]/nctu:.0f}  wait#3 {v[55]/nctu:.0f}")
 print(f"  CTU load {v[48]/nctu:10.0f}  {100*v[48]/tot:5.1f}%   CTU store+terminate {v[49]/nctu:10.0f}  {100*v[49]/tot:5.1f}%")
 stages = ["refs+smooth", "predict", "fwd transform", "rdoq", "last/cg scan", "dequant+inverse", "recon+sse", "binarize"]
 for sc, nm in enumerate(["TU4", "TU8", "TU16", "TU32"]):
