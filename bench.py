@@ -262,7 +262,7 @@ def measure(args, codec, steps, warmup, rank, world, local_rank):
     import torch
     import torch.distributed as dist
     import imcvt_b200
-    from imcvt_b200 import synth
+    from imcvt_b200 import shard, synth
 
     n = args.frames or (FRAMES_PER_GPU if codec == "jls" else HEVC_FRAMES_PER_GPU)
     first = rank * n                                   # disjoint frames per rank (weak scaling)
@@ -286,10 +286,9 @@ def measure(args, codec, steps, warmup, rank, world, local_rank):
         else:
             imcvt_b200.encode_hevc_device(d_frames, HEVC_QPD6, d_out, d_len, None, sptr)
         if world > 1:
-            # the path's only exchange: per-frame stream sizes -> global offsets on every rank
-            sizes = torch.empty(world * n, dtype=torch.int64, device="cuda")
-            dist.all_gather_into_tensor(sizes, d_len)
-            return sizes
+            # the path's only exchange: per-frame stream sizes -> global offsets on every rank (imcvt_b200/shard.py)
+            sizes = shard.gather_sizes(d_len, world * n, world)
+            return shard.global_offsets(sizes)
         return d_len
 
     # --- host-buffer path (e2e) ---

@@ -83,3 +83,31 @@ def test_small_output_slot_is_an_error_not_a_crash():
     ln = (C.c_size_t * 1)()
     rc = imcvt_b200.lib().imcvtEncodeBatchHEVC(img.ctypes.data, 64 * 64, 1, 64, 64, 0, out.ctypes.data, 600, C.cast(ln, C.c_void_p), None, 0)
     assert rc == 1
+
+
+def test_full_hd_streams_decode_to_the_encoders_reconstruction(hevc_path):
+    """BASELINE-size frames (1920x1080) cannot be checked against the CPU oracle inside a test (45 s per frame), so an
+    independent decoder stands in: FFmpeg (through OpenCV) must decode every emitted stream to exactly the reconstruction
+    the encoder kept -- at qpd6 <= 1 the stream's in-loop deblocking leaves the picture unchanged.
+    The first CTU row of frame 0 is also compared with the oracle bit for bit."""
+    cv2 = pytest.importorskip("cv2")
+    frames = synth.batch("natural", 2, 1080, 1920)
+    streams, rcon = imcvt_b200.encode_hevc_batch(frames, 1)
+    assert rcon.shape == (2, 1088, 1920)
+    with tempfile.TemporaryDirectory() as d:
+        for i, s in enumerate(streams):
+            path = os.path.join(d, f"f{i}.h265")
+            open(path, "wb").write(s)
+            cap = cv2.VideoCapture(path, cv2.CAP_FFMPEG)
+            cap.set(cv2.CAP_PROP_CONVERT_RGB, 0)
+            ok, img = cap.read()
+            assert ok, f"frame {i}: FFmpeg could not decode the stream"
+            y = img.reshape(-1)[: 1088 * 1920].reshape(1088, 1920)
+            assert np.array_equal(y, rcon[i]), f"frame {i}: decoded picture differs from the encoder's reconstruction"
+            psnr = 10 * np.log10(255.0 ** 2 / np.mean((y[:1080].astype(np.float64) - frames[i]) ** 2))
+            assert psnr > 45, psnr
+    # one CTU row against the oracle: the first 32 rows of the picture are coded before anything below them is read
+    s_row, r_row = imcvt_b200.encode_hevc_batch(frames[:1, :32], 1)
+    want, want_r = oracle_hevc(frames[0, :32], 1)
+    assert s_row[0] == want and np.array_equal(r_row[0], want_r)
+    assert np.array_equal(rcon[0][:32], want_r)      # intra prediction never reads below a CTU row
