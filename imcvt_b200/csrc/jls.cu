@@ -840,10 +840,9 @@ int encode_device(const uint8_t *d_frames, size_t frame_stride, int n, int is_rg
             IMCVT_CUDA(cudaFuncSetAttribute(tile::jls_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(tile::Smem)));
             attr_set = true;
         }
-        // Two SMs per plane (cluster of two CTAs: producers | chains + packers) only on request: measured on B200 it is
-        // not faster than one CTA per plane (7.2 vs 6.9 ms for 64 x 1080p) because a tile's tick is bounded by its
-        // longest context chain, which runs on one warp either way.  See DESIGN.md section 3.
-        const bool pair = E.jls_path == 3;
+        // Few planes: two SMs per plane (a cluster of two CTAs: rank 0 = producers, rank 1 = two chain stages + packers).
+        // Many planes: one CTA per plane keeps every SM on a plane of its own.
+        const bool pair = E.jls_path == 3 || (E.jls_path == 0 && 2 * P <= E.sm_count);
         IMCVT_CUDA(cudaMemsetAsync(next, 0, sizeof(int), st));
         tile::Params TP;
         TP.pix = planes; TP.plane_stride = plane_stride; TP.P = P; TP.W = (int)W; TP.H = (int)H;

@@ -31,6 +31,7 @@
 #define JLS_PAIR_RANK()  (emu::S().tid / imcvt::jls::tile::NTHREADS)
 #define JLS_PAIR_TID()   (emu::S().tid % imcvt::jls::tile::NTHREADS)
 #define JLS_PAIR_SMEM(r) (emu::S().smem + (size_t)(r) * imcvt::jls::tile::SMEM_STRIDE)
+#define JLS_OWN_SMEM(r)  JLS_PAIR_SMEM(r)
 #define JLS_PAIR_SYNC()  __syncthreads()
 #define JLS_CLUSTER_DIMS
 #else
@@ -42,6 +43,7 @@ extern __shared__ __align__(16) unsigned char jls_dyn_smem[];
 #define JLS_PAIR_RANK()  ((int)cooperative_groups::this_cluster().block_rank())
 #define JLS_PAIR_TID()   ((int)threadIdx.x)
 #define JLS_PAIR_SMEM(r) (cooperative_groups::this_cluster().map_shared_rank(jls_dyn_smem, (r)))
+#define JLS_OWN_SMEM(r)  (jls_dyn_smem)      /* the CTA's own image through the shared window: LDS/STS, not generic LD/ST */
 #define JLS_PAIR_SYNC()  cooperative_groups::this_cluster().sync()
 #define JLS_CLUSTER_DIMS __cluster_dims__(2, 1, 1)
 #endif
@@ -149,23 +151,26 @@ struct Smem {
     uint32_t sorted[2][TSMAX];      // records of a tile, grouped by context, raster order inside a context
     uint32_t codes[2][CODE_SLOTS];  // Golomb code per sample, raster order (code_idx)
     uint32_t temp_rec[TSMAX];       // producers: bucket | record payload << 9 per sample, raster order (pass 1 -> pass 2)
-    uint16_t bstart[2][HSLOTS + 2]; // start of every context's slice inside sorted[]
+    uint16_t bstart[3][HSLOTS + 2]; // start of every context's slice inside the sorted tile (third entry: pair kernel)
     alignas(4) uint16_t cursor[NWARPS][HSLOTS + 2];       // producers: per-warp histogram, then scatter cursor (pair kernel: every warp of rank 0)
     uint32_t ubits[UBITS_WORDS];    // packer: un-stuffed bits of one tile
     uint32_t chunk_bits[8];         // packer: code bits per chunk
     uint8_t  lens[2][LEN_SLOTS];    // code length per sample (0 = nothing), raster order (len_idx)
     uint8_t  pix[3][PIXBUF];        // rows of a tile (+ the row above, + the sample two rows above column 0)
     int ctx[NCTX][4];               // (A, B, C, N) of every regular context of the plane in flight
+    int ctx_a[NCTX];                // pair kernel: A lives with the second chain stage
     int run_state[8];               // run_index, A/B/N of the two run-interruption contexts, pending run length
-    uint16_t order[2][CHAIN_WARPS * 32];   // chain thread -> bucket for a tile: buckets sorted by slice size (big slices share warps)
+    uint16_t order[3][CHAIN_WARPS * 32];   // chain thread -> bucket for a tile: buckets sorted by slice size (big slices share warps)
     int cls_cnt[16], cls_pos[16];
     uint32_t blk_tot[32];           // producers: histogram totals per block of 32 buckets
     int8_t qlut[512];               // quantised gradient of g at [g + 255]
     int plane;
 };
+// sorted tile number b: the pair kernel keeps three tiles in flight; the consumer CTA has no use for temp_rec
+__device__ __forceinline__ uint32_t *sorted_buf(Smem &sm, int b) { return b < 2 ? sm.sorted[b] : sm.temp_rec; }
 constexpr size_t SMEM_STRIDE = (sizeof(Smem) + 127) & ~(size_t)127;     // host emulator: distance of the two images of a pair
 
-// records: regular sample  pos | (sign*(x-MED) + 255) << 13 | clamp window << 22     (rewritten by its chain as pos | (e & 255) << 13 | k << 21 | map << 25)
+// records: regular sample  pos | (sign*(x-MED) + 256) << 13 | clamp window << 22     (rewritten by its chain as pos | (e & 255) << 13 | k << 21 | map << 25)
 //          run event       pos | run length << 13 | row-end flag << 28 | partial flag << 29 (the run goes on in the next segment) | first column << 30
 __device__ __forceinline__ uint8_t *pix_row(uint8_t *buf, int local_row, int W) { return buf + 16 + (local_row + 1) * W; }
 
@@ -278,7 +283,7 @@ __device__ __forceinline__ void classify_segment(Smem &sm, uint8_t *pb, int W, i
                 bucket = (neg ? -Q : Q) - 1;
                 const int d0 = neg ? med - s.x : s.x - med;
                 const int nlo = neg ? 255 - med : med;
-                rec = (uint32_t)(d0 + 255) | ((uint32_t)nlo << 9);
+                rec = (uint32_t)(d0 + 256) | ((uint32_t)nlo << 9);
             } else if (is_int || is_eol || is_part) {
                 bucket = NCTX;
                 const uint32_t sm_ = S & lane_le;
@@ -316,14 +321,14 @@ constexpr int NBLK = (NBUCKET + 1 + 31) / 32;      // blocks of 32 histogram slo
 
 // sm: the producers' own shared memory; cons: where the sorted tile goes (the same image, or the partner CTA's)
 template <int NPW>
-__device__ __forceinline__ void producer_tick(Smem &sm, Smem &cons, const Params &P, const uint8_t *img, int rows_per_tile, int t, int ntiles, int pw, int lane)
+__device__ __forceinline__ void producer_tick(Smem &sm, Smem &cons, const Params &P, const uint8_t *img, int rows_per_tile, int t, int ntiles, int nbuf, int pw, int lane)
 {
     constexpr int PROD_WARPS = NPW, PROD_THREADS = NPW * 32;
     const int W = P.W, H = P.H;
     const int ptid = pw * 32 + lane;
     JPROF_T0();
     if (t < ntiles) {
-        const int buf = t & 1;
+        const int buf = t % nbuf;                  // tiles in flight: 2 (one CTA) or 3 (pair)
         uint8_t *pb = sm.pix[t % 3];
         const int r0 = t * rows_per_tile, R = min(H, r0 + rows_per_tile) - r0;
         // work units = 32-sample chunks of the tile's rows in raster order; every warp takes an equal contiguous range of
@@ -380,7 +385,7 @@ __device__ __forceinline__ void producer_tick(Smem &sm, Smem &cons, const Params
         JLS_NAMED_BARRIER(1, PROD_THREADS);
         for (int r = ra; r <= rb; r++) {
             const int c0 = max(ua - r * chunks, 0) * 32, c1 = min(W, min(ub - r * chunks, chunks) * 32);
-            scatter_segment(sm, cons.sorted[buf], W, r, c0, c1, lane, h);
+            scatter_segment(sm, sorted_buf(cons, buf), W, r, c0, c1, lane, h);
         }
         JPROF(11, ptid == 0);
         // chain thread i of the tile takes the i-th biggest slice (by size class): similar slices share a warp; the run
@@ -417,7 +422,7 @@ struct RunState { int run_index, A0, B0, N0, A1, B1, N1, pending; };
 // flag are outputs.  No branches: a warp's chain threads run different contexts in lock step.
 __device__ __forceinline__ uint32_t regular_step(uint32_t rec, RegularState &s)
 {
-    const int d0 = (int)((rec >> 13) & 0x1FFu) - 255;   // sign * (x - MED)
+    const int d0 = (int)((rec >> 13) & 0x1FFu);         // sign * (x - MED) + 256: the bias vanishes in the modulo reduction
     const int nlo = (int)((rec >> 22) & 0xFFu);         // sign * (Px - MED) = clamp(C, lo, hi), lo = -nlo, hi = 255 - nlo  (:349 + the [0,255] clip)
     const int dlo = d0 + nlo, dhi = dlo - 255;          // d0 - lo, d0 - hi
     const int k = golomb_k(s.A, s.N);
@@ -701,6 +706,92 @@ __device__ __forceinline__ void chain_tick(Smem &sm, const Params &P, int t, int
     JPROF(4, tid == 0);
 }
 
+// ---- pair kernel: the chain in two stages ----------------------------------------------------------
+// A warp issues one integer instruction every other cycle, so the tick of a tile is (samples of its biggest context) x
+// (instructions of a chain step) x 2 cycles.  The pair kernel therefore keeps only the true recurrence on the critical
+// thread -- stage 1: C -> error -> B -> bias, plus N -- and leaves A, the Golomb parameter, the mapping and the code to
+// stage 2, which walks the same slice one tick later on other warps.
+struct C1State { int B, C, N; };
+__device__ __forceinline__ uint32_t chain1_step(uint32_t rec, C1State &s)
+{
+    const int d0 = (int)((rec >> 13) & 0x1FFu);         // sign * (x - MED) + 256
+    const int dlo = d0 + (int)(rec >> 22), dhi = dlo - 255;     // d0 - lo, d0 - hi of the clamp window (regular_step)
+    const int rs = s.N >> 6;                            // N <= 64: halve when it is 64 (:378-383)
+    const int N1 = (s.N >> rs) + 1;
+    const uint32_t cond = (uint32_t)(2 * s.B + s.N - 1) >> 31;  // 2B <= -N: the mapping of :367 applies when k turns out 0
+    const int e = (int)(int8_t)max(min(d0 - s.C, dlo), dhi);
+    const uint32_t out = (rec & 0x1FFFu) | ((uint32_t)(e & 0xFF) << 13) | (cond << 21) | ((uint32_t)s.N << 22);
+    const int B1 = (s.B + e) >> rs;
+    s.N = N1;
+    const int sdn = (B1 + N1 - 1) >> 31, sup = (-B1) >> 31;
+    const int dC = sdn - sup;
+    s.B = min(max(B1 - N1 * dC, 1 - N1), 0);
+    s.C = min(max(s.C + dC, -128), 127);
+    return out;
+}
+__device__ __forceinline__ void chain1_tick(Smem &sm, int t, int tid)
+{
+    const int buf = t % 3;
+    uint32_t *rec = sorted_buf(sm, buf);
+    if (tid < NCTX) {
+        const int bucket = sm.order[buf][tid];
+        const int b0 = sm.bstart[buf][bucket], b1 = sm.bstart[buf][bucket + 1];
+        if (b1 > b0) {
+            C1State cs; cs.B = sm.ctx[bucket][1]; cs.C = sm.ctx[bucket][2]; cs.N = sm.ctx[bucket][3];
+            uint32_t r = rec[b0];
+            for (int i = b0; i < b1; i++) {
+                const uint32_t cur = r;
+                if (i + 1 < b1) r = rec[i + 1];
+                rec[i] = chain1_step(cur, cs);
+            }
+            sm.ctx[bucket][1] = cs.B; sm.ctx[bucket][2] = cs.C; sm.ctx[bucket][3] = cs.N;
+        }
+    }
+}
+// stage 2, CHAIN2_WARPS warps: thread j walks the j-th biggest and the j-th smallest slice of the tile (A, k, map, Golomb
+// code into the raster slots); the last thread walks the run events
+constexpr int CHAIN2_WARPS = 6;
+__device__ __forceinline__ void chain2_slice(Smem &sm, uint32_t *rec, int bucket, int buf)
+{
+    const int b0 = sm.bstart[buf][bucket], b1 = sm.bstart[buf][bucket + 1];
+    if (b1 <= b0) return;
+    int A = sm.ctx_a[bucket];
+    uint32_t w = rec[b0];
+    for (int i = b0; i < b1; i++) {
+        const uint32_t cur = w;
+        if (i + 1 < b1) w = rec[i + 1];
+        const int e = (int)(int8_t)(cur >> 13), N = (int)((cur >> 22) & 0x7Fu);
+        const int k = golomb_k(A, N);
+        const uint32_t map = (k == 0) ? (cur >> 21) & 1u : 0u;
+        rec[i] = (cur & 0x1FFFFFu) | ((uint32_t)k << 21) | (map << 25);     // what regular_code reads: pos | error | k | map
+        A = (A + (e < 0 ? -e : e)) >> (N >> 6);
+    }
+    sm.ctx_a[bucket] = A;
+}
+__device__ __forceinline__ void chain2_tick(Smem &sm, int t, int W, int j)
+{
+    const int buf = t % 3, cb = t & 1;
+    uint32_t *rec = sorted_buf(sm, buf);
+    if (j < NCTX / 2) {
+        chain2_slice(sm, rec, sm.order[buf][j], buf);
+        chain2_slice(sm, rec, sm.order[buf][NCTX - 1 - j], buf);
+    } else if (j == CHAIN2_WARPS * 32 - 1) {
+        const int b0 = sm.bstart[buf][NCTX], b1 = sm.bstart[buf][NCTX + 1];
+        if (b1 > b0) {
+            RunState us;
+            us.run_index = sm.run_state[0]; us.A0 = sm.run_state[1]; us.B0 = sm.run_state[2]; us.N0 = sm.run_state[3];
+            us.A1 = sm.run_state[4]; us.B1 = sm.run_state[5]; us.N1 = sm.run_state[6]; us.pending = sm.run_state[7];
+            for (int i = b0; i < b1; i++) run_step(rec[i], us, sm.pix[t % 3], W, sm.codes[cb], sm.lens[cb]);
+            sm.run_state[0] = us.run_index; sm.run_state[1] = us.A0; sm.run_state[2] = us.B0; sm.run_state[3] = us.N0;
+            sm.run_state[4] = us.A1; sm.run_state[5] = us.B1; sm.run_state[6] = us.N1; sm.run_state[7] = us.pending;
+        }
+    }
+    JLS_NAMED_BARRIER(5, CHAIN2_WARPS * 32);
+    // all stage-2 threads: Golomb codes of the tile's regular samples into their raster slots
+    const int nreg = sm.bstart[buf][NCTX];
+    for (int i = j; i < nreg; i += CHAIN2_WARPS * 32) regular_code(rec[i], sm.codes[cb], sm.lens[cb]);
+}
+
 // PAIR = false: one CTA per plane, its warps split into chains | producers | packers.
 // PAIR = true : a cluster of two CTAs per plane.  Rank 0: every warp is a producer and scatters the sorted tile into
 //               the shared memory of rank 1.  Rank 1: chains | packers | the remaining warps stage the rows the run
@@ -714,14 +805,18 @@ __device__ __forceinline__ void tile_body(const Params &P)
     const int hw_tid = PAIR ? JLS_PAIR_TID() : (int)threadIdx.x;
     const int lane = hw_tid & 31, warp = NWARPS - 1 - (hw_tid >> 5);
     const int tid = warp * 32 + lane;
-    Smem &sm   = *reinterpret_cast<Smem *>(PAIR ? (unsigned char *)JLS_PAIR_SMEM(rank) : (unsigned char *)JLS_DYN_SMEM());
+    Smem &sm   = *reinterpret_cast<Smem *>(PAIR ? (unsigned char *)JLS_OWN_SMEM(rank) : (unsigned char *)JLS_DYN_SMEM());
+    // where the producers put the sorted tile: the same image, or rank 1's through distributed shared memory
     Smem &cons = *reinterpret_cast<Smem *>(PAIR ? (unsigned char *)JLS_PAIR_SMEM(1) : (unsigned char *)JLS_DYN_SMEM());
     const int W = P.W, H = P.H;
     const int rows_per_tile = max(1, TSMAX / W);
     const int ntiles = (H + rows_per_tile - 1) / rows_per_tile;
     const bool producer_cta = !PAIR || rank == 0, consumer_cta = !PAIR || rank == 1;
-    constexpr int PACK0 = PAIR ? CHAIN_WARPS : CHAIN_WARPS + PROD_WARPS;          // first packer warp
-    constexpr int STAGE0 = CHAIN_WARPS + PACK_WARPS;                              // pair, rank 1: first staging warp
+    constexpr int CHAIN2_0 = CHAIN_WARPS;                                         // pair, rank 1: first warp of chain stage 2
+    constexpr int PACK0 = PAIR ? CHAIN_WARPS + CHAIN2_WARPS : CHAIN_WARPS + PROD_WARPS;     // first packer warp
+    constexpr int STAGE0 = PACK0 + PACK_WARPS;                                    // pair, rank 1: first staging warp
+    static_assert(!PAIR || STAGE0 < NWARPS, "the consumer CTA needs at least one staging warp");
+    constexpr int NTICK_EXTRA = PAIR ? 3 : 2;                                     // pipeline depth behind the producers
 
     if (consumer_cta) for (int i = tid; i < 2 * LEN_SLOTS / 4; i += NTHREADS) reinterpret_cast<uint32_t *>(&sm.lens[0][0])[i] = 0;
     if (producer_cta) build_qlut(sm.qlut, tid, NTHREADS);
@@ -737,25 +832,31 @@ __device__ __forceinline__ void tile_body(const Params &P)
         PackState ps; ps.out_pos = 0; ps.carry_bits = 0; ps.carry = 0; ps.pz = 0; ps.dst = nullptr; ps.cap = 0;
         if (consumer_cta) {
             // :256-261 (a_init = 4 for RANGE 256), :250, :263-267
-            for (int i = tid; i < NCTX; i += NTHREADS) { sm.ctx[i][0] = 4; sm.ctx[i][1] = 0; sm.ctx[i][2] = 0; sm.ctx[i][3] = 1; }
+            for (int i = tid; i < NCTX; i += NTHREADS) { sm.ctx[i][0] = 4; sm.ctx[i][1] = 0; sm.ctx[i][2] = 0; sm.ctx[i][3] = 1; sm.ctx_a[i] = 4; }
             if (tid < 8) sm.run_state[tid] = (tid == 1 || tid == 4) ? 4 : (tid == 3 || tid == 6) ? 1 : 0;
             ps.dst = plane_dst(P.L, p, ps.cap);
         }
         if (producer_cta) stage_tile(sm.pix[0], img, W, H, rows_per_tile, 0, tid, NTHREADS);
         if (PAIR) JLS_PAIR_SYNC(); else __syncthreads();
 
-        for (int tick = 0; tick < ntiles + 2; tick++) {
+        for (int tick = 0; tick < ntiles + NTICK_EXTRA; tick++) {
             JPROF_T0();
 #if !(defined(IMCVT_JLS_PROF) && !defined(IMCVT_HOST_EMU))
             const long long jp_t0 = 0;
 #endif
             if (PAIR) {
                 if (rank == 0) {
-                    producer_tick<NWARPS>(sm, cons, P, img, rows_per_tile, tick, ntiles, warp, lane);
+                    producer_tick<NWARPS>(sm, cons, P, img, rows_per_tile, tick, ntiles, 3, warp, lane);
+                    JPROF(1, tid == 0);
                 } else if (warp < CHAIN_WARPS) {
-                    if (tick >= 1 && tick - 1 < ntiles) chain_tick(sm, P, tick - 1, W, tid, jp_t0);
+                    if (tick >= 1 && tick - 1 < ntiles) chain1_tick(sm, tick - 1, tid);
+                    JPROF(0, tid == 0);
+                } else if (warp < PACK0) {
+                    if (tick >= 2 && tick - 2 < ntiles) chain2_tick(sm, tick - 2, W, tid - CHAIN2_0 * 32);
+                    JPROF(6, tid == CHAIN2_0 * 32);
+                    JPROF(7, tid == PACK0 * 32 - 1);
                 } else if (warp < STAGE0) {
-                    const int t = tick - 2;
+                    const int t = tick - 3;
                     if (t >= 0 && t < ntiles) {
                         const int r0 = t * rows_per_tile, n = (min(H, r0 + rows_per_tile) - r0) * W;
                         packer_tile(sm, P, ps, sm.codes[t & 1], sm.lens[t & 1], n, t == ntiles - 1, warp - PACK0, lane);
@@ -764,10 +865,12 @@ __device__ __forceinline__ void tile_body(const Params &P)
                     // the rows of tile `tick`, read by its run events one tick later
                     if (tick < ntiles) stage_tile(sm.pix[tick % 3], img, W, H, rows_per_tile, tick, tid - STAGE0 * 32, NTHREADS - STAGE0 * 32);
                 }
+                JPROF(2, rank == 1 && warp == PACK0 && lane == 0);
                 JLS_PAIR_SYNC();
+                JPROF(3, rank == 1 && tid == 0);
             } else {
                 if (warp >= CHAIN_WARPS && warp < CHAIN_WARPS + PROD_WARPS) {
-                    producer_tick<PROD_WARPS>(sm, sm, P, img, rows_per_tile, tick, ntiles, warp - CHAIN_WARPS, lane);
+                    producer_tick<PROD_WARPS>(sm, sm, P, img, rows_per_tile, tick, ntiles, 2, warp - CHAIN_WARPS, lane);
                     JPROF(1, warp == CHAIN_WARPS && lane == 0);
                     JPROF(5, warp == CHAIN_WARPS + PROD_WARPS - 1 && lane == 0);
                 } else if (warp < CHAIN_WARPS) {

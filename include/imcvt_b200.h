@@ -81,9 +81,10 @@ long imcvtLaunchCount(void);                         /* total kernels launched s
 
 /* Debug / cross-check: force the fully serial JPEG-LS scan kernel also for NEAR=0 (default 0). */
 void imcvtDebugJLSForceSerial(int on);
-/* Debug / cross-check of the NEAR=0 paths: 0 = default (planes up to 6144 wide: shared-memory tile kernel, one CTA
- * per plane), 1 = force the multi-kernel pipeline that wider planes use, 2 = same as 0, 3 = the tile kernel on a
- * cluster of two CTAs per plane (rank 0 produces sorted tiles into the shared memory of rank 1). */
+/* Debug / cross-check of the NEAR=0 paths: 0 = default (planes up to 6144 wide: shared-memory tile kernel, on a
+ * cluster of two CTAs per plane when the batch has at most SMs/2 planes, else one CTA per plane), 1 = force the
+ * multi-kernel pipeline that wider planes use, 2 = force one CTA per plane, 3 = force the two-CTA cluster (rank 0
+ * produces sorted tiles into the shared memory of rank 1). */
 void imcvtDebugJLSPath(int path);
 /* Debug / cross-check of the H.265 paths: 0 = default (a cluster of two CTAs per frame when the batch has at most SMs/2
  * frames, else one CTA per frame), 1 = force one CTA per frame, 2 = force the two-CTA cluster. */
