@@ -7,7 +7,7 @@
 namespace imcvt {
 namespace jls {
 int encode_device(const uint8_t *d_frames, size_t frame_stride, int n, int is_rgb, uint32_t H, uint32_t W, int near_,
-                  uint8_t *d_out, size_t out_stride, uint64_t *d_out_len, int *d_overflow, cudaStream_t st);
+                  uint8_t *d_out, size_t out_stride, uint64_t *d_out_len, int *d_overflow, cudaStream_t st, Workspace *wsp = nullptr);
 }
 namespace hevc {
 int encode_device(const uint8_t *d_frames, size_t frame_stride, int n, uint32_t H, uint32_t W, int qpd6,
@@ -63,6 +63,71 @@ static int run_host_batch(const uint8_t *frames, size_t frame_stride, size_t fra
     return 0;
 }
 
+// JPEG-LS host batches of 8 frames or more: the batch is cut into NCHUNK chunks, each on a stream of its own with a
+// workspace of its own, so that the upload of chunk c+1 and the download of chunk c-1 overlap the kernel of chunk c
+// (a plane occupies one or two SMs for the whole kernel, so chunk kernels run side by side on different SMs).
+static int run_host_jls_chunked(const uint8_t *frames, size_t frame_stride, size_t frame_bytes, int n, int is_rgb,
+                                uint32_t height, uint32_t width, int near_, uint8_t *out, size_t out_stride, size_t bound, size_t *out_len)
+{
+    Engine &E = engine();
+    constexpr int NCH = Engine::NCHUNK;
+    for (int c = 0; c < NCH; c++)
+        if (!E.chunk_stream[c]) IMCVT_CUDA(cudaStreamCreateWithFlags(&E.chunk_stream[c], cudaStreamNonBlocking));
+    const size_t dev_in_stride  = (frame_bytes + 255) & ~(size_t)255;
+    const size_t dev_out_stride = ((out_stride < bound ? out_stride : bound) + 255) & ~(size_t)255;
+    if (E.io.reserve((size_t)n * (dev_in_stride + dev_out_stride) + (size_t)n * 8 + 4096)) return 1;
+    uint8_t  *d_in   = E.io.take<uint8_t>((size_t)n * dev_in_stride);
+    uint8_t  *d_out  = E.io.take<uint8_t>((size_t)n * dev_out_stride);
+    uint64_t *d_len  = E.io.take<uint64_t>((size_t)n);
+    int      *d_flag = E.io.take<int>(1);
+    if (!d_in || !d_out || !d_len || !d_flag) { set_error("io arena carve failed"); return 1; }
+    IMCVT_CUDA(cudaMemsetAsync(d_flag, 0, sizeof(int), E.stream));
+    IMCVT_CUDA(cudaStreamSynchronize(E.stream));
+
+    const int per = (n + NCH - 1) / NCH;
+    // the lengths come back into PINNED memory: a copy into pageable memory would block the host until the chunk's kernel
+    // has finished and serialise the chunks
+    static uint64_t *lens = nullptr;
+    static int lens_cap = 0;
+    if (lens_cap < n) {
+        if (lens) cudaFreeHost(lens);
+        lens = nullptr; lens_cap = 0;
+        IMCVT_CUDA(cudaHostAlloc((void **)&lens, (size_t)n * 8, cudaHostAllocDefault));
+        lens_cap = n;
+    }
+    int nch = 0;
+    for (int c = 0; c < NCH; c++) {
+        const int first = c * per, cnt = n - first < per ? n - first : per;
+        if (cnt <= 0) break;
+        nch = c + 1;
+        cudaStream_t st = E.chunk_stream[c];
+        IMCVT_CUDA(cudaMemcpy2DAsync(d_in + (size_t)first * dev_in_stride, dev_in_stride, frames + (size_t)first * frame_stride, frame_stride,
+                                     frame_bytes, cnt, cudaMemcpyHostToDevice, st));
+        if (jls::encode_device(d_in + (size_t)first * dev_in_stride, dev_in_stride, cnt, is_rgb, height, width, near_,
+                               d_out + (size_t)first * dev_out_stride, dev_out_stride, d_len + first, d_flag, st, &E.ws_chunk[c])) return 1;
+        IMCVT_CUDA(cudaMemcpyAsync(lens + first, d_len + first, (size_t)cnt * 8, cudaMemcpyDeviceToHost, st));
+    }
+    for (int c = 0; c < nch; c++) {
+        const int first = c * per, cnt = n - first < per ? n - first : per;
+        cudaStream_t st = E.chunk_stream[c];
+        IMCVT_CUDA(cudaStreamSynchronize(st));
+        for (int i = first; i < first + cnt; i++) {
+            if (lens[i] == 0 || lens[i] > out_stride) {
+                for (int k = 0; k < nch; k++) cudaStreamSynchronize(E.chunk_stream[k]);
+                set_error("image %d: encoder produced an invalid length %llu (output slot too small?)", i, (unsigned long long)lens[i]);
+                return 1;
+            }
+            out_len[i] = (size_t)lens[i];
+            IMCVT_CUDA(cudaMemcpyAsync(out + (size_t)i * out_stride, d_out + (size_t)i * dev_out_stride, (size_t)lens[i], cudaMemcpyDeviceToHost, st));
+        }
+    }
+    for (int c = 0; c < nch; c++) IMCVT_CUDA(cudaStreamSynchronize(E.chunk_stream[c]));
+    int flag = 0;
+    IMCVT_CUDA(cudaMemcpy(&flag, d_flag, sizeof(int), cudaMemcpyDeviceToHost));
+    if (flag) { set_error("output slot too small for at least one image (out_stride = %zu)", out_stride); return 1; }
+    return 0;
+}
+
 extern "C" {
 
 size_t imcvtJLSBound(int is_rgb, uint32_t height, uint32_t width)
@@ -107,6 +172,9 @@ int imcvtEncodeBatchJLS(const uint8_t *frames, size_t frame_stride, int n, int i
     const size_t frame_bytes = (size_t)height * width * (is_rgb ? 3 : 1);
     if (frame_stride < frame_bytes) { set_error("frame_stride smaller than one frame"); return 1; }
     if (ensure_engine()) return 1;
+    if (n >= 8)
+        return run_host_jls_chunked(frames, frame_stride, frame_bytes, n, is_rgb, height, width, near_, out, out_stride,
+                                    imcvtJLSBound(is_rgb, height, width), out_len);
     auto enc = [&](uint8_t *d_in, size_t in_stride, uint8_t *d_out, size_t dev_out_stride, size_t usable, uint64_t *d_len,
                    uint8_t *, size_t, int *d_flag, cudaStream_t st) {
         (void)usable;

@@ -46,6 +46,9 @@ struct Engine {
     Workspace ws;           // scratch for the device pipelines
     Workspace io;           // staging for the host-buffer entry points (frames in, streams out)
     cudaStream_t stream = nullptr;      // engine-owned stream for the host-buffer entry points
+    static constexpr int NCHUNK = 4;    // host-buffer JPEG-LS batches are cut into chunks whose copies and kernels overlap
+    Workspace ws_chunk[NCHUNK];
+    cudaStream_t chunk_stream[NCHUNK] = {nullptr, nullptr, nullptr, nullptr};
     bool profile = false;
     long launches = 0;
     std::map<std::string, KernelStat> stats;

@@ -147,6 +147,11 @@ void imcvtShutdown(void)
     E.event_pool.clear();
     E.ws.release();
     E.io.release();
+    for (int c = 0; c < Engine::NCHUNK; c++) {
+        E.ws_chunk[c].release();
+        if (E.chunk_stream[c]) cudaStreamDestroy(E.chunk_stream[c]);
+        E.chunk_stream[c] = nullptr;
+    }
     if (E.stream) cudaStreamDestroy(E.stream);
     E.stream = nullptr;
     E.ready = false;

@@ -768,9 +768,10 @@ static unsigned long long *g_jls_prof = nullptr;
 // d_frames: device, interleaved.  d_out / d_out_len: device.  Queues everything on `st`.
 // d_overflow: device int set to 1 when a slot was too small.
 int encode_device(const uint8_t *d_frames, size_t frame_stride, int n, int is_rgb, uint32_t H, uint32_t W, int near_,
-                  uint8_t *d_out, size_t out_stride, uint64_t *d_out_len, int *d_overflow, cudaStream_t st)
+                  uint8_t *d_out, size_t out_stride, uint64_t *d_out_len, int *d_overflow, cudaStream_t st, Workspace *wsp)
 {
     Engine &E = engine();
+    Workspace &WS = wsp ? *wsp : E.ws;                  // concurrent calls (chunks of a host batch) bring their own workspace
     const int ncomp = is_rgb ? 3 : 1;
     const int P = n * ncomp;
     const size_t npix = (size_t)H * W;
@@ -806,12 +807,12 @@ int encode_device(const uint8_t *d_frames, size_t frame_stride, int n, int is_rg
     }
     add((size_t)P * 8);                            // plane_bytes
     if (ncomp > 1) add((size_t)P * scratch_stride);
-    if (E.ws.reserve(bytes)) return 1;
+    if (WS.reserve(bytes)) return 1;
 
     const uint8_t *planes = d_frames;
     size_t plane_stride = frame_stride;
     if (need_planes) {
-        uint8_t *pl = E.ws.take<uint8_t>((size_t)P * slot_stride);
+        uint8_t *pl = WS.take<uint8_t>((size_t)P * slot_stride);
         plane_stride = slot_stride;
         if (is_rgb) {
             LaunchScope ls("jls_deinterleave", st);
@@ -830,9 +831,9 @@ int encode_device(const uint8_t *d_frames, size_t frame_stride, int n, int is_rg
     uint64_t *plane_bytes = nullptr;
 
     if (use_tile) {
-        int *next = E.ws.take<int>(1);
-        plane_bytes = E.ws.take<uint64_t>((size_t)P);
-        if (ncomp > 1) Lay.scratch = E.ws.take<uint8_t>((size_t)P * scratch_stride);
+        int *next = WS.take<int>(1);
+        plane_bytes = WS.take<uint64_t>((size_t)P);
+        if (ncomp > 1) Lay.scratch = WS.take<uint8_t>((size_t)P * scratch_stride);
         if (!next || !plane_bytes || (ncomp > 1 && !Lay.scratch)) { set_error("workspace carve failed"); return 1; }
         static bool attr_set = false;
         if (!attr_set) {
@@ -863,19 +864,19 @@ int encode_device(const uint8_t *d_frames, size_t frame_stride, int n, int is_rg
             tile::jls_tile_kernel<<<P < E.sm_count ? P : E.sm_count, tile::NTHREADS, sizeof(tile::Smem), st>>>(TP);
         }
     } else if (lossless) {
-        uint32_t *hist         = E.ws.take<uint32_t>((size_t)P * NBUCKET * T);
-        uint32_t *bucket_total = E.ws.take<uint32_t>((size_t)P * NBUCKET);
-        uint32_t *bucket_start = E.ws.take<uint32_t>((size_t)P * NBUCKET);
-        uint32_t *rec_pos      = E.ws.take<uint32_t>((size_t)P * slot_stride);
-        uint16_t *rec_aux      = E.ws.take<uint16_t>((size_t)P * slot_stride);
-        uint32_t *codes        = E.ws.take<uint32_t>((size_t)P * slot_stride);
-        uint8_t  *lens         = E.ws.take<uint8_t>((size_t)P * slot_stride);
-        uint32_t *tile_bits    = E.ws.take<uint32_t>((size_t)P * PT);
-        uint64_t *tile_off     = E.ws.take<uint64_t>((size_t)P * PT);
-        uint64_t *plane_bits   = E.ws.take<uint64_t>((size_t)P);
-        uint32_t *ubits        = E.ws.take<uint32_t>((size_t)P * uw_stride);
-        plane_bytes            = E.ws.take<uint64_t>((size_t)P);
-        if (ncomp > 1) Lay.scratch = E.ws.take<uint8_t>((size_t)P * scratch_stride);
+        uint32_t *hist         = WS.take<uint32_t>((size_t)P * NBUCKET * T);
+        uint32_t *bucket_total = WS.take<uint32_t>((size_t)P * NBUCKET);
+        uint32_t *bucket_start = WS.take<uint32_t>((size_t)P * NBUCKET);
+        uint32_t *rec_pos      = WS.take<uint32_t>((size_t)P * slot_stride);
+        uint16_t *rec_aux      = WS.take<uint16_t>((size_t)P * slot_stride);
+        uint32_t *codes        = WS.take<uint32_t>((size_t)P * slot_stride);
+        uint8_t  *lens         = WS.take<uint8_t>((size_t)P * slot_stride);
+        uint32_t *tile_bits    = WS.take<uint32_t>((size_t)P * PT);
+        uint64_t *tile_off     = WS.take<uint64_t>((size_t)P * PT);
+        uint64_t *plane_bits   = WS.take<uint64_t>((size_t)P);
+        uint32_t *ubits        = WS.take<uint32_t>((size_t)P * uw_stride);
+        plane_bytes            = WS.take<uint64_t>((size_t)P);
+        if (ncomp > 1) Lay.scratch = WS.take<uint8_t>((size_t)P * scratch_stride);
         if (!ubits || !plane_bytes || (ncomp > 1 && !Lay.scratch)) { set_error("workspace carve failed"); return 1; }
 
         const int total_tiles = P * T;
@@ -923,9 +924,9 @@ int encode_device(const uint8_t *d_frames, size_t frame_stride, int n, int is_rg
             stuff_kernel<<<P, 32, 0, st>>>(ubits, uw_stride, plane_bits, Lay, plane_bytes);
         }
     } else {
-        uint8_t *recon = E.ws.take<uint8_t>((size_t)P * slot_stride);
-        plane_bytes    = E.ws.take<uint64_t>((size_t)P);
-        if (ncomp > 1) Lay.scratch = E.ws.take<uint8_t>((size_t)P * scratch_stride);
+        uint8_t *recon = WS.take<uint8_t>((size_t)P * slot_stride);
+        plane_bytes    = WS.take<uint64_t>((size_t)P);
+        if (ncomp > 1) Lay.scratch = WS.take<uint8_t>((size_t)P * scratch_stride);
         if (!recon || !plane_bytes || (ncomp > 1 && !Lay.scratch)) { set_error("workspace carve failed"); return 1; }
         // the serial kernel addresses the reconstruction with the input's plane stride (<= slot_stride)
         SerialParams SP = make_params(near_);
