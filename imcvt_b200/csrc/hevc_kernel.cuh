@@ -48,8 +48,14 @@ namespace hevc {
 // development aid: cycles of thread 0 between phase marks, accumulated per (CU level, phase) in Params::prof
 #if defined(IMCVT_HEVC_PROF) && !defined(IMCVT_HOST_EMU)
 #define HPROF(K, id) do { if (threadIdx.x == 0 && (K).prof_on) { const long long t__ = clock64(); atomicAdd(&(K).P->prof[(id)], (unsigned long long)(t__ - (K).prof_t)); (K).prof_t = t__; } } while (0)
+// stage counters inside the TU pipeline distort the phase counters: a separate switch (make PROF=1 TPROF=1)
+#ifdef IMCVT_HEVC_TPROF
 #define TPROF(sm, id) do { if (threadIdx.x == 0) { const long long t__ = clock64(); atomicAdd(&(sm).prof[(id)], (unsigned long long)(t__ - (sm).prof_t)); (sm).prof_t = t__; } } while (0)
 #define TPROF_START(sm) do { if (threadIdx.x == 0) (sm).prof_t = clock64(); } while (0)
+#else
+#define TPROF(sm, id) do { } while (0)
+#define TPROF_START(sm) do { } while (0)
+#endif
 #else
 #define HPROF(K, id) do { } while (0)
 #define TPROF(sm, id) do { } while (0)
@@ -87,6 +93,7 @@ constexpr int REFS_BYTES = 448;         // per warp: reference samples of its tr
 constexpr int CXN = 142, CXP = 144;     // context bytes (padded to words)
 constexpr int SCR_BYTES = 8192;         // private trial stream per candidate (reference bound: 3200, :794)
 constexpr int I32MAX = 0x7fffffff;
+constexpr int SMEM_LIMIT = 232448;     // 227 KB: the most dynamic shared memory a CTA can ask for on sm_100
 constexpr int NSCAN = 1520;
 constexpr int NCAND = 2 * NMODE;        // candidates coded together: 35 one-TU trials + 35 four-TU trials
 constexpr int NXN = NCAND + NMODE;      // 8x8 CUs: slots NCAND..NXN-1 = stand-alone 4x4 trials of the round in flight, slot NXN = the NxN trial
@@ -196,6 +203,8 @@ struct Smem {
     unsigned long long *prof; long long prof_t;     // development build: stage counters of thread 0
 #endif
 };
+
+static_assert(sizeof(Smem) <= SMEM_LIMIT, "hevc Smem does not fit the 227 KB a CTA can have");
 
 // ------------------------------------------------------------------------------------------------
 // small helpers
@@ -1079,6 +1088,23 @@ __device__ __forceinline__ void publish_tu(Smem &sm, unsigned short *lists, int 
     }
 }
 
+// Best of candidates first..first+n-1 in the reference order (`best >= cost` while walking up: a later candidate wins
+// ties, :1439).  One full warp; every lane returns the result (win = -1 when n == 0).
+template <int SET>
+__device__ __forceinline__ void warp_best(Smem &sm, const RdK &rd, int first, int n, int lane, int &bc, int &win)
+{
+    bc = I32MAX; win = -1;
+    for (int c = first + lane; c < first + n; c += 32) {
+        const int v = rd.cost(sm.csse[SET][c], sm.cbits[SET][c]);
+        if (bc >= v) { bc = v; win = c; }
+    }
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) {
+        const int ob = __shfl_xor_sync(0xffffffffu, bc, d), ow = __shfl_xor_sync(0xffffffffu, win, d);
+        if (ow >= 0 && (win < 0 || ob < bc || (ob == bc && ow > win))) { bc = ob; win = ow; }
+    }
+}
+
 // CABAC trial encode of candidate c of a coding unit from the unit's entry state (:1422-1437, :1455-1473): c < 35 one
 // transform unit, c >= 35 four.  One lane.
 template <int SZ>
@@ -1261,13 +1287,10 @@ HEVC_PHASE void eval_b(Ctx &K)
         }
     }
     __syncthreads();
-    if (tid == 0) {
-        int bc = I32MAX, win = -1;
-        for (int c = 0; c < NCAND; c++) {
-            const int cost = K.rd.cost(sm.csse[SET][c], sm.cbits[SET][c]);
-            if (bc >= cost) { bc = cost; win = c; }
-        }
-        sm.eval_cost[LV] = bc; sm.eval_win[LV] = win;
+    if (tid < 32) {
+        int bc, win;
+        warp_best<SET>(sm, K.rd, 0, NCAND, tid, bc, win);
+        if (tid == 0) { sm.eval_cost[LV] = bc; sm.eval_win[LV] = win; }
     }
     __syncthreads();
 }
@@ -1393,9 +1416,11 @@ HEVC_PHASE void search_cu8(Ctx &K, int y0, int x0, int avail)
     HPROF(K, LV * 16 + 2);
 
     if (warp >= 10) {
-        // ---- CABAC trials of the one-TU candidates ----
+        // ---- CABAC trials of the one-TU candidates, and -- once the last round's pipelines are done -- of the four-TU ones ----
         const int c = (warp - 10) * 18 + lane;
         if (lane < 18 && c < NMODE) trial_cu<SZ>(K, c, entry, entry_bits_rel, 0, mode_l, mode_a);
+        HEVC_NAMED_BARRIER(5, NT);
+        if (lane < 18 && c < NMODE) trial_cu<SZ>(K, NMODE + c, entry, entry_bits_rel, 0, mode_l, mode_a);
     } else {
         // ---- four rounds over the 4x4 blocks ----
         const bool grp3 = warp < 5;                                         // four-TU candidates; else stand-alone PUs
@@ -1418,6 +1443,7 @@ HEVC_PHASE void search_cu8(Ctx &K, int y0, int x0, int avail)
                 __syncwarp();
                 binarize_warp<H>(sm, warp, lane, K.lists[SET]);
                 __syncwarp();
+                if (i == 3 && active && lane % H == 0) sm.csse[SET][cand] = sse3;
             } else if (i > 0) {
                 const int cand = NCAND + m;
                 Src ps = src; ps.priv = sm.nxn_rec; ps.ppitch = 8;          // the kept blocks of the earlier PUs
@@ -1431,7 +1457,8 @@ HEVC_PHASE void search_cu8(Ctx &K, int y0, int x0, int avail)
                 binarize_warp<H>(sm, warp, lane, K.lists[SET]);
                 __syncwarp();
             }
-            HEVC_NAMED_BARRIER(4, RT);
+            if (i == 3) HEVC_NAMED_BARRIER(5, NT);         // all four blocks of the four-TU candidates are in: warps 10, 11 code them
+            else HEVC_NAMED_BARRIER(4, RT);
             HPROF(K, LV * 16 + 8);
             // stand-alone trial of every mode on a fresh coder: cost = absolute length of the block's residual (:1504-1518)
             {
@@ -1448,15 +1475,15 @@ HEVC_PHASE void search_cu8(Ctx &K, int y0, int x0, int avail)
             }
             HEVC_NAMED_BARRIER(4, RT);
             HPROF(K, LV * 16 + 10);
-            if (tid == 0) {
-                int bc = I32MAX, win = -1;
-                for (int q = 0; q < NMODE; q++) {
-                    const int cost = rd.cost(sm.csse[SET][NCAND + q], sm.cbits[SET][NCAND + q]);
-                    if (bc >= cost) { bc = cost; win = q; }
+            if (warp == 0) {
+                int bc, win;
+                warp_best<SET>(sm, rd, NCAND, NMODE, lane, bc, win);
+                win -= NCAND;
+                if (lane == 0) {
+                    const int from = i == 0 ? NMODE + win : NCAND + win;
+                    sm.win = win;
+                    sm.nxn_mode[i] = win; sm.nxn_last[i] = sm.clast[SET][from][0]; sm.nxn_cg[i] = sm.ccg[SET][from][0][0];
                 }
-                const int from = i == 0 ? NMODE + win : NCAND + win;
-                sm.win = win;
-                sm.nxn_mode[i] = win; sm.nxn_last[i] = sm.clast[SET][from][0]; sm.nxn_cg[i] = sm.ccg[SET][from][0][0];
             }
             // fresh contexts for the next round's trials
             for (int k = tid; k < NMODE * (CXP / 4); k += RT)
@@ -1476,16 +1503,10 @@ HEVC_PHASE void search_cu8(Ctx &K, int y0, int x0, int avail)
             HEVC_NAMED_BARRIER(4, RT);
             HPROF(K, LV * 16 + 11);
         }
-        if (grp3 && active && lane % H == 0) sm.csse[SET][NMODE + m] = sse3;
     }
-    __syncthreads();
-    HPROF(K, LV * 16 + 3);
 
-    // ---- CABAC trials of the four-TU candidates 35..69 (warps 2, 3) and of the NxN coding unit (warp 0) ----
-    if (warp == 2 || warp == 3) {
-        const int c = NMODE + (warp - 2) * 18 + lane;
-        if (lane < 18 && c < NCAND) trial_cu<SZ>(K, c, entry, entry_bits_rel, 0, mode_l, mode_a);
-    } else if (warp == 0) {
+    // ---- the NxN coding unit (warp 0), next to the four-TU trials on warps 10, 11 ----
+    if (warp == 0) {
         int sse = 0;
         for (int q = lane; q < 64; q += 32) { const int d = (int)sm.orig[y0 + (q >> 3)][x0 + (q & 7)] - (int)sm.nxn_rec[q]; sse += d * d; }
         sse = group_sum<32>(sse);
@@ -1512,14 +1533,11 @@ HEVC_PHASE void search_cu8(Ctx &K, int y0, int x0, int avail)
     __syncthreads();
     HPROF(K, LV * 16 + 5);
     // decide (:1437-1446, :1473-1482, :1543-1545)
-    if (tid == 0) {
-        int bc = I32MAX, win = -1;
-        for (int c = 0; c < NCAND; c++) {
-            const int cost = rd.cost(sm.csse[SET][c], sm.cbits[SET][c]);
-            if (bc >= cost) { bc = cost; win = c; }
-        }
+    if (warp == 0) {
+        int bc, win;
+        warp_best<SET>(sm, rd, 0, NCAND, lane, bc, win);
         if (bc >= rd.cost(sm.csse[SET][NXN], sm.cbits[SET][NXN])) win = NXN;
-        sm.win = win;
+        if (lane == 0) sm.win = win;
     }
     __syncthreads();
     HPROF(K, LV * 16 + 6);
