@@ -181,7 +181,8 @@ struct Smem {
     uint8_t msz[9][12], mmd[9][12];                 // CU size / luma mode per 4x4 cell; row 0 / column 0 = above / left CTU
     uint8_t left_sz[8], left_md[8];                 // right-most column of the previous CTU
     uint8_t nxn_rec[8 * 8];
-    unsigned short nxn_list[4][SLOT], nxn_hdr[4];   // bin lists of the four kept 4x4 blocks
+    alignas(16) unsigned short nxn_list[4][SLOT];   // bin lists of the four kept 4x4 blocks
+    unsigned short nxn_hdr[4];
     int nxn_mode[4], nxn_last[4];
     unsigned nxn_cg[4];
     CoderRegs cur, entry[3];
@@ -603,6 +604,17 @@ HEVC_BIGFN void binarize_warp(Smem &sm, int warp, int lane, unsigned short *list
     TPROF(sm, 64 + SizeClass<TS>::v * 8 + 7);
 }
 
+// Eight bin-list entries at a time: the lists live in (L2-backed) global memory, and a trial lane that fetched them one
+// by one would pay a memory round trip per bin.  Group slots are 16-byte aligned (SLOT * 2 = 224 bytes).
+struct alignas(16) Entry8 { unsigned w[4]; };
+__device__ __forceinline__ unsigned entry_of(const Entry8 &v, int k)
+{
+    const int i = k & 7;
+    const unsigned lo = (i & 2) ? v.w[1] : v.w[0], hi = (i & 2) ? v.w[3] : v.w[2];
+    const unsigned w = (i & 4) ? hi : lo;
+    return (i & 1) ? w >> 16 : w & 0xFFFFu;
+}
+
 // Arithmetic coding of one transform unit from its bin lists (one lane).  slots / hdrs point at the unit's group 0.
 HEVC_BIGFN void code_block(Coder &c, int sz, int mode, int last, unsigned cgp0, unsigned cgp1, unsigned sg0, unsigned sg1,
                                            const unsigned short *slots, const unsigned short *hdrs, const uint8_t (*scan_all)[2])
@@ -612,13 +624,16 @@ HEVC_BIGFN void code_block(Coder &c, int sz, int mode, int last, unsigned cgp0, 
     put_last_pos(c, sz, st, scan[last][0], scan[last][1]);
     int cg = last >> 4, prevbig = 0, add = 0, k = 0;
     unsigned h = hdrs[cg];
+    const Entry8 *sp = reinterpret_cast<const Entry8 *>(slots + cg * SLOT);
+    Entry8 ev = sp[0];
     int cnt = (int)(h & 0x7Fu);
-    const unsigned short *sp = slots + cg * SLOT;
     for (;;) {
         int isb = 0, a = 0, b = 0;
         bool emit = false;
         if (k < cnt) {
-            const unsigned e = sp[k++];
+            if (k > 0 && (k & 7) == 0) ev = sp[k >> 3];
+            const unsigned e = entry_of(ev, k);
+            k++;
             const int type = (int)(e >> 14);
             if (type == 3) { isb = 1; a = (int)(e & 0xFFu); b = (int)((e >> 8) & 15u); }
             else { a = (int)(e & 0xFFu) + (type == 1 ? 4 * add : type == 2 ? add : 0); b = (int)((e >> 8) & 1u); }
@@ -632,8 +647,12 @@ HEVC_BIGFN void code_block(Coder &c, int sz, int mode, int last, unsigned cgp0, 
             const int right = xc < ncg - 1 && ((br < 32 ? cgp0 >> br : cgp1 >> (br - 32)) & 1u);
             const int below = yc < ncg - 1 && ((bb < 32 ? cgp0 >> bb : cgp1 >> (bb - 32)) & 1u);
             if (cg > 0) { a = CX_SIGCG + ((right | below) != 0); b = cgs; emit = true; }      // coded_sub_block_flag
-            if (cgs || cg == 0) { h = hdrs[cg]; cnt = (int)(h & 0x7Fu); sp = slots + cg * SLOT; add = prevbig; }
-            else { h = 0; cnt = 0; }
+            if (cgs || cg == 0) {
+                h = hdrs[cg];
+                sp = reinterpret_cast<const Entry8 *>(slots + cg * SLOT);
+                ev = sp[0];
+                cnt = (int)(h & 0x7Fu); add = prevbig;
+            } else { h = 0; cnt = 0; }
             k = 0;
         }
         if (emit) { if (isb) c.bypass_chunk(a, b); else c.bin(b, a); }
@@ -1021,21 +1040,22 @@ __device__ __forceinline__ void copy_words(void *dst, const void *src, int nword
     for (int i = tid; i < nwords; i += nthreads) d[i] = s[i];
 }
 
-// Trial encodes run on warps 0..3 (one per SM sub-partition): candidates [0,35) = one-TU trials on warps 0,1,
-// candidates [35,70) = four-TU trials on warps 2,3, so that the lanes of a warp walk the same syntax.
+// Trial encodes are one lane each, and the lanes of a warp that code different candidates sit in different places of
+// the syntax, i.e. run one after the other.  So the trials are spread thin: a few lanes on every warp.
+// 70 candidates of a unit over all 12 warps: 6 lanes each
 __device__ __forceinline__ int candidate_of_thread(int tid, int ncand)
 {
     const int lane = tid & 31, warp = tid >> 5;
-    if (warp >= 4 || lane >= 18) return -1;
-    const int c = (warp >> 1) * NMODE + (warp & 1) * 18 + lane;
-    return (c < (warp >> 1) * NMODE + NMODE && c < ncand) ? c : -1;
+    if (lane >= 6) return -1;
+    const int c = warp * 6 + lane;
+    return c < ncand ? c : -1;
 }
-// the 35 stand-alone 4x4 trials of step 4: 9 per warp
-__device__ __forceinline__ int candidate4_of_thread(int tid)
+// 35 trials over warps w0 .. w0+8: 4 lanes each
+__device__ __forceinline__ int candidate35_of_thread(int tid, int w0)
 {
-    const int lane = tid & 31, warp = tid >> 5;
-    if (warp >= 4 || lane >= 9) return -1;
-    const int c = warp * 9 + lane;
+    const int lane = tid & 31, warp = (tid >> 5) - w0;
+    if (warp < 0 || warp >= 9 || lane >= 4) return -1;
+    const int c = warp * 4 + lane;
     return c < NMODE ? c : -1;
 }
 
@@ -1108,7 +1128,7 @@ __device__ __forceinline__ void warp_best(Smem &sm, const RdK &rd, int first, in
 // CABAC trial encode of candidate c of a coding unit from the unit's entry state (:1422-1437, :1455-1473): c < 35 one
 // transform unit, c >= 35 four.  One lane.
 template <int SZ>
-__device__ __forceinline__ void trial_cu(Ctx &K, int c, const CoderRegs &entry, int entry_bits_rel, int split_ctx, int mode_l, int mode_a)
+HEVC_PHASE void trial_cu(Ctx &K, int c, const CoderRegs &entry, int entry_bits_rel, int split_ctx, int mode_l, int mode_a)
 {
     Smem &sm = *K.sm;
     constexpr int H = SZ / 2, SET = Level<SZ>::set;
@@ -1416,11 +1436,9 @@ HEVC_PHASE void search_cu8(Ctx &K, int y0, int x0, int avail)
     HPROF(K, LV * 16 + 2);
 
     if (warp >= 10) {
-        // ---- CABAC trials of the one-TU candidates, and -- once the last round's pipelines are done -- of the four-TU ones ----
+        // ---- CABAC trials of the one-TU candidates ----
         const int c = (warp - 10) * 18 + lane;
         if (lane < 18 && c < NMODE) trial_cu<SZ>(K, c, entry, entry_bits_rel, 0, mode_l, mode_a);
-        HEVC_NAMED_BARRIER(5, NT);
-        if (lane < 18 && c < NMODE) trial_cu<SZ>(K, NMODE + c, entry, entry_bits_rel, 0, mode_l, mode_a);
     } else {
         // ---- four rounds over the 4x4 blocks ----
         const bool grp3 = warp < 5;                                         // four-TU candidates; else stand-alone PUs
@@ -1430,39 +1448,33 @@ HEVC_PHASE void search_cu8(Ctx &K, int y0, int x0, int avail)
         const int loff = (lane / H) * H * (H + 2);
         int sse3 = 0;
         for (int i = 0; i < 4; i++) {
-            if (grp3) {
-                const int cand = NMODE + m;
-                Src ps = src; ps.priv = sm.rec1[cand];                       // earlier blocks of the same trial
+            if (grp3 || i > 0) {
+                // one call site for both groups (the pipeline is big; two inlined copies cost instruction-cache misses)
+                const int cand = grp3 ? NMODE + m : NCAND + m;
+                Src ps = src;
+                ps.priv = grp3 ? sm.rec1[cand] : sm.nxn_rec;               // earlier blocks of the same trial | the kept blocks of the earlier PUs
+                ps.ppitch = 8;
+                uint8_t *rec = grp3 ? sm.rec1[cand] + (sub_y[i] - y0) * SZ + (sub_x[i] - x0) : sm.rec4[m];
                 TuResult r = tu_pipeline<H>(sm, warp, lane, active, ps, sub_y[i], sub_x[i], sub_avail[i], m, qpd6, rd,
-                                            sm.lev[warp] + loff, sm.rec1[cand] + (sub_y[i] - y0) * SZ + (sub_x[i] - x0), SZ);
+                                            sm.lev[warp] + loff, rec, grp3 ? SZ : H);
                 sse3 += r.sse;
                 if (lane % H == 0) {
-                    publish_tu<SET>(sm, K.lists[SET], warp, lane / H, active, cand, i, 1, m, warp * LEV_STRIDE + loff, r);
-                    if (active && i == 0) sm.sse0[m] = r.sse;
-                }
-                __syncwarp();
-                binarize_warp<H>(sm, warp, lane, K.lists[SET]);
-                __syncwarp();
-                if (i == 3 && active && lane % H == 0) sm.csse[SET][cand] = sse3;
-            } else if (i > 0) {
-                const int cand = NCAND + m;
-                Src ps = src; ps.priv = sm.nxn_rec; ps.ppitch = 8;          // the kept blocks of the earlier PUs
-                TuResult r = tu_pipeline<H>(sm, warp, lane, active, ps, sub_y[i], sub_x[i], sub_avail[i], m, qpd6, rd,
-                                            sm.lev[warp] + loff, sm.rec4[m], H);
-                if (lane % H == 0) {
-                    publish_tu<SET>(sm, K.lists[SET], warp, lane / H, active, cand, 0, 1, m, warp * LEV_STRIDE + loff, r);
-                    if (active) sm.csse[SET][cand] = r.sse;
+                    publish_tu<SET>(sm, K.lists[SET], warp, lane / H, active, cand, grp3 ? i : 0, 1, m, warp * LEV_STRIDE + loff, r);
+                    if (active) {
+                        if (!grp3) sm.csse[SET][cand] = r.sse;
+                        else if (i == 0) sm.sse0[m] = r.sse;
+                        else if (i == 3) sm.csse[SET][cand] = sse3;
+                    }
                 }
                 __syncwarp();
                 binarize_warp<H>(sm, warp, lane, K.lists[SET]);
                 __syncwarp();
             }
-            if (i == 3) HEVC_NAMED_BARRIER(5, NT);         // all four blocks of the four-TU candidates are in: warps 10, 11 code them
-            else HEVC_NAMED_BARRIER(4, RT);
+            HEVC_NAMED_BARRIER(4, RT);
             HPROF(K, LV * 16 + 8);
             // stand-alone trial of every mode on a fresh coder: cost = absolute length of the block's residual (:1504-1518)
             {
-                const int c = candidate4_of_thread(tid);
+                const int c = candidate35_of_thread(tid, 0);
                 if (c >= 0) {
                     const int from = i == 0 ? NMODE + c : NCAND + c;
                     Coder cd; cd.fresh();
@@ -1473,6 +1485,7 @@ HEVC_PHASE void search_cu8(Ctx &K, int y0, int x0, int avail)
                     if (i == 0) sm.csse[SET][NCAND + c] = sm.sse0[c];
                 }
             }
+            HPROF(K, LV * 16 + 9);
             HEVC_NAMED_BARRIER(4, RT);
             HPROF(K, LV * 16 + 10);
             if (warp == 0) {
@@ -1505,7 +1518,11 @@ HEVC_PHASE void search_cu8(Ctx &K, int y0, int x0, int avail)
         }
     }
 
-    // ---- the NxN coding unit (warp 0), next to the four-TU trials on warps 10, 11 ----
+    // ---- CABAC trials of the four-TU candidates (warps 1..9, four lanes each) next to the NxN coding unit (warp 0) ----
+    {
+        const int c = candidate35_of_thread(tid, 1);
+        if (c >= 0) trial_cu<SZ>(K, NMODE + c, entry, entry_bits_rel, 0, mode_l, mode_a);
+    }
     if (warp == 0) {
         int sse = 0;
         for (int q = lane; q < 64; q += 32) { const int d = (int)sm.orig[y0 + (q >> 3)][x0 + (q & 7)] - (int)sm.nxn_rec[q]; sse += d * d; }
