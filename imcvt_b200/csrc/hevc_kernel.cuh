@@ -98,6 +98,7 @@ constexpr int NSCAN = 1520;
 constexpr int NCAND = 2 * NMODE;        // candidates coded together: 35 one-TU trials + 35 four-TU trials
 constexpr int NXN = NCAND + NMODE;      // 8x8 CUs: slots NCAND..NXN-1 = stand-alone 4x4 trials of the round in flight, slot NXN = the NxN trial
 constexpr int NALL = NXN + 1;
+constexpr int PRE_MAX = 40;             // entries of a trial's prefix list: head (<= 9; NxN 16) + <= 4 cbf flags + last position (<= 24; 4x4: 6)
 constexpr int SLOT = 112;               // bin-list entries per coefficient group (worst case 107)
 constexpr int CAND_LIST_U16 = 64 * SLOT + 64;   // 64 group slots + 64 group headers per candidate
 
@@ -175,6 +176,7 @@ struct Smem {
     unsigned ccg[2][NALL][4][2];                    // significant groups by position: bit yc*8+xc
     unsigned csg[2][NALL][4][2];                    // significant groups by scan index
     int sse0[NMODE];                                // 8x8 CUs: squared error of the first 4x4 block per mode
+    unsigned short tpre[NALL][PRE_MAX];             // per trial: syntax waiting in front of a block's coefficient groups (PreList)
     // CTU state
     uint8_t orig[CTU][CTU];
     uint8_t rc[CTU + 1][RCP];                       // reconstruction window: row 0 / column 0 are the neighbours (:1588-1589)
@@ -371,8 +373,18 @@ __device__ __forceinline__ void mpm_list(int l, int a, int m[3])                
     } else { m[0] = 0; m[1] = 1; m[2] = 26; }
 }
 
+// The lanes of a warp code different candidates: if each syntax element called the arithmetic coder where it is
+// produced, lanes would sit at different call sites and run one after the other.  So the syntax in front of a block's
+// coefficient groups (coding-unit head, cbf flags, last position) is first written as bin-list entries into a small
+// per-trial list, and the coder is only ever stepped from the loop of code_block / emit_list, where the lanes converge.
+struct PreList {
+    unsigned short *p; int n;
+    __device__ __forceinline__ void ctx(int ci, int bin) { p[n++] = (unsigned short)((bin << 8) | ci); }                       // = ent_ctx(0, ci, bin)
+    __device__ __forceinline__ void byp(int val, int len) { p[n++] = (unsigned short)((3 << 14) | (len << 8) | (val & ((1 << len) - 1))); }   // = ent_byp, len <= 8
+};
+
 // all prev_intra_luma_pred flags first, then mpm_idx / rem_intra_luma_pred_mode (putYpmode :984-1017)
-__device__ inline void put_luma_modes(Coder &c, int count, const int *mode, const int *left, const int *above)
+__device__ inline void build_luma_modes(PreList &L, int count, const int *mode, const int *left, const int *above)
 {
     int hit[4];
     for (int i = 0; i < count; i++) {
@@ -380,12 +392,12 @@ __device__ inline void put_luma_modes(Coder &c, int count, const int *mode, cons
         mpm_list(left[i], above[i], m);
         hit[i] = -1;
         for (int j = 0; j < 3; j++) if (m[j] == mode[i]) hit[i] = j;
-        c.bin(hit[i] >= 0, CX_YMODE);
+        L.ctx(CX_YMODE, hit[i] >= 0);
     }
     for (int i = 0; i < count; i++) {
         if (hit[i] >= 0) {
-            c.bypass(hit[i] > 0, 1);
-            if (hit[i] > 0) c.bypass(hit[i] - 1, 1);
+            L.byp(hit[i] > 0, 1);
+            if (hit[i] > 0) L.byp(hit[i] - 1, 1);
         } else {
             int m[3], t, rem = mode[i];
             mpm_list(left[i], above[i], m);
@@ -393,7 +405,7 @@ __device__ inline void put_luma_modes(Coder &c, int count, const int *mode, cons
             if (m[1] < m[2]) { t = m[1]; m[1] = m[2]; m[2] = t; }
             if (m[0] < m[1]) { t = m[0]; m[0] = m[1]; m[1] = t; }
             for (int j = 0; j < 3; j++) if (rem > m[j]) rem--;
-            c.bypass(rem, 5);
+            L.byp(rem, 5);
         }
     }
 }
@@ -407,18 +419,18 @@ __device__ __forceinline__ int group_min(int g)        // :1047
     return g < 4 ? g : g == 4 ? 4 : g == 5 ? 6 : g == 6 ? 8 : g == 7 ? 12 : g == 8 ? 16 : 24;
 }
 
-__device__ inline void put_last_pos(Coder &c, int sz, int scan_type, int y, int x)     // putLastSignificantXY :1045-1086 (luma)
+__device__ inline void build_last_pos(PreList &L, int sz, int scan_type, int y, int x)     // putLastSignificantXY :1045-1086 (luma)
 {
     const int sc = size_class(sz), base = sc * 5, sft = sc == 0 ? 0 : 1;
     int ty = scan_type == 2 ? x : y, tx = scan_type == 2 ? y : x;
     const int gy = pos_group(ty), gx = pos_group(tx), gmax = pos_group(sz - 1);
     int i;
-    for (i = 0; i < gx; i++) c.bin(1, CX_LASTX + base + (i >> sft));
-    if (gx < gmax) c.bin(0, CX_LASTX + base + (gx >> sft));
-    for (i = 0; i < gy; i++) c.bin(1, CX_LASTY + base + (i >> sft));
-    if (gy < gmax) c.bin(0, CX_LASTY + base + (gy >> sft));
-    if (gx > 3) { tx -= group_min(gx); for (i = ((gx - 2) >> 1) - 1; i >= 0; i--) c.bypass((tx >> i) & 1, 1); }
-    if (gy > 3) { ty -= group_min(gy); for (i = ((gy - 2) >> 1) - 1; i >= 0; i--) c.bypass((ty >> i) & 1, 1); }
+    for (i = 0; i < gx; i++) L.ctx(CX_LASTX + base + (i >> sft), 1);
+    if (gx < gmax) L.ctx(CX_LASTX + base + (gx >> sft), 0);
+    for (i = 0; i < gy; i++) L.ctx(CX_LASTY + base + (i >> sft), 1);
+    if (gy < gmax) L.ctx(CX_LASTY + base + (gy >> sft), 0);
+    if (gx > 3) { tx -= group_min(gx); for (i = ((gx - 2) >> 1) - 1; i >= 0; i--) L.byp((tx >> i) & 1, 1); }
+    if (gy > 3) { ty -= group_min(gy); for (i = ((gy - 2) >> 1) - 1; i >= 0; i--) L.byp((ty >> i) & 1, 1); }
 }
 
 __device__ __forceinline__ int sig_ctx_index(int sz, int scan_type, int y, int x, int nb)      // getSigCtxIdx :1091-1121 (luma)
@@ -617,12 +629,13 @@ __device__ __forceinline__ unsigned entry_of(const Entry8 &v, int k)
 
 // Arithmetic coding of one transform unit from its bin lists (one lane).  slots / hdrs point at the unit's group 0.
 HEVC_BIGFN void code_block(Coder &c, int sz, int mode, int last, unsigned cgp0, unsigned cgp1, unsigned sg0, unsigned sg1,
-                                           const unsigned short *slots, const unsigned short *hdrs, const uint8_t (*scan_all)[2])
+                                           const unsigned short *slots, const unsigned short *hdrs, const uint8_t (*scan_all)[2], PreList &pre)
 {
+    // the entries waiting in `pre` (head of the coding unit, cbf flags) go first, then the last position, then the groups
     const int st = scan_type_for(sz, mode), ncg = sz >> 2;
     const uint8_t (*scan)[2] = scan_all + scan_base(st, size_class(sz));
-    put_last_pos(c, sz, st, scan[last][0], scan[last][1]);
-    int cg = last >> 4, prevbig = 0, add = 0, k = 0;
+    build_last_pos(pre, sz, st, scan[last][0], scan[last][1]);
+    int cg = last >> 4, prevbig = 0, add = 0, k = 0, pk = 0;
     unsigned h = hdrs[cg];
     const Entry8 *sp = reinterpret_cast<const Entry8 *>(slots + cg * SLOT);
     Entry8 ev = sp[0];
@@ -630,7 +643,12 @@ HEVC_BIGFN void code_block(Coder &c, int sz, int mode, int last, unsigned cgp0, 
     for (;;) {
         int isb = 0, a = 0, b = 0;
         bool emit = false;
-        if (k < cnt) {
+        if (pk < pre.n) {
+            const unsigned e = pre.p[pk++];
+            if ((e >> 14) == 3) { isb = 1; a = (int)(e & 0xFFu); b = (int)((e >> 8) & 15u); }
+            else { a = (int)(e & 0xFFu); b = (int)((e >> 8) & 1u); }
+            emit = true;
+        } else if (k < cnt) {
             if (k > 0 && (k & 7) == 0) ev = sp[k >> 3];
             const unsigned e = entry_of(ev, k);
             k++;
@@ -657,17 +675,29 @@ HEVC_BIGFN void code_block(Coder &c, int sz, int mode, int last, unsigned cgp0, 
         }
         if (emit) { if (isb) c.bypass_chunk(a, b); else c.bin(b, a); }
     }
+    pre.n = 0;
+}
+
+// steps the coder through what is left in a prefix list (blocks without coefficients do not call code_block)
+__device__ __forceinline__ void emit_list(Coder &c, PreList &pre)
+{
+    for (int k = 0; k < pre.n; k++) {
+        const unsigned e = pre.p[k];
+        if ((e >> 14) == 3) c.bypass_chunk((int)(e & 0xFFu), (int)((e >> 8) & 15u));
+        else c.bin((int)((e >> 8) & 1u), (int)(e & 0xFFu));
+    }
+    pre.n = 0;
 }
 
 // coding-unit syntax before the residual (putCU_* :1271-1339 up to the cbf flags)
-__device__ __forceinline__ void put_cu_head(Coder &c, int sz, int kind, const int *modes, const int *left, const int *above)
+__device__ __forceinline__ void build_cu_head(PreList &L, int sz, int kind, const int *modes, const int *left, const int *above)
 {
-    if (sz == 8) c.bin(kind != 2, CX_PART);                                            // putPartSize :951-954
-    put_luma_modes(c, kind == 2 ? 4 : 1, modes, left, above);
-    c.bin(0, CX_UVMODE);                                                               // chroma mode "derived" :1020-1022
-    if (kind != 2) c.bin(kind == 1, CX_SPLIT_TU + (sz == 32 ? 0 : sz == 16 ? 1 : 2));  // :1025-1032
-    c.bin(0, CX_UVCBF + 0);                                                            // cbf_cb, cbf_cr at depth 0
-    c.bin(0, CX_UVCBF + 0);
+    if (sz == 8) L.ctx(CX_PART, kind != 2);                                            // putPartSize :951-954
+    build_luma_modes(L, kind == 2 ? 4 : 1, modes, left, above);
+    L.ctx(CX_UVMODE, 0);                                                               // chroma mode "derived" :1020-1022
+    if (kind != 2) L.ctx(CX_SPLIT_TU + (sz == 32 ? 0 : sz == 16 ? 1 : 2), kind == 1);  // :1025-1032
+    L.ctx(CX_UVCBF + 0, 0);                                                            // cbf_cb, cbf_cr at depth 0
+    L.ctx(CX_UVCBF + 0, 0);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1135,17 +1165,19 @@ HEVC_PHASE void trial_cu(Ctx &K, int c, const CoderRegs &entry, int entry_bits_r
     const int kind = c >= NMODE, mode = c - kind * NMODE;
     Coder cd; cd.load(entry); cd.nout = 0;
     attach(cd, sm, sm.cctx[SET][c], K.scratch[SET] + (size_t)c * SCR_BYTES, SCR_BYTES);
-    if (SZ >= 16) cd.bin(0, CX_SPLIT_CU + split_ctx);                // putSplitCUflag :942-946
-    put_cu_head(cd, SZ, kind, &mode, &mode_l, &mode_a);
+    PreList pre; pre.p = sm.tpre[c]; pre.n = 0;
+    if (SZ >= 16) pre.ctx(CX_SPLIT_CU + split_ctx, 0);               // putSplitCUflag :942-946
+    build_cu_head(pre, SZ, kind, &mode, &mode_l, &mode_a);
     const unsigned short *lst = K.lists[SET] + (size_t)c * CAND_LIST_U16;
     const int tsz = kind ? H : SZ, ncg = (tsz / 4) * (tsz / 4);
     for (int i = 0; i < (kind ? 4 : 1); i++) {
         const unsigned g0 = sm.ccg[SET][c][i][0], g1 = sm.ccg[SET][c][i][1];
         const int cbf = (g0 | g1) != 0;
-        cd.bin(cbf, CX_YCBF + (kind ? 0 : 1));                       // :1039
+        pre.ctx(CX_YCBF + (kind ? 0 : 1), cbf);                      // :1039
         if (cbf) code_block(cd, tsz, mode, sm.clast[SET][c][i], g0, g1, sm.csg[SET][c][i][0], sm.csg[SET][c][i][1],
-                            lst + (size_t)i * ncg * SLOT, lst + 64 * SLOT + i * ncg, sm.scan);
+                            lst + (size_t)i * ncg * SLOT, lst + 64 * SLOT + i * ncg, sm.scan, pre);
     }
+    emit_list(cd, pre);
     cd.store(sm.ccoder[SET][c]);
     sm.cbits[SET][c] = cd.bits() - entry_bits_rel;
 }
@@ -1480,7 +1512,8 @@ HEVC_PHASE void search_cu8(Ctx &K, int y0, int x0, int avail)
                     Coder cd; cd.fresh();
                     attach(cd, sm, sm.cctx[SET][NCAND + c], K.scratch[SET] + (size_t)(NCAND + c) * SCR_BYTES, SCR_BYTES);
                     const unsigned short *lst = K.lists[SET] + (size_t)from * CAND_LIST_U16;
-                    code_block(cd, 4, c, sm.clast[SET][from][0], sm.ccg[SET][from][0][0], 0u, sm.csg[SET][from][0][0], 0u, lst, lst + 64 * SLOT, sm.scan);
+                    PreList pre; pre.p = sm.tpre[NCAND + c]; pre.n = 0;
+                    code_block(cd, 4, c, sm.clast[SET][from][0], sm.ccg[SET][from][0][0], 0u, sm.csg[SET][from][0][0], 0u, lst, lst + 64 * SLOT, sm.scan, pre);
                     sm.cbits[SET][NCAND + c] = cd.bits();
                     if (i == 0) sm.csse[SET][NCAND + c] = sm.sse0[c];
                 }
@@ -1536,12 +1569,14 @@ HEVC_PHASE void search_cu8(Ctx &K, int y0, int x0, int avail)
             left[1] = modes[0];                above[1] = sm.mmd[cy][1 + cx + 1];
             left[2] = sm.mmd[1 + cy + 1][cx];  above[2] = modes[0];
             left[3] = modes[2];                above[3] = modes[1];
-            put_cu_head(cd, 8, 2, modes, left, above);
+            PreList pre; pre.p = sm.tpre[NXN]; pre.n = 0;
+            build_cu_head(pre, 8, 2, modes, left, above);
             for (int i = 0; i < 4; i++) {
                 const int cbf = sm.nxn_cg[i] != 0;
-                cd.bin(cbf, CX_YCBF + 0);
-                if (cbf) code_block(cd, 4, modes[i], sm.nxn_last[i], sm.nxn_cg[i], 0u, 1u, 0u, sm.nxn_list[i], &sm.nxn_hdr[i], sm.scan);
+                pre.ctx(CX_YCBF + 0, cbf);
+                if (cbf) code_block(cd, 4, modes[i], sm.nxn_last[i], sm.nxn_cg[i], 0u, 1u, 0u, sm.nxn_list[i], &sm.nxn_hdr[i], sm.scan, pre);
             }
+            emit_list(cd, pre);
             cd.store(sm.ccoder[SET][NXN]);
             sm.cbits[SET][NXN] = cd.bits() - entry_bits_rel;
             sm.csse[SET][NXN] = sse;
