@@ -1468,9 +1468,11 @@ HEVC_PHASE void search_cu8(Ctx &K, int y0, int x0, int avail)
     HPROF(K, LV * 16 + 2);
 
     if (warp >= 10) {
-        // ---- CABAC trials of the one-TU candidates ----
+        // ---- CABAC trials of the one-TU candidates and, once the last round's pipelines are done, of the four-TU ones ----
         const int c = (warp - 10) * 18 + lane;
         if (lane < 18 && c < NMODE) trial_cu<SZ>(K, c, entry, entry_bits_rel, 0, mode_l, mode_a);
+        HEVC_NAMED_BARRIER(5, NT);
+        if (lane < 18 && c < NMODE) trial_cu<SZ>(K, NMODE + c, entry, entry_bits_rel, 0, mode_l, mode_a);
     } else {
         // ---- four rounds over the 4x4 blocks ----
         const bool grp3 = warp < 5;                                         // four-TU candidates; else stand-alone PUs
@@ -1502,7 +1504,8 @@ HEVC_PHASE void search_cu8(Ctx &K, int y0, int x0, int avail)
                 binarize_warp<H>(sm, warp, lane, K.lists[SET]);
                 __syncwarp();
             }
-            HEVC_NAMED_BARRIER(4, RT);
+            if (i == 3) HEVC_NAMED_BARRIER(5, NT);         // all four blocks of the four-TU candidates are in: warps 10, 11 code them
+            else HEVC_NAMED_BARRIER(4, RT);
             HPROF(K, LV * 16 + 8);
             // stand-alone trial of every mode on a fresh coder: cost = absolute length of the block's residual (:1504-1518)
             {
@@ -1551,11 +1554,7 @@ HEVC_PHASE void search_cu8(Ctx &K, int y0, int x0, int avail)
         }
     }
 
-    // ---- CABAC trials of the four-TU candidates (warps 1..9, four lanes each) next to the NxN coding unit (warp 0) ----
-    {
-        const int c = candidate35_of_thread(tid, 1);
-        if (c >= 0) trial_cu<SZ>(K, NMODE + c, entry, entry_bits_rel, 0, mode_l, mode_a);
-    }
+    // ---- the NxN coding unit (warp 0), next to the four-TU trials on warps 10, 11 ----
     if (warp == 0) {
         int sse = 0;
         for (int q = lane; q < 64; q += 32) { const int d = (int)sm.orig[y0 + (q >> 3)][x0 + (q & 7)] - (int)sm.nxn_rec[q]; sse += d * d; }
@@ -1582,6 +1581,7 @@ HEVC_PHASE void search_cu8(Ctx &K, int y0, int x0, int avail)
             sm.csse[SET][NXN] = sse;
         }
     }
+    HPROF(K, LV * 16 + 12);
     __syncthreads();
     HPROF(K, LV * 16 + 5);
     // decide (:1437-1446, :1473-1482, :1543-1545)

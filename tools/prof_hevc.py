@@ -25,8 +25,8 @@ for it in range(2):
     L.imcvtDebugHevcProf(buf)
 v = np.array(list(buf), dtype=np.float64)
 nctu = n * ((h + 31) // 32) * ((w + 31) // 32)
-names = ["entry", "split+children sse", "A one-TU", "A four-TU", "ctx copy", "B trials / CU8: NxN + wait for four-TU trials", "decide", "commit",
-         "4x4 A", "4x4 B: thread 0's own trial", "4x4 B: wait for the other trials", "4x4 decide+keep", "NxN trial", "final copy"]
+names = ["entry", "split+children sse", "A one-TU", "A four-TU", "ctx copy", "B trials / CU8: wait for four-TU trials after NxN", "decide", "commit",
+         "4x4 A", "4x4 B: thread 0's own trial", "4x4 B: wait for the other trials", "4x4 decide+keep", "CU8: NxN trial (thread 0)", "final copy"]
 tot = v.sum()
 print(f"{kind} n={n} qpd6={q} {h}x{w}: {tot/nctu:.0f} cycles per CTU (thread 0 timeline), bytes={int(lens.sum())}")
 for lv, nm in enumerate(["CU32", "CU16", "CU8"]):
