@@ -749,6 +749,221 @@ serial_scan_kernel(const uint8_t *__restrict__ pix, size_t plane_stride, uint8_t
 // ------------------------------------------------------------------------------------------------
 static inline size_t round_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
+// ------------------------------------------------------------------------------------------------
+// Row-pipelined scan: any NEAR, the path for NEAR > 0.  With NEAR > 0 the reconstructed value of a sample feeds the
+// context of the next one (:321-323), so a plane is ONE dependency chain; what can be taken off that chain is:
+//   both warps   per segment of <= 2048 samples of a row: stage the input, and the two gradient terms that only need the
+//                row above, 81*q(d-b) + 9*q(b-c), from the reconstructed row kept in shared memory;
+//   warp 0       lane 0 walks the segment (:276-394): third gradient by table, context state in shared memory, error
+//                quantisation by table (no divisions), code + length per sample into shared memory;
+//   warp 1       meanwhile packs the previous segment's codes (register windows, tile-wide bit buffer) and turns them into
+//                0xFF-stuffed bytes with the packer of the tile kernel.
+// One CTA of two warps per plane.
+// ------------------------------------------------------------------------------------------------
+namespace rowscan {
+constexpr int SEG = 2048;
+constexpr int WMAXR = 32768;                        // :436
+struct Smem {
+    uint8_t row[2][WMAXR + 16];                     // reconstructed rows y-1 / y (index 8 + x)
+    uint8_t in[SEG];
+    short q12[SEG];
+    uint32_t codes[2][SEG + SEG / 32];
+    uint8_t lens[2][SEG + SEG / 8];
+    uint32_t ubits[tile::UBITS_WORDS];
+    int4 ctx[NCTX];
+    signed char gq[512];                            // quantised gradient at [g + 255]
+    short eq[512];                                  // quantised prediction error at [e + 255] (:97-102)
+};
+
+__global__ void __launch_bounds__(64, 1)
+rowscan_kernel(const uint8_t *__restrict__ pix, size_t plane_stride, int W, int H, SerialParams P, FrameLayout L,
+               uint64_t *__restrict__ plane_bytes)
+{
+    extern __shared__ __align__(16) unsigned char rowscan_smem[];
+    Smem &sm = *reinterpret_cast<Smem *>(rowscan_smem);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int p = blockIdx.x;
+    const uint8_t *src = pix + (size_t)p * plane_stride;
+    const int near_ = P.near_, quant = P.quant, range = P.range;
+    const int half = (range + 1) / 2;
+
+    for (int k = tid; k < NCTX; k += 64) sm.ctx[k] = make_int4(P.a_init, 0, 0, 1);
+    for (int i = tid; i < 511; i += 64) {
+        const int g = i - 255;
+        sm.gq[i] = (signed char)grad_q_any(P, g);
+        sm.eq[i] = (short)(g < 0 ? -((near_ - g) / quant) : (near_ + g) / quant);
+    }
+    for (int i = tid; i < WMAXR + 16; i += 64) { sm.row[0][i] = 0; sm.row[1][i] = 0; }      // the row above the picture reads as zeros
+
+    tile::PackState ps; ps.out_pos = 0; ps.carry_bits = 0; ps.carry = 0; ps.pz = 0;
+    ps.dst = plane_dst(L, p, ps.cap);
+
+    int rA[2] = {P.a_init, P.a_init}, rB[2] = {0, 0}, rN[2] = {1, 1};
+    int run_index = 0;
+    const int nseg = (W + SEG - 1) / SEG, total = H * nseg;
+    // row state of the scanning lane
+    bool in_run = false;
+    int run_len = 0, a = 0, b = 0, c = 0, up2 = 0;
+    __syncthreads();
+
+    for (int it = 0; it <= total; it++) {
+        const int y = it / nseg, sg = it - y * nseg, x0 = sg * SEG, n = it < total ? min(SEG, W - x0) : 0;
+        const int buf = it & 1;
+        if (warp == 1 && it > 0) {
+            // ---- pack the previous segment ----
+            const int pit = it - 1, py = pit / nseg, psg = pit - py * nseg, pn = min(SEG, W - psg * SEG), pb = pit & 1;
+            const uint32_t *codes = sm.codes[pb];
+            const uint8_t *lens = sm.lens[pb];
+            uint32_t T = 0;                                              // bits of the segment
+            for (int c0 = 0; c0 < pn; c0 += 1024) {
+                const int s0 = c0 + lane * 32;
+                uint32_t l4[8], mylen = 0;
+#pragma unroll
+                for (int q = 0; q < 8; q++) {
+                    uint32_t v = 0;
+                    if (s0 + 4 * q < pn) v = *reinterpret_cast<const uint32_t *>(lens + tile::len_idx(s0) + 4 * q);
+                    // lengths past the segment end inside the last word are stale: mask them
+                    if (s0 + 4 * q + 4 > pn && s0 + 4 * q < pn) v &= 0xFFFFFFFFu >> (8 * (s0 + 4 * q + 4 - pn));
+                    l4[q] = v;
+                    mylen += (v & 0xFF) + ((v >> 8) & 0xFF) + ((v >> 16) & 0xFF) + (v >> 24);
+                }
+                uint32_t inc = mylen;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) { const uint32_t v = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += v; }
+                const uint32_t ctot = __shfl_sync(0xffffffffu, inc, 31);
+                for (uint32_t w = (T >> 5) + 1 + lane; w < ((T + ctot) >> 5) + 2; w += 32) sm.ubits[w] = 0;
+                if (T == 0 && lane == 0) sm.ubits[0] = 0;
+                __syncwarp();
+                if (mylen) {
+                    const uint32_t bit = T + inc - mylen;
+                    uint32_t w = bit >> 5, nacc = bit & 31u;
+                    uint64_t acc = 0;
+#pragma unroll
+                    for (int q = 0; q < 8; q++) {
+#pragma unroll
+                        for (int r = 0; r < 4; r++) {
+                            const uint32_t len = (l4[q] >> (8 * r)) & 0xFF;
+                            const uint32_t cd = codes[tile::code_idx(s0) + 4 * q + r];
+                            acc = (acc << len) | (len ? (uint64_t)cd : 0ull);
+                            nacc += len;
+                            if (nacc >= 32) { nacc -= 32; atomicOr(&sm.ubits[w], (uint32_t)(acc >> nacc)); w++; }
+                        }
+                    }
+                    if (nacc) atomicOr(&sm.ubits[w], (uint32_t)(acc << (32 - nacc)));
+                }
+                __syncwarp();
+                T += ctot;
+            }
+            tile::stuff_bits(sm.ubits, ps, T, pit == total - 1, lane);
+        }
+        if (n > 0) {
+            // ---- stage the segment: input, and the gradient terms of the row above (warp 0; warp 1 joins when it has packed) ----
+            const uint8_t *up = sm.row[(y + 1) & 1] + 8, *in_row = src + (size_t)y * W + x0;
+            if (warp == 0) {
+                for (int i = lane; i < n; i += 32) {
+                    const int x = x0 + i;
+                    sm.in[i] = in_row[i];
+                    const int bb = up[x], cc = x > 0 ? up[x - 1] : 0, dd = x + 1 < W ? up[x + 1] : bb;
+                    sm.q12[i] = (short)(81 * sm.gq[dd - bb + 255] + 9 * sm.gq[bb - cc + 255]);
+                }
+                __syncwarp();
+                if (lane == 0) {
+                    uint8_t *cur = sm.row[y & 1] + 8;
+                    uint32_t *codes = sm.codes[buf];
+                    uint8_t *lens = sm.lens[buf];
+                    if (x0 == 0) {                                       // row start (:270, :47-56)
+                        in_run = false; run_len = 0;
+                        b = up[0]; a = b; c = up2;
+                        up2 = b;                                         // recon(y-1, 0) is the c of row y+1's first sample
+                    }
+                    for (int i = 0; i < n; i++) {
+                        const int x = x0 + i;
+                        const int d = x + 1 < W ? up[x + 1] : b;
+                        const int v = sm.in[i];
+                        // the first sample of a row has its own c (two rows up), so its second term is recomputed
+                        const int q12 = x > 0 ? (int)sm.q12[i] : 81 * sm.gq[d - b + 255] + 9 * sm.gq[b - c + 255];
+                        const int qv = q12 + sm.gq[c - a + 255];
+                        bool neg = qv < 0;
+                        const int cq = neg ? -qv : qv;
+                        if (cq == 0) in_run = true;
+                        bool hit = false, brk = false;
+                        if (in_run) { hit = abs(v - a) <= near_; brk = !hit; in_run = hit; }
+                        int rx;
+                        uint32_t code = 0; int len = 0;
+                        if (hit) {
+                            rx = a;
+                            run_len++;
+                            const int jj = tile::run_order(run_index);
+                            if (run_len >= (1 << jj)) {
+                                code = 1; len = 1;
+                                run_len -= 1 << jj;
+                                if (run_index < 31) run_index++;
+                            }
+                            if (x == W - 1 && run_len > 0) { code = (code << 1) | 1u; len++; }
+                        } else if (brk) {
+                            const int jj = tile::run_order(run_index);
+                            const int glimit = P.limit - 1 - jj;
+                            const int rem = run_len;
+                            run_len = 0;
+                            if (run_index > 0) run_index--;
+                            const int t = abs(a - b) <= near_;
+                            neg = a > b + near_;
+                            const int px = t ? a : b;
+                            int e = sm.eq[(neg ? px - v : v - px) + 255];
+                            rx = near_ ? min(max(px + (neg ? -quant * e : quant * e), 0), 255) : v;
+                            if (e < 0) e += range;
+                            if (e >= half) e -= range;
+                            const int k = golomb_k(rA[t] + (t ? (rN[t] >> 1) : 0), rN[t]);
+                            const int map = (e != 0) && ((e > 0) == (k == 0 && 2 * rB[t] < rN[t]));
+                            const int me = 2 * abs(e) - t - map;
+                            uint32_t gcode; int glen;
+                            golomb_code(me, k, glimit, P.qbpp, gcode, glen);
+                            code = ((uint32_t)rem << glen) | gcode;      // run remainder in J+1 bits, then the Golomb code (<= 32 bits)
+                            len = jj + 1 + glen;
+                            if (e < 0) rB[t]++;
+                            rA[t] += (me + 1 - t) >> 1;
+                            if (rN[t] >= 64) { rA[t] >>= 1; rB[t] >>= 1; rN[t] >>= 1; }
+                            rN[t]++;
+                        } else {
+                            run_len = 0;
+                            int4 st = sm.ctx[cq - 1];
+                            int px = med3(a, b, c) + (neg ? -st.z : st.z);
+                            px = min(max(px, 0), 255);
+                            int e = sm.eq[(neg ? px - v : v - px) + 255];
+                            rx = near_ ? min(max(px + (neg ? -quant * e : quant * e), 0), 255) : v;
+                            if (e < 0) e += range;
+                            if (e >= half) e -= range;
+                            const int k = golomb_k(st.x, st.w);
+                            const int map = (k == 0) && (2 * st.y <= -st.w) && (near_ == 0);
+                            const int me = 2 * abs(e) + (e < 0 ? -(map + 1) : map);
+                            golomb_code(me, k, P.limit, P.qbpp, code, len);
+                            st.y += e * quant;
+                            st.x += abs(e);
+                            if (st.w >= 64) { st.x >>= 1; st.y >>= 1; st.w >>= 1; }
+                            st.w++;
+                            if (st.y <= -st.w) {
+                                st.y += st.w; if (st.y <= -st.w) st.y = -st.w + 1;
+                                st.z = max(st.z - 1, -128);
+                            } else if (st.y > 0) {
+                                st.y -= st.w; if (st.y > 0) st.y = 0;
+                                st.z = min(st.z + 1, 127);
+                            }
+                            sm.ctx[cq - 1] = st;
+                        }
+                        codes[tile::code_idx(i)] = code;
+                        lens[tile::len_idx(i)] = (uint8_t)len;
+                        cur[x] = (uint8_t)rx;
+                        c = b; b = d; a = rx;                             // slide the template (a = reconstructed left neighbour)
+                    }
+                }
+            }
+        }
+        __syncthreads();
+    }
+    if (tid == 32) plane_bytes[p] = ps.out_pos;
+}
+}  // namespace rowscan
+
 static SerialParams make_params(int near_)               // setParameters :26-38 for bpp = 8
 {
     SerialParams P;
@@ -930,8 +1145,18 @@ int encode_device(const uint8_t *d_frames, size_t frame_stride, int n, int is_rg
         if (!recon || !plane_bytes || (ncomp > 1 && !Lay.scratch)) { set_error("workspace carve failed"); return 1; }
         // the serial kernel addresses the reconstruction with the input's plane stride (<= slot_stride)
         SerialParams SP = make_params(near_);
-        LaunchScope ls("jls_serial_scan", st);
-        serial_scan_kernel<<<P, 32, 0, st>>>(planes, plane_stride, recon, (int)W, (int)H, SP, Lay, plane_bytes);
+        if (E.jls_path == 4) {                          // cross-check: the plain one-thread scan
+            LaunchScope ls("jls_serial_scan", st);
+            serial_scan_kernel<<<P, 32, 0, st>>>(planes, plane_stride, recon, (int)W, (int)H, SP, Lay, plane_bytes);
+        } else {
+            static bool attr_set = false;
+            if (!attr_set) {
+                IMCVT_CUDA(cudaFuncSetAttribute(rowscan::rowscan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(rowscan::Smem)));
+                attr_set = true;
+            }
+            LaunchScope ls("jls_rowscan", st);
+            rowscan::rowscan_kernel<<<P, 64, sizeof(rowscan::Smem), st>>>(planes, plane_stride, (int)W, (int)H, SP, Lay, plane_bytes);
+        }
     }
     {
         LaunchScope ls("jls_assemble", st);

@@ -144,3 +144,32 @@ def test_small_output_slot_is_an_error_not_a_crash():
     img = np.random.default_rng(1).integers(0, 256, (64, 64), dtype=np.uint8)
     with pytest.raises(imcvt_b200.ImcvtError):
         imcvt_b200.encode_jls_batch(img[None], 0, out_stride=512)
+
+
+@pytest.mark.parametrize("near", [0, 1, 3])
+def test_plain_one_thread_scan_kernel_still_matches(near, lossless_path):
+    """jls_path 4 keeps the plain one-thread-per-plane scan (the first kernel of the lossy path) as a cross-check of the
+    row-pipelined one."""
+    if lossless_path != 2:
+        pytest.skip("independent of the lossless path")
+    frames = synth.batch("texture", 3, 45, 77)
+    imcvt_b200.debug_jls_path(4)
+    imcvt_b200.debug_jls_force_serial(True)
+    try:
+        got = imcvt_b200.encode_jls_batch(frames, near)
+    finally:
+        imcvt_b200.debug_jls_force_serial(False)
+        imcvt_b200.debug_jls_path(0)
+    for i in range(3):
+        assert got[i] == oracle_jls(frames[i], near), i
+
+
+def test_lossy_wide_and_tall_planes_cross_segment_boundaries():
+    """The row-pipelined scan cuts rows into segments of 2048 samples: runs, contexts and the bit packer carry across them."""
+    rng = np.random.default_rng(5)
+    wide = np.repeat(rng.integers(0, 256, (3, 300), dtype=np.uint8), 20, axis=1)[:, :5000].copy()
+    wide[1, 2047:2050] += 9
+    for near in (1, 2, 4):
+        for img in (wide, rng.integers(0, 256, (2, 4097), dtype=np.uint8), np.full((3, 2048), 200, np.uint8)):
+            got = imcvt_b200.encode_jls_batch(img[None], near)[0]
+            assert got == oracle_jls(img, near), (near, img.shape)
