@@ -67,11 +67,8 @@ namespace hevc {
 #else
 #define HEVC_NAMED_BARRIER(id, count) asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory")
 #endif
-#if defined(IMCVT_HEVC_NOINLINE) && !defined(IMCVT_HOST_EMU)
-#define HEVC_BIGFN __device__ __noinline__
-#else
+// the transform-unit pipeline, the binariser and the block coder are inlined into the phases that use them
 #define HEVC_BIGFN __device__ __forceinline__
-#endif
 // the phases of a coding unit are real functions: one copy of each in the instruction cache however often they are used
 #ifdef IMCVT_HOST_EMU
 #define HEVC_PHASE __device__
