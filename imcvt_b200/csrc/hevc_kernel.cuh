@@ -1303,8 +1303,8 @@ HEVC_PHASE void eval_a4(Ctx &K)
         Src ps = src; ps.priv = rec_tile<SET>(sm, cand);                     // earlier sub-TUs of the same trial
         const int loff = (lane / H) * H * (H + 2);
         int sse = 0;
-#pragma unroll
-        for (int i = 0; i < 4; i++) {
+#pragma unroll 1
+        for (int i = 0; i < 4; i++) {                                        // one copy of the pipeline in the instruction cache, not four
             TuResult r = tu_pipeline<H>(sm, warp, lane, active, ps, sub.y[i], sub.x[i], sub.avail[i], m, K.qpd6, K.rd,
                                         sm.lev[warp] + loff, rec_tile<SET>(sm, cand) + (sub.y[i] - q.y0) * SZ + (sub.x[i] - q.x0), SZ);
             sse += r.sse;
