@@ -203,3 +203,27 @@ def emu_jls(img, pair=False):
     n = _libs["emu_jls"].emu_jls_encode_mode(img.ctypes.data, h, w, out.ctypes.data, out.size, 1 if pair else 0)
     assert n > 0
     return out[:n].tobytes()
+
+
+def jls_decode(stream):
+    """Independent JPEG-LS decoder (tests/tools/jls_decoder.c, written from ITU-T T.87's decoding procedures; the
+    reference ships no decoder).  Returns (planes uint8 [ncomp, H, W], NEAR of the last scan)."""
+    if "jlsdec" not in _libs:
+        d = os.path.join(ROOT, "tests", "tools")
+        so = os.path.join(d, "libjlsdec.so")
+        src = os.path.join(d, "jls_decoder.c")
+        if not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(src):
+            subprocess.run(["gcc", "-O2", "-shared", "-fPIC", "-o", so, src], check=True, capture_output=True)
+        lib = C.CDLL(so)
+        lib.jls_decode.restype = C.c_long
+        lib.jls_decode.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]
+        _libs["jlsdec"] = lib
+    buf = np.frombuffer(stream, dtype=np.uint8)
+    # dimensions from the SOF55 segment right after SOI (FFD8 FFF7 len P Y X Nf)
+    h, w, nc = (int(buf[7]) << 8) | int(buf[8]), (int(buf[9]) << 8) | int(buf[10]), int(buf[11])
+    out = np.zeros(nc * h * w + 16, dtype=np.uint8)
+    cw, ch, cn, near = C.c_int(), C.c_int(), C.c_int(), C.c_int()
+    rc = _libs["jlsdec"].jls_decode(buf.ctypes.data, len(stream), out.ctypes.data, C.byref(cw), C.byref(ch), C.byref(cn), C.byref(near))
+    assert rc == 0, f"jls_decode failed with {rc}"
+    assert (cw.value, ch.value, cn.value) == (w, h, nc)
+    return out[: nc * h * w].reshape(nc, h, w), near.value

@@ -173,3 +173,27 @@ def test_lossy_wide_and_tall_planes_cross_segment_boundaries():
         for img in (wide, rng.integers(0, 256, (2, 4097), dtype=np.uint8), np.full((3, 2048), 200, np.uint8)):
             got = imcvt_b200.encode_jls_batch(img[None], near)[0]
             assert got == oracle_jls(img, near), (near, img.shape)
+
+
+def test_baseline_size_streams_round_trip_through_an_independent_decoder(lossless_path):
+    """BASELINE.json's shapes, checked with a property that does not need the oracle at that size: the emitted stream must
+    decode (tests/tools/jls_decoder.c, written from T.87) to the pixels (NEAR = 0) or to within NEAR of them (NEAR = 2):
+    1920x1080 gray, 1920x1080 RGB, and one 3840x2160 RGB frame (the lossy configuration's shape)."""
+    if lossless_path == 1:
+        pytest.skip("the multi-kernel path is covered at small sizes; this test is about the bench paths")
+    from tests._util import jls_decode
+    gray = synth.batch("natural", 3, 1080, 1920)
+    for near in (0, 2):
+        for i, s in enumerate(imcvt_b200.encode_jls_batch(gray, near)):
+            got, near_out = jls_decode(s)
+            assert near_out == near
+            err = np.abs(got[0].astype(np.int16) - gray[i].astype(np.int16)).max()
+            assert err <= near, (near, i, int(err))
+    rgb = np.stack([synth.frame(k, 7, 1080, 1920) for k in ("natural", "texture", "noise")], axis=-1)      # H x W x 3
+    got, _ = jls_decode(imcvt_b200.encode_jls_batch(rgb[None], 0)[0])
+    assert np.array_equal(np.moveaxis(got, 0, 2), rgb)
+    if lossless_path == 2:
+        big = np.stack([synth.frame("natural", 11 + c, 2160, 3840) for c in range(3)], axis=-1)
+        got, near_out = jls_decode(imcvt_b200.encode_jls_batch(big[None], 2)[0])
+        assert near_out == 2
+        assert np.abs(np.moveaxis(got, 0, 2).astype(np.int16) - big.astype(np.int16)).max() <= 2
