@@ -87,14 +87,13 @@ static int run_host_jls_chunked(const uint8_t *frames, size_t frame_stride, size
     const int per = (n + NCH - 1) / NCH;
     // the lengths come back into PINNED memory: a copy into pageable memory would block the host until the chunk's kernel
     // has finished and serialise the chunks
-    static uint64_t *lens = nullptr;
-    static int lens_cap = 0;
-    if (lens_cap < n) {
-        if (lens) cudaFreeHost(lens);
-        lens = nullptr; lens_cap = 0;
-        IMCVT_CUDA(cudaHostAlloc((void **)&lens, (size_t)n * 8, cudaHostAllocDefault));
-        lens_cap = n;
+    if (E.pinned_lens_cap < n) {
+        if (E.pinned_lens) cudaFreeHost(E.pinned_lens);
+        E.pinned_lens = nullptr; E.pinned_lens_cap = 0;
+        IMCVT_CUDA(cudaHostAlloc((void **)&E.pinned_lens, (size_t)n * 8, cudaHostAllocDefault));
+        E.pinned_lens_cap = n;
     }
+    uint64_t *lens = E.pinned_lens;
     int nch = 0;
     for (int c = 0; c < NCH; c++) {
         const int first = c * per, cnt = n - first < per ? n - first : per;
@@ -152,12 +151,10 @@ int imcvtEncodeBatchJLSDevice(const void *d_frames, size_t frame_stride, int n, 
     if (near_ < 0 || near_ > 4) { set_error("NEAR must be 0..4 (got %d)", near_); return 1; }
     if (ensure_engine()) return 1;
     Engine &E = engine();
-    // overflow flag lives at the end of the io arena header (allocated once)
-    static int *d_flag = nullptr;
-    if (!d_flag) { IMCVT_CUDA(cudaMalloc(&d_flag, sizeof(int))); }
+    if (!E.d_flag) { IMCVT_CUDA(cudaMalloc(&E.d_flag, sizeof(int))); }
+    int *d_flag = E.d_flag;
     cudaStream_t st = (cudaStream_t)stream;
     IMCVT_CUDA(cudaMemsetAsync(d_flag, 0, sizeof(int), st));
-    (void)E;
     return jls::encode_device((const uint8_t *)d_frames, frame_stride, n, is_rgb, height, width, near_,
                               (uint8_t *)d_out, out_stride, (uint64_t *)d_out_len, d_flag, st);
 }
@@ -193,8 +190,9 @@ int imcvtEncodeBatchHEVCDevice(const void *d_frames, size_t frame_stride, int n,
     if (height < 1 || width < 1) { set_error("empty image"); return 1; }
     if (qpd6 < 0 || qpd6 > 4) { set_error("qpd6 must be 0..4 (got %d)", qpd6); return 1; }
     if (ensure_engine()) return 1;
-    static int *d_flag = nullptr;
-    if (!d_flag) { IMCVT_CUDA(cudaMalloc(&d_flag, sizeof(int))); }
+    Engine &E = engine();
+    if (!E.d_flag) { IMCVT_CUDA(cudaMalloc(&E.d_flag, sizeof(int))); }
+    int *d_flag = E.d_flag;
     cudaStream_t st = (cudaStream_t)stream;
     IMCVT_CUDA(cudaMemsetAsync(d_flag, 0, sizeof(int), st));
     return hevc::encode_device((const uint8_t *)d_frames, frame_stride, n, height, width, qpd6,

@@ -49,6 +49,10 @@ struct Engine {
     static constexpr int NCHUNK = 4;    // host-buffer JPEG-LS batches are cut into chunks whose copies and kernels overlap
     Workspace ws_chunk[NCHUNK];
     cudaStream_t chunk_stream[NCHUNK] = {nullptr, nullptr, nullptr, nullptr};
+    int *d_flag = nullptr;              // device overflow flag of the device-buffer entry points (per engine = per device)
+    bool attr_hevc = false, attr_jls_tile = false, attr_jls_rowscan = false;   // dynamic shared-memory opt-in done on this device
+    uint64_t *pinned_lens = nullptr;    // pinned host buffer the chunks' stream lengths come back into
+    int pinned_lens_cap = 0;
     bool profile = false;
     long launches = 0;
     std::map<std::string, KernelStat> stats;

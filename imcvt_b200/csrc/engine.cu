@@ -147,6 +147,11 @@ void imcvtShutdown(void)
     E.event_pool.clear();
     E.ws.release();
     E.io.release();
+    if (E.d_flag) cudaFree(E.d_flag);
+    E.d_flag = nullptr;
+    E.attr_hevc = E.attr_jls_tile = E.attr_jls_rowscan = false;
+    if (E.pinned_lens) cudaFreeHost(E.pinned_lens);
+    E.pinned_lens = nullptr; E.pinned_lens_cap = 0;
     for (int c = 0; c < Engine::NCHUNK; c++) {
         E.ws_chunk[c].release();
         if (E.chunk_stream[c]) cudaStreamDestroy(E.chunk_stream[c]);

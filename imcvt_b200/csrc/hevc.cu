@@ -24,11 +24,10 @@ int encode_device(const uint8_t *d_frames, size_t frame_stride, int n, uint32_t 
     if (d_rcon && rcon_stride < rbytes) { set_error("rcon_stride smaller than one padded picture"); return 1; }
     if (out_stride > 0xFFFFFFFFull) out_stride = 0xFFFFFFFFull;             // stream positions are 32-bit inside the kernel
 
-    static bool attr_set = false;
-    if (!attr_set) {
+    if (!E.attr_hevc) {
         IMCVT_CUDA(cudaFuncSetAttribute(hevc_frame_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem)));
         IMCVT_CUDA(cudaFuncSetAttribute(hevc_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem)));
-        attr_set = true;
+        E.attr_hevc = true;
     }
     // Few frames: two SMs per frame (a cluster of two CTAs: the spine searches the 8x8 units and decides, the upper CTA
     // evaluates the 16x16 / 32x32 candidates meanwhile).  Many frames: one CTA per frame keeps every SM on its own frame.

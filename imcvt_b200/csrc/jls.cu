@@ -1050,11 +1050,10 @@ int encode_device(const uint8_t *d_frames, size_t frame_stride, int n, int is_rg
         plane_bytes = WS.take<uint64_t>((size_t)P);
         if (ncomp > 1) Lay.scratch = WS.take<uint8_t>((size_t)P * scratch_stride);
         if (!next || !plane_bytes || (ncomp > 1 && !Lay.scratch)) { set_error("workspace carve failed"); return 1; }
-        static bool attr_set = false;
-        if (!attr_set) {
+        if (!E.attr_jls_tile) {
             IMCVT_CUDA(cudaFuncSetAttribute(tile::jls_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(tile::Smem)));
             IMCVT_CUDA(cudaFuncSetAttribute(tile::jls_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(tile::Smem)));
-            attr_set = true;
+            E.attr_jls_tile = true;
         }
         // Few planes: two SMs per plane (a cluster of two CTAs: rank 0 = producers, rank 1 = two chain stages + packers).
         // Many planes: one CTA per plane keeps every SM on a plane of its own.
@@ -1149,10 +1148,9 @@ int encode_device(const uint8_t *d_frames, size_t frame_stride, int n, int is_rg
             LaunchScope ls("jls_serial_scan", st);
             serial_scan_kernel<<<P, 32, 0, st>>>(planes, plane_stride, recon, (int)W, (int)H, SP, Lay, plane_bytes);
         } else {
-            static bool attr_set = false;
-            if (!attr_set) {
+            if (!E.attr_jls_rowscan) {
                 IMCVT_CUDA(cudaFuncSetAttribute(rowscan::rowscan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(rowscan::Smem)));
-                attr_set = true;
+                E.attr_jls_rowscan = true;
             }
             LaunchScope ls("jls_rowscan", st);
             rowscan::rowscan_kernel<<<P, 64, sizeof(rowscan::Smem), st>>>(planes, plane_stride, (int)W, (int)H, SP, Lay, plane_bytes);

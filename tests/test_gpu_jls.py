@@ -197,3 +197,18 @@ def test_baseline_size_streams_round_trip_through_an_independent_decoder(lossles
         got, near_out = jls_decode(imcvt_b200.encode_jls_batch(big[None], 2)[0])
         assert near_out == 2
         assert np.abs(np.moveaxis(got, 0, 2).astype(np.int16) - big.astype(np.int16)).max() <= 2
+
+
+def test_shutdown_and_reinit_keep_working():
+    """imcvtShutdown frees every device / pinned allocation and per-device kernel attribute flag; the next call starts over."""
+    frames = synth.batch("natural", 9, 40, 64)          # >= 8 frames: the chunked host path with its pinned length buffer
+    a = imcvt_b200.encode_jls_batch(frames, 0)
+    imcvt_b200.shutdown()
+    imcvt_b200.init(0)
+    b = imcvt_b200.encode_jls_batch(frames, 0)
+    s, _ = imcvt_b200.encode_hevc_batch(frames[:2, :32, :32], 3)
+    imcvt_b200.shutdown()
+    imcvt_b200.init(0)
+    s2, _ = imcvt_b200.encode_hevc_batch(frames[:2, :32, :32], 3)
+    assert a == b and s == s2
+    assert a[0] == oracle_jls(frames[0], 0)
