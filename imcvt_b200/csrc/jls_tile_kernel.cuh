@@ -772,10 +772,15 @@ __device__ __forceinline__ void chain2_tick(Smem &sm, int t, int W, int j)
 {
     const int buf = t % 3, cb = t & 1;
     uint32_t *rec = sorted_buf(sm, buf);
-    if (j < NCTX / 2) {
-        chain2_slice(sm, rec, sm.order[buf][j], buf);
-        chain2_slice(sm, rec, sm.order[buf][NCTX - 1 - j], buf);
-    } else if (j == CHAIN2_WARPS * 32 - 1) {
+    // which stage-2 warp gets the biggest slices: not the one that shares an SM sub-partition (hardware warp id mod 4) with
+    // stage 1's warp of biggest slices -- both are bound by the integer issue rate of their sub-partition
+    int jr = (j + CHAIN2_WARPS * 32 - 32) % (CHAIN2_WARPS * 32);
+    // ... and the run events (index 191) go to a lane of yet another sub-partition (thread 127 swaps with thread 31)
+    if (j == 127) jr = CHAIN2_WARPS * 32 - 1; else if (j == 31) jr = 95;
+    if (jr < NCTX / 2) {
+        chain2_slice(sm, rec, sm.order[buf][jr], buf);
+        chain2_slice(sm, rec, sm.order[buf][NCTX - 1 - jr], buf);
+    } else if (jr == CHAIN2_WARPS * 32 - 1) {
         const int b0 = sm.bstart[buf][NCTX], b1 = sm.bstart[buf][NCTX + 1];
         if (b1 > b0) {
             RunState us;
