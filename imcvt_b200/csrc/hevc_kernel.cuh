@@ -834,17 +834,19 @@ HEVC_BIGFN TuResult tu_pipeline(Smem &sm, int warp, int lane, bool active, const
     }
     if (l == 0) R[0] = (uint8_t)corner;
     __syncwarp();
-    // [1 2 1]/4 smoothing (:245-256)
+    // [1 2 1]/4 smoothing (:245-256); 4x4 units never use the smoothed samples (:274)
+    if constexpr (TS > 4) {
 #pragma unroll
-    for (int i = l; i < 2 * TS; i += TS) {
-        if (i == 2 * TS - 1) { fleft[i] = left[i]; ftop[i] = top[i]; }
-        else {
-            const int pl = i > 0 ? left[i - 1] : corner, pt = i > 0 ? top[i - 1] : corner;
-            fleft[i] = (uint8_t)((2 + 2 * left[i] + pl + left[i + 1]) >> 2);
-            ftop[i]  = (uint8_t)((2 + 2 * top[i] + pt + top[i + 1]) >> 2);
+        for (int i = l; i < 2 * TS; i += TS) {
+            if (i == 2 * TS - 1) { fleft[i] = left[i]; ftop[i] = top[i]; }
+            else {
+                const int pl = i > 0 ? left[i - 1] : corner, pt = i > 0 ? top[i - 1] : corner;
+                fleft[i] = (uint8_t)((2 + 2 * left[i] + pl + left[i + 1]) >> 2);
+                ftop[i]  = (uint8_t)((2 + 2 * top[i] + pt + top[i + 1]) >> 2);
+            }
         }
+        if (l == 0) R[1] = (uint8_t)((2 + left[0] + top[0] + 2 * corner) >> 2);
     }
-    if (l == 0) R[1] = (uint8_t)((2 + left[0] + top[0] + 2 * corner) >> 2);
     __syncwarp();
 
     TPROF(sm, 64 + SC * 8 + 0);
