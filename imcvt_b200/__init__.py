@@ -30,7 +30,8 @@ EXPORTED_SYMBOLS = [
     "imcvtInit", "imcvtShutdown", "imcvtLastError", "imcvtVersion",
     "imcvtJLSBound", "imcvtHEVCBound",
     "imcvtEncodeBatchJLS", "imcvtEncodeBatchJLSDevice",
-    "imcvtEncodeBatchHEVC", "imcvtEncodeBatchHEVCDevice",
+    "imcvtEncodeBatchHEVC", "imcvtEncodeBatchHEVCDevice", "imcvtEncodeBatchHEVCGreen",
+    "imcvtHostAlloc", "imcvtHostFree",
     "imcvtProfileEnable", "imcvtProfileReset", "imcvtProfileGet", "imcvtProfileList", "imcvtLaunchCount",
     "imcvtDebugJLSForceSerial", "imcvtDebugJLSPath", "imcvtDebugHEVCPath",
     "writeJLSImageFile", "writeHEVCImageFile", "HEVCImageEncoder",
@@ -64,6 +65,9 @@ def lib():
     L.imcvtEncodeBatchJLSDevice.argtypes = [vp, sz, i32, i32, u32, u32, i32, vp, sz, vp, vp]; L.imcvtEncodeBatchJLSDevice.restype = i32
     L.imcvtEncodeBatchHEVC.argtypes = [vp, sz, i32, u32, u32, i32, vp, sz, vp, vp, sz]; L.imcvtEncodeBatchHEVC.restype = i32
     L.imcvtEncodeBatchHEVCDevice.argtypes = [vp, sz, i32, u32, u32, i32, vp, sz, vp, vp, sz, vp]; L.imcvtEncodeBatchHEVCDevice.restype = i32
+    L.imcvtEncodeBatchHEVCGreen.argtypes = [vp, sz, i32, u32, u32, i32, vp, sz, vp]; L.imcvtEncodeBatchHEVCGreen.restype = i32
+    L.imcvtHostAlloc.argtypes = [sz]; L.imcvtHostAlloc.restype = vp
+    L.imcvtHostFree.argtypes = [vp]; L.imcvtHostFree.restype = None
     L.imcvtProfileEnable.argtypes = [i32]; L.imcvtProfileEnable.restype = None
     L.imcvtProfileReset.argtypes = []; L.imcvtProfileReset.restype = None
     L.imcvtProfileGet.argtypes = [C.c_char_p, C.POINTER(i32), C.POINTER(C.c_double)]; L.imcvtProfileGet.restype = i32
@@ -145,6 +149,21 @@ def encode_hevc_batch(frames, qpd6=4, want_rcon=True):
                                       out.ctypes.data, out_stride, C.cast(lens, C.c_void_p),
                                       rcon.ctypes.data if want_rcon else None, hp * wp), "imcvtEncodeBatchHEVC")
     return [out[i * out_stride:i * out_stride + lens[i]].tobytes() for i in range(n)], rcon
+
+
+def encode_hevc_green_batch(frames, qpd6=4):
+    """frames: uint8 [n,H,W,3] interleaved RGB.  Encodes the green channel (what the reference's writeHEVCImageFile does
+    with RGB input, src/imageio_hevc.c:21-26); the channel is extracted on the device.  Returns the n .h265 streams."""
+    frames = np.ascontiguousarray(frames, dtype=np.uint8)
+    if frames.ndim != 4 or frames.shape[3] != 3:
+        raise ValueError("frames must be [n,H,W,3] uint8")
+    n, h, w = frames.shape[:3]
+    out_stride = hevc_bound(h, w)
+    out = np.empty(n * out_stride, dtype=np.uint8)
+    lens = (C.c_size_t * n)()
+    _check(lib().imcvtEncodeBatchHEVCGreen(frames.ctypes.data, h * w * 3, n, h, w, int(qpd6),
+                                           out.ctypes.data, out_stride, C.cast(lens, C.c_void_p)), "imcvtEncodeBatchHEVCGreen")
+    return [out[i * out_stride:i * out_stride + lens[i]].tobytes() for i in range(n)]
 
 
 # ---------------------------------------------------------------------------------------------

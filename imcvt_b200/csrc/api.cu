@@ -22,19 +22,36 @@ static bool jls_dims_ok(uint32_t h, uint32_t w) { return w >= 1 && w <= 32767 &&
 
 static inline uint32_t pad32(uint32_t v) { uint32_t c = v > 8192 ? 8192 : v; return (c + 31) / 32 * 32; }   // HEVCe.c:1580-1581
 
+// Green plane of interleaved RGB24 frames (replaces the host loop of the reference's wrapper, src/imageio_hevc.c:24-26):
+// one thread per four pixels, three aligned 32-bit loads -> one 32-bit store.  Frame bases are 256-byte aligned.
+__global__ void green_plane_kernel(const uint8_t *rgb, size_t rgb_stride, uint8_t *gray, size_t gray_stride, size_t npix)
+{
+    const size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x;         // group of four pixels
+    const uint8_t *src = rgb + (size_t)blockIdx.y * rgb_stride;
+    uint8_t *dst = gray + (size_t)blockIdx.y * gray_stride;
+    if (4 * g + 4 <= npix) {
+        const uint32_t *s = reinterpret_cast<const uint32_t *>(src) + 3 * g;
+        const uint32_t a = s[0], b = s[1], c = s[2];                       // R0 G0 B0 R1 | G1 B1 R2 G2 | B2 R3 G3 B3
+        reinterpret_cast<uint32_t *>(dst)[g] = ((a >> 8) & 0xFF) | ((b & 0xFF) << 8) | ((b >> 24) << 16) | (((c >> 16) & 0xFF) << 24);
+    } else {
+        for (size_t p = 4 * g; p < npix; p++) dst[p] = src[3 * p + 1];
+    }
+}
+
 // shared host-buffer driver: H2D, encode, D2H of lengths then of exactly the produced bytes
 template <class EncodeFn>
 static int run_host_batch(const uint8_t *frames, size_t frame_stride, size_t frame_bytes, int n,
                           uint8_t *out, size_t out_stride, size_t bound, size_t *out_len,
-                          uint8_t *rcon, size_t rcon_stride, size_t rcon_bytes, EncodeFn encode)
+                          uint8_t *rcon, size_t rcon_stride, size_t rcon_bytes, size_t scratch_stride, EncodeFn encode)
 {
     Engine &E = engine();
     cudaStream_t st = E.stream;
     const size_t dev_in_stride  = (frame_bytes + 255) & ~(size_t)255;
     const size_t dev_out_stride = ((out_stride < bound ? out_stride : bound) + 255) & ~(size_t)255;
     const size_t dev_rc_stride  = rcon ? ((rcon_bytes + 255) & ~(size_t)255) : 0;
-    if (E.io.reserve((size_t)n * (dev_in_stride + dev_out_stride + dev_rc_stride) + (size_t)n * 8 + 4096)) return 1;
+    if (E.io.reserve((size_t)n * (dev_in_stride + dev_out_stride + dev_rc_stride + scratch_stride) + (size_t)n * 8 + 4096)) return 1;
     uint8_t  *d_in   = E.io.take<uint8_t>((size_t)n * dev_in_stride);
+    uint8_t  *d_scr  = scratch_stride ? E.io.take<uint8_t>((size_t)n * scratch_stride) : nullptr;   // per-frame scratch of the caller's encode step
     uint8_t  *d_out  = E.io.take<uint8_t>((size_t)n * dev_out_stride);
     uint8_t  *d_rc   = rcon ? E.io.take<uint8_t>((size_t)n * dev_rc_stride) : nullptr;
     uint64_t *d_len  = E.io.take<uint64_t>((size_t)n);
@@ -44,7 +61,7 @@ static int run_host_batch(const uint8_t *frames, size_t frame_stride, size_t fra
     IMCVT_CUDA(cudaMemcpy2DAsync(d_in, dev_in_stride, frames, frame_stride, frame_bytes, n, cudaMemcpyHostToDevice, st));
     IMCVT_CUDA(cudaMemsetAsync(d_flag, 0, sizeof(int), st));
     const size_t usable = out_stride < dev_out_stride ? out_stride : dev_out_stride;
-    if (encode(d_in, dev_in_stride, d_out, dev_out_stride, usable, d_len, d_rc, dev_rc_stride, d_flag, st)) return 1;
+    if (encode(d_in, dev_in_stride, d_out, dev_out_stride, usable, d_len, d_rc, dev_rc_stride, d_flag, d_scr, st)) return 1;
 
     std::vector<uint64_t> lens(n);
     int flag = 0;
@@ -173,12 +190,12 @@ int imcvtEncodeBatchJLS(const uint8_t *frames, size_t frame_stride, int n, int i
         return run_host_jls_chunked(frames, frame_stride, frame_bytes, n, is_rgb, height, width, near_, out, out_stride,
                                     imcvtJLSBound(is_rgb, height, width), out_len);
     auto enc = [&](uint8_t *d_in, size_t in_stride, uint8_t *d_out, size_t dev_out_stride, size_t usable, uint64_t *d_len,
-                   uint8_t *, size_t, int *d_flag, cudaStream_t st) {
+                   uint8_t *, size_t, int *d_flag, uint8_t *, cudaStream_t st) {
         (void)usable;
         return jls::encode_device(d_in, in_stride, n, is_rgb, height, width, near_, d_out, dev_out_stride, d_len, d_flag, st);
     };
     return run_host_batch(frames, frame_stride, frame_bytes, n, out, out_stride, imcvtJLSBound(is_rgb, height, width), out_len,
-                          nullptr, 0, 0, enc);
+                          nullptr, 0, 0, 0, enc);
 }
 
 int imcvtEncodeBatchHEVCDevice(const void *d_frames, size_t frame_stride, int n,
@@ -213,12 +230,57 @@ int imcvtEncodeBatchHEVC(const uint8_t *frames, size_t frame_stride, int n,
     if (rcon && rcon_stride < rcon_bytes) { set_error("rcon_stride smaller than one padded picture"); return 1; }
     if (ensure_engine()) return 1;
     auto enc = [&](uint8_t *d_in, size_t in_stride, uint8_t *d_out, size_t dev_out_stride, size_t usable, uint64_t *d_len,
-                   uint8_t *d_rc, size_t rc_stride, int *d_flag, cudaStream_t st) {
+                   uint8_t *d_rc, size_t rc_stride, int *d_flag, uint8_t *, cudaStream_t st) {
         (void)usable;
         return hevc::encode_device(d_in, in_stride, n, height, width, qpd6, d_out, dev_out_stride, d_len, d_rc, rc_stride, d_flag, st);
     };
     return run_host_batch(frames, frame_stride, frame_bytes, n, out, out_stride, imcvtHEVCBound(height, width), out_len,
-                          rcon, rcon_stride, rcon_bytes, enc);
+                          rcon, rcon_stride, rcon_bytes, 0, enc);
+}
+
+int imcvtEncodeBatchHEVCGreen(const uint8_t *rgb_frames, size_t frame_stride, int n,
+                              uint32_t height, uint32_t width, int qpd6,
+                              uint8_t *out, size_t out_stride, size_t *out_len)
+{
+    if (n <= 0 || !rgb_frames || !out || !out_len) { set_error("bad arguments"); return 1; }
+    if (height < 1 || width < 1) { set_error("empty image"); return 1; }
+    if (qpd6 < 0 || qpd6 > 4) { set_error("qpd6 must be 0..4 (got %d)", qpd6); return 1; }
+    const size_t npix = (size_t)height * width;
+    if (frame_stride < 3 * npix) { set_error("frame_stride smaller than one RGB frame"); return 1; }
+    if (ensure_engine()) return 1;
+    const size_t gray_stride = (npix + 255) & ~(size_t)255;
+    auto enc = [&](uint8_t *d_in, size_t in_stride, uint8_t *d_out, size_t dev_out_stride, size_t usable, uint64_t *d_len,
+                   uint8_t *, size_t, int *d_flag, uint8_t *d_gray, cudaStream_t st) {
+        (void)usable;
+        {
+            LaunchScope ls("green_plane", st);
+            const unsigned groups = (unsigned)((npix + 3) / 4);
+            dim3 grid((groups + 255) / 256, (unsigned)n);
+            green_plane_kernel<<<grid, 256, 0, st>>>(d_in, in_stride, d_gray, gray_stride, npix);
+        }
+        IMCVT_CUDA(cudaGetLastError());
+        return hevc::encode_device(d_gray, gray_stride, n, height, width, qpd6, d_out, dev_out_stride, d_len, nullptr, 0, d_flag, st);
+    };
+    return run_host_batch(rgb_frames, frame_stride, 3 * npix, n, out, out_stride, imcvtHEVCBound(height, width), out_len,
+                          nullptr, 0, 0, gray_stride, enc);
+}
+
+void *imcvtHostAlloc(size_t bytes)
+{
+    void *p = nullptr;
+    if (ensure_engine()) return nullptr;
+    cudaError_t e = cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault);
+    if (e != cudaSuccess) {
+        (void)cudaGetLastError();
+        set_error("pinned host allocation of %zu bytes failed: %s", bytes, cudaGetErrorString(e));
+        return nullptr;
+    }
+    return p;
+}
+
+void imcvtHostFree(void *p)
+{
+    if (p) cudaFreeHost(p);
 }
 
 }  // extern "C"

@@ -62,24 +62,21 @@ int HEVCImageEncoder(unsigned char *pbuffer, const unsigned char *img, unsigned 
 
 int writeHEVCImageFile(const char *p_filename, const uint8_t *p_buf, int is_rgb, uint32_t height, uint32_t width, int qpd6)
 {
-    size_t i, npix = (size_t)height * width, len = 0, cap;
-    uint8_t *stream, *gray;
+    size_t npix = (size_t)height * width, len = 0, cap;
+    uint8_t *stream;
     int failed;
     if (height < 1 || width < 1)
         return 1;
     cap = imcvtHEVCBound(height, width);
-    stream = (uint8_t *)malloc(cap + npix);
+    stream = (uint8_t *)malloc(cap);
     if (stream == NULL)
         return 1;
-    gray = stream + cap;
-    if (is_rgb) {
+    if (is_rgb) {       /* the green channel is picked on the device (imcvtEncodeBatchHEVCGreen), the warning stays */
         printf("   warning: this HEVCencoder currently only support gray 8-bit image instead of RGB image. Only compress the green channel of this image.\n");
-        for (i = 0; i < npix; i++)
-            gray[i] = p_buf[i * 3 + 1];
+        failed = imcvtEncodeBatchHEVCGreen(p_buf, npix * 3, 1, height, width, qpd6, stream, cap, &len);
     } else {
-        memcpy(gray, p_buf, npix);
+        failed = imcvtEncodeBatchHEVC(p_buf, npix, 1, height, width, qpd6, stream, cap, &len, NULL, 0);
     }
-    failed = imcvtEncodeBatchHEVC(gray, npix, 1, height, width, qpd6, stream, cap, &len, NULL, 0);
     if (!failed && len == 0)
         failed = 1;
     if (!failed)

@@ -1,0 +1,513 @@
+/* imcvt_cli.c -- batch front-end of the ImCvt command line on the B200 engine.
+ *
+ * Same command line, same stdout and same exit codes as the reference's CLI (src/main.c): usage text (:8-28), switch and
+ * file-pair parsing (:87-132), per-file progress / error lines (:135-140, :177-208), default ".png" output name (:171-175),
+ * summary (:214-221), exit code = number of failed files (:223).  What is different is WHEN the work happens: the
+ * reference encodes one file at a time (:162-211); here consecutive `.jls` / `.h265` outputs of the same shape are read
+ * straight into one page-locked staging arena and encoded by ONE call of the batch C-ABI (imcvtEncodeBatchJLS /
+ * imcvtEncodeBatchHEVC / imcvtEncodeBatchHEVCGreen, include/imcvt_b200.h), which is what keeps the GPU busy.  Each file's
+ * lines are collected and printed in file order, so the text is the reference's byte for byte.
+ *
+ * A pending batch is flushed before a file is looked at whenever that file's source or destination is the destination of
+ * a pending job: the reference's sequential semantics (an output used as a later input, the "already exist" guard on a
+ * name written earlier in the same call) stay observable.
+ *
+ * Formats: PNM in / out is this repo's own reader (pnm_io.c).  The PNG / BMP / QOI loaders and writers are the
+ * reference's format files (out of scope for this engine); they are WEAK references here: linked
+ * in (oracle/Makefile: _ref/ImCvt_batch) they work as in the reference, left out such inputs fail with the reference's
+ * "open ... failed" line and such outputs with its "write ... failed" line.
+ *
+ * Deliberate deviation: `-o <file>` in front of any input makes the reference write dst_fnames[-1];
+ * here that output name is ignored.
+ *
+ * Environment: IMCVT_DEVICE = CUDA device ordinal (default: current), IMCVT_BATCH = most frames per batch (default 256).
+ */
+#include <stdint.h>
+#include <stdlib.h>
+#include <stdio.h>
+#include <string.h>
+#include <stdarg.h>
+#include <limits.h>
+#include <unistd.h>
+#include "imcvt_b200.h"
+#include "imcvt_pnm.h"
+
+int      writePNMImageFile(const char *, const uint8_t *, int, uint32_t, uint32_t);
+extern uint8_t *loadPNGImageFile(const char *, int *, uint32_t *, uint32_t *) __attribute__((weak));
+extern uint8_t *loadBMPImageFile(const char *, int *, uint32_t *, uint32_t *) __attribute__((weak));
+extern uint8_t *loadQOIImageFile(const char *, int *, uint32_t *, uint32_t *) __attribute__((weak));
+extern int writePNGImageFile(const char *, const uint8_t *, int, uint32_t, uint32_t) __attribute__((weak));
+extern int writeBMPImageFile(const char *, const uint8_t *, int, uint32_t, uint32_t) __attribute__((weak));
+extern int writeQOIImageFile(const char *, const uint8_t *, int, uint32_t, uint32_t) __attribute__((weak));
+
+static const char *const USAGE_LINES[] = {
+    "|------------------------------------------------------------------------------------|",
+    "| ImageConverter (v0.5)  by https://github.com/WangXuan95/                           |",
+    "|------------------------------------------------------------------------------------|",
+    "| Usage:                                                                             |",
+    "|   ImCvt [-switches]  <in1> -o <out1>  [<in2> -o <out2]  ...                        |",
+    "|                                                                                    |",
+    "| Where <in> and <out> can be:                                                       |",
+    "|   .pnm (Portable Any Map)          : gray 8-bit or RGB 24-bit                      |",
+    "|   .pgm (Portable Gray Map)         : gray 8-bit                                    |",
+    "|   .ppm (Portable Pix Map)          : RGB 24-bit                                    |",
+    "|   .png (Portable Network Graphics) : gray 8-bit or RGB 24-bit                      |",
+    "|   .bmp (Bitmap Image File)         : gray 8-bit or RGB 24-bit                      |",
+    "|   .qoi (Quite OK Image)            : RGB 24-bit                                    |",
+    "|   .jls (JPEG-LS Image)             : gray 8-bit or RGB 24-bit, can be <out> only!  |",
+    "|   .h265 (H.265/HEVC Image)         : gray 8-bit              , can be <out> only!  |",
+    "|                                                                                    |",
+    "| switches:    -f                    : force overwrite of output file                |",
+    "|              -0, -1, -2, -3, -4    : JPEG-LS near value or H.265 (qp-4)/6 value    |",
+    "|------------------------------------------------------------------------------------|",
+    "",
+};
+
+#define MAX_FILES 999                   /* src/main.c:84 */
+#define HEVC_RGB_WARNING "   warning: this HEVCencoder currently only support gray 8-bit image instead of RGB image. Only compress the green channel of this image.\n"
+
+enum { OUT_NONE = 0, OUT_PNM, OUT_PNG, OUT_BMP, OUT_QOI, OUT_JLS, OUT_HEVC };
+
+typedef struct {
+    const char *src, *dst;
+    char *dst_own;                      /* default "<src>.png" name when no -o was given */
+    char *canon_dst;                    /* canonical destination path, for the hazard check */
+    char *text;                         /* this file's stdout lines */
+    size_t text_len, text_cap;
+    int resolved;                       /* nothing more will be appended to text */
+    int ok;
+} Job;
+
+typedef struct {
+    int kind, is_rgb, n, max_n;
+    uint32_t h, w;
+    size_t frame_bytes;
+    int idx[MAX_FILES];                 /* job index of each frame of the batch */
+    uint8_t *arena;                     /* page-locked when the engine is up, else malloc'd (the encode call then fails) */
+    size_t arena_cap;
+    int arena_pinned;
+} Batch;
+
+static Job g_jobs[MAX_FILES];
+static int g_njobs, g_printed, g_setting, g_batch_limit = 256;
+static Batch g_batch;
+
+static void say(Job *j, const char *fmt, ...)
+{
+    va_list ap;
+    int need;
+    va_start(ap, fmt);
+    need = vsnprintf(NULL, 0, fmt, ap);
+    va_end(ap);
+    if (j->text_len + (size_t)need + 1 > j->text_cap) {
+        j->text_cap = (j->text_len + (size_t)need + 1) * 2;
+        j->text = (char *)realloc(j->text, j->text_cap);
+        if (j->text == NULL) { fprintf(stderr, "out of memory\n"); exit(-1); }
+    }
+    va_start(ap, fmt);
+    vsnprintf(j->text + j->text_len, (size_t)need + 1, fmt, ap);
+    va_end(ap);
+    j->text_len += (size_t)need;
+}
+
+/* a file's lines go out as soon as every file in front of it is resolved */
+static void print_resolved(void)
+{
+    while (g_printed < g_njobs && g_jobs[g_printed].resolved) {
+        Job *j = &g_jobs[g_printed++];
+        if (j->text_len)
+            fwrite(j->text, 1, j->text_len, stdout);
+        free(j->text);
+        j->text = NULL;
+        j->text_len = j->text_cap = 0;
+    }
+    fflush(stdout);
+}
+
+static void fail(Job *j, const char *fmt, const char *name)
+{
+    say(j, "   ***ERROR: ");
+    say(j, fmt, name);
+    say(j, "\n");
+    j->resolved = 1;
+}
+
+static int ends_with_nocase(const char *s, const char *suffix)
+{
+    size_t n = strlen(s), m = strlen(suffix), i;
+    if (m > n)
+        return 0;
+    for (i = 0; i < m; i++) {
+        int a = s[n - m + i], b = suffix[i];
+        if (a >= 'A' && a <= 'Z') a += 32;
+        if (b >= 'A' && b <= 'Z') b += 32;
+        if (a != b)
+            return 0;
+    }
+    return 1;
+}
+
+static int out_kind(const char *dst)            /* suffix dispatch of src/main.c:189-204 (no dot required there either) */
+{
+    if (ends_with_nocase(dst, "pnm") || ends_with_nocase(dst, "ppm") || ends_with_nocase(dst, "pgm")) return OUT_PNM;
+    if (ends_with_nocase(dst, "png")) return OUT_PNG;
+    if (ends_with_nocase(dst, "bmp")) return OUT_BMP;
+    if (ends_with_nocase(dst, "qoi")) return OUT_QOI;
+    if (ends_with_nocase(dst, "jls")) return OUT_JLS;
+    if (ends_with_nocase(dst, "h265") || ends_with_nocase(dst, "265") || ends_with_nocase(dst, "hevc")) return OUT_HEVC;
+    return OUT_NONE;
+}
+
+/* "<src minus its last suffix>.png" (src/main.c:50-74: the suffix is looked for after the last path separator only) */
+static char *default_png_name(const char *src)
+{
+    size_t n = strlen(src), cut = n, i;
+    char *s = (char *)malloc(n + 5);
+    if (s == NULL) { fprintf(stderr, "out of memory\n"); exit(-1); }
+    for (i = n; i-- > 0;) {
+        if (src[i] == '/' || src[i] == '\\')
+            break;
+        if (src[i] == '.') { cut = i; break; }
+    }
+    memcpy(s, src, cut);
+    memcpy(s + cut, ".png", 5);
+    return s;
+}
+
+static int file_exists(const char *name)
+{
+    FILE *fp = fopen(name, "rb");
+    if (fp)
+        fclose(fp);
+    return fp != NULL;
+}
+
+/* canonical form of a path that may not exist yet: realpath of its directory + its last component */
+static char *canon_path(const char *path)
+{
+    char buf[PATH_MAX], dir[PATH_MAX];
+    const char *slash = strrchr(path, '/'), *base = slash ? slash + 1 : path;
+    char *out;
+    size_t n;
+    if (realpath(path, buf))
+        return strdup(buf);
+    if (slash == NULL) {
+        strcpy(dir, ".");
+    } else {
+        n = (size_t)(slash - path);
+        if (n == 0) n = 1;                                          /* "/name" */
+        if (n >= sizeof dir)
+            return strdup(path);
+        memcpy(dir, path, n);
+        dir[n] = 0;
+    }
+    if (!realpath(dir, buf))
+        return strdup(path);
+    out = (char *)malloc(strlen(buf) + strlen(base) + 2);
+    if (out)
+        sprintf(out, "%s/%s", buf, base);
+    return out;
+}
+
+static int dump(const char *name, const uint8_t *buf, size_t len)
+{
+    int failed = 1;
+    FILE *fp = fopen(name, "wb");
+    if (fp) {
+        failed = (len != fwrite(buf, 1, len, fp));
+        fclose(fp);
+    }
+    return failed;
+}
+
+/* ---- the pending batch ------------------------------------------------------------------------------------------- */
+
+static void flush_batch(void)
+{
+    Batch *B = &g_batch;
+    size_t bound, *len;
+    uint8_t *out;
+    int failed, i;
+    if (B->n == 0)
+        return;
+    bound = B->kind == OUT_JLS ? imcvtJLSBound(B->is_rgb, B->h, B->w) : imcvtHEVCBound(B->h, B->w);
+    out = (uint8_t *)malloc((size_t)B->n * bound);
+    len = (size_t *)calloc((size_t)B->n, sizeof *len);
+    failed = (out == NULL || len == NULL);
+    if (!failed) {
+        if (B->kind == OUT_JLS)
+            failed = imcvtEncodeBatchJLS(B->arena, B->frame_bytes, B->n, B->is_rgb, B->h, B->w, g_setting, out, bound, len);
+        else if (B->is_rgb)
+            failed = imcvtEncodeBatchHEVCGreen(B->arena, B->frame_bytes, B->n, B->h, B->w, g_setting, out, bound, len);
+        else
+            failed = imcvtEncodeBatchHEVC(B->arena, B->frame_bytes, B->n, B->h, B->w, g_setting, out, bound, len, NULL, 0);
+        if (failed)
+            fprintf(stderr, "imcvt_b200: %s\n", imcvtLastError());
+    }
+    for (i = 0; i < B->n; i++) {
+        Job *j = &g_jobs[B->idx[i]];
+        if (failed || len[i] == 0 || dump(j->dst, out + (size_t)i * bound, len[i])) {
+            fail(j, "write %s failed", j->dst);
+        } else {
+            j->ok = 1;
+            j->resolved = 1;
+        }
+    }
+    free(out);
+    free(len);
+    B->n = 0;
+    print_resolved();
+}
+
+static void arena_release(void)
+{
+    Batch *B = &g_batch;
+    if (B->arena) {
+        if (B->arena_pinned) imcvtHostFree(B->arena); else free(B->arena);
+    }
+    B->arena = NULL;
+    B->arena_cap = 0;
+}
+
+/* opens a batch for frames of this key unless the pending one already has it; returns the slot of the next frame */
+static uint8_t *batch_slot(int kind, int is_rgb, uint32_t h, uint32_t w)
+{
+    Batch *B = &g_batch;
+    const size_t frame_bytes = (size_t)h * w * (is_rgb ? 3 : 1);
+    if (B->n && (B->kind != kind || B->is_rgb != is_rgb || B->h != h || B->w != w || B->n >= B->max_n))
+        flush_batch();
+    if (B->n == 0) {
+        /* frames per batch: the limit, and at most about 2 GiB of staged pixels */
+        size_t fit = ((size_t)2 << 30) / frame_bytes, need;
+        B->kind = kind; B->is_rgb = is_rgb; B->h = h; B->w = w; B->frame_bytes = frame_bytes;
+        B->max_n = (int)(fit < 1 ? 1 : fit > (size_t)g_batch_limit ? (size_t)g_batch_limit : fit);
+        /* the arena only grows, and in whole batches of the CURRENT shape as long as files of it may follow */
+        need = frame_bytes * (size_t)B->max_n;
+        if (need > B->arena_cap) {
+            int remaining = g_njobs, cap_n;
+            cap_n = remaining < B->max_n ? remaining : B->max_n;
+            need = frame_bytes * (size_t)cap_n;
+            B->max_n = cap_n;
+        }
+        if (need > B->arena_cap) {
+            arena_release();
+            B->arena = (uint8_t *)imcvtHostAlloc(need);
+            B->arena_pinned = B->arena != NULL;
+            if (B->arena == NULL)
+                B->arena = (uint8_t *)malloc(need);     /* no device: the encode call reports it, the job fails like a write */
+            if (B->arena == NULL)
+                return NULL;
+            B->arena_cap = need;
+        }
+    }
+    return B->arena + (size_t)B->n * frame_bytes;
+}
+
+/* The linked-in format files print their warnings straight to stdout (src/imageio_png.c:170); while they run, stdout is
+ * pointed at a temporary file whose content is then appended to the job's own lines, so the order stays the reference's. */
+static FILE *g_cap_file;
+static int g_cap_saved = -1;
+
+static void capture_begin(void)
+{
+    fflush(stdout);
+    g_cap_file = tmpfile();
+    if (g_cap_file == NULL)
+        return;
+    g_cap_saved = dup(1);
+    if (g_cap_saved < 0 || dup2(fileno(g_cap_file), 1) < 0) {
+        if (g_cap_saved >= 0) close(g_cap_saved);
+        g_cap_saved = -1;
+        fclose(g_cap_file);
+        g_cap_file = NULL;
+    }
+}
+
+static void capture_end(Job *j)
+{
+    char buf[1024];
+    size_t n;
+    if (g_cap_file == NULL)
+        return;
+    fflush(stdout);
+    dup2(g_cap_saved, 1);
+    close(g_cap_saved);
+    g_cap_saved = -1;
+    rewind(g_cap_file);
+    while ((n = fread(buf, 1, sizeof buf - 1, g_cap_file)) > 0) {
+        buf[n] = 0;
+        say(j, "%s", buf);
+    }
+    fclose(g_cap_file);
+    g_cap_file = NULL;
+}
+
+/* ---- one file ----------------------------------------------------------------------------------------------------- */
+
+static uint8_t *load_other_formats(Job *j, const char *src, int *is_rgb, uint32_t *h, uint32_t *w)
+{
+    uint8_t *img = NULL;
+    if (!loadPNGImageFile && !loadBMPImageFile && !loadQOIImageFile)
+        return NULL;
+    capture_begin();
+    if (img == NULL && loadPNGImageFile) img = loadPNGImageFile(src, is_rgb, h, w);
+    if (img == NULL && loadBMPImageFile) img = loadBMPImageFile(src, is_rgb, h, w);
+    if (img == NULL && loadQOIImageFile) img = loadQOIImageFile(src, is_rgb, h, w);
+    capture_end(j);
+    return img;
+}
+
+static void convert(int i_file, int force_write)
+{
+    Job *j = &g_jobs[i_file];
+    const int kind = out_kind(j->dst);
+    uint8_t *img = NULL, *slot = NULL;
+    uint32_t h = 0, w = 0;
+    int is_rgb = 0, failed = 0, i, staged = 0;
+    FILE *fp;
+
+    /* sequential semantics: nothing this file reads or guards may still be owed by the pending batch */
+    if (g_batch.n) {
+        char *cs = canon_path(j->src);
+        for (i = 0; i < g_batch.n; i++) {
+            const char *pd = g_jobs[g_batch.idx[i]].canon_dst;
+            if (pd && ((cs && !strcmp(cs, pd)) || (j->canon_dst && !strcmp(j->canon_dst, pd)))) {
+                flush_batch();
+                break;
+            }
+        }
+        free(cs);
+    }
+
+    say(j, "(%d/%d)  %s -> %s\n", i_file + 1, g_njobs, j->src, j->dst);
+    if (!file_exists(j->src)) { fail(j, "%s not exist", j->src); return; }
+    if (!force_write && file_exists(j->dst)) { fail(j, "%s already exist", j->dst); return; }
+
+    /* load: PNM first (src/main.c:183); pixels of a codec job land in the staging arena, not in a buffer of their own */
+    if ((fp = fopen(j->src, "rb")) != NULL) {
+        ImcvtPNMHeader hd;
+        if (!imcvtPNMReadHeader(fp, &hd)) {
+            const int jls_dims_bad = hd.width > 32767 || hd.height > 32767;                 /* src/imageio_jls.c:436 */
+            if ((kind == OUT_JLS && !jls_dims_bad) || kind == OUT_HEVC) {
+                slot = batch_slot(kind, hd.is_rgb, hd.height, hd.width);
+                if (slot && !imcvtPNMReadPixels(fp, &hd, slot)) {
+                    staged = 1;
+                    is_rgb = hd.is_rgb; h = hd.height; w = hd.width;
+                }
+            } else if ((img = (uint8_t *)malloc(hd.bytes + 8)) != NULL) {
+                if (imcvtPNMReadPixels(fp, &hd, img)) {
+                    free(img);
+                    img = NULL;
+                } else {
+                    is_rgb = hd.is_rgb; h = hd.height; w = hd.width;
+                }
+            }
+        }
+        fclose(fp);
+    }
+    if (!staged && img == NULL)
+        img = load_other_formats(j, j->src, &is_rgb, &h, &w);
+    if (!staged && img == NULL) { fail(j, "open %s failed", j->src); return; }
+
+    if (kind == OUT_NONE) {
+        free(img);
+        fail(j, "unsupported output suffix: %s", j->dst);
+        return;
+    }
+    if (kind == OUT_JLS || kind == OUT_HEVC) {
+        if (kind == OUT_HEVC && is_rgb)
+            say(j, HEVC_RGB_WARNING);                                                       /* src/imageio_hevc.c:22 */
+        if (!staged) {
+            /* decoded by one of the other loaders (or JPEG-LS dimensions out of range): copy into the arena */
+            if ((kind == OUT_JLS && (w < 1 || w > 32767 || h < 1 || h > 32767)) || w < 1 || h < 1 ||
+                (slot = batch_slot(kind, is_rgb, h, w)) == NULL) {
+                free(img);
+                fail(j, "write %s failed", j->dst);
+                return;
+            }
+            memcpy(slot, img, (size_t)h * w * (is_rgb ? 3 : 1));
+            free(img);
+        }
+        g_batch.idx[g_batch.n++] = i_file;          /* resolved by flush_batch() */
+        return;
+    }
+    capture_begin();
+    switch (kind) {
+    case OUT_PNM: failed = writePNMImageFile(j->dst, img, is_rgb, h, w); break;
+    case OUT_PNG: failed = writePNGImageFile ? writePNGImageFile(j->dst, img, is_rgb, h, w) : 1; break;
+    case OUT_BMP: failed = writeBMPImageFile ? writeBMPImageFile(j->dst, img, is_rgb, h, w) : 1; break;
+    default:      failed = writeQOIImageFile ? writeQOIImageFile(j->dst, img, is_rgb, h, w) : 1; break;
+    }
+    capture_end(j);
+    free(img);
+    if (failed) { fail(j, "write %s failed", j->dst); return; }
+    j->ok = 1;
+    j->resolved = 1;
+}
+
+int main(int argc, char **argv)
+{
+    int switches[128] = {0}, i, next_is_dst = 0, n_file = -1, force_write, n_success = 0, n_failed;
+    const char *env;
+
+    for (i = 1; i < argc; i++) {                                    /* src/main.c:87-132 */
+        const char *arg = argv[i];
+        if (arg[0] == '-') {
+            for (arg++; *arg; arg++) {
+                if ((unsigned char)*arg < 128)
+                    switches[(unsigned char)*arg] = 1;
+                if (*arg == 'o')
+                    next_is_dst = 1;
+            }
+        } else if (n_file + 1 < MAX_FILES) {
+            if (next_is_dst) {
+                next_is_dst = 0;
+                if (n_file >= 0)
+                    g_jobs[n_file].dst = arg;
+            } else {
+                g_jobs[++n_file].src = arg;
+            }
+        }
+    }
+    g_njobs = n_file + 1;
+    force_write = switches['F'] || switches['f'];
+    g_setting = switches['4'] ? 4 : switches['3'] ? 3 : switches['2'] ? 2 : switches['1'] ? 1 : 0;
+    if (g_njobs <= 0) {
+        for (i = 0; i < (int)(sizeof USAGE_LINES / sizeof USAGE_LINES[0]); i++)
+            printf("%s\n", USAGE_LINES[i]);
+        return -1;
+    }
+    if ((env = getenv("IMCVT_BATCH")) != NULL && atoi(env) > 0)
+        g_batch_limit = atoi(env) < MAX_FILES ? atoi(env) : MAX_FILES;
+    if ((env = getenv("IMCVT_DEVICE")) != NULL)
+        imcvtInit(atoi(env));                                       /* a failure shows up at the first encode call */
+
+    for (i = 0; i < g_njobs; i++) {
+        Job *j = &g_jobs[i];
+        if (j->dst == NULL)
+            j->dst = j->dst_own = default_png_name(j->src);
+        j->canon_dst = canon_path(j->dst);
+    }
+    for (i = 0; i < g_njobs; i++) {
+        convert(i, force_write);
+        print_resolved();
+    }
+    flush_batch();
+    print_resolved();
+    arena_release();
+    imcvtShutdown();
+
+    for (i = 0; i < g_njobs; i++) {
+        n_success += g_jobs[i].ok;
+        free(g_jobs[i].dst_own);
+        free(g_jobs[i].canon_dst);
+    }
+    n_failed = g_njobs - n_success;
+    if (g_njobs > 1) {
+        printf("\nsummary:");
+        if (n_success) printf("  %d file converted", n_success);
+        if (n_failed)  printf("  %d failed", n_failed);
+        printf("\n");
+    }
+    return n_failed;
+}

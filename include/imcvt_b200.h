@@ -64,10 +64,24 @@ int imcvtEncodeBatchHEVC(const uint8_t *frames, size_t frame_stride, int n,
                          uint8_t *out, size_t out_stride, size_t *out_len,
                          uint8_t *rcon, size_t rcon_stride);
 
+/* Same as imcvtEncodeBatchHEVC without rcon, for interleaved RGB24 frames: the engine encodes the GREEN channel, which is
+ * what the reference's wrapper does with RGB input (src/imageio_hevc.c:21-26; the caller prints its warning line).  The
+ * channel is picked on the device by a small kernel instead of a host loop over every pixel. */
+int imcvtEncodeBatchHEVCGreen(const uint8_t *rgb_frames, size_t frame_stride, int n,
+                              uint32_t height, uint32_t width, int qpd6,
+                              uint8_t *out, size_t out_stride, size_t *out_len);
+
 int imcvtEncodeBatchHEVCDevice(const void *d_frames, size_t frame_stride, int n,
                                uint32_t height, uint32_t width, int qpd6,
                                void *d_out, size_t out_stride, void *d_out_len,
                                void *d_rcon, size_t rcon_stride, void *stream);
+
+/* ---- staging memory ---------------------------------------------------------------------------- */
+/* Page-locked host memory for the frames / out arguments of the host-buffer entry points: copies from and to it run at
+ * full PCIe rate and overlap the kernels.  A loader that reads image files straight into such a buffer replaces the
+ * reference's malloc per image (src/imageio_pnm.c:112) plus a staging copy.  NULL on failure (imcvtLastError()). */
+void *imcvtHostAlloc(size_t bytes);
+void  imcvtHostFree(void *p);
 
 /* ---- instrumentation ------------------------------------------------------------------------- */
 /* When enabled, every kernel launch of the engine is bracketed by CUDA events on its own stream;
