@@ -751,31 +751,40 @@ static inline size_t round_up(size_t v, size_t a) { return (v + a - 1) / a * a; 
 
 // ------------------------------------------------------------------------------------------------
 // Row-pipelined scan: any NEAR, the path for NEAR > 0.  With NEAR > 0 the reconstructed value of a sample feeds the
-// context of the next one (:321-323), so a plane is ONE dependency chain; what can be taken off that chain is:
-//   both warps   per segment of <= 2048 samples of a row: stage the input, and the two gradient terms that only need the
-//                row above, 81*q(d-b) + 9*q(b-c), from the reconstructed row kept in shared memory;
-//   warp 0       lane 0 walks the segment (:276-394): third gradient by table, context state in shared memory, error
-//                quantisation by table (no divisions), code + length per sample into shared memory;
-//   warp 1       meanwhile packs the previous segment's codes (register windows, tile-wide bit buffer) and turns them into
+// context of the next one (:321-323), so a plane is ONE dependency chain; everything that is not on that chain is taken
+// off the thread that walks it.  Three warps per plane, each a segment (<= 2048 samples of a row) behind the previous one:
+//   warp 0       all lanes stage the input and the two gradient terms that only need the row above, 81*q(d-b) + 9*q(b-c),
+//                from the reconstructed row kept in shared memory.  Then lane 0 walks the segment with ONLY the
+//                recurrence: third gradient by table, run state, prediction with the bias C of the context, error
+//                quantisation by table (no divisions), reconstruction, and the B / C / N update the next prediction of
+//                that context needs (:346-394 without A, k and the code).  It leaves one record per sample.
+//   warp 2       lane 0 turns the previous segment's records into codes: A and N per context (N evolves the same way in
+//                both stages), Golomb parameter, mapping, code + length; run-length counting and the run-interruption
+//                samples with their own A / B / N (:291-344) live here too -- none of them feeds the reconstruction.
+//   warp 1       packs the codes of the segment before that (register windows, tile-wide bit buffer) and turns them into
 //                0xFF-stuffed bytes with the packer of the tile kernel.
-// One CTA of two warps per plane.
 // ------------------------------------------------------------------------------------------------
 namespace rowscan {
 constexpr int SEG = 2048;
 constexpr int WMAXR = 32768;                        // :436
+constexpr int NT = 96;
+// record of one sample, stage 1 -> stage 2
+constexpr uint32_t REC_REGULAR = 0, REC_HIT = 1, REC_BREAK = 2;
 struct Smem {
     uint8_t row[2][WMAXR + 16];                     // reconstructed rows y-1 / y (index 8 + x)
     uint8_t in[SEG];
     short q12[SEG];
+    uint32_t rec[2][SEG];                           // type | context << 2 (break: RItype << 2) | map hint << 11 | (error + 256) << 12
     uint32_t codes[2][SEG + SEG / 32];
     uint8_t lens[2][SEG + SEG / 8];
     uint32_t ubits[tile::UBITS_WORDS];
-    int4 ctx[NCTX];
+    int4 ctx[NCTX];                                 // stage 1: (unused, B, C, N)
+    int2 ctx2[NCTX];                                // stage 2: (A, N)
     signed char gq[512];                            // quantised gradient at [g + 255]
     short eq[512];                                  // quantised prediction error at [e + 255] (:97-102)
 };
 
-__global__ void __launch_bounds__(64, 1)
+__global__ void __launch_bounds__(NT, 1)
 rowscan_kernel(const uint8_t *__restrict__ pix, size_t plane_stride, int W, int H, SerialParams P, FrameLayout L,
                uint64_t *__restrict__ plane_bytes)
 {
@@ -787,31 +796,30 @@ rowscan_kernel(const uint8_t *__restrict__ pix, size_t plane_stride, int W, int 
     const int near_ = P.near_, quant = P.quant, range = P.range;
     const int half = (range + 1) / 2;
 
-    for (int k = tid; k < NCTX; k += 64) sm.ctx[k] = make_int4(P.a_init, 0, 0, 1);
-    for (int i = tid; i < 511; i += 64) {
+    for (int k = tid; k < NCTX; k += NT) { sm.ctx[k] = make_int4(0, 0, 0, 1); sm.ctx2[k] = make_int2(P.a_init, 1); }
+    for (int i = tid; i < 511; i += NT) {
         const int g = i - 255;
         sm.gq[i] = (signed char)grad_q_any(P, g);
         sm.eq[i] = (short)(g < 0 ? -((near_ - g) / quant) : (near_ + g) / quant);
     }
-    for (int i = tid; i < WMAXR + 16; i += 64) { sm.row[0][i] = 0; sm.row[1][i] = 0; }      // the row above the picture reads as zeros
+    for (int i = tid; i < WMAXR + 16; i += NT) { sm.row[0][i] = 0; sm.row[1][i] = 0; }      // the row above the picture reads as zeros
 
     tile::PackState ps; ps.out_pos = 0; ps.carry_bits = 0; ps.carry = 0; ps.pz = 0;
     ps.dst = plane_dst(L, p, ps.cap);
 
-    int rA[2] = {P.a_init, P.a_init}, rB[2] = {0, 0}, rN[2] = {1, 1};
-    int run_index = 0;
     const int nseg = (W + SEG - 1) / SEG, total = H * nseg;
-    // row state of the scanning lane
+    // stage 1 (lane 0 of warp 0): row state of the walk
     bool in_run = false;
-    int run_len = 0, a = 0, b = 0, c = 0, up2 = 0;
+    int a = 0, b = 0, c = 0, up2 = 0;
+    // stage 2 (lane 0 of warp 2): run state and the two run-interruption contexts
+    int rA0 = P.a_init, rA1 = P.a_init, rB0 = 0, rB1 = 0, rN0 = 1, rN1 = 1;      // scalars: an indexed array would live in local memory
+    int run_index = 0, run_len = 0;
     __syncthreads();
 
-    for (int it = 0; it <= total; it++) {
-        const int y = it / nseg, sg = it - y * nseg, x0 = sg * SEG, n = it < total ? min(SEG, W - x0) : 0;
-        const int buf = it & 1;
-        if (warp == 1 && it > 0) {
-            // ---- pack the previous segment ----
-            const int pit = it - 1, py = pit / nseg, psg = pit - py * nseg, pn = min(SEG, W - psg * SEG), pb = pit & 1;
+    for (int it = 0; it < total + 2; it++) {
+        if (warp == 1 && it >= 2) {
+            // ---- pack the segment before the previous one ----
+            const int pit = it - 2, py = pit / nseg, psg = pit - py * nseg, pn = min(SEG, W - psg * SEG), pb = pit & 1;
             const uint32_t *codes = sm.codes[pb];
             const uint8_t *lens = sm.lens[pb];
             uint32_t T = 0;                                              // bits of the segment
@@ -856,105 +864,133 @@ rowscan_kernel(const uint8_t *__restrict__ pix, size_t plane_stride, int W, int 
             }
             tile::stuff_bits(sm.ubits, ps, T, pit == total - 1, lane);
         }
-        if (n > 0) {
-            // ---- stage the segment: input, and the gradient terms of the row above (warp 0; warp 1 joins when it has packed) ----
-            const uint8_t *up = sm.row[(y + 1) & 1] + 8, *in_row = src + (size_t)y * W + x0;
-            if (warp == 0) {
-                for (int i = lane; i < n; i += 32) {
-                    const int x = x0 + i;
-                    sm.in[i] = in_row[i];
-                    const int bb = up[x], cc = x > 0 ? up[x - 1] : 0, dd = x + 1 < W ? up[x + 1] : bb;
-                    sm.q12[i] = (short)(81 * sm.gq[dd - bb + 255] + 9 * sm.gq[bb - cc + 255]);
+        if (warp == 2 && lane == 0 && it >= 1 && it <= total) {
+            // ---- stage 2: records of the previous segment -> code + length per sample ----
+            const int pit = it - 1, py = pit / nseg, psg = pit - py * nseg, px0 = psg * SEG, pn = min(SEG, W - px0), pb = pit & 1;
+            const uint32_t *rec = sm.rec[pb];
+            uint32_t *codes = sm.codes[pb];
+            uint8_t *lens = sm.lens[pb];
+            if (px0 == 0) run_len = 0;                                   // :270
+            for (int i = 0; i < pn; i++) {
+                const uint32_t r = rec[i];
+                const uint32_t type = r & 3u;
+                int e = (int)((r >> 12) & 1023u) - 256;
+                uint32_t code = 0; int len = 0;
+                if (type == REC_REGULAR) {
+                    const int q = (int)((r >> 2) & 511u);
+                    int2 st = sm.ctx2[q];
+                    const int k = golomb_k(st.x, st.y);
+                    const int map = (k == 0) && ((r >> 11) & 1u);        // the hint is (2B <= -N) && NEAR == 0 (:367)
+                    const int me = 2 * abs(e) + (e < 0 ? -(map + 1) : map);
+                    golomb_code(me, k, P.limit, P.qbpp, code, len);
+                    st.x += abs(e);
+                    if (st.y >= 64) { st.x >>= 1; st.y >>= 1; }
+                    st.y++;
+                    sm.ctx2[q] = st;
+                } else if (type == REC_HIT) {
+                    run_len++;
+                    const int jj = tile::run_order(run_index);
+                    if (run_len >= (1 << jj)) {
+                        code = 1; len = 1;
+                        run_len -= 1 << jj;
+                        if (run_index < 31) run_index++;
+                    }
+                    if (px0 + i == W - 1 && run_len > 0) { code = (code << 1) | 1u; len++; }
+                } else {
+                    const int t = (int)((r >> 2) & 1u);
+                    const int jj = tile::run_order(run_index);
+                    const int glimit = P.limit - 1 - jj;
+                    const int rem = run_len;
+                    run_len = 0;
+                    if (run_index > 0) run_index--;
+                    int At = t ? rA1 : rA0, Bt = t ? rB1 : rB0, Nt = t ? rN1 : rN0;
+                    const int k = golomb_k(At + (t ? (Nt >> 1) : 0), Nt);
+                    const int map = (e != 0) && ((e > 0) == (k == 0 && 2 * Bt < Nt));
+                    const int me = 2 * abs(e) - t - map;
+                    uint32_t gcode; int glen;
+                    golomb_code(me, k, glimit, P.qbpp, gcode, glen);
+                    code = ((uint32_t)rem << glen) | gcode;              // run remainder in J+1 bits, then the Golomb code (<= 32 bits)
+                    len = jj + 1 + glen;
+                    if (e < 0) Bt++;
+                    At += (me + 1 - t) >> 1;
+                    if (Nt >= 64) { At >>= 1; Bt >>= 1; Nt >>= 1; }
+                    Nt++;
+                    if (t) { rA1 = At; rB1 = Bt; rN1 = Nt; } else { rA0 = At; rB0 = Bt; rN0 = Nt; }
                 }
-                __syncwarp();
-                if (lane == 0) {
-                    uint8_t *cur = sm.row[y & 1] + 8;
-                    uint32_t *codes = sm.codes[buf];
-                    uint8_t *lens = sm.lens[buf];
-                    if (x0 == 0) {                                       // row start (:270, :47-56)
-                        in_run = false; run_len = 0;
-                        b = up[0]; a = b; c = up2;
-                        up2 = b;                                         // recon(y-1, 0) is the c of row y+1's first sample
-                    }
-                    for (int i = 0; i < n; i++) {
-                        const int x = x0 + i;
-                        const int d = x + 1 < W ? up[x + 1] : b;
-                        const int v = sm.in[i];
-                        // the first sample of a row has its own c (two rows up), so its second term is recomputed
-                        const int q12 = x > 0 ? (int)sm.q12[i] : 81 * sm.gq[d - b + 255] + 9 * sm.gq[b - c + 255];
-                        const int qv = q12 + sm.gq[c - a + 255];
-                        bool neg = qv < 0;
-                        const int cq = neg ? -qv : qv;
-                        if (cq == 0) in_run = true;
-                        bool hit = false, brk = false;
-                        if (in_run) { hit = abs(v - a) <= near_; brk = !hit; in_run = hit; }
-                        int rx;
-                        uint32_t code = 0; int len = 0;
-                        if (hit) {
-                            rx = a;
-                            run_len++;
-                            const int jj = tile::run_order(run_index);
-                            if (run_len >= (1 << jj)) {
-                                code = 1; len = 1;
-                                run_len -= 1 << jj;
-                                if (run_index < 31) run_index++;
-                            }
-                            if (x == W - 1 && run_len > 0) { code = (code << 1) | 1u; len++; }
-                        } else if (brk) {
-                            const int jj = tile::run_order(run_index);
-                            const int glimit = P.limit - 1 - jj;
-                            const int rem = run_len;
-                            run_len = 0;
-                            if (run_index > 0) run_index--;
-                            const int t = abs(a - b) <= near_;
-                            neg = a > b + near_;
-                            const int px = t ? a : b;
-                            int e = sm.eq[(neg ? px - v : v - px) + 255];
-                            rx = near_ ? min(max(px + (neg ? -quant * e : quant * e), 0), 255) : v;
-                            if (e < 0) e += range;
-                            if (e >= half) e -= range;
-                            const int k = golomb_k(rA[t] + (t ? (rN[t] >> 1) : 0), rN[t]);
-                            const int map = (e != 0) && ((e > 0) == (k == 0 && 2 * rB[t] < rN[t]));
-                            const int me = 2 * abs(e) - t - map;
-                            uint32_t gcode; int glen;
-                            golomb_code(me, k, glimit, P.qbpp, gcode, glen);
-                            code = ((uint32_t)rem << glen) | gcode;      // run remainder in J+1 bits, then the Golomb code (<= 32 bits)
-                            len = jj + 1 + glen;
-                            if (e < 0) rB[t]++;
-                            rA[t] += (me + 1 - t) >> 1;
-                            if (rN[t] >= 64) { rA[t] >>= 1; rB[t] >>= 1; rN[t] >>= 1; }
-                            rN[t]++;
-                        } else {
-                            run_len = 0;
-                            int4 st = sm.ctx[cq - 1];
-                            int px = med3(a, b, c) + (neg ? -st.z : st.z);
-                            px = min(max(px, 0), 255);
-                            int e = sm.eq[(neg ? px - v : v - px) + 255];
-                            rx = near_ ? min(max(px + (neg ? -quant * e : quant * e), 0), 255) : v;
-                            if (e < 0) e += range;
-                            if (e >= half) e -= range;
-                            const int k = golomb_k(st.x, st.w);
-                            const int map = (k == 0) && (2 * st.y <= -st.w) && (near_ == 0);
-                            const int me = 2 * abs(e) + (e < 0 ? -(map + 1) : map);
-                            golomb_code(me, k, P.limit, P.qbpp, code, len);
-                            st.y += e * quant;
-                            st.x += abs(e);
-                            if (st.w >= 64) { st.x >>= 1; st.y >>= 1; st.w >>= 1; }
-                            st.w++;
-                            if (st.y <= -st.w) {
-                                st.y += st.w; if (st.y <= -st.w) st.y = -st.w + 1;
-                                st.z = max(st.z - 1, -128);
-                            } else if (st.y > 0) {
-                                st.y -= st.w; if (st.y > 0) st.y = 0;
-                                st.z = min(st.z + 1, 127);
-                            }
-                            sm.ctx[cq - 1] = st;
+                codes[tile::code_idx(i)] = code;
+                lens[tile::len_idx(i)] = (uint8_t)len;
+            }
+        }
+        if (warp == 0 && it < total) {
+            // ---- stage the segment (input + the gradient terms of the row above), then stage 1 on lane 0 ----
+            const int y = it / nseg, sg = it - y * nseg, x0 = sg * SEG, n = min(SEG, W - x0);
+            const uint8_t *up = sm.row[(y + 1) & 1] + 8, *in_row = src + (size_t)y * W + x0;
+            for (int i = lane; i < n; i += 32) {
+                const int x = x0 + i;
+                sm.in[i] = in_row[i];
+                const int bb = up[x], cc = x > 0 ? up[x - 1] : 0, dd = x + 1 < W ? up[x + 1] : bb;
+                sm.q12[i] = (short)(81 * sm.gq[dd - bb + 255] + 9 * sm.gq[bb - cc + 255]);
+            }
+            __syncwarp();
+            if (lane == 0) {
+                uint8_t *cur = sm.row[y & 1] + 8;
+                uint32_t *rec = sm.rec[it & 1];
+                if (x0 == 0) {                                           // row start (:270, :47-56)
+                    in_run = false;
+                    b = up[0]; a = b; c = up2;
+                    up2 = b;                                             // recon(y-1, 0) is the c of row y+1's first sample
+                }
+                for (int i = 0; i < n; i++) {
+                    const int x = x0 + i;
+                    const int d = x + 1 < W ? up[x + 1] : b;
+                    const int v = sm.in[i];
+                    // the first sample of a row has its own c (two rows up), so its second term is recomputed
+                    const int q12 = x > 0 ? (int)sm.q12[i] : 81 * sm.gq[d - b + 255] + 9 * sm.gq[b - c + 255];
+                    const int qv = q12 + sm.gq[c - a + 255];
+                    bool neg = qv < 0;
+                    const int cq = neg ? -qv : qv;
+                    if (cq == 0) in_run = true;
+                    bool hit = false, brk = false;
+                    if (in_run) { hit = abs(v - a) <= near_; brk = !hit; in_run = hit; }
+                    int rx;
+                    uint32_t r;
+                    if (hit) {
+                        rx = a;
+                        r = REC_HIT;
+                    } else if (brk) {
+                        const int t = abs(a - b) <= near_;
+                        neg = a > b + near_;
+                        const int px = t ? a : b;
+                        int e = sm.eq[(neg ? px - v : v - px) + 255];
+                        rx = near_ ? min(max(px + (neg ? -quant * e : quant * e), 0), 255) : v;
+                        if (e < 0) e += range;
+                        if (e >= half) e -= range;
+                        r = REC_BREAK | ((uint32_t)t << 2) | ((uint32_t)(e + 256) << 12);
+                    } else {
+                        int4 st = sm.ctx[cq - 1];
+                        int px = med3(a, b, c) + (neg ? -st.z : st.z);
+                        px = min(max(px, 0), 255);
+                        int e = sm.eq[(neg ? px - v : v - px) + 255];
+                        rx = near_ ? min(max(px + (neg ? -quant * e : quant * e), 0), 255) : v;
+                        if (e < 0) e += range;
+                        if (e >= half) e -= range;
+                        const uint32_t hint = (near_ == 0) && (2 * st.y <= -st.w);
+                        r = REC_REGULAR | ((uint32_t)(cq - 1) << 2) | (hint << 11) | ((uint32_t)(e + 256) << 12);
+                        st.y += e * quant;
+                        if (st.w >= 64) { st.y >>= 1; st.w >>= 1; }
+                        st.w++;
+                        if (st.y <= -st.w) {
+                            st.y += st.w; if (st.y <= -st.w) st.y = -st.w + 1;
+                            st.z = max(st.z - 1, -128);
+                        } else if (st.y > 0) {
+                            st.y -= st.w; if (st.y > 0) st.y = 0;
+                            st.z = min(st.z + 1, 127);
                         }
-                        codes[tile::code_idx(i)] = code;
-                        lens[tile::len_idx(i)] = (uint8_t)len;
-                        cur[x] = (uint8_t)rx;
-                        c = b; b = d; a = rx;                             // slide the template (a = reconstructed left neighbour)
+                        sm.ctx[cq - 1] = st;
                     }
+                    rec[i] = r;
+                    cur[x] = (uint8_t)rx;
+                    c = b; b = d; a = rx;                                 // slide the template (a = reconstructed left neighbour)
                 }
             }
         }
@@ -1153,7 +1189,7 @@ int encode_device(const uint8_t *d_frames, size_t frame_stride, int n, int is_rg
                 E.attr_jls_rowscan = true;
             }
             LaunchScope ls("jls_rowscan", st);
-            rowscan::rowscan_kernel<<<P, 64, sizeof(rowscan::Smem), st>>>(planes, plane_stride, (int)W, (int)H, SP, Lay, plane_bytes);
+            rowscan::rowscan_kernel<<<P, rowscan::NT, sizeof(rowscan::Smem), st>>>(planes, plane_stride, (int)W, (int)H, SP, Lay, plane_bytes);
         }
     }
     {

@@ -20,7 +20,8 @@
  * Deliberate deviation: `-o <file>` in front of any input makes the reference write dst_fnames[-1];
  * here that output name is ignored.
  *
- * Environment: IMCVT_DEVICE = CUDA device ordinal (default: current), IMCVT_BATCH = most frames per batch (default 256).
+ * Environment: IMCVT_DEVICE = CUDA device ordinal (default: current), IMCVT_BATCH = most frames per batch (default 256),
+ * IMCVT_TIMING = 1 prints where the wall-clock time of the call went (stderr).
  */
 #include <stdint.h>
 #include <stdlib.h>
@@ -29,6 +30,7 @@
 #include <stdarg.h>
 #include <limits.h>
 #include <unistd.h>
+#include <time.h>
 #include "imcvt_b200.h"
 #include "imcvt_pnm.h"
 
@@ -87,6 +89,16 @@ typedef struct {
     size_t arena_cap;
     int arena_pinned;
 } Batch;
+
+/* wall-clock phases of the call (IMCVT_TIMING=1) */
+enum { T_STAGE_ALLOC = 0, T_READ, T_ENCODE, T_WRITE, T_SHUTDOWN, T_COUNT };
+static double g_phase[T_COUNT];
+static double now_s(void)
+{
+    struct timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return (double)ts.tv_sec + 1e-9 * (double)ts.tv_nsec;
+}
 
 static Job g_jobs[MAX_FILES];
 static int g_njobs, g_printed, g_setting, g_batch_limit = 256;
@@ -227,6 +239,7 @@ static void flush_batch(void)
     Batch *B = &g_batch;
     size_t bound, *len;
     uint8_t *out;
+    double t_write;
     int failed, i;
     if (B->n == 0)
         return;
@@ -235,6 +248,7 @@ static void flush_batch(void)
     len = (size_t *)calloc((size_t)B->n, sizeof *len);
     failed = (out == NULL || len == NULL);
     if (!failed) {
+        const double t0 = now_s();
         if (B->kind == OUT_JLS)
             failed = imcvtEncodeBatchJLS(B->arena, B->frame_bytes, B->n, B->is_rgb, B->h, B->w, g_setting, out, bound, len);
         else if (B->is_rgb)
@@ -243,7 +257,9 @@ static void flush_batch(void)
             failed = imcvtEncodeBatchHEVC(B->arena, B->frame_bytes, B->n, B->h, B->w, g_setting, out, bound, len, NULL, 0);
         if (failed)
             fprintf(stderr, "imcvt_b200: %s\n", imcvtLastError());
+        g_phase[T_ENCODE] += now_s() - t0;
     }
+    t_write = now_s();
     for (i = 0; i < B->n; i++) {
         Job *j = &g_jobs[B->idx[i]];
         if (failed || len[i] == 0 || dump(j->dst, out + (size_t)i * bound, len[i])) {
@@ -253,6 +269,7 @@ static void flush_batch(void)
             j->resolved = 1;
         }
     }
+    g_phase[T_WRITE] += now_s() - t_write;
     free(out);
     free(len);
     B->n = 0;
@@ -290,11 +307,13 @@ static uint8_t *batch_slot(int kind, int is_rgb, uint32_t h, uint32_t w)
             B->max_n = cap_n;
         }
         if (need > B->arena_cap) {
+            const double t0 = now_s();
             arena_release();
             B->arena = (uint8_t *)imcvtHostAlloc(need);
             B->arena_pinned = B->arena != NULL;
             if (B->arena == NULL)
                 B->arena = (uint8_t *)malloc(need);     /* no device: the encode call reports it, the job fails like a write */
+            g_phase[T_STAGE_ALLOC] += now_s() - t0;
             if (B->arena == NULL)
                 return NULL;
             B->arena_cap = need;
@@ -389,8 +408,11 @@ static void convert(int i_file, int force_write)
         if (!imcvtPNMReadHeader(fp, &hd)) {
             const int jls_dims_bad = hd.width > 32767 || hd.height > 32767;                 /* src/imageio_jls.c:436 */
             if ((kind == OUT_JLS && !jls_dims_bad) || kind == OUT_HEVC) {
+                double t0;
                 slot = batch_slot(kind, hd.is_rgb, hd.height, hd.width);
+                t0 = now_s();
                 if (slot && !imcvtPNMReadPixels(fp, &hd, slot)) {
+                    g_phase[T_READ] += now_s() - t0;
                     staged = 1;
                     is_rgb = hd.is_rgb; h = hd.height; w = hd.width;
                 }
@@ -449,6 +471,7 @@ int main(int argc, char **argv)
 {
     int switches[128] = {0}, i, next_is_dst = 0, n_file = -1, force_write, n_success = 0, n_failed;
     const char *env;
+    const double t_start = now_s();
 
     for (i = 1; i < argc; i++) {                                    /* src/main.c:87-132 */
         const char *arg = argv[i];
@@ -494,8 +517,16 @@ int main(int argc, char **argv)
     }
     flush_batch();
     print_resolved();
-    arena_release();
-    imcvtShutdown();
+    {
+        const double t0 = now_s();
+        arena_release();
+        imcvtShutdown();
+        g_phase[T_SHUTDOWN] = now_s() - t0;
+    }
+    if ((env = getenv("IMCVT_TIMING")) != NULL && atoi(env) > 0)
+        fprintf(stderr, "imcvt_b200 timing: engine start + staging arena %.3f s, pixel reads %.3f s, encode calls %.3f s, "
+                        "stream writes %.3f s, shutdown %.3f s, total %.3f s\n",
+                g_phase[T_STAGE_ALLOC], g_phase[T_READ], g_phase[T_ENCODE], g_phase[T_WRITE], g_phase[T_SHUTDOWN], now_s() - t_start);
 
     for (i = 0; i < g_njobs; i++) {
         n_success += g_jobs[i].ok;

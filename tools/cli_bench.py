@@ -34,10 +34,11 @@ def main():
         res = {"codec": codec, "frames": n, "shape": [h, w]}
         for rep in range(2):                    # second run: files in the page cache, driver warm
             t0 = time.perf_counter()
-            p = subprocess.run([CLI] + args, cwd=d, capture_output=True)
+            p = subprocess.run([CLI] + args, cwd=d, capture_output=True, env=dict(os.environ, IMCVT_TIMING="1"))
             dt = time.perf_counter() - t0
             assert p.returncode == 0, (p.stdout[-400:], p.stderr[-400:])
             res[f"batch_cli_s_run{rep}"] = round(dt, 3)
+            res[f"phases_run{rep}"] = p.stderr.decode().strip().splitlines()[-1]
         res["batch_cli_mpixel_s"] = round(n * h * w / dt / 1e6, 1)
         if os.path.exists(REF):
             m = 4 if codec == "jls" else 1
