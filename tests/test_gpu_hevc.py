@@ -111,3 +111,37 @@ def test_full_hd_streams_decode_to_the_encoders_reconstruction(hevc_path):
     want, want_r = oracle_hevc(frames[0, :32], 1)
     assert s_row[0] == want and np.array_equal(r_row[0], want_r)
     assert np.array_equal(rcon[0][:32], want_r)      # intra prediction never reads below a CTU row
+
+
+def test_4k_qp_sweep_decodes_and_orders(hevc_path):
+    """BASELINE configs[4] shape: one 3840x2160 gray frame through the sweep the reference can express ("QP
+    22/27/32/37" runs as qpd6 1..4 = QP 10/16/22/28).  180 s per encode on the CPU oracle, so the checks are the ones that
+    do not depend on size: FFmpeg decodes every stream (exactly the encoder's reconstruction at qpd6 1, within the in-loop
+    deblocking's reach above that), sizes and PSNR fall with the quantiser, and the first CTU row of every stream's
+    reconstruction is the oracle's bit for bit."""
+    if hevc_path != 2:
+        pytest.skip("one launch shape is enough for the size check (a single frame runs on the cluster pair by default)")
+    cv2 = pytest.importorskip("cv2")
+    frame = synth.batch("natural", 1, 2160, 3840)
+    sizes, psnrs = [], []
+    with tempfile.TemporaryDirectory() as d:
+        for qpd6 in (1, 2, 3, 4):
+            streams, rcon = imcvt_b200.encode_hevc_batch(frame, qpd6)
+            assert rcon.shape == (1, 2176, 3840)
+            path = os.path.join(d, f"q{qpd6}.h265")
+            open(path, "wb").write(streams[0])
+            cap = cv2.VideoCapture(path, cv2.CAP_FFMPEG)
+            cap.set(cv2.CAP_PROP_CONVERT_RGB, 0)
+            ok, img = cap.read()
+            assert ok, f"qpd6 {qpd6}: FFmpeg could not decode the stream"
+            y = img.reshape(-1)[: 2176 * 3840].reshape(2176, 3840)
+            diff = np.abs(y.astype(np.int32) - rcon[0].astype(np.int32))
+            if qpd6 == 1:
+                assert diff.max() == 0
+            else:
+                assert diff.max() <= 6 and np.mean(diff != 0) < 0.2, (qpd6, int(diff.max()), float(np.mean(diff != 0)))
+            sizes.append(len(streams[0]))
+            psnrs.append(10 * np.log10(255.0 ** 2 / np.mean((rcon[0][:2160].astype(np.float64) - frame[0]) ** 2)))
+            want, want_r = oracle_hevc(frame[0, :32], qpd6)
+            assert np.array_equal(rcon[0][:32], want_r), qpd6
+    assert sizes == sorted(sizes, reverse=True) and psnrs == sorted(psnrs, reverse=True), (sizes, psnrs)
