@@ -121,7 +121,7 @@ def run_reference(args, rank, world):
         "e2e": {"value": v, "unit": "Mpixels/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -252,7 +252,7 @@ def run_ours(args, rank, world, local_rank):
         if rank == 0:
             line["hevc"] = {k: sec[k] for k in ("metric", "value", "unit", "steps", "warmup", "ms_per_step", "config", "e2e", "gpu_launches", "clocks", "roofline", "cpu_baseline") if k in sec}
     if rank == 0:
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
@@ -423,7 +423,26 @@ def measure(args, codec, steps, warmup, rank, world, local_rank):
     return None
 
 
+_JSON_FD = None
+
+
+def emit(line):
+    """The ONE JSON line of the contract, written to the process's original stdout."""
+    data = (json.dumps(line) + "\n").encode()
+    if _JSON_FD is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_JSON_FD, data)
+
+
 def main():
+    # Native libraries print to stdout too (NCCL's "NCCL version ..." banner on the multi-GPU boxes): everything but the
+    # JSON line goes to stderr, so that stdout carries exactly one line.
+    global _JSON_FD
+    sys.stdout.flush()
+    _JSON_FD = os.dup(1)
+    os.dup2(2, 1)
     args = parse()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -435,6 +454,7 @@ def main():
         # launched without torchrun: re-exec under torch.distributed.run
         cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
                "--master-addr", "127.0.0.1", "--master-port", "29541", os.path.abspath(__file__)] + sys.argv[1:]
+        os.dup2(_JSON_FD, 1)            # the re-executed ranks redirect for themselves
         os.execv(sys.executable, cmd)
     run_ours(args, rank, world, local_rank)
 
