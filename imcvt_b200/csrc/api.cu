@@ -83,7 +83,7 @@ static int run_host_batch(const uint8_t *frames, size_t frame_stride, size_t fra
 // JPEG-LS host batches of 8 frames or more: the batch is cut into NCHUNK chunks, each on a stream of its own with a
 // workspace of its own, so that the upload of chunk c+1 and the download of chunk c-1 overlap the kernel of chunk c
 // (a plane occupies one or two SMs for the whole kernel, so chunk kernels run side by side on different SMs).
-static int run_host_jls_chunked(const uint8_t *frames, size_t frame_stride, size_t frame_bytes, int n, int is_rgb,
+static int run_host_jls_chunked_impl(const uint8_t *frames, size_t frame_stride, size_t frame_bytes, int n, int is_rgb,
                                 uint32_t height, uint32_t width, int near_, uint8_t *out, size_t out_stride, size_t bound, size_t *out_len)
 {
     Engine &E = engine();
@@ -144,6 +144,20 @@ static int run_host_jls_chunked(const uint8_t *frames, size_t frame_stride, size
     return 0;
 }
 
+static int run_host_jls_chunked(const uint8_t *frames, size_t frame_stride, size_t frame_bytes, int n, int is_rgb,
+                                uint32_t height, uint32_t width, int near_, uint8_t *out, size_t out_stride, size_t bound, size_t *out_len)
+{
+    const int rc = run_host_jls_chunked_impl(frames, frame_stride, frame_bytes, n, is_rgb, height, width, near_, out, out_stride, bound, out_len);
+    if (rc) {
+        // a failed call must not leave chunk streams running on the arena and the workspaces the next call will carve again
+        Engine &E = engine();
+        for (int c = 0; c < Engine::NCHUNK; c++)
+            if (E.chunk_stream[c]) cudaStreamSynchronize(E.chunk_stream[c]);
+        (void)cudaGetLastError();
+    }
+    return rc;
+}
+
 extern "C" {
 
 size_t imcvtJLSBound(int is_rgb, uint32_t height, uint32_t width)
@@ -163,6 +177,7 @@ int imcvtEncodeBatchJLSDevice(const void *d_frames, size_t frame_stride, int n, 
                               uint32_t height, uint32_t width, int near_,
                               void *d_out, size_t out_stride, void *d_out_len, void *stream)
 {
+    IMCVT_API_LOCK();
     if (n <= 0) { set_error("batch size must be positive"); return 1; }
     if (!jls_dims_ok(height, width)) { set_error("JPEG-LS dimensions must be 1..32767 (got %ux%u)", width, height); return 1; }
     if (near_ < 0 || near_ > 4) { set_error("NEAR must be 0..4 (got %d)", near_); return 1; }
@@ -180,6 +195,7 @@ int imcvtEncodeBatchJLS(const uint8_t *frames, size_t frame_stride, int n, int i
                         uint32_t height, uint32_t width, int near_,
                         uint8_t *out, size_t out_stride, size_t *out_len)
 {
+    IMCVT_API_LOCK();
     if (n <= 0 || !frames || !out || !out_len) { set_error("bad arguments"); return 1; }
     if (!jls_dims_ok(height, width)) { set_error("JPEG-LS dimensions must be 1..32767 (got %ux%u)", width, height); return 1; }
     if (near_ < 0 || near_ > 4) { set_error("NEAR must be 0..4 (got %d)", near_); return 1; }
@@ -203,6 +219,7 @@ int imcvtEncodeBatchHEVCDevice(const void *d_frames, size_t frame_stride, int n,
                                void *d_out, size_t out_stride, void *d_out_len,
                                void *d_rcon, size_t rcon_stride, void *stream)
 {
+    IMCVT_API_LOCK();
     if (n <= 0) { set_error("batch size must be positive"); return 1; }
     if (height < 1 || width < 1) { set_error("empty image"); return 1; }
     if (qpd6 < 0 || qpd6 > 4) { set_error("qpd6 must be 0..4 (got %d)", qpd6); return 1; }
@@ -221,6 +238,7 @@ int imcvtEncodeBatchHEVC(const uint8_t *frames, size_t frame_stride, int n,
                          uint8_t *out, size_t out_stride, size_t *out_len,
                          uint8_t *rcon, size_t rcon_stride)
 {
+    IMCVT_API_LOCK();
     if (n <= 0 || !frames || !out || !out_len) { set_error("bad arguments"); return 1; }
     if (height < 1 || width < 1) { set_error("empty image"); return 1; }
     if (qpd6 < 0 || qpd6 > 4) { set_error("qpd6 must be 0..4 (got %d)", qpd6); return 1; }
@@ -242,6 +260,7 @@ int imcvtEncodeBatchHEVCGreen(const uint8_t *rgb_frames, size_t frame_stride, in
                               uint32_t height, uint32_t width, int qpd6,
                               uint8_t *out, size_t out_stride, size_t *out_len)
 {
+    IMCVT_API_LOCK();
     if (n <= 0 || !rgb_frames || !out || !out_len) { set_error("bad arguments"); return 1; }
     if (height < 1 || width < 1) { set_error("empty image"); return 1; }
     if (qpd6 < 0 || qpd6 > 4) { set_error("qpd6 must be 0..4 (got %d)", qpd6); return 1; }
@@ -268,6 +287,7 @@ int imcvtEncodeBatchHEVCGreen(const uint8_t *rgb_frames, size_t frame_stride, in
 void *imcvtHostAlloc(size_t bytes)
 {
     void *p = nullptr;
+    IMCVT_API_LOCK();
     if (ensure_engine()) return nullptr;
     cudaError_t e = cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault);
     if (e != cudaSuccess) {

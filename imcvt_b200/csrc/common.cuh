@@ -7,6 +7,7 @@
 #include <string>
 #include <vector>
 #include <map>
+#include <mutex>
 
 namespace imcvt {
 
@@ -36,6 +37,11 @@ struct Workspace {
         return p;
     }
     void release();
+    // A workspace is carved anew by every call, while the kernels of the call before may still be running on ANOTHER stream
+    // (the device-buffer entry points do not synchronise): the new call's stream first waits for the previous user.
+    cudaEvent_t busy = nullptr;
+    int wait_previous(cudaStream_t st);             // after reserve(), before anything is queued that writes the workspace
+    int mark_busy(cudaStream_t st);                 // after the last kernel of the call has been queued
 };
 
 struct KernelStat { int launches = 0; double ms = 0.0; };
@@ -67,6 +73,10 @@ struct Engine {
 
 Engine &engine();
 int ensure_engine();
+// The engine is one per process; the extern "C" entry points serialise on this lock, so calls from several host threads are
+// safe (they do not overlap each other; overlap comes from the streams inside a call).
+std::recursive_mutex &api_mutex();
+#define IMCVT_API_LOCK() std::lock_guard<std::recursive_mutex> imcvt_api_lock__(imcvt::api_mutex())
 
 // RAII bracket around one kernel launch: counts it and (when profiling) times it with events on `s`.
 struct LaunchScope {

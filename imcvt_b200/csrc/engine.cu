@@ -49,6 +49,27 @@ void Workspace::release()
 {
     if (base) cudaFree(base);
     base = nullptr; cap = used = 0;
+    if (busy) cudaEventDestroy(busy);
+    busy = nullptr;
+}
+
+int Workspace::wait_previous(cudaStream_t st)
+{
+    if (busy) IMCVT_CUDA(cudaStreamWaitEvent(st, busy, 0));
+    return 0;
+}
+
+int Workspace::mark_busy(cudaStream_t st)
+{
+    if (!busy) IMCVT_CUDA(cudaEventCreateWithFlags(&busy, cudaEventDisableTiming));
+    IMCVT_CUDA(cudaEventRecord(busy, st));
+    return 0;
+}
+
+std::recursive_mutex &api_mutex()
+{
+    static std::recursive_mutex m;
+    return m;
 }
 
 int ensure_engine()
@@ -131,6 +152,7 @@ extern "C" {
 
 int imcvtInit(int device)
 {
+    IMCVT_API_LOCK();
     Engine &E = engine();
     if (E.ready && E.device != device) imcvtShutdown();
     E.device = device;
@@ -139,6 +161,7 @@ int imcvtInit(int device)
 
 void imcvtShutdown(void)
 {
+    IMCVT_API_LOCK();
     Engine &E = engine();
     if (!E.ready) return;
     cudaSetDevice(E.device);
@@ -170,6 +193,7 @@ void imcvtProfileEnable(int on) { engine().profile = on != 0; }
 
 void imcvtProfileReset(void)
 {
+    IMCVT_API_LOCK();
     profile_collect();
     engine().stats.clear();
     engine().launches = 0;
@@ -177,6 +201,7 @@ void imcvtProfileReset(void)
 
 int imcvtProfileGet(const char *kernel, int *launches, double *total_ms)
 {
+    IMCVT_API_LOCK();
     profile_collect();
     auto &st = engine().stats;
     auto it = st.find(kernel);
@@ -188,6 +213,7 @@ int imcvtProfileGet(const char *kernel, int *launches, double *total_ms)
 
 int imcvtProfileList(char *buf, size_t cap)
 {
+    IMCVT_API_LOCK();
     profile_collect();
     std::string s;
     for (auto &kv : engine().stats) {

@@ -38,6 +38,7 @@ int encode_device(const uint8_t *d_frames, size_t frame_stride, int n, uint32_t 
     size_t bytes = 4096 + (size_t)grid * 2 * NALL * SCR_BYTES + 256 + (size_t)grid * 2 * NALL * CAND_LIST_U16 * 2 + 256;
     if (!d_rcon) bytes += (size_t)n * rstride + 256;
     if (E.ws.reserve(bytes)) return 1;
+    if (E.ws.wait_previous(st)) return 1;
     uint8_t *scratch = E.ws.take<uint8_t>((size_t)grid * 2 * NALL * SCR_BYTES);
     unsigned short *lists = E.ws.take<unsigned short>((size_t)grid * 2 * NALL * CAND_LIST_U16);
     int *next = E.ws.take<int>(1);
@@ -69,7 +70,7 @@ int encode_device(const uint8_t *d_frames, size_t frame_stride, int n, uint32_t 
         else hevc_frame_kernel<<<grid, NT, sizeof(Smem), st>>>(P);
     }
     IMCVT_CUDA(cudaGetLastError());
-    return 0;
+    return E.ws.mark_busy(st);
 }
 
 }  // namespace hevc

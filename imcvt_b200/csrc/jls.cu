@@ -1059,6 +1059,7 @@ int encode_device(const uint8_t *d_frames, size_t frame_stride, int n, int is_rg
     add((size_t)P * 8);                            // plane_bytes
     if (ncomp > 1) add((size_t)P * scratch_stride);
     if (WS.reserve(bytes)) return 1;
+    if (WS.wait_previous(st)) return 1;
 
     const uint8_t *planes = d_frames;
     size_t plane_stride = frame_stride;
@@ -1198,7 +1199,7 @@ int encode_device(const uint8_t *d_frames, size_t frame_stride, int n, int is_rg
         assemble_kernel<<<grid, 256, 0, st>>>(Lay, (int)H, (int)W, near_, plane_bytes, d_out_len, d_overflow);
     }
     IMCVT_CUDA(cudaGetLastError());
-    return 0;
+    return WS.mark_busy(st);
 }
 
 }  // namespace jls

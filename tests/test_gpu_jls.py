@@ -212,3 +212,45 @@ def test_shutdown_and_reinit_keep_working():
     s2, _ = imcvt_b200.encode_hevc_batch(frames[:2, :32, :32], 3)
     assert a == b and s == s2
     assert a[0] == oracle_jls(frames[0], 0)
+
+
+def test_device_calls_on_two_streams_share_the_workspace_in_order():
+    """The device-buffer entry points only queue work.  Two calls on DIFFERENT streams carve the same engine workspace one
+    after the other: the second stream has to wait for the first call's kernels (Workspace::wait_previous)."""
+    import torch
+    a = synth.batch("natural", 6, 200, 333)
+    b = synth.batch("texture", 5, 120, 517)
+    streams = [torch.cuda.Stream(), torch.cuda.Stream()]
+    jobs = []
+    for frames, near, k in ((a, 0, 0), (b, 2, 1), (a, 1, 1), (b, 0, 0)):
+        n, h, w = frames.shape
+        jobs.append(dict(frames=frames, near=near, stream=streams[k], d=torch.from_numpy(frames).cuda(),
+                         out=torch.zeros((n, imcvt_b200.jls_bound(0, h, w)), dtype=torch.uint8, device="cuda"),
+                         lens=torch.zeros(n, dtype=torch.int64, device="cuda")))
+    torch.cuda.synchronize()
+    for j in jobs:                                      # no synchronisation between the calls
+        imcvt_b200.encode_jls_device(j["d"], j["near"], j["out"], j["lens"], j["stream"].cuda_stream)
+    torch.cuda.synchronize()
+    for j in jobs:
+        for i in range(j["frames"].shape[0]):
+            got = j["out"][i, : int(j["lens"][i])].cpu().numpy().tobytes()
+            assert got == oracle_jls(j["frames"][i], j["near"]), (j["near"], i)
+
+
+def test_host_calls_from_two_threads_are_serialised():
+    import threading
+    jobs = [(synth.batch("natural", 9, 96, 160), 0), (synth.batch("noise", 3, 64, 64), 3), (synth.batch("texture", 8, 70, 131), 0)]
+    got = [None] * len(jobs)
+
+    def work(k):
+        got[k] = imcvt_b200.encode_jls_batch(jobs[k][0], jobs[k][1])
+
+    threads = [threading.Thread(target=work, args=(k,)) for k in range(len(jobs))]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    for k, (frames, near) in enumerate(jobs):
+        assert got[k] is not None
+        for i in range(frames.shape[0]):
+            assert got[k][i] == oracle_jls(frames[i], near), (k, i)
