@@ -784,6 +784,8 @@ struct Smem {
     short eq[512];                                  // quantised prediction error at [e + 255] (:97-102)
 };
 
+// LOSSY = NEAR > 0 (the reconstruction differs from the input); the lossless instance only serves the forced-serial cross-check
+template <bool LOSSY>
 __global__ void __launch_bounds__(NT, 1)
 rowscan_kernel(const uint8_t *__restrict__ pix, size_t plane_stride, int W, int H, SerialParams P, FrameLayout L,
                uint64_t *__restrict__ plane_bytes)
@@ -928,7 +930,7 @@ rowscan_kernel(const uint8_t *__restrict__ pix, size_t plane_stride, int W, int 
             for (int i = lane; i < n; i += 32) {
                 const int x = x0 + i;
                 sm.in[i] = in_row[i];
-                const int bb = up[x], cc = x > 0 ? up[x - 1] : 0, dd = x + 1 < W ? up[x + 1] : bb;
+                const int bb = up[x], cc = x > 0 ? up[x - 1] : 0, dd = up[x + 1];      // up[W] repeats up[W - 1] (:57-58)
                 sm.q12[i] = (short)(81 * sm.gq[dd - bb + 255] + 9 * sm.gq[bb - cc + 255]);
             }
             __syncwarp();
@@ -939,14 +941,14 @@ rowscan_kernel(const uint8_t *__restrict__ pix, size_t plane_stride, int W, int 
                     in_run = false;
                     b = up[0]; a = b; c = up2;
                     up2 = b;                                             // recon(y-1, 0) is the c of row y+1's first sample
+                    // the first sample of a row has its own c (two rows up): its staged gradient terms are replaced
+                    sm.q12[0] = (short)(81 * sm.gq[up[1] - b + 255] + 9 * sm.gq[b - c + 255]);
                 }
                 for (int i = 0; i < n; i++) {
                     const int x = x0 + i;
-                    const int d = x + 1 < W ? up[x + 1] : b;
+                    const int d = up[x + 1];
                     const int v = sm.in[i];
-                    // the first sample of a row has its own c (two rows up), so its second term is recomputed
-                    const int q12 = x > 0 ? (int)sm.q12[i] : 81 * sm.gq[d - b + 255] + 9 * sm.gq[b - c + 255];
-                    const int qv = q12 + sm.gq[c - a + 255];
+                    const int qv = (int)sm.q12[i] + sm.gq[c - a + 255];
                     bool neg = qv < 0;
                     const int cq = neg ? -qv : qv;
                     if (cq == 0) in_run = true;
@@ -962,7 +964,7 @@ rowscan_kernel(const uint8_t *__restrict__ pix, size_t plane_stride, int W, int 
                         neg = a > b + near_;
                         const int px = t ? a : b;
                         int e = sm.eq[(neg ? px - v : v - px) + 255];
-                        rx = near_ ? min(max(px + (neg ? -quant * e : quant * e), 0), 255) : v;
+                        rx = LOSSY ? min(max(px + (neg ? -quant * e : quant * e), 0), 255) : v;
                         if (e < 0) e += range;
                         if (e >= half) e -= range;
                         r = REC_BREAK | ((uint32_t)t << 2) | ((uint32_t)(e + 256) << 12);
@@ -971,10 +973,10 @@ rowscan_kernel(const uint8_t *__restrict__ pix, size_t plane_stride, int W, int 
                         int px = med3(a, b, c) + (neg ? -st.z : st.z);
                         px = min(max(px, 0), 255);
                         int e = sm.eq[(neg ? px - v : v - px) + 255];
-                        rx = near_ ? min(max(px + (neg ? -quant * e : quant * e), 0), 255) : v;
+                        rx = LOSSY ? min(max(px + (neg ? -quant * e : quant * e), 0), 255) : v;
                         if (e < 0) e += range;
                         if (e >= half) e -= range;
-                        const uint32_t hint = (near_ == 0) && (2 * st.y <= -st.w);
+                        const uint32_t hint = !LOSSY && (2 * st.y <= -st.w);
                         r = REC_REGULAR | ((uint32_t)(cq - 1) << 2) | (hint << 11) | ((uint32_t)(e + 256) << 12);
                         st.y += e * quant;
                         if (st.w >= 64) { st.y >>= 1; st.w >>= 1; }
@@ -992,6 +994,7 @@ rowscan_kernel(const uint8_t *__restrict__ pix, size_t plane_stride, int W, int 
                     cur[x] = (uint8_t)rx;
                     c = b; b = d; a = rx;                                 // slide the template (a = reconstructed left neighbour)
                 }
+                if (x0 + n == W) cur[W] = (uint8_t)a;                    // right neighbour of the last sample of the row below
             }
         }
         __syncthreads();
@@ -1186,11 +1189,13 @@ int encode_device(const uint8_t *d_frames, size_t frame_stride, int n, int is_rg
             serial_scan_kernel<<<P, 32, 0, st>>>(planes, plane_stride, recon, (int)W, (int)H, SP, Lay, plane_bytes);
         } else {
             if (!E.attr_jls_rowscan) {
-                IMCVT_CUDA(cudaFuncSetAttribute(rowscan::rowscan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(rowscan::Smem)));
+                IMCVT_CUDA(cudaFuncSetAttribute(rowscan::rowscan_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(rowscan::Smem)));
+                IMCVT_CUDA(cudaFuncSetAttribute(rowscan::rowscan_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(rowscan::Smem)));
                 E.attr_jls_rowscan = true;
             }
             LaunchScope ls("jls_rowscan", st);
-            rowscan::rowscan_kernel<<<P, rowscan::NT, sizeof(rowscan::Smem), st>>>(planes, plane_stride, (int)W, (int)H, SP, Lay, plane_bytes);
+            if (near_ > 0) rowscan::rowscan_kernel<true><<<P, rowscan::NT, sizeof(rowscan::Smem), st>>>(planes, plane_stride, (int)W, (int)H, SP, Lay, plane_bytes);
+            else rowscan::rowscan_kernel<false><<<P, rowscan::NT, sizeof(rowscan::Smem), st>>>(planes, plane_stride, (int)W, (int)H, SP, Lay, plane_bytes);
         }
     }
     {
