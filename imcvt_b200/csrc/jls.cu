@@ -781,7 +781,8 @@ struct Smem {
     int4 ctx[NCTX];                                 // stage 1: (unused, B, C, N)
     int2 ctx2[NCTX];                                // stage 2: (A, N)
     signed char gq[512];                            // quantised gradient at [g + 255]
-    short eq[512];                                  // quantised prediction error at [e + 255] (:97-102)
+    short eq[512];                                  // quantised prediction error at [d + 255] (:97-102), wrapped into the code range (:105-111)
+    short qe[512];                                  // the reconstruction step it stands for: quant * (quantised error, not wrapped)
 };
 
 // LOSSY = NEAR > 0 (the reconstruction differs from the input); the lossless instance only serves the forced-serial cross-check
@@ -802,7 +803,11 @@ rowscan_kernel(const uint8_t *__restrict__ pix, size_t plane_stride, int W, int 
     for (int i = tid; i < 511; i += NT) {
         const int g = i - 255;
         sm.gq[i] = (signed char)grad_q_any(P, g);
-        sm.eq[i] = (short)(g < 0 ? -((near_ - g) / quant) : (near_ + g) / quant);
+        int e = g < 0 ? -((near_ - g) / quant) : (near_ + g) / quant;
+        sm.qe[i] = (short)(quant * e);
+        if (e < 0) e += range;
+        if (e >= half) e -= range;
+        sm.eq[i] = (short)e;
     }
     for (int i = tid; i < WMAXR + 16; i += NT) { sm.row[0][i] = 0; sm.row[1][i] = 0; }      // the row above the picture reads as zeros
 
@@ -866,12 +871,15 @@ rowscan_kernel(const uint8_t *__restrict__ pix, size_t plane_stride, int W, int 
             }
             tile::stuff_bits(sm.ubits, ps, T, pit == total - 1, lane);
         }
-        if (warp == 2 && lane == 0 && it >= 1 && it <= total) {
-            // ---- stage 2: records of the previous segment -> code + length per sample ----
+        if (warp == 2 && it >= 1 && it <= total) {
+            // ---- stage 2: records of the previous segment -> code + length per sample.  Lane 0 walks what is serial (A / N
+            //      per context -> Golomb parameter and mapped error; run lengths; run interruptions), then the whole warp
+            //      turns the (mapped error, k) pairs of the regular samples into codes ----
             const int pit = it - 1, py = pit / nseg, psg = pit - py * nseg, px0 = psg * SEG, pn = min(SEG, W - px0), pb = pit & 1;
             const uint32_t *rec = sm.rec[pb];
             uint32_t *codes = sm.codes[pb];
             uint8_t *lens = sm.lens[pb];
+            if (lane == 0) {
             if (px0 == 0) run_len = 0;                                   // :270
             for (int i = 0; i < pn; i++) {
                 const uint32_t r = rec[i];
@@ -884,7 +892,8 @@ rowscan_kernel(const uint8_t *__restrict__ pix, size_t plane_stride, int W, int 
                     const int k = golomb_k(st.x, st.y);
                     const int map = (k == 0) && ((r >> 11) & 1u);        // the hint is (2B <= -N) && NEAR == 0 (:367)
                     const int me = 2 * abs(e) + (e < 0 ? -(map + 1) : map);
-                    golomb_code(me, k, P.limit, P.qbpp, code, len);
+                    code = (uint32_t)me | ((uint32_t)k << 16);           // finished by the warp below
+                    len = 0xFF;
                     st.x += abs(e);
                     if (st.y >= 64) { st.x >>= 1; st.y >>= 1; }
                     st.y++;
@@ -919,6 +928,16 @@ rowscan_kernel(const uint8_t *__restrict__ pix, size_t plane_stride, int W, int 
                     Nt++;
                     if (t) { rA1 = At; rB1 = Bt; rN1 = Nt; } else { rA0 = At; rB0 = Bt; rN0 = Nt; }
                 }
+                codes[tile::code_idx(i)] = code;
+                lens[tile::len_idx(i)] = (uint8_t)len;
+            }
+            }
+            __syncwarp();
+            for (int i = lane; i < pn; i += 32) {
+                if (lens[tile::len_idx(i)] != 0xFF) continue;            // run samples carry their final code already (<= 32 bits)
+                const uint32_t mk = codes[tile::code_idx(i)];
+                uint32_t code; int len;
+                golomb_code((int)(mk & 0xFFFFu), (int)(mk >> 16), P.limit, P.qbpp, code, len);
                 codes[tile::code_idx(i)] = code;
                 lens[tile::len_idx(i)] = (uint8_t)len;
             }
@@ -963,19 +982,17 @@ rowscan_kernel(const uint8_t *__restrict__ pix, size_t plane_stride, int W, int 
                         const int t = abs(a - b) <= near_;
                         neg = a > b + near_;
                         const int px = t ? a : b;
-                        int e = sm.eq[(neg ? px - v : v - px) + 255];
-                        rx = LOSSY ? min(max(px + (neg ? -quant * e : quant * e), 0), 255) : v;
-                        if (e < 0) e += range;
-                        if (e >= half) e -= range;
+                        const int di = (neg ? px - v : v - px) + 255;
+                        const int e = sm.eq[di], step = sm.qe[di];
+                        rx = LOSSY ? min(max(px + (neg ? -step : step), 0), 255) : v;
                         r = REC_BREAK | ((uint32_t)t << 2) | ((uint32_t)(e + 256) << 12);
                     } else {
                         int4 st = sm.ctx[cq - 1];
                         int px = med3(a, b, c) + (neg ? -st.z : st.z);
                         px = min(max(px, 0), 255);
-                        int e = sm.eq[(neg ? px - v : v - px) + 255];
-                        rx = LOSSY ? min(max(px + (neg ? -quant * e : quant * e), 0), 255) : v;
-                        if (e < 0) e += range;
-                        if (e >= half) e -= range;
+                        const int di = (neg ? px - v : v - px) + 255;
+                        const int e = sm.eq[di], step = sm.qe[di];
+                        rx = LOSSY ? min(max(px + (neg ? -step : step), 0), 255) : v;
                         const uint32_t hint = !LOSSY && (2 * st.y <= -st.w);
                         r = REC_REGULAR | ((uint32_t)(cq - 1) << 2) | (hint << 11) | ((uint32_t)(e + 256) << 12);
                         st.y += e * quant;
