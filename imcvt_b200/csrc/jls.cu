@@ -768,13 +768,15 @@ namespace rowscan {
 constexpr int SEG = 2048;
 constexpr int WMAXR = 32768;                        // :436
 constexpr int NT = 96;
-// record of one sample, stage 1 -> stage 2
-constexpr uint32_t REC_REGULAR = 0, REC_HIT = 1, REC_BREAK = 2;
+// One 32-bit slot per sample of a segment, used twice.  Staged (all lanes of warp 0):
+//     sample | (81*q(d-b) + 9*q(b-c) + 512) << 8 | d << 24            (everything the walk needs that is known beforehand)
+// and, once lane 0 has walked the sample, its record for stage 2:
+//     low half: wrapped error (signed) | high half: 0 = run sample, 0x8000 | RItype = run interruption,
+//     else context number 1..364 (| 1 << 9: the mapping hint 2B <= -N of the lossless instance, :367)
+constexpr uint32_t REC_BREAK = 0x8000u;
 struct Smem {
     uint8_t row[2][WMAXR + 16];                     // reconstructed rows y-1 / y (index 8 + x)
-    uint8_t in[SEG];
-    short q12[SEG];
-    uint32_t rec[2][SEG];                           // type | context << 2 (break: RItype << 2) | map hint << 11 | (error + 256) << 12
+    uint32_t rec[2][SEG];
     uint32_t codes[2][SEG + SEG / 32];
     uint8_t lens[2][SEG + SEG / 8];
     uint32_t ubits[tile::UBITS_WORDS];
@@ -883,14 +885,14 @@ rowscan_kernel(const uint8_t *__restrict__ pix, size_t plane_stride, int W, int 
             if (px0 == 0) run_len = 0;                                   // :270
             for (int i = 0; i < pn; i++) {
                 const uint32_t r = rec[i];
-                const uint32_t type = r & 3u;
-                int e = (int)((r >> 12) & 1023u) - 256;
+                const uint32_t hi = r >> 16;
+                const int e = (int)(short)(r & 0xFFFFu);
                 uint32_t code = 0; int len = 0;
-                if (type == REC_REGULAR) {
-                    const int q = (int)((r >> 2) & 511u);
+                if (hi != 0 && !(hi & REC_BREAK)) {
+                    const int q = (int)(hi & 511u) - 1;
                     int2 st = sm.ctx2[q];
                     const int k = golomb_k(st.x, st.y);
-                    const int map = (k == 0) && ((r >> 11) & 1u);        // the hint is (2B <= -N) && NEAR == 0 (:367)
+                    const int map = (k == 0) && ((hi >> 9) & 1u);        // the hint is (2B <= -N) && NEAR == 0 (:367)
                     const int me = 2 * abs(e) + (e < 0 ? -(map + 1) : map);
                     code = (uint32_t)me | ((uint32_t)k << 16);           // finished by the warp below
                     len = 0xFF;
@@ -898,7 +900,7 @@ rowscan_kernel(const uint8_t *__restrict__ pix, size_t plane_stride, int W, int 
                     if (st.y >= 64) { st.x >>= 1; st.y >>= 1; }
                     st.y++;
                     sm.ctx2[q] = st;
-                } else if (type == REC_HIT) {
+                } else if (hi == 0) {
                     run_len++;
                     const int jj = tile::run_order(run_index);
                     if (run_len >= (1 << jj)) {
@@ -908,7 +910,7 @@ rowscan_kernel(const uint8_t *__restrict__ pix, size_t plane_stride, int W, int 
                     }
                     if (px0 + i == W - 1 && run_len > 0) { code = (code << 1) | 1u; len++; }
                 } else {
-                    const int t = (int)((r >> 2) & 1u);
+                    const int t = (int)(hi & 1u);
                     const int jj = tile::run_order(run_index);
                     const int glimit = P.limit - 1 - jj;
                     const int rem = run_len;
@@ -943,50 +945,51 @@ rowscan_kernel(const uint8_t *__restrict__ pix, size_t plane_stride, int W, int 
             }
         }
         if (warp == 0 && it < total) {
-            // ---- stage the segment (input + the gradient terms of the row above), then stage 1 on lane 0 ----
+            // ---- stage the segment (input + everything that only needs the row above), then stage 1 on lane 0 ----
             const int y = it / nseg, sg = it - y * nseg, x0 = sg * SEG, n = min(SEG, W - x0);
             const uint8_t *up = sm.row[(y + 1) & 1] + 8, *in_row = src + (size_t)y * W + x0;
+            uint32_t *rec = sm.rec[it & 1];
             for (int i = lane; i < n; i += 32) {
                 const int x = x0 + i;
-                sm.in[i] = in_row[i];
                 const int bb = up[x], cc = x > 0 ? up[x - 1] : 0, dd = up[x + 1];      // up[W] repeats up[W - 1] (:57-58)
-                sm.q12[i] = (short)(81 * sm.gq[dd - bb + 255] + 9 * sm.gq[bb - cc + 255]);
+                const int q12 = 81 * sm.gq[dd - bb + 255] + 9 * sm.gq[bb - cc + 255];
+                rec[i] = (uint32_t)in_row[i] | ((uint32_t)(q12 + 512) << 8) | ((uint32_t)dd << 24);
             }
             __syncwarp();
             if (lane == 0) {
-                uint8_t *cur = sm.row[y & 1] + 8;
-                uint32_t *rec = sm.rec[it & 1];
+                uint8_t *curp = sm.row[y & 1] + 8 + x0;
                 if (x0 == 0) {                                           // row start (:270, :47-56)
                     in_run = false;
                     b = up[0]; a = b; c = up2;
                     up2 = b;                                             // recon(y-1, 0) is the c of row y+1's first sample
                     // the first sample of a row has its own c (two rows up): its staged gradient terms are replaced
-                    sm.q12[0] = (short)(81 * sm.gq[up[1] - b + 255] + 9 * sm.gq[b - c + 255]);
+                    const int q12 = 81 * sm.gq[up[1] - b + 255] + 9 * sm.gq[b - c + 255];
+                    rec[0] = (rec[0] & ~(0x3FFu << 8)) | ((uint32_t)(q12 + 512) << 8);
                 }
                 for (int i = 0; i < n; i++) {
-                    const int x = x0 + i;
-                    const int d = up[x + 1];
-                    const int v = sm.in[i];
-                    const int qv = (int)sm.q12[i] + sm.gq[c - a + 255];
-                    bool neg = qv < 0;
-                    const int cq = neg ? -qv : qv;
-                    if (cq == 0) in_run = true;
-                    bool hit = false, brk = false;
-                    if (in_run) { hit = abs(v - a) <= near_; brk = !hit; in_run = hit; }
+                    const uint32_t w = rec[i];
+                    const int v = (int)(w & 0xFFu), d = (int)(w >> 24);
+                    const int qv = (int)((w >> 8) & 0x3FFu) - 512 + sm.gq[c - a + 255];
                     int rx;
                     uint32_t r;
-                    if (hit) {
-                        rx = a;
-                        r = REC_HIT;
-                    } else if (brk) {
-                        const int t = abs(a - b) <= near_;
-                        neg = a > b + near_;
-                        const int px = t ? a : b;
-                        const int di = (neg ? px - v : v - px) + 255;
-                        const int e = sm.eq[di], step = sm.qe[di];
-                        rx = LOSSY ? min(max(px + (neg ? -step : step), 0), 255) : v;
-                        r = REC_BREAK | ((uint32_t)t << 2) | ((uint32_t)(e + 256) << 12);
+                    if (in_run || qv == 0) {
+                        if (abs(v - a) <= near_) {                       // run sample (:291-303): counted by stage 2
+                            in_run = true;
+                            rx = a;
+                            r = 0;
+                        } else {                                         // run interruption (:305-344)
+                            in_run = false;
+                            const int t = abs(a - b) <= near_;
+                            const bool neg = a > b + near_;
+                            const int px = t ? a : b;
+                            const int di = (neg ? px - v : v - px) + 255;
+                            const int e = sm.eq[di], step = sm.qe[di];
+                            rx = LOSSY ? min(max(px + (neg ? -step : step), 0), 255) : v;
+                            r = ((uint32_t)e & 0xFFFFu) | ((REC_BREAK | (uint32_t)t) << 16);
+                        }
                     } else {
+                        const bool neg = qv < 0;
+                        const int cq = neg ? -qv : qv;
                         int4 st = sm.ctx[cq - 1];
                         int px = med3(a, b, c) + (neg ? -st.z : st.z);
                         px = min(max(px, 0), 255);
@@ -994,7 +997,7 @@ rowscan_kernel(const uint8_t *__restrict__ pix, size_t plane_stride, int W, int 
                         const int e = sm.eq[di], step = sm.qe[di];
                         rx = LOSSY ? min(max(px + (neg ? -step : step), 0), 255) : v;
                         const uint32_t hint = !LOSSY && (2 * st.y <= -st.w);
-                        r = REC_REGULAR | ((uint32_t)(cq - 1) << 2) | (hint << 11) | ((uint32_t)(e + 256) << 12);
+                        r = ((uint32_t)e & 0xFFFFu) | (((uint32_t)cq | (hint << 9)) << 16);
                         st.y += e * quant;
                         if (st.w >= 64) { st.y >>= 1; st.w >>= 1; }
                         st.w++;
@@ -1008,10 +1011,10 @@ rowscan_kernel(const uint8_t *__restrict__ pix, size_t plane_stride, int W, int 
                         sm.ctx[cq - 1] = st;
                     }
                     rec[i] = r;
-                    cur[x] = (uint8_t)rx;
+                    curp[i] = (uint8_t)rx;
                     c = b; b = d; a = rx;                                 // slide the template (a = reconstructed left neighbour)
                 }
-                if (x0 + n == W) cur[W] = (uint8_t)a;                    // right neighbour of the last sample of the row below
+                if (x0 + n == W) curp[n] = (uint8_t)a;                   // right neighbour of the last sample of the row below
             }
         }
         __syncthreads();
