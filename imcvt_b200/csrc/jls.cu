@@ -818,7 +818,7 @@ rowscan_kernel(const uint8_t *__restrict__ pix, size_t plane_stride, int W, int 
 
     const int nseg = (W + SEG - 1) / SEG, total = H * nseg;
     // stage 1 (lane 0 of warp 0): row state of the walk
-    bool in_run = false;
+    int in_run = 0;                                 // an int: a bool would be kept as a byte of a shared register
     int a = 0, b = 0, c = 0, up2 = 0;
     // stage 2 (lane 0 of warp 2): run state and the two run-interruption contexts
     int rA0 = P.a_init, rA1 = P.a_init, rB0 = 0, rB1 = 0, rN0 = 1, rN1 = 1;      // scalars: an indexed array would live in local memory
@@ -959,26 +959,27 @@ rowscan_kernel(const uint8_t *__restrict__ pix, size_t plane_stride, int W, int 
             if (lane == 0) {
                 uint8_t *curp = sm.row[y & 1] + 8 + x0;
                 if (x0 == 0) {                                           // row start (:270, :47-56)
-                    in_run = false;
+                    in_run = 0;
                     b = up[0]; a = b; c = up2;
                     up2 = b;                                             // recon(y-1, 0) is the c of row y+1's first sample
                     // the first sample of a row has its own c (two rows up): its staged gradient terms are replaced
                     const int q12 = 81 * sm.gq[up[1] - b + 255] + 9 * sm.gq[b - c + 255];
                     rec[0] = (rec[0] & ~(0x3FFu << 8)) | ((uint32_t)(q12 + 512) << 8);
                 }
-                for (int i = 0; i < n; i++) {
-                    const uint32_t w = rec[i];
+                uint32_t *slot = rec;
+                for (int i = 0; i < n; i++, slot++) {
+                    const uint32_t w = *slot;
                     const int v = (int)(w & 0xFFu), d = (int)(w >> 24);
                     const int qv = (int)((w >> 8) & 0x3FFu) - 512 + sm.gq[c - a + 255];
                     int rx;
                     uint32_t r;
-                    if (in_run || qv == 0) {
+                    if ((in_run | (qv == 0)) != 0) {
                         if (abs(v - a) <= near_) {                       // run sample (:291-303): counted by stage 2
-                            in_run = true;
+                            in_run = 1;
                             rx = a;
                             r = 0;
                         } else {                                         // run interruption (:305-344)
-                            in_run = false;
+                            in_run = 0;
                             const int t = abs(a - b) <= near_;
                             const bool neg = a > b + near_;
                             const int px = t ? a : b;
@@ -1010,7 +1011,7 @@ rowscan_kernel(const uint8_t *__restrict__ pix, size_t plane_stride, int W, int 
                         }
                         sm.ctx[cq - 1] = st;
                     }
-                    rec[i] = r;
+                    *slot = r;
                     curp[i] = (uint8_t)rx;
                     c = b; b = d; a = rx;                                 // slide the template (a = reconstructed left neighbour)
                 }
