@@ -411,7 +411,10 @@ def measure(args, codec, steps, warmup, rank, world, local_rank):
                 "bytes_out_per_step_rank0": total_bytes,
             },
             "e2e": {"value": world * npix * K / (e2e_ms / 1e3) / 1e6, "unit": "Mpixels/s",
-                    "h2d_bytes_per_step": npix, "d2h_bytes_per_step": d2h},
+                    "h2d_bytes_per_step": npix, "d2h_bytes_per_step": d2h,
+                    "transfer": ("page-locked host frames and slots through imcvtEncodeBatchJLS: the kernel reads the frames and writes "
+                                 "the streams in place over PCIe every step (no staging copy in HBM)") if codec == "jls" else
+                                "page-locked host frames uploaded, streams downloaded through imcvtEncodeBatchHEVC every step"},
             "gpu_launches": launches,
             "wall_ms_per_step": wall_ms / K,
             "clocks": clocks,

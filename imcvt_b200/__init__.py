@@ -31,7 +31,7 @@ EXPORTED_SYMBOLS = [
     "imcvtJLSBound", "imcvtHEVCBound",
     "imcvtEncodeBatchJLS", "imcvtEncodeBatchJLSDevice",
     "imcvtEncodeBatchHEVC", "imcvtEncodeBatchHEVCDevice", "imcvtEncodeBatchHEVCGreen",
-    "imcvtHostAlloc", "imcvtHostFree",
+    "imcvtHostAlloc", "imcvtHostFree", "imcvtJLSHostMode",
     "imcvtProfileEnable", "imcvtProfileReset", "imcvtProfileGet", "imcvtProfileList", "imcvtLaunchCount",
     "imcvtDebugJLSForceSerial", "imcvtDebugJLSPath", "imcvtDebugHEVCPath",
     "writeJLSImageFile", "writeHEVCImageFile", "HEVCImageEncoder",
@@ -68,6 +68,7 @@ def lib():
     L.imcvtEncodeBatchHEVCGreen.argtypes = [vp, sz, i32, u32, u32, i32, vp, sz, vp]; L.imcvtEncodeBatchHEVCGreen.restype = i32
     L.imcvtHostAlloc.argtypes = [sz]; L.imcvtHostAlloc.restype = vp
     L.imcvtHostFree.argtypes = [vp]; L.imcvtHostFree.restype = None
+    L.imcvtJLSHostMode.argtypes = [i32]; L.imcvtJLSHostMode.restype = None
     L.imcvtProfileEnable.argtypes = [i32]; L.imcvtProfileEnable.restype = None
     L.imcvtProfileReset.argtypes = []; L.imcvtProfileReset.restype = None
     L.imcvtProfileGet.argtypes = [C.c_char_p, C.POINTER(i32), C.POINTER(C.c_double)]; L.imcvtProfileGet.restype = i32

@@ -9,6 +9,7 @@ namespace jls {
 int encode_device(const uint8_t *d_frames, size_t frame_stride, int n, int is_rgb, uint32_t H, uint32_t W, int near_,
                   uint8_t *d_out, size_t out_stride, uint64_t *d_out_len, int *d_overflow, cudaStream_t st, Workspace *wsp = nullptr);
 }
+namespace jls { bool host_in_place_ok(int n, int is_rgb, uint32_t W, int near_); }
 namespace hevc {
 int encode_device(const uint8_t *d_frames, size_t frame_stride, int n, uint32_t H, uint32_t W, int qpd6,
                   uint8_t *d_out, size_t out_stride, uint64_t *d_out_len, uint8_t *d_rcon, size_t rcon_stride,
@@ -144,6 +145,59 @@ static int run_host_jls_chunked_impl(const uint8_t *frames, size_t frame_stride,
     return 0;
 }
 
+// Device-side alias of a page-locked host range (cudaHostAlloc / cudaHostRegister memory is mapped under unified addressing),
+// or nullptr when the range is ordinary pageable memory.
+static void *mapped_alias(const void *p, size_t bytes)
+{
+    cudaPointerAttributes a, b;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess || cudaPointerGetAttributes(&b, (const char *)p + (bytes ? bytes - 1 : 0)) != cudaSuccess) {
+        (void)cudaGetLastError();
+        return nullptr;
+    }
+    if (a.type != cudaMemoryTypeHost || b.type != cudaMemoryTypeHost || !a.devicePointer) return nullptr;
+    return a.devicePointer;
+}
+
+// Page-locked input: the kernels read the frames IN PLACE over PCIe (each sample is read once by the producers, a second
+// time out of L2 by the run-event stage), so there is no upload in front of the kernel -- the pixels cross the bus while
+// the planes are being coded.  zero_copy_out: the streams are written straight into the caller's page-locked slots as well.
+static int run_host_jls_mapped(const uint8_t *d_frames, size_t frame_stride, int n, int is_rgb, uint32_t height, uint32_t width, int near_,
+                               uint8_t *out, uint8_t *d_out_mapped, size_t out_stride, size_t bound, size_t *out_len)
+{
+    Engine &E = engine();
+    cudaStream_t st = E.stream;
+    const size_t dev_out_stride = d_out_mapped ? out_stride : ((out_stride < bound ? out_stride : bound) + 255) & ~(size_t)255;
+    if (E.io.reserve((d_out_mapped ? 0 : (size_t)n * dev_out_stride) + (size_t)n * 8 + 4096)) return 1;
+    uint8_t  *d_out  = d_out_mapped ? d_out_mapped : E.io.take<uint8_t>((size_t)n * dev_out_stride);
+    uint64_t *d_len  = E.io.take<uint64_t>((size_t)n);
+    int      *d_flag = E.io.take<int>(1);
+    if (!d_out || !d_len || !d_flag) { set_error("io arena carve failed"); return 1; }
+    if (E.pinned_lens_cap < n + 1) {
+        if (E.pinned_lens) cudaFreeHost(E.pinned_lens);
+        E.pinned_lens = nullptr; E.pinned_lens_cap = 0;
+        IMCVT_CUDA(cudaHostAlloc((void **)&E.pinned_lens, (size_t)(n + 1) * 8, cudaHostAllocDefault));
+        E.pinned_lens_cap = n + 1;
+    }
+    uint64_t *lens = E.pinned_lens;
+    IMCVT_CUDA(cudaMemsetAsync(d_flag, 0, sizeof(int), st));
+    E.jls_out_is_host = d_out_mapped != nullptr;
+    const int enc_rc = jls::encode_device(d_frames, frame_stride, n, is_rgb, height, width, near_, d_out, dev_out_stride, d_len, d_flag, st);
+    E.jls_out_is_host = false;
+    if (enc_rc) return 1;
+    IMCVT_CUDA(cudaMemcpyAsync(lens, d_len, (size_t)n * 8, cudaMemcpyDeviceToHost, st));
+    IMCVT_CUDA(cudaMemcpyAsync(lens + n, d_flag, sizeof(int), cudaMemcpyDeviceToHost, st));
+    IMCVT_CUDA(cudaStreamSynchronize(st));
+    if ((int)lens[n]) { set_error("output slot too small for at least one image (out_stride = %zu)", out_stride); return 1; }
+    for (int i = 0; i < n; i++) {
+        if (lens[i] == 0 || lens[i] > out_stride) { set_error("image %d: encoder produced an invalid length %llu", i, (unsigned long long)lens[i]); return 1; }
+        out_len[i] = (size_t)lens[i];
+        if (!d_out_mapped)
+            IMCVT_CUDA(cudaMemcpyAsync(out + (size_t)i * out_stride, d_out + (size_t)i * dev_out_stride, (size_t)lens[i], cudaMemcpyDeviceToHost, st));
+    }
+    if (!d_out_mapped) IMCVT_CUDA(cudaStreamSynchronize(st));
+    return 0;
+}
+
 static int run_host_jls_chunked(const uint8_t *frames, size_t frame_stride, size_t frame_bytes, int n, int is_rgb,
                                 uint32_t height, uint32_t width, int near_, uint8_t *out, size_t out_stride, size_t bound, size_t *out_len)
 {
@@ -202,6 +256,17 @@ int imcvtEncodeBatchJLS(const uint8_t *frames, size_t frame_stride, int n, int i
     const size_t frame_bytes = (size_t)height * width * (is_rgb ? 3 : 1);
     if (frame_stride < frame_bytes) { set_error("frame_stride smaller than one frame"); return 1; }
     if (ensure_engine()) return 1;
+    // page-locked frames and slots: read and written in place by the kernels when the batch runs on the launch shape built
+    // for it (mode -1, the default), or whenever the caller says so (imcvtJLSHostMode 1 / 2)
+    int mode = engine().jls_host_mode;
+    if (mode < 0) mode = jls::host_in_place_ok(n, is_rgb, width, near_) ? 2 : 0;
+    if (mode > 0) {
+        void *d_in = mapped_alias(frames, (size_t)(n - 1) * frame_stride + frame_bytes);
+        void *d_o = mode > 1 ? mapped_alias(out, (size_t)n * out_stride) : nullptr;
+        if (d_in)
+            return run_host_jls_mapped((const uint8_t *)d_in, frame_stride, n, is_rgb, height, width, near_, out, (uint8_t *)d_o,
+                                       out_stride, imcvtJLSBound(is_rgb, height, width), out_len);
+    }
     if (n >= 8)
         return run_host_jls_chunked(frames, frame_stride, frame_bytes, n, is_rgb, height, width, near_, out, out_stride,
                                     imcvtJLSBound(is_rgb, height, width), out_len);

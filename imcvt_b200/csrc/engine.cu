@@ -231,5 +231,6 @@ long imcvtLaunchCount(void) { return engine().launches; }
 void imcvtDebugJLSForceSerial(int on) { engine().jls_force_serial = on != 0; }
 void imcvtDebugJLSPath(int path) { engine().jls_path = path; }
 void imcvtDebugHEVCPath(int path) { engine().hevc_path = path; }
+void imcvtJLSHostMode(int mode) { engine().jls_host_mode = mode; }
 
 }  // extern "C"

@@ -813,8 +813,12 @@ rowscan_kernel(const uint8_t *__restrict__ pix, size_t plane_stride, int W, int 
     }
     for (int i = tid; i < WMAXR + 16; i += NT) { sm.row[0][i] = 0; sm.row[1][i] = 0; }      // the row above the picture reads as zeros
 
-    tile::PackState ps; ps.out_pos = 0; ps.carry_bits = 0; ps.carry = 0; ps.pz = 0;
-    ps.dst = plane_dst(L, p, ps.cap);
+    tile::PackState ps;
+    {
+        size_t cap;
+        uint8_t *dst = plane_dst(L, p, cap);
+        tile::pack_state_init(ps, dst, cap, nullptr);
+    }
 
     const int nseg = (W + SEG - 1) / SEG, total = H * nseg;
     // stage 1 (lane 0 of warp 0): row state of the walk
@@ -1042,6 +1046,17 @@ static unsigned long long *g_jls_prof = nullptr;
 #endif
 // d_frames: device, interleaved.  d_out / d_out_len: device.  Queues everything on `st`.
 // d_overflow: device int set to 1 when a slot was too small.
+// Whether a gray batch of n planes would run on the cluster-pair tile kernel: the one launch shape that is built for frames
+// and streams in page-locked HOST memory (rows requested a tick ahead of their use, output in whole 128-byte lines).
+bool host_in_place_ok(int n, int is_rgb, uint32_t W, int near_)
+{
+    Engine &E = engine();
+    const bool lossless = (near_ == 0) && !E.jls_force_serial;
+    const bool use_tile = lossless && (int)W <= tile::WMAX && E.jls_path != 1;
+    const bool pair = E.jls_path == 3 || (E.jls_path == 0 && 2 * n <= E.sm_count);
+    return !is_rgb && use_tile && pair;
+}
+
 int encode_device(const uint8_t *d_frames, size_t frame_stride, int n, int is_rgb, uint32_t H, uint32_t W, int near_,
                   uint8_t *d_out, size_t out_stride, uint64_t *d_out_len, int *d_overflow, cudaStream_t st, Workspace *wsp)
 {
@@ -1124,6 +1139,7 @@ int encode_device(const uint8_t *d_frames, size_t frame_stride, int n, int is_rg
         TP.pix = planes; TP.plane_stride = plane_stride; TP.P = P; TP.W = (int)W; TP.H = (int)H;
         TP.L = Lay; TP.plane_bytes = (unsigned long long *)plane_bytes; TP.next_plane = next;
         TP.prof = nullptr;
+        TP.line_out = (E.jls_out_is_host && ncomp == 1) ? 1 : 0;     // RGB scans 1, 2 go through device scratch and assemble_kernel
 #ifdef IMCVT_JLS_PROF
         {
             if (!g_jls_prof) { IMCVT_CUDA(cudaMalloc(&g_jls_prof, 16 * 8)); IMCVT_CUDA(cudaMemset(g_jls_prof, 0, 16 * 8)); }

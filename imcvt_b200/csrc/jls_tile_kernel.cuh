@@ -137,6 +137,7 @@ struct Params {
     unsigned long long *plane_bytes;           // [P] stuffed scan length
     int *next_plane;                           // plane queue
     unsigned long long *prof;                  // role cycle counters (development build IMCVT_JLS_PROF only)
+    int line_out;                              // 1: the output slots are page-locked HOST memory: write whole 128-byte lines
 };
 
 #if defined(IMCVT_JLS_PROF) && !defined(IMCVT_HOST_EMU)
@@ -162,6 +163,7 @@ struct Smem {
     int run_state[8];               // run_index, A/B/N of the two run-interruption contexts, pending run length
     uint16_t order[3][CHAIN_WARPS * 32];   // chain thread -> bucket for a tile: buckets sorted by slice size (big slices share warps)
     int cls_cnt[16], cls_pos[16];
+    alignas(16) uint8_t out_ring[256];      // packer, output in host memory: stuffed bytes until a 128-byte line is complete
     uint32_t blk_tot[32];           // producers: histogram totals per block of 32 buckets
     int8_t qlut[512];               // quantised gradient of g at [g + 255]
     int plane;
@@ -200,6 +202,70 @@ __device__ __forceinline__ void stage_tile(uint8_t *buf, const uint8_t *img, int
         for (int i = tid; i < n; i += nthr) dst[i] = src[i];
     }
     if (tid == 0) buf[0] = r0 >= 2 ? img[(size_t)(r0 - 2) * W] : 0;
+}
+
+// stage_tile in two halves for a CTA whose every thread is a producer (the pair kernel's rank 0): the global loads of tile
+// t + 1 are ISSUED at the start of the tick into registers and only stored to shared memory at its end, so their latency
+// -- a PCIe round trip when the picture is read in place from page-locked host memory -- is covered by the tick's work.
+template <int NREG>
+struct StageRegs { uint32_t w[NREG]; uint32_t edge; bool fast; };
+template <int NREG>
+__device__ __forceinline__ void stage_issue(StageRegs<NREG> &g, const uint8_t *buf, const uint8_t *img, int W, int H, int rows_per_tile, int t, int tid, int nthr)
+{
+    g.fast = false;
+    const int r0 = t * rows_per_tile;
+    if (r0 >= H) return;
+    const int r1 = min(H, r0 + rows_per_tile);
+    const int first = r0 > 0 ? r0 - 1 : 0;
+    const uint8_t *src = img + (size_t)first * W;
+    const uint8_t *dst = buf + 16 + (first - (r0 - 1)) * W;
+    const int n = (r1 - first) * W;
+    const int mis = (int)((size_t)src & 3);
+    const int head = min(n, (4 - mis) & 3), words = (n - head) >> 2, done = head + words * 4;
+    if (((size_t)dst & 3) != (size_t)mis || words > NREG * nthr) return;       // stage_commit falls back to stage_tile
+    g.fast = true;
+    const uint32_t *s4 = reinterpret_cast<const uint32_t *>(src + head);
+#pragma unroll
+    for (int k = 0; k < NREG; k++) { const int i = tid + k * nthr; g.w[k] = i < words ? s4[i] : 0u; }
+    // the few bytes around the words, and the sample two rows above column 0: one byte each in `edge`
+    g.edge = 0;
+    if (tid < head) g.edge = src[tid];
+    else if (tid >= 32 && tid - 32 < n - done) g.edge = src[done + tid - 32];
+    else if (tid == 64 && r0 >= 2) g.edge = img[(size_t)(r0 - 2) * W];
+}
+template <int NREG>
+__device__ __forceinline__ void stage_commit(const StageRegs<NREG> &g, uint8_t *buf, const uint8_t *img, int W, int H, int rows_per_tile, int t, int tid, int nthr)
+{
+    if (!g.fast) { stage_tile(buf, img, W, H, rows_per_tile, t, tid, nthr); return; }
+    const int r0 = t * rows_per_tile;
+    const int r1 = min(H, r0 + rows_per_tile);
+    if (r0 == 0) for (int i = tid; i < W; i += nthr) buf[16 + i] = 0;
+    const int first = r0 > 0 ? r0 - 1 : 0;
+    const uint8_t *src = img + (size_t)first * W;
+    uint8_t *dst = buf + 16 + (first - (r0 - 1)) * W;
+    const int n = (r1 - first) * W;
+    const int mis = (int)((size_t)src & 3);
+    const int head = min(n, (4 - mis) & 3), words = (n - head) >> 2, done = head + words * 4;
+    uint32_t *d4 = reinterpret_cast<uint32_t *>(dst + head);
+#pragma unroll
+    for (int k = 0; k < NREG; k++) { const int i = tid + k * nthr; if (i < words) d4[i] = g.w[k]; }
+    if (tid < head) dst[tid] = (uint8_t)g.edge;
+    else if (tid >= 32 && tid - 32 < n - done) dst[done + tid - 32] = (uint8_t)g.edge;
+    else if (tid == 64) buf[0] = r0 >= 2 ? (uint8_t)g.edge : 0;
+}
+
+// Pair kernel, consumer CTA: the rows of tile t as the producer CTA staged them a tick earlier, fetched from ITS shared memory
+// (distributed shared memory loads) instead of a second read of the picture: global memory -- or, with page-locked input
+// read in place, the PCIe link -- sees every sample once.
+__device__ __forceinline__ void pull_tile(uint8_t *dst, const uint8_t *remote, int W, int H, int rows_per_tile, int t, int tid, int nthr)
+{
+    const int r0 = t * rows_per_tile;
+    if (r0 >= H) return;
+    const int R = min(H, r0 + rows_per_tile) - r0;
+    const int words = (16 + (R + 1) * W + 3) >> 2;          // slot of the sample two rows up | row above | R rows
+    const uint32_t *s4 = reinterpret_cast<const uint32_t *>(remote);
+    uint32_t *d4 = reinterpret_cast<uint32_t *>(dst);
+    for (int i = tid; i < words; i += nthr) d4[i] = s4[i];
 }
 
 // ---- producers ------------------------------------------------------------------------------------
@@ -327,6 +393,12 @@ __device__ __forceinline__ void producer_tick(Smem &sm, Smem &cons, const Params
     const int W = P.W, H = P.H;
     const int ptid = pw * 32 + lane;
     JPROF_T0();
+    // every thread of the CTA is a producer (pair kernel): the next tile's rows are requested now and stored at the end
+    constexpr bool SPLIT_STAGE = (NPW == NWARPS);
+    constexpr int NREG = SPLIT_STAGE ? (TSMAX + WMAX + 4 * NPW * 32 - 1) / (4 * NPW * 32) : 1;
+    StageRegs<NREG> sregs;
+    sregs.fast = false;
+    if (SPLIT_STAGE && t + 1 < ntiles) stage_issue<NREG>(sregs, sm.pix[(t + 1) % 3], img, W, H, rows_per_tile, t + 1, ptid, PROD_THREADS);
     if (t < ntiles) {
         const int buf = t % nbuf;                  // tiles in flight: 2 (one CTA) or 3 (pair)
         uint8_t *pb = sm.pix[t % 3];
@@ -406,7 +478,10 @@ __device__ __forceinline__ void producer_tick(Smem &sm, Smem &cons, const Params
         }
     }
     // rows of the next tile
-    if (t + 1 < ntiles) stage_tile(sm.pix[(t + 1) % 3], img, W, H, rows_per_tile, t + 1, ptid, PROD_THREADS);
+    if (t + 1 < ntiles) {
+        if (SPLIT_STAGE) stage_commit<NREG>(sregs, sm.pix[(t + 1) % 3], img, W, H, rows_per_tile, t + 1, ptid, PROD_THREADS);
+        else stage_tile(sm.pix[(t + 1) % 3], img, W, H, rows_per_tile, t + 1, ptid, PROD_THREADS);
+    }
 }
 
 // ---- chains ---------------------------------------------------------------------------------------
@@ -522,7 +597,39 @@ struct PackState {
     uint32_t carry_bits;        // un-stuffed bits of earlier tiles still to be written (< 8)
     uint32_t carry;             // ... right-aligned
     uint32_t pz;                // 1: the next byte starts with a stuffed 0 bit (previous byte was 0xFF)
+    // Output straight into page-locked host memory (imcvtJLSHostMode 2): byte stores would cross PCIe one by one, so the
+    // stuffed bytes collect in a 256-byte shared-memory ring and leave as whole, 128-byte aligned lines (one 4-byte store
+    // per lane = one write transaction per line).  ring == nullptr: bytes go straight to dst.
+    uint8_t *ring;
+    uint32_t mis;               // dst & 127: ring / line positions are counted from the 128-byte line dst lies in
+    uint32_t flushed;           // first position (from that line's start) not yet written to dst; a multiple of 128
 };
+__device__ __forceinline__ void pack_state_init(PackState &ps, uint8_t *dst, size_t cap, uint8_t *ring)
+{
+    ps.out_pos = 0; ps.carry_bits = 0; ps.carry = 0; ps.pz = 0; ps.dst = dst; ps.cap = cap;
+    ps.ring = ring; ps.mis = (uint32_t)((size_t)dst & 127u); ps.flushed = 0;
+}
+// lines that are complete below `vend` leave the ring (the first one may start inside a line: bytes)
+__device__ __forceinline__ void ring_flush_lines(PackState &ps, uint32_t vend, int lane)
+{
+    while (ps.flushed + 128u <= vend) {
+        uint8_t *g = ps.dst - ps.mis + ps.flushed;                      // 128-byte aligned
+        const uint8_t *r = ps.ring + (ps.flushed & 255u);
+        if (ps.flushed >= ps.mis) {
+            reinterpret_cast<uint32_t *>(g)[lane] = reinterpret_cast<const uint32_t *>(r)[lane];
+        } else {
+#pragma unroll
+            for (int k = 0; k < 4; k++) { const uint32_t v = 4u * lane + k; if (v >= ps.mis) g[v] = r[v]; }
+        }
+        ps.flushed += 128u;
+    }
+}
+// the bytes of the last, incomplete line
+__device__ __forceinline__ void ring_flush_tail(PackState &ps, uint32_t vend, int lane)
+{
+    for (uint32_t v = ps.flushed + lane; v < vend; v += 32) if (v >= ps.mis) ps.dst[v - ps.mis] = ps.ring[v & 255u];
+    ps.flushed = vend;
+}
 
 __device__ __forceinline__ uint32_t ubits_word(const uint32_t *buf, int32_t w, uint32_t carry)
 {
@@ -560,10 +667,22 @@ __device__ __forceinline__ void stuff_bits(const uint32_t *buf, PackState &ps, u
             const uint32_t cut = 4u * f + (uint32_t)__shfl_sync(0xffffffffu, fb, f) + 1u;
             if (cut <= nbytes) { nbytes = cut; ends_ff = true; }
         }
+        if (ps.ring) {
 #pragma unroll
-        for (int k = 0; k < 4; k++) {
-            const uint32_t bi = 4u * lane + k;
-            if (bi < nbytes && ps.out_pos + bi < ps.cap) ps.dst[ps.out_pos + bi] = (uint8_t)(v >> (24 - 8 * k));
+            for (int k = 0; k < 4; k++) {
+                const uint32_t bi = 4u * lane + k;
+                if (bi < nbytes && ps.out_pos + bi < ps.cap) ps.ring[(ps.mis + (uint32_t)ps.out_pos + bi) & 255u] = (uint8_t)(v >> (24 - 8 * k));
+            }
+            __syncwarp();
+            const size_t end = ps.out_pos + nbytes < ps.cap ? ps.out_pos + nbytes : ps.cap;
+            ring_flush_lines(ps, ps.mis + (uint32_t)end, lane);
+            __syncwarp();
+        } else {
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const uint32_t bi = 4u * lane + k;
+                if (bi < nbytes && ps.out_pos + bi < ps.cap) ps.dst[ps.out_pos + bi] = (uint8_t)(v >> (24 - 8 * k));
+            }
         }
         ps.out_pos += nbytes;
         in_pos = s + (int32_t)(8u * nbytes);
@@ -576,6 +695,11 @@ __device__ __forceinline__ void stuff_bits(const uint32_t *buf, PackState &ps, u
         rest = __funnelshift_l(ubits_word(buf, w + 1, carry), ubits_word(buf, w, carry), (uint32_t)in_pos & 31u) & ~(0xFFFFFFFFu >> left);
     }
     if (flush) {
+        if (ps.ring) {                                  // what is left of the last line; the one or two closing bytes go direct
+            const size_t end = ps.out_pos < ps.cap ? ps.out_pos : ps.cap;
+            __syncwarp();
+            ring_flush_tail(ps, ps.mis + (uint32_t)end, lane);
+        }
         if (left > 0) {                                 // flushBits :177-184: pad the last byte with zeros
             if (lane == 0 && ps.out_pos < ps.cap) ps.dst[ps.out_pos] = (uint8_t)(ps.pz ? (rest >> 25) : (rest >> 24));
             ps.out_pos++; ps.pz = 0;
@@ -813,6 +937,9 @@ __device__ __forceinline__ void tile_body(const Params &P)
     Smem &sm   = *reinterpret_cast<Smem *>(PAIR ? (unsigned char *)JLS_OWN_SMEM(rank) : (unsigned char *)JLS_DYN_SMEM());
     // where the producers put the sorted tile: the same image, or rank 1's through distributed shared memory
     Smem &cons = *reinterpret_cast<Smem *>(PAIR ? (unsigned char *)JLS_PAIR_SMEM(1) : (unsigned char *)JLS_DYN_SMEM());
+    // the producer CTA's image as the consumer CTA sees it (rows of a tile are pulled from there)
+    Smem &prod = *reinterpret_cast<Smem *>(PAIR ? (unsigned char *)JLS_PAIR_SMEM(0) : (unsigned char *)JLS_DYN_SMEM());
+    static_assert(offsetof(Smem, pix) % 4 == 0 && PIXBUF % 4 == 0, "pull_tile copies words");
     const int W = P.W, H = P.H;
     const int rows_per_tile = max(1, TSMAX / W);
     const int ntiles = (H + rows_per_tile - 1) / rows_per_tile;
@@ -834,12 +961,15 @@ __device__ __forceinline__ void tile_body(const Params &P)
         if (p >= P.P) break;
         const uint8_t *img = P.pix + (size_t)p * P.plane_stride;
 
-        PackState ps; ps.out_pos = 0; ps.carry_bits = 0; ps.carry = 0; ps.pz = 0; ps.dst = nullptr; ps.cap = 0;
+        PackState ps;
+        pack_state_init(ps, nullptr, 0, nullptr);
         if (consumer_cta) {
             // :256-261 (a_init = 4 for RANGE 256), :250, :263-267
             for (int i = tid; i < NCTX; i += NTHREADS) { sm.ctx[i][0] = 4; sm.ctx[i][1] = 0; sm.ctx[i][2] = 0; sm.ctx[i][3] = 1; sm.ctx_a[i] = 4; }
             if (tid < 8) sm.run_state[tid] = (tid == 1 || tid == 4) ? 4 : (tid == 3 || tid == 6) ? 1 : 0;
-            ps.dst = plane_dst(P.L, p, ps.cap);
+            size_t cap;
+            uint8_t *dst = plane_dst(P.L, p, cap);
+            pack_state_init(ps, dst, cap, P.line_out ? sm.out_ring : nullptr);
         }
         if (producer_cta) stage_tile(sm.pix[0], img, W, H, rows_per_tile, 0, tid, NTHREADS);
         if (PAIR) JLS_PAIR_SYNC(); else __syncthreads();
@@ -867,8 +997,9 @@ __device__ __forceinline__ void tile_body(const Params &P)
                         packer_tile(sm, P, ps, sm.codes[t & 1], sm.lens[t & 1], n, t == ntiles - 1, warp - PACK0, lane);
                     }
                 } else {
-                    // the rows of tile `tick`, read by its run events one tick later
-                    if (tick < ntiles) stage_tile(sm.pix[tick % 3], img, W, H, rows_per_tile, tick, tid - STAGE0 * 32, NTHREADS - STAGE0 * 32);
+                    // the rows of tile `tick`, read by its run events two ticks later: the producer CTA staged them during the
+                    // tick before and works on them now (it stages tile tick + 1 into another buffer meanwhile)
+                    if (tick < ntiles) pull_tile(sm.pix[tick % 3], prod.pix[tick % 3], W, H, rows_per_tile, tick, tid - STAGE0 * 32, NTHREADS - STAGE0 * 32);
                 }
                 JPROF(2, rank == 1 && warp == PACK0 && lane == 0);
                 JLS_PAIR_SYNC();

@@ -76,6 +76,15 @@ int imcvtEncodeBatchHEVCDevice(const void *d_frames, size_t frame_stride, int n,
                                void *d_out, size_t out_stride, void *d_out_len,
                                void *d_rcon, size_t rcon_stride, void *stream);
 
+/* How imcvtEncodeBatchJLS moves PAGE-LOCKED host buffers (cudaHostAlloc / imcvtHostAlloc / cudaHostRegister memory; pageable
+ * buffers are always staged through device memory):
+ *  -1 (default) = in place when the batch is one the in-place kernel is built for (gray, NEAR 0, planes up to 6144 wide, at
+ *       most SMs/2 frames: the cluster-pair kernel requests rows over PCIe a tick ahead of their use and writes the stream in
+ *       whole 128-byte lines), otherwise staged;
+ *   0 = always upload, encode, download (chunked and overlapped);
+ *   1 = frames read in place, streams downloaded;   2 = frames read and streams written in place, whatever the kernel. */
+void imcvtJLSHostMode(int mode);
+
 /* ---- staging memory ---------------------------------------------------------------------------- */
 /* Page-locked host memory for the frames / out arguments of the host-buffer entry points: copies from and to it run at
  * full PCIe rate and overlap the kernels.  A loader that reads image files straight into such a buffer replaces the

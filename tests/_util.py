@@ -185,7 +185,7 @@ def emu_hevc(img, qpd6, pair=False):
     return out[:n].tobytes(), rcon.reshape(hp, wp).copy()
 
 
-def emu_jls(img, pair=False):
+def emu_jls(img, pair=False, line_out=False):
     """The SOURCE of the CUDA JPEG-LS tile kernel (NEAR = 0, gray) run under the CPU SIMT emulator (tests/emu);
     pair=True: the two-CTA cluster variant (rank 0 producers, rank 1 chains + packers)."""
     if "emu_jls" not in _libs:
@@ -199,10 +199,14 @@ def emu_jls(img, pair=False):
         _libs["emu_jls"] = lib
     img = np.ascontiguousarray(img, dtype=np.uint8)
     h, w = img.shape
-    out = np.zeros(8 * h * w + 65536, dtype=np.uint8)
-    n = _libs["emu_jls"].emu_jls_encode_mode(img.ctypes.data, h, w, out.ctypes.data, out.size, 1 if pair else 0)
+    # line_out: the packer's 128-byte line ring (the output path for page-locked host slots); the slot then starts at an
+    # arbitrary offset inside a line so that the partial first line is exercised
+    out = np.zeros(8 * h * w + 65536 + 256, dtype=np.uint8)
+    off = (int(line_out) * (37 + 128 - out.ctypes.data % 128)) % 128 if line_out else 0
+    n = _libs["emu_jls"].emu_jls_encode_mode(img.ctypes.data, h, w, out.ctypes.data + off, out.size - 256,
+                                             (1 if pair else 0) | (2 if line_out else 0))
     assert n > 0
-    return out[:n].tobytes()
+    return out[off:off + n].tobytes()
 
 
 def jls_decode(stream):

@@ -45,3 +45,15 @@ def test_multi_tile_planes_match_oracle(pair):
     cases.append(("runs+interrupts", img))
     for name, img in cases:
         assert emu_jls(img, pair) == oracle_jls(img, 0), name
+
+
+@pytest.mark.parametrize("pair", [False, True], ids=["one-cta", "cluster-pair"])
+def test_line_ring_output_matches(pair):
+    """The output path for page-locked host slots (imcvtJLSHostMode 2): stuffed bytes leave the packer as whole 128-byte
+    lines through a shared-memory ring; the slot starts inside a line (offset 37 + 25 header bytes)."""
+    rng = np.random.default_rng(11)
+    cases = [("natural", synth.frame("natural", 5, 100, 480)), ("noise", synth.frame("noise", 1, 40, 333)),
+             ("constant", synth.frame("constant", 0, 64, 64)), ("tiny", rng.integers(0, 256, (1, 1), dtype=np.uint8)),
+             ("binary", (rng.integers(0, 2, (60, 700)) * 255).astype(np.uint8)), ("short", rng.integers(0, 256, (3, 17), dtype=np.uint8))]
+    for name, img in cases:
+        assert emu_jls(img, pair, line_out=True) == oracle_jls(img, 0), name

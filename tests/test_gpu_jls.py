@@ -254,3 +254,35 @@ def test_host_calls_from_two_threads_are_serialised():
         assert got[k] is not None
         for i in range(frames.shape[0]):
             assert got[k][i] == oracle_jls(frames[i], near), (k, i)
+
+
+@pytest.mark.parametrize("mode", [-1, 1, 2])
+def test_page_locked_buffers_read_and_written_in_place(mode):
+    """imcvtJLSHostMode: with page-locked buffers the kernels read the frames (mode 1) and write the streams (mode 2) in
+    place over PCIe instead of staging them through device memory (-1, the default: when the batch runs on the cluster-pair
+    kernel).  Same bytes in every mode; pageable buffers fall back to staging whatever the mode says."""
+    import ctypes as C
+    import torch
+    L = imcvt_b200.lib()
+    try:
+        for frames, near in ((synth.batch("natural", 9, 120, 333), 0), (synth.batch("texture", 3, 64, 96, rgb=True), 0),
+                             (synth.batch("natural", 5, 70, 131), 2), (synth.batch("noise", 2, 33, 6200), 0)):
+            L.imcvtJLSHostMode(0)
+            want = imcvt_b200.encode_jls_batch(frames, near)
+            L.imcvtJLSHostMode(mode)
+            assert imcvt_b200.encode_jls_batch(frames, near) == want            # pageable numpy buffers: staged
+            n, h, w = frames.shape[:3]
+            is_rgb = int(frames.ndim == 4)
+            stride = imcvt_b200.jls_bound(is_rgb, h, w)
+            h_in = torch.from_numpy(frames).pin_memory()
+            h_out = torch.zeros(n * stride, dtype=torch.uint8).pin_memory()
+            lens = (C.c_size_t * n)()
+            rc = L.imcvtEncodeBatchJLS(h_in.numpy().ctypes.data, frames[0].nbytes, n, is_rgb, h, w, near,
+                                       h_out.numpy().ctypes.data, stride, C.cast(lens, C.c_void_p))
+            assert rc == 0, imcvt_b200.last_error()
+            got = [h_out.numpy()[i * stride:i * stride + lens[i]].tobytes() for i in range(n)]
+            assert got == want, (mode, frames.shape, near)
+            for i in range(n):
+                assert got[i] == oracle_jls(frames[i], near)
+    finally:
+        L.imcvtJLSHostMode(-1)
