@@ -234,6 +234,29 @@ def measured_peak():
 # ------------------------------------------------------------------------------------------------
 # our arm
 # ------------------------------------------------------------------------------------------------
+def bind_to_gpu_numa_node(local_rank):
+    """One process per GPU: run on the CPUs NVML names as local to this GPU, so that the page-locked frame / stream buffers
+    (first touched by this process) sit on the NUMA node whose PCIe root the GPU hangs on.  The host-buffer leg moves
+    ~200 MB per step and GPU; with eight ranks floating over two sockets half of that crossed the socket link."""
+    try:
+        import pynvml
+        import torch
+        pynvml.nvmlInit()
+        pr = torch.cuda.get_device_properties(local_rank)
+        h = pynvml.nvmlDeviceGetHandleByPciBusId(f"{pr.pci_domain_id:08X}:{pr.pci_bus_id:02X}:{pr.pci_device_id:02X}.0")
+        ncpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
+        cpus = [i for i in range(ncpu) if (words[i // 64] >> (i % 64)) & 1]
+        allowed = os.sched_getaffinity(0)
+        cpus = [c for c in cpus if c in allowed]
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return len(cpus)
+    except Exception as e:                      # no NVML / no affinity information: stay where the launcher put us
+        print(f"bench: NUMA binding skipped ({e})", file=sys.stderr)
+    return 0
+
+
 def run_ours(args, rank, world, local_rank):
     import torch
     import torch.distributed as dist
@@ -241,6 +264,8 @@ def run_ours(args, rank, world, local_rank):
     from imcvt_b200 import synth
 
     torch.cuda.set_device(local_rank)
+    if world > 1:
+        bind_to_gpu_numa_node(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     imcvt_b200.init(local_rank)

@@ -30,7 +30,7 @@ EXPORTED_SYMBOLS = [
     "imcvtInit", "imcvtShutdown", "imcvtLastError", "imcvtVersion",
     "imcvtJLSBound", "imcvtHEVCBound",
     "imcvtEncodeBatchJLS", "imcvtEncodeBatchJLSDevice",
-    "imcvtEncodeBatchHEVC", "imcvtEncodeBatchHEVCDevice", "imcvtEncodeBatchHEVCGreen",
+    "imcvtEncodeBatchHEVC", "imcvtEncodeBatchHEVCDevice", "imcvtEncodeBatchHEVCGreen", "imcvtEncodeBatchHEVCSweep",
     "imcvtHostAlloc", "imcvtHostFree", "imcvtJLSHostMode",
     "imcvtProfileEnable", "imcvtProfileReset", "imcvtProfileGet", "imcvtProfileList", "imcvtLaunchCount",
     "imcvtDebugJLSForceSerial", "imcvtDebugJLSPath", "imcvtDebugHEVCPath",
@@ -66,6 +66,7 @@ def lib():
     L.imcvtEncodeBatchHEVC.argtypes = [vp, sz, i32, u32, u32, i32, vp, sz, vp, vp, sz]; L.imcvtEncodeBatchHEVC.restype = i32
     L.imcvtEncodeBatchHEVCDevice.argtypes = [vp, sz, i32, u32, u32, i32, vp, sz, vp, vp, sz, vp]; L.imcvtEncodeBatchHEVCDevice.restype = i32
     L.imcvtEncodeBatchHEVCGreen.argtypes = [vp, sz, i32, u32, u32, i32, vp, sz, vp]; L.imcvtEncodeBatchHEVCGreen.restype = i32
+    L.imcvtEncodeBatchHEVCSweep.argtypes = [vp, sz, i32, u32, u32, C.POINTER(i32), i32, vp, sz, vp]; L.imcvtEncodeBatchHEVCSweep.restype = i32
     L.imcvtHostAlloc.argtypes = [sz]; L.imcvtHostAlloc.restype = vp
     L.imcvtHostFree.argtypes = [vp]; L.imcvtHostFree.restype = None
     L.imcvtJLSHostMode.argtypes = [i32]; L.imcvtJLSHostMode.restype = None
@@ -150,6 +151,23 @@ def encode_hevc_batch(frames, qpd6=4, want_rcon=True):
                                       out.ctypes.data, out_stride, C.cast(lens, C.c_void_p),
                                       rcon.ctypes.data if want_rcon else None, hp * wp), "imcvtEncodeBatchHEVC")
     return [out[i * out_stride:i * out_stride + lens[i]].tobytes() for i in range(n)], rcon
+
+
+def encode_hevc_sweep(frames, qpd6_list):
+    """frames: uint8 [n,H,W]; qpd6_list: 1..8 settings.  One launch codes every frame at every setting.
+    Returns a list of n lists: streams[i][k] = frame i at qpd6_list[k] (same bytes as encode_hevc_batch per setting)."""
+    frames = np.ascontiguousarray(frames, dtype=np.uint8)
+    if frames.ndim != 3:
+        raise ValueError("frames must be [n,H,W] uint8")
+    n, h, w = frames.shape
+    nq = len(qpd6_list)
+    q = (C.c_int * nq)(*[int(x) for x in qpd6_list])
+    out_stride = hevc_bound(h, w)
+    out = np.empty(n * nq * out_stride, dtype=np.uint8)
+    lens = (C.c_size_t * (n * nq))()
+    _check(lib().imcvtEncodeBatchHEVCSweep(frames.ctypes.data, h * w, n, h, w, q, nq, out.ctypes.data, out_stride,
+                                           C.cast(lens, C.c_void_p)), "imcvtEncodeBatchHEVCSweep")
+    return [[out[(i * nq + k) * out_stride:(i * nq + k) * out_stride + lens[i * nq + k]].tobytes() for k in range(nq)] for i in range(n)]
 
 
 def encode_hevc_green_batch(frames, qpd6=4):

@@ -7,13 +7,14 @@
 namespace imcvt {
 namespace jls {
 int encode_device(const uint8_t *d_frames, size_t frame_stride, int n, int is_rgb, uint32_t H, uint32_t W, int near_,
-                  uint8_t *d_out, size_t out_stride, uint64_t *d_out_len, int *d_overflow, cudaStream_t st, Workspace *wsp = nullptr);
+                  uint8_t *d_out, size_t out_stride, uint64_t *d_out_len, int *d_overflow, cudaStream_t st, Workspace *wsp = nullptr,
+                  bool out_is_host = false);     // out_is_host: d_out aliases page-locked host memory (whole-line stores)
 }
 namespace jls { bool host_in_place_ok(int n, int is_rgb, uint32_t W, int near_); }
 namespace hevc {
 int encode_device(const uint8_t *d_frames, size_t frame_stride, int n, uint32_t H, uint32_t W, int qpd6,
                   uint8_t *d_out, size_t out_stride, uint64_t *d_out_len, uint8_t *d_rcon, size_t rcon_stride,
-                  int *d_overflow, cudaStream_t st);
+                  int *d_overflow, cudaStream_t st, const int *qlist = nullptr, int nq = 0);
 }
 }  // namespace imcvt
 
@@ -180,10 +181,8 @@ static int run_host_jls_mapped(const uint8_t *d_frames, size_t frame_stride, int
     }
     uint64_t *lens = E.pinned_lens;
     IMCVT_CUDA(cudaMemsetAsync(d_flag, 0, sizeof(int), st));
-    E.jls_out_is_host = d_out_mapped != nullptr;
-    const int enc_rc = jls::encode_device(d_frames, frame_stride, n, is_rgb, height, width, near_, d_out, dev_out_stride, d_len, d_flag, st);
-    E.jls_out_is_host = false;
-    if (enc_rc) return 1;
+    if (jls::encode_device(d_frames, frame_stride, n, is_rgb, height, width, near_, d_out, dev_out_stride, d_len, d_flag, st, nullptr,
+                           d_out_mapped != nullptr)) return 1;
     IMCVT_CUDA(cudaMemcpyAsync(lens, d_len, (size_t)n * 8, cudaMemcpyDeviceToHost, st));
     IMCVT_CUDA(cudaMemcpyAsync(lens + n, d_flag, sizeof(int), cudaMemcpyDeviceToHost, st));
     IMCVT_CUDA(cudaStreamSynchronize(st));
@@ -347,6 +346,50 @@ int imcvtEncodeBatchHEVCGreen(const uint8_t *rgb_frames, size_t frame_stride, in
     };
     return run_host_batch(rgb_frames, frame_stride, 3 * npix, n, out, out_stride, imcvtHEVCBound(height, width), out_len,
                           nullptr, 0, 0, gray_stride, enc);
+}
+
+int imcvtEncodeBatchHEVCSweep(const uint8_t *frames, size_t frame_stride, int n,
+                              uint32_t height, uint32_t width, const int *qpd6, int nq,
+                              uint8_t *out, size_t out_stride, size_t *out_len)
+{
+    IMCVT_API_LOCK();
+    if (n <= 0 || !frames || !out || !out_len || !qpd6) { set_error("bad arguments"); return 1; }
+    if (nq < 1 || nq > 8) { set_error("a sweep takes 1..8 settings (got %d)", nq); return 1; }
+    if (height < 1 || width < 1) { set_error("empty image"); return 1; }
+    for (int k = 0; k < nq; k++)
+        if (qpd6[k] < 0 || qpd6[k] > 4) { set_error("qpd6 must be 0..4 (got %d)", qpd6[k]); return 1; }
+    if ((long long)n * nq > 0x7FFFFFFF) { set_error("too many jobs"); return 1; }
+    const size_t frame_bytes = (size_t)height * width;
+    if (frame_stride < frame_bytes) { set_error("frame_stride smaller than one frame"); return 1; }
+    if (ensure_engine()) return 1;
+    Engine &E = engine();
+    cudaStream_t st = E.stream;
+    const int jobs = n * nq;
+    const size_t bound = imcvtHEVCBound(height, width);
+    const size_t dev_in_stride  = (frame_bytes + 255) & ~(size_t)255;
+    const size_t dev_out_stride = ((out_stride < bound ? out_stride : bound) + 255) & ~(size_t)255;
+    if (E.io.reserve((size_t)n * dev_in_stride + (size_t)jobs * dev_out_stride + (size_t)jobs * 8 + 4096)) return 1;
+    uint8_t  *d_in   = E.io.take<uint8_t>((size_t)n * dev_in_stride);
+    uint8_t  *d_out  = E.io.take<uint8_t>((size_t)jobs * dev_out_stride);
+    uint64_t *d_len  = E.io.take<uint64_t>((size_t)jobs);
+    int      *d_flag = E.io.take<int>(1);
+    if (!d_in || !d_out || !d_len || !d_flag) { set_error("io arena carve failed"); return 1; }
+    IMCVT_CUDA(cudaMemcpy2DAsync(d_in, dev_in_stride, frames, frame_stride, frame_bytes, n, cudaMemcpyHostToDevice, st));
+    IMCVT_CUDA(cudaMemsetAsync(d_flag, 0, sizeof(int), st));
+    if (hevc::encode_device(d_in, dev_in_stride, n, height, width, qpd6[0], d_out, dev_out_stride, d_len, nullptr, 0, d_flag, st, qpd6, nq)) return 1;
+    std::vector<uint64_t> lens(jobs);
+    int flag = 0;
+    IMCVT_CUDA(cudaMemcpyAsync(lens.data(), d_len, (size_t)jobs * 8, cudaMemcpyDeviceToHost, st));
+    IMCVT_CUDA(cudaMemcpyAsync(&flag, d_flag, sizeof(int), cudaMemcpyDeviceToHost, st));
+    IMCVT_CUDA(cudaStreamSynchronize(st));
+    if (flag) { set_error("output slot too small for at least one image (out_stride = %zu)", out_stride); return 1; }
+    for (int j = 0; j < jobs; j++) {
+        if (lens[j] == 0 || lens[j] > out_stride) { set_error("job %d: encoder produced an invalid length %llu", j, (unsigned long long)lens[j]); return 1; }
+        out_len[j] = (size_t)lens[j];
+        IMCVT_CUDA(cudaMemcpyAsync(out + (size_t)j * out_stride, d_out + (size_t)j * dev_out_stride, (size_t)lens[j], cudaMemcpyDeviceToHost, st));
+    }
+    IMCVT_CUDA(cudaStreamSynchronize(st));
+    return 0;
 }
 
 void *imcvtHostAlloc(size_t bytes)

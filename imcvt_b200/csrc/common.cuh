@@ -68,7 +68,6 @@ struct Engine {
     bool jls_force_serial = false;
     int jls_path = 0;       // 0 = default (tile kernel when the plane fits), 1 = force the multi-kernel pipeline, 3 = tile kernel on CTA pairs
     int jls_host_mode = -1; // host-buffer JPEG-LS batches with page-locked buffers: -1 = in place when the batch runs on the cluster-pair kernel, 0 = always staged through HBM, 1 = frames read in place over PCIe, 2 = streams written in place too
-    bool jls_out_is_host = false;   // set around the launch by the host-buffer path that hands page-locked output slots to the kernels
     int hevc_path = 0;      // 0 = default (CTA pair per frame when the batch has at most SMs/2 frames), 1 = one CTA per frame, 2 = CTA pair
     int sm_count = 148;
 };

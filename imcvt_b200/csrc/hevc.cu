@@ -16,9 +16,13 @@ static inline int pad32(uint32_t v) { uint32_t c = v > 8192 ? 8192 : v; return (
 // d_frames: device, n gray8 images.  d_out / d_out_len / d_rcon (optional): device.  Queues everything on `st`.
 int encode_device(const uint8_t *d_frames, size_t frame_stride, int n, uint32_t H, uint32_t W, int qpd6,
                   uint8_t *d_out, size_t out_stride, uint64_t *d_out_len, uint8_t *d_rcon, size_t rcon_stride,
-                  int *d_overflow, cudaStream_t st)
+                  int *d_overflow, cudaStream_t st, const int *qlist, int nq)
 {
+    // qlist / nq: a sweep (nq > 0) -- every frame is coded at each of the nq settings; job j = frame j / nq at qlist[j % nq]
+    // writes slot j of d_out / d_out_len / d_rcon.  The jobs of a sweep fill the GPU where one setting's batch would not.
     Engine &E = engine();
+    const int n_frames = n;
+    if (nq > 0) n = n * nq;                             // from here on n counts jobs (= output slots)
     const int hp = pad32(H), wp = pad32(W);
     const size_t rbytes = (size_t)hp * wp;
     if (d_rcon && rcon_stride < rbytes) { set_error("rcon_stride smaller than one padded picture"); return 1; }
@@ -50,12 +54,15 @@ int encode_device(const uint8_t *d_frames, size_t frame_stride, int n, uint32_t 
 
     Params P;
     P.frames = d_frames; P.frame_stride = frame_stride;
-    P.n = n; P.H = (int)H; P.W = (int)W; P.hp = hp; P.wp = wp; P.qpd6 = qpd6;
+    P.n = n_frames; P.H = (int)H; P.W = (int)W; P.hp = hp; P.wp = wp; P.qpd6 = qpd6;
     P.out = d_out; P.out_stride = out_stride;
     P.out_len = (unsigned long long *)d_out_len;
     P.rcon = rc; P.rcon_stride = rcs;
     P.scratch = scratch; P.lists = lists; P.overflow = d_overflow; P.next_frame = next;
     P.prof = nullptr;
+    P.nq = nq > 0 ? nq : 0;
+    for (int k = 0; k < 8; k++) P.qlist[k] = (nq > 0 && k < nq) ? qlist[k] : 0;
+    if (nq > 0) P.qpd6 = qlist[0];
 #ifdef IMCVT_HEVC_PROF
     {
         static unsigned long long *d_prof = nullptr;

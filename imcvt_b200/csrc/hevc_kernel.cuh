@@ -141,6 +141,7 @@ IMCVT_CONSTANT unsigned char c_slice_tail[5][2] = {{0x16,0xDE},{0x10,0xDE},{0x2B
 struct Params {
     const uint8_t *frames; size_t frame_stride;     // n gray8 images H x W
     int n, H, W, hp, wp, qpd6;                       // hp, wp: padded to x32 (and clipped to 8192, :1580-1581)
+    int nq, qlist[8];                                // nq > 0: a sweep -- job j codes frame j / nq at qpd6 = qlist[j % nq] into slot j
     uint8_t *out; size_t out_stride;                 // output slots
     unsigned long long *out_len;                     // [n]
     uint8_t *rcon; size_t rcon_stride;               // [n][hp*wp] reconstruction (also the line buffer between CTU rows)
@@ -1782,13 +1783,14 @@ __device__ __forceinline__ void push_result(Ctx &K)
 //     32x32 unit and of each 16x16 unit meanwhile.  Per 16x16 unit the two meet twice at a cluster barrier: once when the
 //     unit's entry state is in the upper CTA's shared memory, once when the upper CTA's result is in the spine's.
 template <bool PAIR>
-__device__ inline void encode_frame(Ctx &K, int f, int rank)
+__device__ inline void encode_frame(Ctx &K, int job, int rank)
 {
     Smem &sm = *K.sm;
     const Params &P = *K.P;
     const int tid = threadIdx.x;
-    const int hp = P.hp, wp = P.wp, qpd6 = P.qpd6;
-    const uint8_t *img = P.frames + (size_t)f * P.frame_stride;
+    const int hp = P.hp, wp = P.wp, qpd6 = K.qpd6;
+    const int f = job;                                                          // slot of the stream / reconstruction / length
+    const uint8_t *img = P.frames + (size_t)(P.nq > 0 ? job / P.nq : job) * P.frame_stride;
     uint8_t *rcon = P.rcon + (size_t)f * P.rcon_stride;
     K.out = P.out + (size_t)f * P.out_stride;
 
@@ -1892,7 +1894,13 @@ __device__ __forceinline__ void frame_kernel_body(const Params &P)
         if (threadIdx.x == 0 && rank == 0) { const int f = atomicAdd(P.next_frame, 1); sm.win = f; if (PAIR) K.peer->win = f; }
         if (PAIR) HEVC_PAIR_SYNC(); else __syncthreads();
         const int f = sm.win;
-        if (f >= P.n) break;
+        if (f >= (P.nq > 0 ? P.n * P.nq : P.n)) break;
+        if (P.nq > 0 && P.qlist[f % P.nq] != K.qpd6) {                          // a sweep: the context initialisation follows the QP
+            K.qpd6 = P.qlist[f % P.nq];
+            K.rd.init(K.qpd6);
+            __syncthreads();
+            build_tables(sm, K.qpd6);
+        }
         encode_frame<PAIR>(K, f, rank);
     }
 }

@@ -1058,7 +1058,7 @@ bool host_in_place_ok(int n, int is_rgb, uint32_t W, int near_)
 }
 
 int encode_device(const uint8_t *d_frames, size_t frame_stride, int n, int is_rgb, uint32_t H, uint32_t W, int near_,
-                  uint8_t *d_out, size_t out_stride, uint64_t *d_out_len, int *d_overflow, cudaStream_t st, Workspace *wsp)
+                  uint8_t *d_out, size_t out_stride, uint64_t *d_out_len, int *d_overflow, cudaStream_t st, Workspace *wsp, bool out_is_host)
 {
     Engine &E = engine();
     Workspace &WS = wsp ? *wsp : E.ws;                  // concurrent calls (chunks of a host batch) bring their own workspace
@@ -1139,7 +1139,7 @@ int encode_device(const uint8_t *d_frames, size_t frame_stride, int n, int is_rg
         TP.pix = planes; TP.plane_stride = plane_stride; TP.P = P; TP.W = (int)W; TP.H = (int)H;
         TP.L = Lay; TP.plane_bytes = (unsigned long long *)plane_bytes; TP.next_plane = next;
         TP.prof = nullptr;
-        TP.line_out = (E.jls_out_is_host && ncomp == 1) ? 1 : 0;     // RGB scans 1, 2 go through device scratch and assemble_kernel
+        TP.line_out = (out_is_host && ncomp == 1) ? 1 : 0;     // RGB scans 1, 2 go through device scratch and assemble_kernel
 #ifdef IMCVT_JLS_PROF
         {
             if (!g_jls_prof) { IMCVT_CUDA(cudaMalloc(&g_jls_prof, 16 * 8)); IMCVT_CUDA(cudaMemset(g_jls_prof, 0, 16 * 8)); }

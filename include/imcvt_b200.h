@@ -71,6 +71,14 @@ int imcvtEncodeBatchHEVCGreen(const uint8_t *rgb_frames, size_t frame_stride, in
                               uint32_t height, uint32_t width, int qpd6,
                               uint8_t *out, size_t out_stride, size_t *out_len);
 
+/* A quantiser sweep in ONE launch (BASELINE configs[4]: every frame at several QPs): frame i is coded at each of the nq
+ * settings qpd6[0..nq-1] (1 <= nq <= 8, each 0..4); the stream of (frame i, setting k) lands in slot i*nq + k of out /
+ * out_len.  Same bytes as nq calls of imcvtEncodeBatchHEVC, but the n*nq jobs share the GPU: where a batch of n frames leaves
+ * SMs idle (n < SMs/2), the sweep's jobs fill them. */
+int imcvtEncodeBatchHEVCSweep(const uint8_t *frames, size_t frame_stride, int n,
+                              uint32_t height, uint32_t width, const int *qpd6, int nq,
+                              uint8_t *out, size_t out_stride, size_t *out_len);
+
 int imcvtEncodeBatchHEVCDevice(const void *d_frames, size_t frame_stride, int n,
                                uint32_t height, uint32_t width, int qpd6,
                                void *d_out, size_t out_stride, void *d_out_len,

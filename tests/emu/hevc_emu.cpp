@@ -27,6 +27,7 @@ extern "C" long emu_hevc_encode_mode(uint8_t *stream, size_t cap, const uint8_t 
     P.rcon = img_rcon; P.rcon_stride = (size_t)hp * wp;
     P.scratch = scratch.data(); P.lists = lists.data(); P.overflow = &overflow; P.next_frame = &next;
     P.prof = nullptr;
+    P.nq = 0;
     if (pair) emu::launch(1, NT, sizeof(Smem), [&] { hevc_pair_kernel(P); }, 2);
     else emu::launch(1, NT, sizeof(Smem), [&] { hevc_frame_kernel(P); });
     *ysz = hp; *xsz = wp;

@@ -145,3 +145,29 @@ def test_4k_qp_sweep_decodes_and_orders(hevc_path):
             want, want_r = oracle_hevc(frame[0, :32], qpd6)
             assert np.array_equal(rcon[0][:32], want_r), qpd6
     assert sizes == sorted(sizes, reverse=True) and psnrs == sorted(psnrs, reverse=True), (sizes, psnrs)
+
+
+def test_sweep_in_one_launch_equals_one_batch_per_setting():
+    """imcvtEncodeBatchHEVCSweep (BASELINE configs[4]: every frame at several QPs): job i*nq + k = frame i at the k-th setting,
+    all jobs in one launch; the bytes are those of one batch call per setting, i.e. the oracle's."""
+    frames = synth.batch("natural", 3, 72, 136)
+    qs = [1, 4, 2, 3, 0]
+    got = imcvt_b200.encode_hevc_sweep(frames, qs)
+    for k, q in enumerate(qs):
+        per, _ = imcvt_b200.encode_hevc_batch(frames, q, want_rcon=False)
+        for i in range(3):
+            assert got[i][k] == per[i], (i, q)
+    for i in range(3):
+        assert got[i][1] == oracle_hevc(frames[i], 4)[0] and got[i][4] == oracle_hevc(frames[i], 0)[0]
+    # more jobs than SMs: the job queue
+    many = synth.batch("texture", 60, 32, 64)
+    sw = imcvt_b200.encode_hevc_sweep(many, [4, 1, 3])
+    ref = {q: imcvt_b200.encode_hevc_batch(many, q, want_rcon=False)[0] for q in (4, 1, 3)}
+    for i in (0, 17, 49, 59):
+        assert [sw[i][0], sw[i][1], sw[i][2]] == [ref[4][i], ref[1][i], ref[3][i]], i
+    L = imcvt_b200.lib()
+    import ctypes as C
+    bad = (C.c_int * 2)(1, 7)
+    out = np.zeros(4096, np.uint8)
+    ln = (C.c_size_t * 2)()
+    assert L.imcvtEncodeBatchHEVCSweep(many.ctypes.data, 32 * 64, 1, 32, 64, bad, 2, out.ctypes.data, 2048, C.cast(ln, C.c_void_p)) == 1
