@@ -23,6 +23,12 @@ CLI = os.path.join(ROOT, "imcvt_b200", "ImCvt_b200")
 REF = os.path.join(ROOT, "oracle", "_ref", "ImCvt_ref")
 
 
+@pytest.fixture(scope="module", autouse=True)
+def built():
+    if not os.path.exists(CLI):
+        subprocess.run(["make", "-C", os.path.join(ROOT, "imcvt_b200", "csrc")], check=True, capture_output=True)
+
+
 def write_pnm(path, img):
     h, w = img.shape[:2]
     with open(path, "wb") as f:
