@@ -1303,7 +1303,9 @@ HEVC_PHASE void eval_a4(Ctx &K)
         const int item = base + warp * G + lane / H;
         const bool active = item < NMODE;
         const int m = active ? item : 0, cand = NMODE + m;
-        Src ps = src; ps.priv = rec_tile<SET>(sm, cand);                     // earlier sub-TUs of the same trial
+        // earlier sub-TUs of the same trial.  An idle group (item >= NMODE) runs the pipeline with its stores masked; it must not
+        // read candidate 0's tile while that candidate's own group writes it (values unused, but a shared-memory race)
+        Src ps = src; ps.priv = active ? rec_tile<SET>(sm, cand) : nullptr;
         const int loff = (lane / H) * H * (H + 2);
         int sse = 0;
 #pragma unroll 1
@@ -1486,7 +1488,7 @@ HEVC_PHASE void search_cu8(Ctx &K, int y0, int x0, int avail)
                 // one call site for both groups (the pipeline is big; two inlined copies cost instruction-cache misses)
                 const int cand = grp3 ? NMODE + m : NCAND + m;
                 Src ps = src;
-                ps.priv = grp3 ? sm.rec1[cand] : sm.nxn_rec;               // earlier blocks of the same trial | the kept blocks of the earlier PUs
+                ps.priv = !active ? nullptr : grp3 ? sm.rec1[cand] : sm.nxn_rec;   // earlier blocks of the same trial | the kept blocks of the earlier PUs (idle groups: none)
                 ps.ppitch = 8;
                 uint8_t *rec = grp3 ? sm.rec1[cand] + (sub_y[i] - y0) * SZ + (sub_x[i] - x0) : sm.rec4[m];
                 TuResult r = tu_pipeline<H>(sm, warp, lane, active, ps, sub_y[i], sub_x[i], sub_avail[i], m, qpd6, rd,
