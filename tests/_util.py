@@ -231,3 +231,21 @@ def jls_decode(stream):
     assert rc == 0, f"jls_decode failed with {rc}"
     assert (cw.value, ch.value, cn.value) == (w, h, nc)
     return out[: nc * h * w].reshape(nc, h, w), near.value
+
+
+def emu_jls_rowscan(img, near):
+    """The SOURCE of the row-pipelined JPEG-LS scan kernel (imcvt_b200/csrc/jls_rowscan_kernel.cuh, the path for NEAR > 0)
+    run under the CPU SIMT emulator (tests/emu); gray images, any NEAR."""
+    if "emu_rowscan" not in _libs:
+        d = os.path.join(ROOT, "tests", "emu")
+        subprocess.run(["make", "-C", d, "-s", "libjls_rowscan_emu.so"], check=True, capture_output=True)
+        lib = C.CDLL(os.path.join(d, "libjls_rowscan_emu.so"))
+        lib.emu_jls_rowscan_encode.restype = C.c_size_t
+        lib.emu_jls_rowscan_encode.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_size_t]
+        _libs["emu_rowscan"] = lib
+    img = np.ascontiguousarray(img, dtype=np.uint8)
+    h, w = img.shape
+    out = np.zeros(8 * h * w + 65536, dtype=np.uint8)
+    n = _libs["emu_rowscan"].emu_jls_rowscan_encode(img.ctypes.data, h, w, int(near), out.ctypes.data, out.size)
+    assert n > 0
+    return out[:n].tobytes()

@@ -291,6 +291,10 @@ inline unsigned __funnelshift_l(unsigned lo, unsigned hi, unsigned sh)
 template <class T> inline T __ldg(const T *p) { return *p; }
 using std::min;
 using std::max;
+struct int2 { int x, y; };
+struct int4 { int x, y, z, w; };
+inline int2 make_int2(int x, int y) { int2 v = {x, y}; return v; }
+inline int4 make_int4(int x, int y, int z, int w) { int4 v = {x, y, z, w}; return v; }
 inline unsigned atomicOr(unsigned *p, unsigned v) { unsigned o = *p; *p |= v; return o; }
 inline int atomicExch(int *p, int v) { int o = *p; *p = v; return o; }
 inline int atomicAdd(int *p, int v) { int o = *p; *p += v; return o; }
