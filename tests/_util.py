@@ -185,6 +185,27 @@ def emu_hevc(img, qpd6, pair=False):
     return out[:n].tobytes(), rcon.reshape(hp, wp).copy()
 
 
+def emu_hevc_sweep(img, qlist, pair=False):
+    """A quantiser sweep (one frame at every qpd6 of qlist, the job queue of imcvtEncodeBatchHEVCSweep) on one emulated CTA /
+    CTA pair: the per-job switch of quantiser and context tables.  Returns [(stream, rcon), ...] in qlist order."""
+    emu_hevc(np.zeros((8, 8), np.uint8), 4)                       # loads the library
+    lib = _libs["emu"]
+    lib.emu_hevc_sweep.restype = C.c_int
+    lib.emu_hevc_sweep.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_int), C.c_int,
+                                   C.POINTER(C.c_ulonglong), C.c_int]
+    img = np.ascontiguousarray(img, dtype=np.uint8)
+    h, w = img.shape
+    hp, wp = (min(h, 8192) + 31) // 32 * 32, (min(w, 8192) + 31) // 32 * 32
+    nq = len(qlist)
+    cap = 2 * (wp + 32) * (hp + 32) + 65536
+    out = np.zeros(nq * cap, dtype=np.uint8)
+    rcon = np.zeros((nq, hp, wp), dtype=np.uint8)
+    lens = (C.c_ulonglong * nq)()
+    q = (C.c_int * nq)(*[int(x) for x in qlist])
+    assert lib.emu_hevc_sweep(out.ctypes.data, cap, img.ctypes.data, rcon.ctypes.data, h, w, q, nq, lens, 1 if pair else 0) == 0
+    return [(out[k * cap:k * cap + lens[k]].tobytes(), rcon[k].copy()) for k in range(nq)]
+
+
 def emu_jls(img, pair=False, line_out=False):
     """The SOURCE of the CUDA JPEG-LS tile kernel (NEAR = 0, gray) run under the CPU SIMT emulator (tests/emu);
     pair=True: the two-CTA cluster variant (rank 0 producers, rank 1 chains + packers)."""

@@ -34,5 +34,27 @@ extern "C" long emu_hevc_encode_mode(uint8_t *stream, size_t cap, const uint8_t 
     return overflow ? 0 : (long)len;
 }
 
+// a quantiser sweep on ONE emulated CTA (or pair): job k codes the frame at qlist[k] into slot k (stream slot `cap` bytes apart,
+// reconstructions hp*wp apart); lens[k] receives the stream lengths.  Returns 0 on success.
+extern "C" int emu_hevc_sweep(uint8_t *streams, size_t cap, const uint8_t *img, uint8_t *rcons, int H, int W, const int *qlist, int nq,
+                              unsigned long long *lens, int pair)
+{
+    const int hp = (std::min(H, 8192) + 31) / 32 * 32, wp = (std::min(W, 8192) + 31) / 32 * 32;
+    Params P;
+    int overflow = 0, next = 0;
+    std::vector<uint8_t> scratch((size_t)2 * 2 * NALL * SCR_BYTES);
+    std::vector<unsigned short> lists((size_t)2 * 2 * NALL * CAND_LIST_U16, 0xDEAD);
+    P.frames = img; P.frame_stride = (size_t)H * W; P.n = 1; P.H = H; P.W = W; P.hp = hp; P.wp = wp; P.qpd6 = qlist[0];
+    P.out = streams; P.out_stride = cap; P.out_len = lens;
+    P.rcon = rcons; P.rcon_stride = (size_t)hp * wp;
+    P.scratch = scratch.data(); P.lists = lists.data(); P.overflow = &overflow; P.next_frame = &next;
+    P.prof = nullptr;
+    P.nq = nq;
+    for (int k = 0; k < 8; k++) P.qlist[k] = k < nq ? qlist[k] : 0;
+    if (pair) emu::launch(1, NT, sizeof(Smem), [&] { hevc_pair_kernel(P); }, 2);
+    else emu::launch(1, NT, sizeof(Smem), [&] { hevc_frame_kernel(P); });
+    return overflow;
+}
+
 extern "C" long emu_smem_bytes(void) { return (long)sizeof(Smem); }
 extern "C" long emu_barrier_count(int which) { return which ? emu::S().n_warp_barriers : emu::S().n_block_barriers; }

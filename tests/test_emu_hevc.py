@@ -25,3 +25,18 @@ def test_kernel_source_matches_oracle(qpd6, pair):
         s2, r2 = oracle_hevc(img, qpd6)
         assert s == s2, f"{name}: stream differs"
         assert np.array_equal(r, r2), f"{name}: reconstruction differs"
+
+
+@pytest.mark.parametrize("pair", [False, True], ids=["one-cta", "cluster-pair"])
+def test_sweep_jobs_switch_quantiser_and_context_tables(pair):
+    """imcvtEncodeBatchHEVCSweep's job queue on one emulated CTA / CTA pair: consecutive jobs of different qpd6 (the CTA rebuilds
+    its context-initialisation table in between), and a repeated setting."""
+    from imcvt_b200 import synth
+    from tests._util import emu_hevc_sweep
+    img = synth.frame("natural", 3, 40, 64)
+    qs = [4, 1, 1, 3]
+    got = emu_hevc_sweep(img, qs, pair)
+    for k, q in enumerate(qs):
+        want, want_r = oracle_hevc(img, q)
+        assert got[k][0] == want, (k, q)
+        assert np.array_equal(got[k][1], want_r), (k, q)
