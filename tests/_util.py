@@ -163,6 +163,22 @@ def ref_hevc(img, qpd6):
     return _hevc_call(ref_lib().HEVCImageEncoder, img, qpd6)
 
 
+def check_jls(img, near):
+    """The checker of the GPU tier: the UNMODIFIED reference (oracle/_ref, which travels to the GPU box prebuilt) whenever
+    it is there, this repo's restatement only as the fallback."""
+    return ref_jls(img, near) if ref_lib() is not None else oracle_jls(img, near)
+
+
+def check_hevc(img, qpd6):
+    return ref_hevc(img, qpd6) if ref_lib() is not None else oracle_hevc(img, qpd6)
+
+
+def fullsize_table():
+    """(length, sha256) of the reference's streams for synthetic frames at BASELINE sizes (tests/golden/make_golden_fullsize.py)."""
+    with open(os.path.join(GOLDEN, "fullsize_answers.json")) as f:
+        return json.load(f)
+
+
 def emu_hevc(img, qpd6, pair=False):
     """The SOURCE of the CUDA HEVC kernel run under the CPU SIMT emulator (tests/emu, test infrastructure)."""
     if "emu" not in _libs:
