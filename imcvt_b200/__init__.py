@@ -31,6 +31,8 @@ EXPORTED_SYMBOLS = [
     "imcvtJLSBound", "imcvtHEVCBound",
     "imcvtEncodeBatchJLS", "imcvtEncodeBatchJLSDevice",
     "imcvtEncodeBatchHEVC", "imcvtEncodeBatchHEVCDevice", "imcvtEncodeBatchHEVCGreen", "imcvtEncodeBatchHEVCSweep",
+    "imcvtDeviceCount", "imcvtEncodeBatchJLSMulti", "imcvtEncodeBatchHEVCMulti", "imcvtEncodeBatchHEVCGreenMulti",
+    "imcvtEncodeBatchHEVCSweepMulti",
     "imcvtHostAlloc", "imcvtHostFree", "imcvtJLSHostMode",
     "imcvtProfileEnable", "imcvtProfileReset", "imcvtProfileGet", "imcvtProfileList", "imcvtLaunchCount",
     "imcvtDebugJLSForceSerial", "imcvtDebugJLSPath", "imcvtDebugHEVCPath",
@@ -67,6 +69,12 @@ def lib():
     L.imcvtEncodeBatchHEVCDevice.argtypes = [vp, sz, i32, u32, u32, i32, vp, sz, vp, vp, sz, vp]; L.imcvtEncodeBatchHEVCDevice.restype = i32
     L.imcvtEncodeBatchHEVCGreen.argtypes = [vp, sz, i32, u32, u32, i32, vp, sz, vp]; L.imcvtEncodeBatchHEVCGreen.restype = i32
     L.imcvtEncodeBatchHEVCSweep.argtypes = [vp, sz, i32, u32, u32, C.POINTER(i32), i32, vp, sz, vp]; L.imcvtEncodeBatchHEVCSweep.restype = i32
+    ip = C.POINTER(i32)
+    L.imcvtDeviceCount.argtypes = []; L.imcvtDeviceCount.restype = i32
+    L.imcvtEncodeBatchJLSMulti.argtypes = [vp, sz, i32, i32, u32, u32, i32, vp, sz, vp, ip, i32]; L.imcvtEncodeBatchJLSMulti.restype = i32
+    L.imcvtEncodeBatchHEVCMulti.argtypes = [vp, sz, i32, u32, u32, i32, vp, sz, vp, vp, sz, ip, i32]; L.imcvtEncodeBatchHEVCMulti.restype = i32
+    L.imcvtEncodeBatchHEVCGreenMulti.argtypes = [vp, sz, i32, u32, u32, i32, vp, sz, vp, ip, i32]; L.imcvtEncodeBatchHEVCGreenMulti.restype = i32
+    L.imcvtEncodeBatchHEVCSweepMulti.argtypes = [vp, sz, i32, u32, u32, ip, i32, vp, sz, vp, ip, i32]; L.imcvtEncodeBatchHEVCSweepMulti.restype = i32
     L.imcvtHostAlloc.argtypes = [sz]; L.imcvtHostAlloc.restype = vp
     L.imcvtHostFree.argtypes = [vp]; L.imcvtHostFree.restype = None
     L.imcvtJLSHostMode.argtypes = [i32]; L.imcvtJLSHostMode.restype = None
@@ -117,9 +125,25 @@ def pad32(v):
 # ---------------------------------------------------------------------------------------------
 # host-buffer batch API
 # ---------------------------------------------------------------------------------------------
-def encode_jls_batch(frames, near=0, out=None, out_stride=None):
+def device_count():
+    return int(lib().imcvtDeviceCount())
+
+
+def _devlist(devices):
+    """None -> (NULL, 0) = all visible devices; an int k -> devices 0..k-1; a list -> those ordinals."""
+    if devices is None:
+        return None, 0
+    if isinstance(devices, int):
+        devices = list(range(devices))
+    arr = (C.c_int * len(devices))(*[int(d) for d in devices])
+    return arr, len(devices)
+
+
+def encode_jls_batch(frames, near=0, out=None, out_stride=None, devices=0):
     """frames: uint8 array [n,H,W] (gray) or [n,H,W,3] (RGB), C-contiguous (may be pinned).
-    Returns a list of n `bytes` (.jls streams, bit-identical to the reference's writeJLSImageFile)."""
+    Returns a list of n `bytes` (.jls streams, bit-identical to the reference's writeJLSImageFile).
+    devices: 0 = the engine's device (imcvtEncodeBatchJLS); None / k / [ordinals] = sharded over all / the first k / those
+    devices (imcvtEncodeBatchJLSMulti) -- the same bytes."""
     frames = np.ascontiguousarray(frames, dtype=np.uint8)
     if frames.ndim not in (3, 4) or (frames.ndim == 4 and frames.shape[3] != 3):
         raise ValueError("frames must be [n,H,W] or [n,H,W,3] uint8")
@@ -131,13 +155,18 @@ def encode_jls_batch(frames, near=0, out=None, out_stride=None):
         out = np.empty(n * out_stride, dtype=np.uint8)
     lens = (C.c_size_t * n)()
     frame_stride = h * w * (3 if is_rgb else 1)
-    _check(lib().imcvtEncodeBatchJLS(frames.ctypes.data, frame_stride, n, is_rgb, h, w, int(near),
-                                     out.ctypes.data, out_stride, C.cast(lens, C.c_void_p)), "imcvtEncodeBatchJLS")
+    if devices == 0:
+        _check(lib().imcvtEncodeBatchJLS(frames.ctypes.data, frame_stride, n, is_rgb, h, w, int(near),
+                                         out.ctypes.data, out_stride, C.cast(lens, C.c_void_p)), "imcvtEncodeBatchJLS")
+    else:
+        dl, nd = _devlist(devices)
+        _check(lib().imcvtEncodeBatchJLSMulti(frames.ctypes.data, frame_stride, n, is_rgb, h, w, int(near),
+                                              out.ctypes.data, out_stride, C.cast(lens, C.c_void_p), dl, nd), "imcvtEncodeBatchJLSMulti")
     return [out[i * out_stride:i * out_stride + lens[i]].tobytes() for i in range(n)]
 
 
-def encode_hevc_batch(frames, qpd6=4, want_rcon=True):
-    """frames: uint8 [n,H,W].  Returns (list of n .h265 streams, rcon uint8 [n,H',W'] or None)."""
+def encode_hevc_batch(frames, qpd6=4, want_rcon=True, devices=0):
+    """frames: uint8 [n,H,W].  Returns (list of n .h265 streams, rcon uint8 [n,H',W'] or None).  devices: see encode_jls_batch."""
     frames = np.ascontiguousarray(frames, dtype=np.uint8)
     if frames.ndim != 3:
         raise ValueError("frames must be [n,H,W] uint8")
@@ -147,13 +176,19 @@ def encode_hevc_batch(frames, qpd6=4, want_rcon=True):
     lens = (C.c_size_t * n)()
     hp, wp = pad32(h), pad32(w)
     rcon = np.empty((n, hp, wp), dtype=np.uint8) if want_rcon else None
-    _check(lib().imcvtEncodeBatchHEVC(frames.ctypes.data, h * w, n, h, w, int(qpd6),
-                                      out.ctypes.data, out_stride, C.cast(lens, C.c_void_p),
-                                      rcon.ctypes.data if want_rcon else None, hp * wp), "imcvtEncodeBatchHEVC")
+    if devices == 0:
+        _check(lib().imcvtEncodeBatchHEVC(frames.ctypes.data, h * w, n, h, w, int(qpd6),
+                                          out.ctypes.data, out_stride, C.cast(lens, C.c_void_p),
+                                          rcon.ctypes.data if want_rcon else None, hp * wp), "imcvtEncodeBatchHEVC")
+    else:
+        dl, nd = _devlist(devices)
+        _check(lib().imcvtEncodeBatchHEVCMulti(frames.ctypes.data, h * w, n, h, w, int(qpd6),
+                                               out.ctypes.data, out_stride, C.cast(lens, C.c_void_p),
+                                               rcon.ctypes.data if want_rcon else None, hp * wp, dl, nd), "imcvtEncodeBatchHEVCMulti")
     return [out[i * out_stride:i * out_stride + lens[i]].tobytes() for i in range(n)], rcon
 
 
-def encode_hevc_sweep(frames, qpd6_list):
+def encode_hevc_sweep(frames, qpd6_list, devices=0):
     """frames: uint8 [n,H,W]; qpd6_list: 1..8 settings.  One launch codes every frame at every setting.
     Returns a list of n lists: streams[i][k] = frame i at qpd6_list[k] (same bytes as encode_hevc_batch per setting)."""
     frames = np.ascontiguousarray(frames, dtype=np.uint8)
@@ -165,12 +200,17 @@ def encode_hevc_sweep(frames, qpd6_list):
     out_stride = hevc_bound(h, w)
     out = np.empty(n * nq * out_stride, dtype=np.uint8)
     lens = (C.c_size_t * (n * nq))()
-    _check(lib().imcvtEncodeBatchHEVCSweep(frames.ctypes.data, h * w, n, h, w, q, nq, out.ctypes.data, out_stride,
-                                           C.cast(lens, C.c_void_p)), "imcvtEncodeBatchHEVCSweep")
+    if devices == 0:
+        _check(lib().imcvtEncodeBatchHEVCSweep(frames.ctypes.data, h * w, n, h, w, q, nq, out.ctypes.data, out_stride,
+                                               C.cast(lens, C.c_void_p)), "imcvtEncodeBatchHEVCSweep")
+    else:
+        dl, nd = _devlist(devices)
+        _check(lib().imcvtEncodeBatchHEVCSweepMulti(frames.ctypes.data, h * w, n, h, w, q, nq, out.ctypes.data, out_stride,
+                                                    C.cast(lens, C.c_void_p), dl, nd), "imcvtEncodeBatchHEVCSweepMulti")
     return [[out[(i * nq + k) * out_stride:(i * nq + k) * out_stride + lens[i * nq + k]].tobytes() for k in range(nq)] for i in range(n)]
 
 
-def encode_hevc_green_batch(frames, qpd6=4):
+def encode_hevc_green_batch(frames, qpd6=4, devices=0):
     """frames: uint8 [n,H,W,3] interleaved RGB.  Encodes the green channel (what the reference's writeHEVCImageFile does
     with RGB input, src/imageio_hevc.c:21-26); the channel is extracted on the device.  Returns the n .h265 streams."""
     frames = np.ascontiguousarray(frames, dtype=np.uint8)
@@ -180,8 +220,13 @@ def encode_hevc_green_batch(frames, qpd6=4):
     out_stride = hevc_bound(h, w)
     out = np.empty(n * out_stride, dtype=np.uint8)
     lens = (C.c_size_t * n)()
-    _check(lib().imcvtEncodeBatchHEVCGreen(frames.ctypes.data, h * w * 3, n, h, w, int(qpd6),
-                                           out.ctypes.data, out_stride, C.cast(lens, C.c_void_p)), "imcvtEncodeBatchHEVCGreen")
+    if devices == 0:
+        _check(lib().imcvtEncodeBatchHEVCGreen(frames.ctypes.data, h * w * 3, n, h, w, int(qpd6),
+                                               out.ctypes.data, out_stride, C.cast(lens, C.c_void_p)), "imcvtEncodeBatchHEVCGreen")
+    else:
+        dl, nd = _devlist(devices)
+        _check(lib().imcvtEncodeBatchHEVCGreenMulti(frames.ctypes.data, h * w * 3, n, h, w, int(qpd6),
+                                                    out.ctypes.data, out_stride, C.cast(lens, C.c_void_p), dl, nd), "imcvtEncodeBatchHEVCGreenMulti")
     return [out[i * out_stride:i * out_stride + lens[i]].tobytes() for i in range(n)]
 
 

@@ -26,18 +26,46 @@ static inline uint32_t pad32(uint32_t v) { uint32_t c = v > 8192 ? 8192 : v; ret
 
 // Green plane of interleaved RGB24 frames (replaces the host loop of the reference's wrapper, src/imageio_hevc.c:24-26):
 // one thread per four pixels, three aligned 32-bit loads -> one 32-bit store.  Frame bases are 256-byte aligned.
-__global__ void green_plane_kernel(const uint8_t *rgb, size_t rgb_stride, uint8_t *gray, size_t gray_stride, size_t npix)
+__global__ void green_plane_kernel(const uint8_t *rgb, size_t rgb_stride, uint8_t *gray, size_t gray_stride, size_t npix, int n)
 {
     const size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x;         // group of four pixels
-    const uint8_t *src = rgb + (size_t)blockIdx.y * rgb_stride;
-    uint8_t *dst = gray + (size_t)blockIdx.y * gray_stride;
-    if (4 * g + 4 <= npix) {
-        const uint32_t *s = reinterpret_cast<const uint32_t *>(src) + 3 * g;
-        const uint32_t a = s[0], b = s[1], c = s[2];                       // R0 G0 B0 R1 | G1 B1 R2 G2 | B2 R3 G3 B3
-        reinterpret_cast<uint32_t *>(dst)[g] = ((a >> 8) & 0xFF) | ((b & 0xFF) << 8) | ((b >> 24) << 16) | (((c >> 16) & 0xFF) << 24);
-    } else {
-        for (size_t p = 4 * g; p < npix; p++) dst[p] = src[3 * p + 1];
+    for (int f = blockIdx.y; f < n; f += gridDim.y) {                       // grid.y is capped at 65535: frames beyond it loop
+        const uint8_t *src = rgb + (size_t)f * rgb_stride;
+        uint8_t *dst = gray + (size_t)f * gray_stride;
+        if (4 * g + 4 <= npix) {
+            const uint32_t *s = reinterpret_cast<const uint32_t *>(src) + 3 * g;
+            const uint32_t a = s[0], b = s[1], c = s[2];                   // R0 G0 B0 R1 | G1 B1 R2 G2 | B2 R3 G3 B3
+            reinterpret_cast<uint32_t *>(dst)[g] = ((a >> 8) & 0xFF) | ((b & 0xFF) << 8) | ((b >> 24) << 16) | (((c >> 16) & 0xFF) << 24);
+        } else {
+            for (size_t p = 4 * g; p < npix; p++) dst[p] = src[3 * p + 1];
+        }
     }
+}
+
+// limits the kernels index safely: frames per call, H.265 picture dimensions (int arithmetic on H * W inside the kernels)
+static bool batch_ok(int n) { if (n <= 0 || n > (1 << 24)) { set_error("batch size must be 1..16777216 (got %d)", n); return false; } return true; }
+static bool hevc_dims_ok(uint32_t h, uint32_t w)
+{
+    if (h < 1 || w < 1) { set_error("empty image"); return false; }
+    if (h > (1u << 20) || w > (1u << 20) || (uint64_t)h * w > (1ull << 31) - 1) { set_error("H.265 picture %ux%u is beyond what the engine indexes (H * W < 2^31)", w, h); return false; }
+    return true;
+}
+
+// The device-buffer entry points take one of the engine's overflow flags in turn (calls on different streams do not share
+// one) and check what they can about the caller's pointers: non-null, on the engine's device.
+static int *next_device_flag(Engine &E)
+{
+    if (!E.d_flag && cudaMalloc(&E.d_flag, Engine::NFLAG * sizeof(int)) != cudaSuccess) { (void)cudaGetLastError(); E.d_flag = nullptr; return nullptr; }
+    return E.d_flag + (E.flag_next++ % Engine::NFLAG);
+}
+static bool on_engine_device(Engine &E, const void *p, const char *what)
+{
+    cudaPointerAttributes a;
+    if (!p) { set_error("%s is NULL", what); return false; }
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { (void)cudaGetLastError(); set_error("%s is not a CUDA pointer", what); return false; }
+    if (a.type == cudaMemoryTypeDevice && a.device != E.device) { set_error("%s lives on device %d, the engine on device %d", what, a.device, E.device); return false; }
+    if (a.type == cudaMemoryTypeUnregistered) { set_error("%s is pageable host memory, not a device pointer", what); return false; }
+    return true;
 }
 
 // shared host-buffer driver: H2D, encode, D2H of lengths then of exactly the produced bytes
@@ -231,13 +259,15 @@ int imcvtEncodeBatchJLSDevice(const void *d_frames, size_t frame_stride, int n, 
                               void *d_out, size_t out_stride, void *d_out_len, void *stream)
 {
     IMCVT_API_LOCK();
-    if (n <= 0) { set_error("batch size must be positive"); return 1; }
+    if (!batch_ok(n)) return 1;
     if (!jls_dims_ok(height, width)) { set_error("JPEG-LS dimensions must be 1..32767 (got %ux%u)", width, height); return 1; }
     if (near_ < 0 || near_ > 4) { set_error("NEAR must be 0..4 (got %d)", near_); return 1; }
+    if (frame_stride < (size_t)height * width * (is_rgb ? 3 : 1)) { set_error("frame_stride smaller than one frame"); return 1; }
     if (ensure_engine()) return 1;
     Engine &E = engine();
-    if (!E.d_flag) { IMCVT_CUDA(cudaMalloc(&E.d_flag, sizeof(int))); }
-    int *d_flag = E.d_flag;
+    if (!on_engine_device(E, d_frames, "d_frames") || !on_engine_device(E, d_out, "d_out") || !on_engine_device(E, d_out_len, "d_out_len")) return 1;
+    int *d_flag = next_device_flag(E);
+    if (!d_flag) { set_error("device flag allocation failed"); return 1; }
     cudaStream_t st = (cudaStream_t)stream;
     IMCVT_CUDA(cudaMemsetAsync(d_flag, 0, sizeof(int), st));
     return jls::encode_device((const uint8_t *)d_frames, frame_stride, n, is_rgb, height, width, near_,
@@ -249,7 +279,8 @@ int imcvtEncodeBatchJLS(const uint8_t *frames, size_t frame_stride, int n, int i
                         uint8_t *out, size_t out_stride, size_t *out_len)
 {
     IMCVT_API_LOCK();
-    if (n <= 0 || !frames || !out || !out_len) { set_error("bad arguments"); return 1; }
+    if (!frames || !out || !out_len) { set_error("bad arguments"); return 1; }
+    if (!batch_ok(n)) return 1;
     if (!jls_dims_ok(height, width)) { set_error("JPEG-LS dimensions must be 1..32767 (got %ux%u)", width, height); return 1; }
     if (near_ < 0 || near_ > 4) { set_error("NEAR must be 0..4 (got %d)", near_); return 1; }
     const size_t frame_bytes = (size_t)height * width * (is_rgb ? 3 : 1);
@@ -284,13 +315,15 @@ int imcvtEncodeBatchHEVCDevice(const void *d_frames, size_t frame_stride, int n,
                                void *d_rcon, size_t rcon_stride, void *stream)
 {
     IMCVT_API_LOCK();
-    if (n <= 0) { set_error("batch size must be positive"); return 1; }
-    if (height < 1 || width < 1) { set_error("empty image"); return 1; }
+    if (!batch_ok(n) || !hevc_dims_ok(height, width)) return 1;
     if (qpd6 < 0 || qpd6 > 4) { set_error("qpd6 must be 0..4 (got %d)", qpd6); return 1; }
+    if (frame_stride < (size_t)height * width) { set_error("frame_stride smaller than one frame"); return 1; }
     if (ensure_engine()) return 1;
     Engine &E = engine();
-    if (!E.d_flag) { IMCVT_CUDA(cudaMalloc(&E.d_flag, sizeof(int))); }
-    int *d_flag = E.d_flag;
+    if (!on_engine_device(E, d_frames, "d_frames") || !on_engine_device(E, d_out, "d_out") || !on_engine_device(E, d_out_len, "d_out_len")) return 1;
+    if (d_rcon && !on_engine_device(E, d_rcon, "d_rcon")) return 1;
+    int *d_flag = next_device_flag(E);
+    if (!d_flag) { set_error("device flag allocation failed"); return 1; }
     cudaStream_t st = (cudaStream_t)stream;
     IMCVT_CUDA(cudaMemsetAsync(d_flag, 0, sizeof(int), st));
     return hevc::encode_device((const uint8_t *)d_frames, frame_stride, n, height, width, qpd6,
@@ -303,8 +336,8 @@ int imcvtEncodeBatchHEVC(const uint8_t *frames, size_t frame_stride, int n,
                          uint8_t *rcon, size_t rcon_stride)
 {
     IMCVT_API_LOCK();
-    if (n <= 0 || !frames || !out || !out_len) { set_error("bad arguments"); return 1; }
-    if (height < 1 || width < 1) { set_error("empty image"); return 1; }
+    if (!frames || !out || !out_len) { set_error("bad arguments"); return 1; }
+    if (!batch_ok(n) || !hevc_dims_ok(height, width)) return 1;
     if (qpd6 < 0 || qpd6 > 4) { set_error("qpd6 must be 0..4 (got %d)", qpd6); return 1; }
     const size_t frame_bytes = (size_t)height * width;
     if (frame_stride < frame_bytes) { set_error("frame_stride smaller than one frame"); return 1; }
@@ -325,8 +358,8 @@ int imcvtEncodeBatchHEVCGreen(const uint8_t *rgb_frames, size_t frame_stride, in
                               uint8_t *out, size_t out_stride, size_t *out_len)
 {
     IMCVT_API_LOCK();
-    if (n <= 0 || !rgb_frames || !out || !out_len) { set_error("bad arguments"); return 1; }
-    if (height < 1 || width < 1) { set_error("empty image"); return 1; }
+    if (!rgb_frames || !out || !out_len) { set_error("bad arguments"); return 1; }
+    if (!batch_ok(n) || !hevc_dims_ok(height, width)) return 1;
     if (qpd6 < 0 || qpd6 > 4) { set_error("qpd6 must be 0..4 (got %d)", qpd6); return 1; }
     const size_t npix = (size_t)height * width;
     if (frame_stride < 3 * npix) { set_error("frame_stride smaller than one RGB frame"); return 1; }
@@ -337,9 +370,9 @@ int imcvtEncodeBatchHEVCGreen(const uint8_t *rgb_frames, size_t frame_stride, in
         (void)usable;
         {
             LaunchScope ls("green_plane", st);
-            const unsigned groups = (unsigned)((npix + 3) / 4);
-            dim3 grid((groups + 255) / 256, (unsigned)n);
-            green_plane_kernel<<<grid, 256, 0, st>>>(d_in, in_stride, d_gray, gray_stride, npix);
+            const unsigned groups = (unsigned)((npix + 3) / 4);             // npix < 2^31 (hevc_dims_ok)
+            dim3 grid((groups + 255) / 256, (unsigned)(n < 65535 ? n : 65535));
+            green_plane_kernel<<<grid, 256, 0, st>>>(d_in, in_stride, d_gray, gray_stride, npix, n);
         }
         IMCVT_CUDA(cudaGetLastError());
         return hevc::encode_device(d_gray, gray_stride, n, height, width, qpd6, d_out, dev_out_stride, d_len, nullptr, 0, d_flag, st);
@@ -353,9 +386,9 @@ int imcvtEncodeBatchHEVCSweep(const uint8_t *frames, size_t frame_stride, int n,
                               uint8_t *out, size_t out_stride, size_t *out_len)
 {
     IMCVT_API_LOCK();
-    if (n <= 0 || !frames || !out || !out_len || !qpd6) { set_error("bad arguments"); return 1; }
+    if (!frames || !out || !out_len || !qpd6) { set_error("bad arguments"); return 1; }
     if (nq < 1 || nq > 8) { set_error("a sweep takes 1..8 settings (got %d)", nq); return 1; }
-    if (height < 1 || width < 1) { set_error("empty image"); return 1; }
+    if (!batch_ok(n) || !hevc_dims_ok(height, width)) return 1;
     for (int k = 0; k < nq; k++)
         if (qpd6[k] < 0 || qpd6[k] > 4) { set_error("qpd6 must be 0..4 (got %d)", qpd6[k]); return 1; }
     if ((long long)n * nq > 0x7FFFFFFF) { set_error("too many jobs"); return 1; }
@@ -392,12 +425,136 @@ int imcvtEncodeBatchHEVCSweep(const uint8_t *frames, size_t frame_stride, int n,
     return 0;
 }
 
+// ---- multi-device entry points -------------------------------------------------------------------------------------
+// Frames are independent units (JLSencodeScan / HEVCImageEncoder re-initialise all state per call, imageio_jls.c:256-267,
+// HEVCe.c:1577-1599), so a batch shards over the devices of the box in contiguous blocks of ceil(n / ndev) frames -- the
+// multi-file loop of the reference's main (main.c:162-211) spread over GPUs.  One host thread per device drives that
+// device's engine through the single-device entry point on its block; results land in the caller's slots directly, the
+// sizes in the caller's out_len -- one process, no collective.
+}  // extern "C"
+
+#include <thread>
+
+static std::mutex g_multi_mu;
+
+static int resolve_devices(const int *devices, int ndev, std::vector<int> &list)
+{
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count <= 0) {
+        (void)cudaGetLastError();
+        set_error("no CUDA device available: libimcvt_b200 has no CPU fallback");
+        return 1;
+    }
+    if (!devices || ndev <= 0) {
+        for (int d = 0; d < count; d++) list.push_back(d);
+        return 0;
+    }
+    for (int k = 0; k < ndev; k++) {
+        if (devices[k] < 0 || devices[k] >= count) { set_error("device %d does not exist (%d visible)", devices[k], count); return 1; }
+        for (int j = 0; j < k; j++)
+            if (devices[j] == devices[k]) { set_error("device %d is listed twice", devices[k]); return 1; }
+        list.push_back(devices[k]);
+    }
+    return 0;
+}
+
+// call(first, count) runs the single-device entry point on frames [first, first + count) with the worker's engine selected
+template <class Call>
+static int run_multi(int n, const int *devices, int ndev, Call call)
+{
+    std::lock_guard<std::mutex> serial(g_multi_mu);
+    std::vector<int> list;
+    if (resolve_devices(devices, ndev, list)) return 1;
+    const int G = (int)list.size();
+    const int per = (n + G - 1) / G;                                  // frame f -> block f / per (imcvt_b200/shard.py: frame_block)
+    std::vector<std::thread> workers;
+    std::vector<int> rc(G, 0);
+    std::vector<std::string> err(G);
+    for (int g = 0; g < G; g++) {
+        const int first = g * per, count = n - first < per ? n - first : per;
+        if (count <= 0) break;
+        workers.emplace_back([&, g, first, count]() {
+            Engine *E = device_engine(list[g]);
+            if (!E) { rc[g] = 1; err[g] = "no engine for the device"; return; }
+            select_engine(E);
+            rc[g] = call(first, count);
+            if (rc[g]) err[g] = imcvtLastError();
+            select_engine(nullptr);
+        });
+    }
+    for (auto &w : workers) w.join();
+    for (int g = 0; g < G; g++)
+        if (rc[g]) { set_error("device %d: %s", list[g], err[g].c_str()); return 1; }
+    return 0;
+}
+
+extern "C" {
+
+int imcvtDeviceCount(void)
+{
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess) { (void)cudaGetLastError(); return 0; }
+    return count;
+}
+
+int imcvtEncodeBatchJLSMulti(const uint8_t *frames, size_t frame_stride, int n, int is_rgb,
+                             uint32_t height, uint32_t width, int near_,
+                             uint8_t *out, size_t out_stride, size_t *out_len, const int *devices, int ndev)
+{
+    if (!frames || !out || !out_len) { set_error("bad arguments"); return 1; }
+    if (!batch_ok(n)) return 1;
+    return run_multi(n, devices, ndev, [&](int first, int count) {
+        return imcvtEncodeBatchJLS(frames + (size_t)first * frame_stride, frame_stride, count, is_rgb, height, width, near_,
+                                   out + (size_t)first * out_stride, out_stride, out_len + first);
+    });
+}
+
+int imcvtEncodeBatchHEVCMulti(const uint8_t *frames, size_t frame_stride, int n,
+                              uint32_t height, uint32_t width, int qpd6,
+                              uint8_t *out, size_t out_stride, size_t *out_len,
+                              uint8_t *rcon, size_t rcon_stride, const int *devices, int ndev)
+{
+    if (!frames || !out || !out_len) { set_error("bad arguments"); return 1; }
+    if (!batch_ok(n)) return 1;
+    return run_multi(n, devices, ndev, [&](int first, int count) {
+        return imcvtEncodeBatchHEVC(frames + (size_t)first * frame_stride, frame_stride, count, height, width, qpd6,
+                                    out + (size_t)first * out_stride, out_stride, out_len + first,
+                                    rcon ? rcon + (size_t)first * rcon_stride : nullptr, rcon_stride);
+    });
+}
+
+int imcvtEncodeBatchHEVCGreenMulti(const uint8_t *rgb_frames, size_t frame_stride, int n,
+                                   uint32_t height, uint32_t width, int qpd6,
+                                   uint8_t *out, size_t out_stride, size_t *out_len, const int *devices, int ndev)
+{
+    if (!rgb_frames || !out || !out_len) { set_error("bad arguments"); return 1; }
+    if (!batch_ok(n)) return 1;
+    return run_multi(n, devices, ndev, [&](int first, int count) {
+        return imcvtEncodeBatchHEVCGreen(rgb_frames + (size_t)first * frame_stride, frame_stride, count, height, width, qpd6,
+                                         out + (size_t)first * out_stride, out_stride, out_len + first);
+    });
+}
+
+int imcvtEncodeBatchHEVCSweepMulti(const uint8_t *frames, size_t frame_stride, int n,
+                                   uint32_t height, uint32_t width, const int *qpd6, int nq,
+                                   uint8_t *out, size_t out_stride, size_t *out_len, const int *devices, int ndev)
+{
+    if (!frames || !out || !out_len || !qpd6) { set_error("bad arguments"); return 1; }
+    if (nq < 1 || nq > 8) { set_error("a sweep takes 1..8 settings (got %d)", nq); return 1; }
+    if (!batch_ok(n)) return 1;
+    return run_multi(n, devices, ndev, [&](int first, int count) {
+        return imcvtEncodeBatchHEVCSweep(frames + (size_t)first * frame_stride, frame_stride, count, height, width, qpd6, nq,
+                                         out + (size_t)first * nq * out_stride, out_stride, out_len + (size_t)first * nq);
+    });
+}
+
 void *imcvtHostAlloc(size_t bytes)
 {
     void *p = nullptr;
     IMCVT_API_LOCK();
     if (ensure_engine()) return nullptr;
-    cudaError_t e = cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault);
+    // portable: page-locked for every device's context, so the multi-device entry points copy from / to it at full rate
+    cudaError_t e = cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocPortable);
     if (e != cudaSuccess) {
         (void)cudaGetLastError();
         set_error("pinned host allocation of %zu bytes failed: %s", bytes, cudaGetErrorString(e));

@@ -49,13 +49,16 @@ struct KernelStat { int launches = 0; double ms = 0.0; };
 struct Engine {
     int device = -1;
     bool ready = false;
+    std::recursive_mutex mu;    // the extern "C" entry points serialise on the engine they run on
     Workspace ws;           // scratch for the device pipelines
     Workspace io;           // staging for the host-buffer entry points (frames in, streams out)
     cudaStream_t stream = nullptr;      // engine-owned stream for the host-buffer entry points
     static constexpr int NCHUNK = 4;    // host-buffer JPEG-LS batches are cut into chunks whose copies and kernels overlap
     Workspace ws_chunk[NCHUNK];
     cudaStream_t chunk_stream[NCHUNK] = {nullptr, nullptr, nullptr, nullptr};
-    int *d_flag = nullptr;              // device overflow flag of the device-buffer entry points (per engine = per device)
+    static constexpr int NFLAG = 64;
+    int *d_flag = nullptr;              // device overflow flags of the device-buffer entry points: NFLAG of them, one per call in
+    unsigned flag_next = 0;             // turn, so that calls queued on different streams do not share one
     bool attr_hevc = false, attr_jls_tile = false, attr_jls_rowscan = false;   // dynamic shared-memory opt-in done on this device
     uint64_t *pinned_lens = nullptr;    // pinned host buffer the chunks' stream lengths come back into
     int pinned_lens_cap = 0;
@@ -72,12 +75,25 @@ struct Engine {
     int sm_count = 148;
 };
 
+// The engine the calling thread works on: the process-wide default engine (bound by imcvtInit, else to the current device),
+// or -- on the worker threads of the multi-device entry points -- the engine of that worker's device.
 Engine &engine();
+Engine *device_engine(int device);      // the engine of one device (created on first use; the default engine when it sits on that device)
+void select_engine(Engine *e);          // this thread's engine from now on (nullptr = the default engine)
+void shutdown_all_engines();
+void for_each_engine(void (*fn)(Engine &, int), int v);
 int ensure_engine();
-// The engine is one per process; the extern "C" entry points serialise on this lock, so calls from several host threads are
-// safe (they do not overlap each other; overlap comes from the streams inside a call).
+// The extern "C" entry points serialise on their engine's lock, so calls from several host threads are safe (calls on ONE
+// engine do not overlap each other -- overlap comes from the streams inside a call; calls on different engines, i.e.
+// different devices, run side by side).  The scope also puts the calling thread's current CUDA device back when the entry
+// point returns: the engine's device is only current inside the call.
 std::recursive_mutex &api_mutex();
-#define IMCVT_API_LOCK() std::lock_guard<std::recursive_mutex> imcvt_api_lock__(imcvt::api_mutex())
+struct DeviceScope {
+    int saved = -1;
+    DeviceScope() { if (cudaGetDevice(&saved) != cudaSuccess) { (void)cudaGetLastError(); saved = -1; } }
+    ~DeviceScope() { if (saved >= 0) { int cur = -1; if (cudaGetDevice(&cur) == cudaSuccess && cur != saved) cudaSetDevice(saved); } }
+};
+#define IMCVT_API_LOCK() std::lock_guard<std::recursive_mutex> imcvt_api_lock__(imcvt::api_mutex()); imcvt::DeviceScope imcvt_dev_scope__
 
 // RAII bracket around one kernel launch: counts it and (when profiling) times it with events on `s`.
 struct LaunchScope {

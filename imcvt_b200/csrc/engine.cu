@@ -17,10 +17,33 @@ void set_error(const char *fmt, ...)
     va_end(ap);
 }
 
-Engine &engine()
+// The default engine plus one engine per device for the multi-device entry points (created on first use, never moved:
+// worker threads keep pointers to them).
+static constexpr int MAX_DEVICES = 64;
+static Engine g_default;
+static Engine *g_dev[MAX_DEVICES];
+static std::mutex g_pool_mu;
+static thread_local Engine *tl_engine = nullptr;
+
+Engine &engine() { return tl_engine ? *tl_engine : g_default; }
+
+void select_engine(Engine *e) { tl_engine = e; }
+
+Engine *device_engine(int device)
 {
-    static Engine e;
-    return e;
+    if (device < 0 || device >= MAX_DEVICES) return nullptr;
+    std::lock_guard<std::mutex> g(g_pool_mu);
+    if (g_default.ready && g_default.device == device) return &g_default;     // one context, one workspace per device
+    if (!g_dev[device]) {
+        g_dev[device] = new Engine();
+        g_dev[device]->device = device;
+        // the debug / mode switches of the default engine apply to every device
+        g_dev[device]->jls_force_serial = g_default.jls_force_serial;
+        g_dev[device]->jls_path = g_default.jls_path;
+        g_dev[device]->jls_host_mode = g_default.jls_host_mode;
+        g_dev[device]->hevc_path = g_default.hevc_path;
+    }
+    return g_dev[device];
 }
 
 int Workspace::reserve(size_t bytes)
@@ -66,11 +89,7 @@ int Workspace::mark_busy(cudaStream_t st)
     return 0;
 }
 
-std::recursive_mutex &api_mutex()
-{
-    static std::recursive_mutex m;
-    return m;
-}
+std::recursive_mutex &api_mutex() { return engine().mu; }
 
 int ensure_engine()
 {
@@ -92,7 +111,7 @@ int ensure_engine()
     IMCVT_CUDA(cudaSetDevice(dev));
     cudaDeviceProp prop;
     IMCVT_CUDA(cudaGetDeviceProperties(&prop, dev));
-    if (prop.major < 10) {
+    if (prop.major != 10 || prop.minor != 0) {       // sm_100a code is architecture-specific: it runs on sm_100 only (not sm_103 / sm_12x)
         set_error("device %d (%s, sm_%d%d) is not a Blackwell sm_100 part; this library only carries sm_100a code",
                   dev, prop.name, prop.major, prop.minor);
         return 1;
@@ -144,26 +163,12 @@ void profile_collect()
     E.pending.clear();
 }
 
-}  // namespace imcvt
-
-using namespace imcvt;
-
-extern "C" {
-
-int imcvtInit(int device)
+static void shutdown_engine(Engine &E)
 {
-    IMCVT_API_LOCK();
-    Engine &E = engine();
-    if (E.ready && E.device != device) imcvtShutdown();
-    E.device = device;
-    return ensure_engine();
-}
-
-void imcvtShutdown(void)
-{
-    IMCVT_API_LOCK();
-    Engine &E = engine();
+    std::lock_guard<std::recursive_mutex> lock(E.mu);
     if (!E.ready) return;
+    Engine *prev = tl_engine;
+    tl_engine = &E;                                   // profile_collect() and friends work on the calling thread's engine
     cudaSetDevice(E.device);
     profile_collect();
     for (auto ev : E.event_pool) cudaEventDestroy(ev);
@@ -183,7 +188,46 @@ void imcvtShutdown(void)
     if (E.stream) cudaStreamDestroy(E.stream);
     E.stream = nullptr;
     E.ready = false;
-    E.device = -1;
+    tl_engine = prev;
+}
+
+void for_each_engine(void (*fn)(Engine &, int), int v)
+{
+    fn(g_default, v);
+    std::lock_guard<std::mutex> g(g_pool_mu);
+    for (int d = 0; d < MAX_DEVICES; d++)
+        if (g_dev[d]) fn(*g_dev[d], v);
+}
+
+void shutdown_all_engines()
+{
+    shutdown_engine(g_default);
+    g_default.device = -1;
+    std::lock_guard<std::mutex> g(g_pool_mu);
+    for (int d = 0; d < MAX_DEVICES; d++)
+        if (g_dev[d]) shutdown_engine(*g_dev[d]);     // the objects stay: a later multi-device call starts them again
+}
+
+}  // namespace imcvt
+
+using namespace imcvt;
+
+extern "C" {
+
+int imcvtInit(int device)
+{
+    IMCVT_API_LOCK();
+    Engine &E = engine();
+    if (E.ready && E.device != device) shutdown_engine(E);
+    E.device = device;
+    return ensure_engine();
+}
+
+
+void imcvtShutdown(void)
+{
+    imcvt::DeviceScope scope;
+    imcvt::shutdown_all_engines();     // the objects stay: a later multi-device call starts them again
 }
 
 const char *imcvtLastError(void) { return g_err; }
@@ -228,9 +272,10 @@ int imcvtProfileList(char *buf, size_t cap)
 
 long imcvtLaunchCount(void) { return engine().launches; }
 
-void imcvtDebugJLSForceSerial(int on) { engine().jls_force_serial = on != 0; }
-void imcvtDebugJLSPath(int path) { engine().jls_path = path; }
-void imcvtDebugHEVCPath(int path) { engine().hevc_path = path; }
-void imcvtJLSHostMode(int mode) { engine().jls_host_mode = mode; }
+// switches apply to the default engine and to every device engine of the multi-device entry points
+void imcvtDebugJLSForceSerial(int on) { for_each_engine([](Engine &E, int v) { E.jls_force_serial = v != 0; }, on); }
+void imcvtDebugJLSPath(int path) { for_each_engine([](Engine &E, int v) { E.jls_path = v; }, path); }
+void imcvtDebugHEVCPath(int path) { for_each_engine([](Engine &E, int v) { E.hevc_path = v; }, path); }
+void imcvtJLSHostMode(int mode) { for_each_engine([](Engine &E, int v) { E.jls_host_mode = v; }, mode); }
 
 }  // extern "C"

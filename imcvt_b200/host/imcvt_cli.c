@@ -20,8 +20,14 @@
  * Deliberate deviation: `-o <file>` in front of any input makes the reference write dst_fnames[-1];
  * here that output name is ignored.
  *
- * Environment: IMCVT_DEVICE = CUDA device ordinal (default: current), IMCVT_BATCH = most frames per batch (default 256),
- * IMCVT_TIMING = 1 prints where the wall-clock time of the call went (stderr).
+ * Several GPUs: a batch is sharded over the visible devices in contiguous frame blocks by the multi-device entry points
+ * (imcvtEncodeBatch*Multi: one engine and one host thread per device, no collective) -- the reference's file loop
+ * (src/main.c:162-211) spread over the box.  A device only joins when its block is worth a CUDA context: at least 8 frames per
+ * device for JPEG-LS, 2 for H.265.  The files are the same bytes whatever the number of devices.
+ *
+ * Environment: IMCVT_DEVICE = CUDA device ordinal, that device only; IMCVT_DEVICES = "all" (default) | a count k (devices
+ * 0..k-1) | a comma list of ordinals; IMCVT_BATCH = most frames per batch (default 256); IMCVT_TIMING = 1 prints where the
+ * wall-clock time of the call went (stderr).
  */
 #include <stdint.h>
 #include <stdlib.h>
@@ -103,6 +109,42 @@ static double now_s(void)
 static Job g_jobs[MAX_FILES];
 static int g_njobs, g_printed, g_setting, g_batch_limit = 256;
 static Batch g_batch;
+/* devices a batch is sharded over: g_ndev < 0 = the engine's own device only (IMCVT_DEVICE), 0 = all visible, else the list */
+static int g_devs[64], g_ndev = 0;
+
+static void parse_devices(const char *env)
+{
+    if (env == NULL || !strcmp(env, "all") || *env == 0) { g_ndev = 0; return; }
+    if (strchr(env, ',') == NULL) {
+        int k = atoi(env), i;
+        if (k < 1) k = 1;
+        if (k > 64) k = 64;
+        for (i = 0; i < k; i++) g_devs[i] = i;
+        g_ndev = k;
+        return;
+    }
+    g_ndev = 0;
+    while (*env && g_ndev < 64) {
+        g_devs[g_ndev++] = atoi(env);
+        env = strchr(env, ',');
+        if (env == NULL) break;
+        env++;
+    }
+}
+
+/* the devices of this batch: no more than the batch is worth (a CUDA context per device costs more than a few frames) */
+static int batch_devices(int n, int min_per_device, int *list)
+{
+    int visible = imcvtDeviceCount(), want, i, have;
+    if (g_ndev < 0 || visible <= 1)
+        return -1;
+    have = g_ndev > 0 ? g_ndev : (visible < 64 ? visible : 64);
+    want = n / min_per_device;
+    if (want < 1) want = 1;
+    if (want > have) want = have;
+    for (i = 0; i < want; i++) list[i] = g_ndev > 0 ? g_devs[i] : i;
+    return want;
+}
 
 static void say(Job *j, const char *fmt, ...)
 {
@@ -249,7 +291,16 @@ static void flush_batch(void)
     failed = (out == NULL || len == NULL);
     if (!failed) {
         const double t0 = now_s();
-        if (B->kind == OUT_JLS)
+        int devs[64];
+        const int nd = batch_devices(B->n, B->kind == OUT_JLS ? 8 : 2, devs);
+        if (nd > 1 || (nd == 1 && g_ndev > 0)) {
+            if (B->kind == OUT_JLS)
+                failed = imcvtEncodeBatchJLSMulti(B->arena, B->frame_bytes, B->n, B->is_rgb, B->h, B->w, g_setting, out, bound, len, devs, nd);
+            else if (B->is_rgb)
+                failed = imcvtEncodeBatchHEVCGreenMulti(B->arena, B->frame_bytes, B->n, B->h, B->w, g_setting, out, bound, len, devs, nd);
+            else
+                failed = imcvtEncodeBatchHEVCMulti(B->arena, B->frame_bytes, B->n, B->h, B->w, g_setting, out, bound, len, NULL, 0, devs, nd);
+        } else if (B->kind == OUT_JLS)
             failed = imcvtEncodeBatchJLS(B->arena, B->frame_bytes, B->n, B->is_rgb, B->h, B->w, g_setting, out, bound, len);
         else if (B->is_rgb)
             failed = imcvtEncodeBatchHEVCGreen(B->arena, B->frame_bytes, B->n, B->h, B->w, g_setting, out, bound, len);
@@ -502,8 +553,12 @@ int main(int argc, char **argv)
     }
     if ((env = getenv("IMCVT_BATCH")) != NULL && atoi(env) > 0)
         g_batch_limit = atoi(env) < MAX_FILES ? atoi(env) : MAX_FILES;
-    if ((env = getenv("IMCVT_DEVICE")) != NULL)
+    if ((env = getenv("IMCVT_DEVICE")) != NULL) {
         imcvtInit(atoi(env));                                       /* a failure shows up at the first encode call */
+        g_ndev = -1;
+    } else {
+        parse_devices(getenv("IMCVT_DEVICES"));
+    }
 
     for (i = 0; i < g_njobs; i++) {
         Job *j = &g_jobs[i];

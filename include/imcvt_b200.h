@@ -24,7 +24,7 @@ extern "C" {
 
 /* ---- life cycle ------------------------------------------------------------------------------ */
 int         imcvtInit(int device);          /* optional: binds the engine to a CUDA device (default: current) */
-void        imcvtShutdown(void);            /* frees the device workspace */
+void        imcvtShutdown(void);            /* frees the device workspaces (of every device the multi-device calls used) */
 const char *imcvtLastError(void);           /* message of the last failure on this thread */
 int         imcvtVersion(void);
 
@@ -83,6 +83,31 @@ int imcvtEncodeBatchHEVCDevice(const void *d_frames, size_t frame_stride, int n,
                                uint32_t height, uint32_t width, int qpd6,
                                void *d_out, size_t out_stride, void *d_out_len,
                                void *d_rcon, size_t rcon_stride, void *stream);
+
+/* The device-buffer entry points above (imcvtEncodeBatchJLSDevice / imcvtEncodeBatchHEVCDevice) do not synchronise, so a slot
+ * that is too small cannot fail the call: it shows as d_out_len[i] == 0 for that image (nothing is written past the slot).
+ * Pointers must be device (or page-locked host) memory of the engine's device; frame_stride >= one frame. */
+
+/* ---- every GPU of the box (replaces the reference's file-by-file loop, src/main.c:162-211, for a batch) ---------------
+ * Same arguments and results as the single-device entry points; the batch is sharded over `devices[0..ndev-1]` (CUDA
+ * ordinals; NULL / ndev <= 0 = all visible devices) in contiguous blocks of ceil(n / ndev) frames, one host thread and one
+ * engine per device, no collective: frames are independent and the sizes land in out_len directly.  The bytes are those of
+ * the single-device call whatever the number of devices.  Page-locked buffers (imcvtHostAlloc) are read and written by all
+ * devices at full rate. */
+int imcvtDeviceCount(void);
+int imcvtEncodeBatchJLSMulti(const uint8_t *frames, size_t frame_stride, int n, int is_rgb,
+                             uint32_t height, uint32_t width, int near_,
+                             uint8_t *out, size_t out_stride, size_t *out_len, const int *devices, int ndev);
+int imcvtEncodeBatchHEVCMulti(const uint8_t *frames, size_t frame_stride, int n,
+                              uint32_t height, uint32_t width, int qpd6,
+                              uint8_t *out, size_t out_stride, size_t *out_len,
+                              uint8_t *rcon, size_t rcon_stride, const int *devices, int ndev);
+int imcvtEncodeBatchHEVCGreenMulti(const uint8_t *rgb_frames, size_t frame_stride, int n,
+                                   uint32_t height, uint32_t width, int qpd6,
+                                   uint8_t *out, size_t out_stride, size_t *out_len, const int *devices, int ndev);
+int imcvtEncodeBatchHEVCSweepMulti(const uint8_t *frames, size_t frame_stride, int n,
+                                   uint32_t height, uint32_t width, const int *qpd6, int nq,
+                                   uint8_t *out, size_t out_stride, size_t *out_len, const int *devices, int ndev);
 
 /* How imcvtEncodeBatchJLS moves PAGE-LOCKED host buffers (cudaHostAlloc / imcvtHostAlloc / cudaHostRegister memory; pageable
  * buffers are always staged through device memory):
