@@ -59,7 +59,7 @@ struct Engine {
     static constexpr int NFLAG = 64;
     int *d_flag = nullptr;              // device overflow flags of the device-buffer entry points: NFLAG of them, one per call in
     unsigned flag_next = 0;             // turn, so that calls queued on different streams do not share one
-    bool attr_hevc = false, attr_jls_tile = false, attr_jls_rowscan = false;   // dynamic shared-memory opt-in done on this device
+    bool attr_hevc = false, attr_jls_tile = false, attr_jls_rowscan = false, attr_jls_nearscan = false;   // dynamic shared-memory opt-in done on this device
     uint64_t *pinned_lens = nullptr;    // pinned host buffer the chunks' stream lengths come back into
     int pinned_lens_cap = 0;
     bool profile = false;

@@ -177,7 +177,7 @@ static void shutdown_engine(Engine &E)
     E.io.release();
     if (E.d_flag) cudaFree(E.d_flag);
     E.d_flag = nullptr;
-    E.attr_hevc = E.attr_jls_tile = E.attr_jls_rowscan = false;
+    E.attr_hevc = E.attr_jls_tile = E.attr_jls_rowscan = E.attr_jls_nearscan = false;
     if (E.pinned_lens) cudaFreeHost(E.pinned_lens);
     E.pinned_lens = nullptr; E.pinned_lens_cap = 0;
     for (int c = 0; c < Engine::NCHUNK; c++) {

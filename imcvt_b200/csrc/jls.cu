@@ -25,6 +25,7 @@
 
 #include "jls_tile_kernel.cuh"
 #include "jls_rowscan_kernel.cuh"
+#include "jls_nearscan_kernel.cuh"
 
 namespace imcvt {
 namespace jls {
@@ -934,9 +935,28 @@ int encode_device(const uint8_t *d_frames, size_t frame_stride, int n, int is_rg
                 IMCVT_CUDA(cudaFuncSetAttribute(rowscan::rowscan_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(rowscan::Smem)));
                 E.attr_jls_rowscan = true;
             }
-            LaunchScope ls("jls_rowscan", st);
-            if (near_ > 0) rowscan::rowscan_kernel<true><<<P, rowscan::NT, sizeof(rowscan::Smem), st>>>(planes, plane_stride, (int)W, (int)H, SP, Lay, plane_bytes);
-            else rowscan::rowscan_kernel<false><<<P, rowscan::NT, sizeof(rowscan::Smem), st>>>(planes, plane_stride, (int)W, (int)H, SP, Lay, plane_bytes);
+            if (near_ > 0 && E.jls_path != 5) {
+                // NEAR 1..4: candidate-table kernel (jls_nearscan_kernel.cuh); imcvtDebugJLSPath(5) keeps the three-warp row scan as a cross-check
+                if (!E.attr_jls_nearscan) {
+                    IMCVT_CUDA(cudaFuncSetAttribute(nearscan::nearscan_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(nearscan::Smem)));
+                    IMCVT_CUDA(cudaFuncSetAttribute(nearscan::nearscan_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(nearscan::Smem)));
+                    IMCVT_CUDA(cudaFuncSetAttribute(nearscan::nearscan_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(nearscan::Smem)));
+                    IMCVT_CUDA(cudaFuncSetAttribute(nearscan::nearscan_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(nearscan::Smem)));
+                    E.attr_jls_nearscan = true;
+                }
+                LaunchScope ls("jls_nearscan", st);
+                const size_t smem = sizeof(nearscan::Smem);
+                switch (near_) {
+                case 1: nearscan::nearscan_kernel<1><<<P, nearscan::NT, smem, st>>>(planes, plane_stride, (int)W, (int)H, SP, Lay, plane_bytes); break;
+                case 2: nearscan::nearscan_kernel<2><<<P, nearscan::NT, smem, st>>>(planes, plane_stride, (int)W, (int)H, SP, Lay, plane_bytes); break;
+                case 3: nearscan::nearscan_kernel<3><<<P, nearscan::NT, smem, st>>>(planes, plane_stride, (int)W, (int)H, SP, Lay, plane_bytes); break;
+                default: nearscan::nearscan_kernel<4><<<P, nearscan::NT, smem, st>>>(planes, plane_stride, (int)W, (int)H, SP, Lay, plane_bytes); break;
+                }
+            } else {
+                LaunchScope ls("jls_rowscan", st);
+                if (near_ > 0) rowscan::rowscan_kernel<true><<<P, rowscan::NT, sizeof(rowscan::Smem), st>>>(planes, plane_stride, (int)W, (int)H, SP, Lay, plane_bytes);
+                else rowscan::rowscan_kernel<false><<<P, rowscan::NT, sizeof(rowscan::Smem), st>>>(planes, plane_stride, (int)W, (int)H, SP, Lay, plane_bytes);
+            }
         }
     }
     {

@@ -286,3 +286,21 @@ def emu_jls_rowscan(img, near):
     n = _libs["emu_rowscan"].emu_jls_rowscan_encode(img.ctypes.data, h, w, int(near), out.ctypes.data, out.size)
     assert n > 0
     return out[:n].tobytes()
+
+
+def emu_jls_nearscan(img, near):
+    """The SOURCE of the candidate-table JPEG-LS scan kernel (imcvt_b200/csrc/jls_nearscan_kernel.cuh, the path for NEAR 1..4)
+    run under the CPU SIMT emulator (tests/emu); gray images."""
+    if "emu_nearscan" not in _libs:
+        d = os.path.join(ROOT, "tests", "emu")
+        subprocess.run(["make", "-C", d, "-s", "libjls_nearscan_emu.so"], check=True, capture_output=True)
+        lib = C.CDLL(os.path.join(d, "libjls_nearscan_emu.so"))
+        lib.emu_jls_nearscan_encode.restype = C.c_size_t
+        lib.emu_jls_nearscan_encode.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_size_t]
+        _libs["emu_nearscan"] = lib
+    img = np.ascontiguousarray(img, dtype=np.uint8)
+    h, w = img.shape
+    out = np.zeros(8 * h * w + 65536, dtype=np.uint8)
+    n = _libs["emu_nearscan"].emu_jls_nearscan_encode(img.ctypes.data, h, w, int(near), out.ctypes.data, out.size)
+    assert n > 0
+    return out[:n].tobytes()

@@ -96,6 +96,34 @@ def test_rgb_batch_lossless_and_lossy():
             assert got[i] == want, f"near={near}[{i}]: {first_diff(got[i], want)}"
 
 
+@pytest.mark.parametrize("path", [0, 5], ids=["candidate-table", "three-warp-rowscan"])
+def test_near_lossy_kernels_match_oracle(path, lossless_path):
+    """NEAR 1..4 on both kernels that code it: the candidate-table kernel (jls_nearscan_kernel.cuh, the default) and the
+    three-warp row scan (imcvtDebugJLSPath 5): rows of one and of several segments, run-heavy and clamped content."""
+    if lossless_path != 2:
+        pytest.skip("NEAR > 0 does not depend on the lossless path")
+    rng = np.random.default_rng(33)
+    cases = [synth.frame("natural", 1, 40, 1500), synth.frame("texture", 2, 9, 4100), synth.frame("natural", 3, 7, 1024),
+             synth.frame("natural", 4, 5, 2049), rng.integers(0, 256, (6, 2500), dtype=np.uint8),
+             np.full((5, 3000), 200, np.uint8), (100 + rng.integers(0, 3, (20, 700))).astype(np.uint8),
+             rng.integers(0, 4, (16, 600), dtype=np.uint8), (252 + rng.integers(0, 4, (16, 600))).astype(np.uint8),
+             (rng.integers(0, 2, (40, 333)) * 255).astype(np.uint8), synth.frame("texture", 5, 1, 1), synth.frame("noise", 5, 1, 700)]
+    imcvt_b200.debug_jls_path(path)
+    try:
+        for near in (1, 2, 3, 4):
+            for k, img in enumerate(cases):
+                got = imcvt_b200.encode_jls_batch(img[None], near)[0]
+                want = oracle_jls(img, near)
+                assert got == want, f"case {k} near {near}: {first_diff(got, want)}"
+        # a batch with more planes than SMs (plane = CTA), RGB
+        frames = synth.batch("texture", 70, 20, 300, rgb=True)
+        got = imcvt_b200.encode_jls_batch(frames, 2)
+        for i in (0, 33, 69):
+            assert got[i] == oracle_jls(frames[i], 2), i
+    finally:
+        imcvt_b200.debug_jls_path(0)
+
+
 def test_full_hd_frame_matches_oracle():
     for kind in ["natural", "texture"]:
         f = synth.frame(kind, 5, 1080, 1920)

@@ -22,8 +22,17 @@ for path in (0, 2, 1):
     got = imcvt_b200.encode_jls_batch(gray, 0)
     assert all(got[i] == oracle_jls(gray[i], 0) for i in range(3)), path
 imcvt_b200.debug_jls_path(0)
+# NEAR > 0: the candidate-table kernel (rows of one and of several segments, every NEAR), and the three-warp row scan (path 5)
+wide = synth.batch("texture", 2, 6, 1100)
+for near in (1, 2, 3, 4):
+    got = imcvt_b200.encode_jls_batch(gray, near)
+    assert all(got[i] == oracle_jls(gray[i], near) for i in range(3)), near
+    got = imcvt_b200.encode_jls_batch(wide, near)
+    assert all(got[i] == oracle_jls(wide[i], near) for i in range(2)), near
+imcvt_b200.debug_jls_path(5)
 got = imcvt_b200.encode_jls_batch(gray, 2)
 assert all(got[i] == oracle_jls(gray[i], 2) for i in range(3))
+imcvt_b200.debug_jls_path(0)
 rgb = synth.batch("texture", 2, 24, 70, rgb=True)
 got = imcvt_b200.encode_jls_batch(rgb, 1)
 assert all(got[i] == oracle_jls(rgb[i], 1) for i in range(2))
