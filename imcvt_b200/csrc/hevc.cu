@@ -4,6 +4,10 @@
 #include "common.cuh"
 #include "../../include/imcvt_b200.h"
 #include "hevc_kernel.cuh"
+#include <algorithm>
+#include <functional>
+#include <queue>
+#include <vector>
 
 namespace imcvt {
 namespace hevc {
@@ -12,6 +16,22 @@ namespace hevc {
 static unsigned long long *g_prof = nullptr;
 #endif
 static inline int pad32(uint32_t v) { uint32_t c = v > 8192 ? 8192 : v; return (int)((c + 31) / 32 * 32); }   // HEVCe.c:1580-1581
+
+// Relative cost of one job by quantiser (measured on "natural" content, B200: the lower the quantiser, the more bins the CABAC
+// trials step through) and the gain of giving a job two SMs (the cluster-pair kernel).
+static const double kJobCost[5] = {7.0, 4.6, 3.2, 1.9, 1.0};
+static const double kPairGain = 1.6;
+
+// Finishing time of jobs handed out longest first to `machines` workers (what the kernel's dynamic queue does).
+static double makespan(const std::vector<double> &jobs_desc, int machines)
+{
+    if (machines <= 0) return 1e300;
+    std::priority_queue<double, std::vector<double>, std::greater<double>> load;
+    for (int m = 0; m < machines; m++) load.push(0.0);
+    double end = 0.0;
+    for (double j : jobs_desc) { const double t = load.top() + j; load.pop(); load.push(t); end = std::max(end, t); }
+    return end;
+}
 
 // d_frames: device, n gray8 images.  d_out / d_out_len / d_rcon (optional): device.  Queues everything on `st`.
 int encode_device(const uint8_t *d_frames, size_t frame_stride, int n, uint32_t H, uint32_t W, int qpd6,
@@ -35,7 +55,22 @@ int encode_device(const uint8_t *d_frames, size_t frame_stride, int n, uint32_t 
     }
     // Few frames: two SMs per frame (a cluster of two CTAs: the spine searches the 8x8 units and decides, the upper CTA
     // evaluates the 16x16 / 32x32 candidates meanwhile).  Many frames: one CTA per frame keeps every SM on its own frame.
-    const bool pair = E.hevc_path == 2 || (E.hevc_path == 0 && 2 * n <= E.sm_count);
+    // Launch shape: one CTA per job, or a cluster of two CTAs per job (each job 1.6x faster on twice the SMs).  Few jobs: pairs.
+    // Otherwise whichever finishes the queue sooner -- the jobs of a sweep differ several-fold in cost, and with one CTA per job
+    // the launch lasts as long as its costliest job while the SMs of the cheap ones idle.
+    bool pair = 2 * n <= E.sm_count;
+    int qorder[8] = {0, 1, 2, 3, 4, 5, 6, 7};
+    if (nq > 0) std::stable_sort(qorder, qorder + nq, [&](int a, int b) { return qlist[a] < qlist[b]; });
+    if (!pair && n <= 8192) {
+        std::vector<double> jobs;
+        jobs.reserve(n);
+        if (nq > 0) { for (int r = 0; r < nq; r++) for (int f = 0; f < n_frames; f++) jobs.push_back(kJobCost[qlist[qorder[r]]]); }
+        else jobs.assign(n, 1.0);
+        const double t_single = makespan(jobs, E.sm_count), t_pair = makespan(jobs, E.sm_count / 2) / kPairGain;
+        pair = t_pair < 0.97 * t_single;
+    }
+    if (E.hevc_path == 1) pair = false;
+    if (E.hevc_path == 2) pair = true;
     const int grid = pair ? 2 * (n < E.sm_count / 2 ? n : E.sm_count / 2)
                           : (n < E.sm_count ? n : E.sm_count);              // one CTA per SM; frames come from a queue
     const size_t rstride = (rbytes + 255) & ~(size_t)255;
@@ -62,6 +97,7 @@ int encode_device(const uint8_t *d_frames, size_t frame_stride, int n, uint32_t 
     P.prof = nullptr;
     P.nq = nq > 0 ? nq : 0;
     for (int k = 0; k < 8; k++) P.qlist[k] = (nq > 0 && k < nq) ? qlist[k] : 0;
+    for (int k = 0; k < 8; k++) P.qorder[k] = qorder[k];
     if (nq > 0) P.qpd6 = qlist[0];
 #ifdef IMCVT_HEVC_PROF
     {

@@ -142,6 +142,7 @@ struct Params {
     const uint8_t *frames; size_t frame_stride;     // n gray8 images H x W
     int n, H, W, hp, wp, qpd6;                       // hp, wp: padded to x32 (and clipped to 8192, :1580-1581)
     int nq, qlist[8];                                // nq > 0: a sweep -- job j codes frame j / nq at qpd6 = qlist[j % nq] into slot j
+    int qorder[8];                                   // ... the queue hands the jobs out setting by setting, qorder[0] first (the costliest: lowest qpd6)
     uint8_t *out; size_t out_stride;                 // output slots
     unsigned long long *out_len;                     // [n]
     uint8_t *rcon; size_t rcon_stride;               // [n][hp*wp] reconstruction (also the line buffer between CTU rows)
@@ -1895,8 +1896,9 @@ __device__ __forceinline__ void frame_kernel_body(const Params &P)
         if (PAIR) HEVC_PAIR_SYNC(); else __syncthreads();
         if (threadIdx.x == 0 && rank == 0) { const int f = atomicAdd(P.next_frame, 1); sm.win = f; if (PAIR) K.peer->win = f; }
         if (PAIR) HEVC_PAIR_SYNC(); else __syncthreads();
-        const int f = sm.win;
+        int f = sm.win;
         if (f >= (P.nq > 0 ? P.n * P.nq : P.n)) break;
+        if (P.nq > 0) { const int r = f / P.n; f = (f - r * P.n) * P.nq + P.qorder[r]; }      // longest jobs first: the tail of the launch is short jobs
         if (P.nq > 0 && P.qlist[f % P.nq] != K.qpd6) {                          // a sweep: the context initialisation follows the QP
             K.qpd6 = P.qlist[f % P.nq];
             K.rd.init(K.qpd6);

@@ -29,7 +29,7 @@ namespace jls {
 namespace nearscan {
 
 constexpr int SEGCAP = 1024;                        // samples per segment: 1024 (NEAR <= 2) or 512
-constexpr int TWORDS = 10240;                       // one entry buffer: 2 tables x segment x K entries
+constexpr int TWORDS = 13328;                       // one row buffer: (segment + 1) rows of 2 K + 3 words
 constexpr int STAGE_WARPS = 4;
 constexpr int NT = 32 * (3 + STAGE_WARPS);
 constexpr int WMAXR = 32768;                        // :436
@@ -38,31 +38,43 @@ constexpr uint32_t REC_BREAK = 0x8000u;
 template <int NEAR> struct Cfg {
     static constexpr int K = 2 * NEAR + 1;
     static constexpr int SEG = NEAR <= 2 ? 1024 : 512;
-    static constexpr int RUN_OFS = SEG * K * 4;     // byte offset of the in-run table inside an entry buffer
-    static_assert(2 * SEG * K <= TWORDS, "entry buffer too small");
-    static_assert(RUN_OFS % 256 == 0, "the walker stores the low byte of the state offset as the candidate");
+    // One row of words per sample: K entries for a sample reached outside a run | K entries inside a run | the sample's offset
+    // into the walker's table | the walker's record for the coder | the candidate the walker left.  An odd number of words:
+    // the stagers' lanes (a sample each) hit different banks.
+    static constexpr int RS = 2 * K + 3;
+    static constexpr int XW = 2 * K, RECW = 2 * K + 1, SELW = 2 * K + 2;
+    static constexpr int RUN_OFS = K * 4;           // byte offset of the in-run entries inside a row
+    static_assert((SEG + 1) * RS <= TWORDS, "row buffer too small");
 };
 
-// Entries (32 bit), type in [25:24].
+// Entries (32 bit), type in [25:24], stop mark in [26].
 //   0 regular           [15:0] 0x2000 | 16 (q - 1) (= the record's high half, and the context state's byte offset + 0x2000)
 //                       [23:16] MED | [31] sign
 //   2 regular, sample within NEAR of 0 or 255: same fields; the walker also clamps the next candidate to what 0..255 allows
-//   1 run sample        [15:0] next state (byte offset of the candidate, in the in-run table)
+//   1 run sample        [15:0] next state (byte offset of the candidate among the row's in-run entries)
 //   3 run interruption  [5:0] next candidate (x 4) | [14:6] wrapped error | [15] RItype
+//   the row after the segment's last sample holds stop marks: the walker's loop over regular samples needs no counter
 // Records for the coder (one per sample): low half wrapped error | high half: 0 = run sample, REC_BREAK | RItype = run
 // interruption, else 0x2000 | 16 (q - 1).
-// The walker leaves the next candidate of every sample (a byte: 4 (Rx - x + NEAR)); all threads turn a walked segment into
-// reconstructed samples of the row buffer at the start of the next iteration.
+// The walker leaves the state it hands to the next sample (a byte; candidate = 4 (Rx - x + NEAR), + RUN_OFS inside a run); all
+// threads turn a walked segment into reconstructed samples of the row buffer at the start of the next iteration.
+constexpr uint32_t ENT_STOP = 0x07000000u;
+// low half of a | low half of b << 16
+__device__ __forceinline__ uint32_t pack_halves(uint32_t a, uint32_t b)
+{
+#ifdef IMCVT_HOST_EMU
+    return (a & 0xFFFFu) | (b << 16);
+#else
+    return __byte_perm(a, b, 0x5410);
+#endif
+}
 struct Smem {
     uint8_t row[2][WMAXR + 16];                     // reconstructed rows y-1 / y (index 8 + x)
     uint32_t T[2][TWORDS];
-    uint32_t X[2][SEGCAP];                          // per sample: byte offset of dq2[x + 255] | lowest << 16 | highest << 24 next candidate (x 4) the range 0..255 allows
-    uint8_t dsel[2][SEGCAP];                        // walker: next candidate (x 4) per sample = 4 (Rx - x + NEAR)
-    uint32_t rec[2][SEGCAP];
     uint32_t codes[2][SEGCAP + SEGCAP / 32];
     uint8_t lens[2][SEGCAP + SEGCAP / 8];
     uint32_t ubits[tile::UBITS_WORDS];
-    int4 ctx[NCTX];                                 // walker: (unused, B, C, N)
+    int4 ctx[NCTX];                                 // walker: (B, C, N, unused)
     int2 ctx2[NCTX];                                // coder: (A, N)
     uint32_t dq2[1024];                             // [(x - px + 255) | negative-sign << 9]: wrapped error (low half) | next candidate x 4 (high half)
     signed char gq[512];                            // quantised gradient at [g + 255]
@@ -71,13 +83,13 @@ struct Smem {
 };
 
 template <int NEAR>
-__device__ __forceinline__ void stage_segment(Smem &sm, const uint8_t *__restrict__ src, int W, int y, int x0, int n, int buf, int st_tid)
+__device__ __forceinline__ void stage_segment(Smem &sm, const uint8_t *__restrict__ src, int W, int y, int x0, int n, int buf, int st_tid, int st_n)
 {
-    constexpr int K = Cfg<NEAR>::K;
+    constexpr int K = Cfg<NEAR>::K, RS = Cfg<NEAR>::RS;
     const uint8_t *up = sm.row[(y + 1) & 1] + 8;
     const uint8_t *in_row = src + (size_t)y * W + x0;
-    uint32_t *Treg = sm.T[buf], *Trun = Treg + Cfg<NEAR>::SEG * K;
-    for (int i = st_tid; i < n; i += STAGE_WARPS * 32) {
+    uint32_t *T = sm.T[buf];
+    for (int i = st_tid; i < n; i += st_n) {
         const int x = x0 + i;
         const int xv = in_row[i];
         const int b = up[x], d = up[x + 1];                       // up[W] repeats up[W - 1] (:57-58)
@@ -87,6 +99,7 @@ __device__ __forceinline__ void stage_segment(Smem &sm, const uint8_t *__restric
         const int abase = first ? b : (int)in_row[i - 1] - NEAR;
         const int q12 = 81 * sm.gq[d - b + 255] + 9 * sm.gq[b - c + 255];
         const bool edge = xv < NEAR || xv > 255 - NEAR;
+        uint32_t *row = T + i * RS;
 #pragma unroll
         for (int k = 0; k < K; k++) {
             const int a = first ? b : min(max(abase + k, 0), 255);          // a candidate outside 0..255 is never selected
@@ -102,17 +115,18 @@ __device__ __forceinline__ void stage_segment(Smem &sm, const uint8_t *__restric
                 const int rx = min(max(px + (neg ? -step : step), 0), 255);
                 er = (3u << 24) | (uint32_t)((rx - xv + NEAR) * 4) | (((uint32_t)e & 0x1FFu) << 6) | ((uint32_t)t << 15);
             }
-            Trun[i * K + k] = er;
+            row[K + k] = er;
             const int qv = q12 + sm.gq[c - a + 255];
             uint32_t eg = er;                                               // Q == 0 enters run mode (:284-289)
             if (qv != 0) {
                 const int cq = abs(qv);
                 eg = ((uint32_t)(cq - 1) << 4) | 0x2000u | ((uint32_t)med3(a, b, c) << 16) | (qv < 0 ? 0x80000000u : 0u) | (edge ? (2u << 24) : 0u);
             }
-            Treg[i * K + k] = eg;
+            row[k] = eg;
         }
-        sm.X[buf][i] = (uint32_t)((xv + 255) * 4) | ((uint32_t)((max(-xv, -NEAR) + NEAR) * 4) << 16) | ((uint32_t)((min(255 - xv, NEAR) + NEAR) * 4) << 24);
+        row[Cfg<NEAR>::XW] = (uint32_t)((xv + 255) * 4);
     }
+    for (int k = st_tid; k < 2 * K; k += st_n) T[n * RS + k] = ENT_STOP;    // the row after the last sample stops the walker
 }
 
 template <int NEAR>
@@ -120,14 +134,14 @@ __global__ void __launch_bounds__(NT, 1)
 nearscan_kernel(const uint8_t *__restrict__ pix, size_t plane_stride, int W, int H, SerialParams P, FrameLayout L,
                 uint64_t *__restrict__ plane_bytes)
 {
-    constexpr int K = Cfg<NEAR>::K, SEG = Cfg<NEAR>::SEG;
+    constexpr int K = Cfg<NEAR>::K, SEG = Cfg<NEAR>::SEG, RS = Cfg<NEAR>::RS;
     constexpr int quant = 2 * NEAR + 1, range = (256 + 4 * NEAR) / quant, half = (range + 1) / 2;
     Smem &sm = *reinterpret_cast<Smem *>(JLS_ROWSCAN_SMEM());
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int p = blockIdx.x;
     const uint8_t *src = pix + (size_t)p * plane_stride;
 
-    for (int k = tid; k < NCTX; k += NT) { sm.ctx[k] = make_int4(0, 0, 0, 1); sm.ctx2[k] = make_int2(P.a_init, 1); }
+    for (int k = tid; k < NCTX; k += NT) { sm.ctx[k] = make_int4(0, 0, 1, 0); sm.ctx2[k] = make_int2(P.a_init, 1); }
     for (int i = tid; i < 511; i += NT) {
         const int g = i - 255;
         sm.gq[i] = (signed char)grad_q_any(P, g);
@@ -168,17 +182,19 @@ nearscan_kernel(const uint8_t *__restrict__ pix, size_t plane_stride, int W, int
             const int pit = it - 1, py = pit / nseg, psg = pit - py * nseg, px0 = psg * SEG, pn = min(SEG, W - px0);
             const uint8_t *in_prev = src + (size_t)py * W + px0;
             uint8_t *dst = sm.row[py & 1] + 8 + px0;
-            const uint8_t *ds = sm.dsel[pit & 1];
+            const uint32_t *T = sm.T[pit & 1];
             for (int i = tid; i < pn; i += NT) {
-                const int rx = (int)in_prev[i] + (int)(ds[i] >> 2) - NEAR;
+                int k4 = (int)(T[i * RS + Cfg<NEAR>::SELW] & 0xFFu);
+                if (k4 >= Cfg<NEAR>::RUN_OFS) k4 -= Cfg<NEAR>::RUN_OFS;
+                const int rx = (int)in_prev[i] + (k4 >> 2) - NEAR;
                 dst[i] = (uint8_t)rx;
                 if (px0 + i == W - 1) dst[i + 1] = (uint8_t)rx;         // right neighbour of the last sample of the row below (:57-58)
             }
             __syncthreads();
         }
-        // the first segment of a row needs the finished row above: its entries are made here, in front of the walk
+        // the first segment of a row needs the finished row above: its entries are made here, in front of the walk, by everybody
         if (it < total && it % nseg == 0) {
-            if (warp >= 3) stage_segment<NEAR>(sm, src, W, it / nseg, 0, min(SEG, W), it & 1, tid - 96);
+            stage_segment<NEAR>(sm, src, W, it / nseg, 0, min(SEG, W), it & 1, tid, NT);
             __syncthreads();
         }
         if (warp == 1 && it >= 2) {
@@ -226,7 +242,7 @@ nearscan_kernel(const uint8_t *__restrict__ pix, size_t plane_stride, int W, int
         if (warp == 2 && it >= 1 && it <= total) {
             // ---- coder: records of the previous segment -> code + length per sample ----
             const int pit = it - 1, py = pit / nseg, psg = pit - py * nseg, px0 = psg * SEG, pn = min(SEG, W - px0), pb = pit & 1;
-            const uint32_t *rec = sm.rec[pb];
+            const uint32_t *rec = sm.T[pb] + Cfg<NEAR>::RECW;            // record of sample i at rec[i * RS]
             uint32_t *codes = sm.codes[pb];
             uint8_t *lens = sm.lens[pb];
             if (px0 == 0) run_len = 0;                                   // :270
@@ -234,7 +250,7 @@ nearscan_kernel(const uint8_t *__restrict__ pix, size_t plane_stride, int W, int
             for (int base = 0; base < pn; base += 32) {
                 const int i = base + lane;
                 const bool valid = i < pn;
-                const uint32_t r = valid ? rec[i] : 0u;
+                const uint32_t r = valid ? rec[i * RS] : 0u;
                 const uint32_t hi = r >> 16;
                 const int e = (int)(short)(r & 0xFFFFu);
                 const bool isreg = valid && (hi & 0x2000u) != 0 && (hi & REC_BREAK) == 0;
@@ -244,12 +260,9 @@ nearscan_kernel(const uint8_t *__restrict__ pix, size_t plane_stride, int W, int
                 const int rank = __popc(m & lt_mask);
                 int2 st = isreg ? sm.ctx2[q] : make_int2(0, 1);
                 const int ae = abs(e);
-                int maxrank = rank;
-#pragma unroll
-                for (int d = 16; d >= 1; d >>= 1) maxrank = max(maxrank, __shfl_xor_sync(0xffffffffu, maxrank, d));
                 uint32_t mm = m;
                 uint32_t code = 0; int len = 0;
-                for (int t = 0; t <= maxrank; t++) {
+                for (int t = 0; __any_sync(0xffffffffu, isreg && t <= rank); t++) {
                     const int srcl = mm ? __ffs((int)mm) - 1 : lane;
                     mm &= mm - 1u;
                     const int aet = __shfl_sync(0xffffffffu, ae, srcl);
@@ -266,50 +279,69 @@ nearscan_kernel(const uint8_t *__restrict__ pix, size_t plane_stride, int W, int
                     }
                 }
                 if (isreg && rank == __popc(m) - 1) sm.ctx2[q] = st;
-                if (isreg) { codes[tile::code_idx(i)] = code; lens[tile::len_idx(i)] = (uint8_t)len; }
-                // run samples and run interruptions: serial, on lane 0 (run_index, run length, the two interruption contexts)
+                // run samples carry no code unless lane 0 finds a completed block below
+                if (valid) { codes[tile::code_idx(i)] = code; lens[tile::len_idx(i)] = (uint8_t)len; }
+                // run samples and run interruptions: serial, on lane 0 (run_index, run length, the two interruption contexts);
+                // a stretch of run samples is counted block by block (:295-300), not sample by sample
                 uint32_t rm = __ballot_sync(0xffffffffu, valid && !isreg);
+                const uint32_t hm = __ballot_sync(0xffffffffu, valid && hi == 0u);
+                __syncwarp();
                 if (lane == 0) {
                     while (rm) {
                         const int j = __ffs((int)rm) - 1;
+                        if ((hm >> j) & 1u) {
+                            // run samples j .. j + cnt - 1
+                            const uint32_t rest = ~(hm >> j);
+                            int cnt = rest ? __ffs((int)rest) - 1 : 32 - j;
+                            rm &= cnt + j >= 32 ? 0u : ~0u << (j + cnt);
+                            int pos = base + j;
+                            const int end = pos + cnt;
+                            while (pos < end) {
+                                const int jj = tile::run_order(run_index);
+                                const int need = (1 << jj) - run_len;
+                                if (end - pos >= need) {                  // the block completes on sample pos + need - 1: a one (:296-299)
+                                    pos += need;
+                                    codes[tile::code_idx(pos - 1)] = 1u;
+                                    lens[tile::len_idx(pos - 1)] = 1;
+                                    run_len = 0;
+                                    if (run_index < 31) run_index++;
+                                } else {
+                                    run_len += end - pos;
+                                    pos = end;
+                                }
+                            }
+                            if (px0 + end == W && run_len > 0) {          // the run reaches the end of the row: one more one (:302-303)
+                                const uint32_t c0 = codes[tile::code_idx(end - 1)];
+                                const int l0 = lens[tile::len_idx(end - 1)];
+                                codes[tile::code_idx(end - 1)] = (c0 << 1) | 1u;
+                                lens[tile::len_idx(end - 1)] = (uint8_t)(l0 + 1);
+                            }
+                            continue;
+                        }
                         rm &= rm - 1u;
                         const int ii = base + j;
-                        const uint32_t rr = rec[ii];
+                        const uint32_t rr = rec[ii * RS];
                         const uint32_t h2 = rr >> 16;
                         const int e2 = (int)(short)(rr & 0xFFFFu);
-                        uint32_t c2 = 0; int l2 = 0;
-                        if (h2 == 0) {
-                            run_len++;
-                            const int jj = tile::run_order(run_index);
-                            if (run_len >= (1 << jj)) {
-                                c2 = 1; l2 = 1;
-                                run_len -= 1 << jj;
-                                if (run_index < 31) run_index++;
-                            }
-                            if (px0 + ii == W - 1 && run_len > 0) { c2 = (c2 << 1) | 1u; l2++; }
-                        } else {
-                            const int t = (int)(h2 & 1u);
-                            const int jj = tile::run_order(run_index);
-                            const int glimit = P.limit - 1 - jj;
-                            const int rem = run_len;
-                            run_len = 0;
-                            if (run_index > 0) run_index--;
-                            int At = t ? rA1 : rA0, Bt = t ? rB1 : rB0, Nt = t ? rN1 : rN0;
-                            const int k = golomb_k(At + (t ? (Nt >> 1) : 0), Nt);
-                            const int map = (e2 != 0) && ((e2 > 0) == (k == 0 && 2 * Bt < Nt));
-                            const int me = 2 * abs(e2) - t - map;
-                            uint32_t gcode; int glen;
-                            golomb_code(me, k, glimit, P.qbpp, gcode, glen);
-                            c2 = ((uint32_t)rem << glen) | gcode;        // run remainder in J+1 bits, then the Golomb code (<= 32 bits)
-                            l2 = jj + 1 + glen;
-                            if (e2 < 0) Bt++;
-                            At += (me + 1 - t) >> 1;
-                            if (Nt >= 64) { At >>= 1; Bt >>= 1; Nt >>= 1; }
-                            Nt++;
-                            if (t) { rA1 = At; rB1 = Bt; rN1 = Nt; } else { rA0 = At; rB0 = Bt; rN0 = Nt; }
-                        }
-                        codes[tile::code_idx(ii)] = c2;
-                        lens[tile::len_idx(ii)] = (uint8_t)l2;
+                        const int t = (int)(h2 & 1u);
+                        const int jj = tile::run_order(run_index);
+                        const int glimit = P.limit - 1 - jj;
+                        const int rem = run_len;
+                        run_len = 0;
+                        if (run_index > 0) run_index--;
+                        int At = t ? rA1 : rA0, Bt = t ? rB1 : rB0, Nt = t ? rN1 : rN0;
+                        const int k = golomb_k(At + (t ? (Nt >> 1) : 0), Nt);
+                        const int map = (e2 != 0) && ((e2 > 0) == (k == 0 && 2 * Bt < Nt));
+                        const int me = 2 * abs(e2) - t - map;
+                        uint32_t gcode; int glen;
+                        golomb_code(me, k, glimit, P.qbpp, gcode, glen);
+                        codes[tile::code_idx(ii)] = ((uint32_t)rem << glen) | gcode;     // run remainder in J+1 bits, then the Golomb code (<= 32 bits)
+                        lens[tile::len_idx(ii)] = (uint8_t)(jj + 1 + glen);
+                        if (e2 < 0) Bt++;
+                        At += (me + 1 - t) >> 1;
+                        if (Nt >= 64) { At >>= 1; Bt >>= 1; Nt >>= 1; }
+                        Nt++;
+                        if (t) { rA1 = At; rB1 = Bt; rN1 = Nt; } else { rA0 = At; rB0 = Bt; rN0 = Nt; }
                     }
                 }
                 __syncwarp();
@@ -326,66 +358,85 @@ nearscan_kernel(const uint8_t *__restrict__ pix, size_t plane_stride, int W, int
         if (warp >= 3 && it + 1 < total && (it + 1) % nseg != 0) {
             // ---- the entries of the next segment of the same row ----
             const int nit = it + 1, ny = nit / nseg, nsg = nit - ny * nseg, nx0 = nsg * SEG;
-            stage_segment<NEAR>(sm, src, W, ny, nx0, min(SEG, W - nx0), nit & 1, tid - 96);
+            stage_segment<NEAR>(sm, src, W, ny, nx0, min(SEG, W - nx0), nit & 1, tid - 96, STAGE_WARPS * 32);
         }
         if (tid == 0 && it < total) {
             // ---- the walk ----
-            const int y = it / nseg, sg = it - y * nseg, x0 = sg * SEG, n = min(SEG, W - x0);
-            const char *tp = reinterpret_cast<const char *>(sm.T[it & 1]);
-            const uint32_t *xp = sm.X[it & 1];
-            uint16_t *rec = reinterpret_cast<uint16_t *>(sm.rec[it & 1]);
-            uint8_t *dsel = sm.dsel[it & 1];
+            const int x0 = (it % nseg) * SEG;
+            char *tp = reinterpret_cast<char *>(sm.T[it & 1]);
             // state offsets carry the 0x2000 flag of the record's high half: taken off the base once
             char *ctxb = reinterpret_cast<char *>(sm.ctx) - 0x2000;
             const char *dqb = reinterpret_cast<const char *>(sm.dq2);
             if (x0 == 0) sel = NEAR * 4;                                 // row start (:270): not in a run; every candidate entry of column 0 is the same
             uint32_t w = *reinterpret_cast<const uint32_t *>(tp + sel);
-            for (int i = 0; i < n; i++) {
-                tp += K * 4;
-                const uint32_t xi = xp[i];
-                if ((w & 0x01000000u) == 0u) {
-                    // regular sample (:346-394 without A, k and the code)
+            for (;;) {
+                // regular samples (:346-394 without A, k and the code), as long as the next entry is one: the loop's only branch
+#pragma unroll 2
+                while ((w & 0x07000000u) == 0u) {
                     int4 *sp = reinterpret_cast<int4 *>(ctxb + (w & 0xFFFFu));
                     int4 st = *sp;
                     const int sgn = (int)w >> 31;
-                    const int medn = (int)((w >> 16) & 0xFFu) + (int)(w >> 31);       // MED - sign
-                    const char *xa = dqb + ((xi & 0xFFFu) | ((uint32_t)sgn & 2048u));       // dq2[x + 255 | negative << 9]
-                    const int hv = st.w >> 6;                                               // N >= 64: halve (:378-383; N never exceeds 64)
-                    const int nn = (st.w >> hv) + 1;
-                    const int cm = max(st.z - 1, -128), cp = min(st.z + 1, 127);
-                    int px = medn + (st.z ^ sgn);
+                    const int medn = (int)((w >> 16) & 0xFFu) + (int)(w >> 31);            // MED - sign
+                    const uint32_t xo = *reinterpret_cast<const uint32_t *>(tp + Cfg<NEAR>::XW * 4) | ((uint32_t)sgn & 2048u);   // dq2[x + 255 | negative << 9]
+                    const int hv = st.z >> 6;                                               // N >= 64: halve (:378-383; N never exceeds 64)
+                    const int nn = (st.z >> hv) + 1;
+                    const int cm = max(st.y - 1, -128), cp = min(st.y + 1, 127);
+                    int px = medn + (st.y ^ sgn);
                     px = min(max(px, 0), 255);
-                    const uint32_t v = *reinterpret_cast<const uint32_t *>(xa - 4 * px);
+                    const uint32_t v = *reinterpret_cast<const uint32_t *>(dqb + xo - 4 * px);
                     sel = v >> 16;
-                    if (w & 0x02000000u) sel = min(max(sel, (xi >> 16) & 0xFFu), xi >> 24);  // Rx clamped to 0..255 (:321-323)
-                    const uint32_t wn = i + 1 < n ? *reinterpret_cast<const uint32_t *>(tp + sel) : 0u;   // the next entry, before the state update
+                    const uint32_t wn = *reinterpret_cast<const uint32_t *>(tp + RS * 4 + sel);          // the next entry, before the state update
                     const int e = (int)(short)(v & 0xFFFFu);
-                    const int bh = (st.y + e * quant) >> hv;                                // :376-393, branch-free
+                    const int bh = (st.x + e * quant) >> hv;                                // :376-393, branch-free
                     const bool c1 = bh <= -nn, c2 = bh > 0;
                     const int b1 = max(bh + nn, 1 - nn), b2 = min(bh - nn, 0);
-                    st.y = c1 ? b1 : (c2 ? b2 : bh);
-                    st.z = c1 ? cm : (c2 ? cp : st.z);
-                    st.w = nn;
+                    st.x = c1 ? b1 : (c2 ? b2 : bh);
+                    st.y = c1 ? cm : (c2 ? cp : st.y);
+                    st.z = nn;
                     *sp = st;
-                    rec[2 * i] = (uint16_t)v;
-                    rec[2 * i + 1] = (uint16_t)w;
-                    dsel[i] = (uint8_t)sel;
+                    *reinterpret_cast<uint32_t *>(tp + Cfg<NEAR>::RECW * 4) = pack_halves(v, w);
+                    *reinterpret_cast<uint8_t *>(tp + Cfg<NEAR>::SELW * 4) = (uint8_t)sel;
+                    tp += RS * 4;
                     w = wn;
-                } else {
-                    uint32_t lo, hi;
-                    if ((w & 0x02000000u) == 0u) {                       // run sample: counted by the coder
-                        sel = w & 0xFFFFu;
-                        lo = 0; hi = 0;
-                    } else {                                             // run interruption
-                        sel = w & 0x3Cu;
-                        lo = (uint32_t)((int)(w << 17) >> 23) & 0xFFFFu;
-                        hi = REC_BREAK | ((w >> 15) & 1u);
-                    }
-                    rec[2 * i] = (uint16_t)lo;
-                    rec[2 * i + 1] = (uint16_t)hi;
-                    dsel[i] = (uint8_t)sel;                              // the in-run table's offset is a multiple of 256
-                    w = i + 1 < n ? *reinterpret_cast<const uint32_t *>(tp + sel) : 0u;
                 }
+                if (w & 0x04000000u) break;                              // the row after the last sample
+                uint32_t r;
+                if ((w & 0x01000000u) == 0u) {
+                    // a regular sample within NEAR of 0 or 255: as above, and the reconstruction is clamped to 0..255 (:321-323)
+                    int4 *sp = reinterpret_cast<int4 *>(ctxb + (w & 0xFFFFu));
+                    int4 st = *sp;
+                    const int sgn = (int)w >> 31;
+                    const uint32_t xw = *reinterpret_cast<const uint32_t *>(tp + Cfg<NEAR>::XW * 4);
+                    const int xv = (int)(xw >> 2) - 255;
+                    int px = (int)((w >> 16) & 0xFFu) + ((st.y ^ sgn) - sgn);
+                    px = min(max(px, 0), 255);
+                    const uint32_t v = *reinterpret_cast<const uint32_t *>(dqb + (xw | ((uint32_t)sgn & 2048u)) - 4 * px);
+                    const int e = (int)(short)(v & 0xFFFFu);
+                    const int lo = (max(-xv, -NEAR) + NEAR) * 4, hi = (min(255 - xv, NEAR) + NEAR) * 4;
+                    sel = (uint32_t)min(max((int)(v >> 16), lo), hi);
+                    st.x += e * quant;
+                    if (st.z >= 64) { st.x >>= 1; st.z >>= 1; }
+                    st.z++;
+                    if (st.x <= -st.z) {
+                        st.x += st.z; if (st.x <= -st.z) st.x = -st.z + 1;
+                        st.y = max(st.y - 1, -128);
+                    } else if (st.x > 0) {
+                        st.x -= st.z; if (st.x > 0) st.x = 0;
+                        st.y = min(st.y + 1, 127);
+                    }
+                    *sp = st;
+                    r = (v & 0xFFFFu) | (w << 16);
+                } else if ((w & 0x02000000u) == 0u) {                    // run sample: counted by the coder
+                    sel = w & 0xFFFFu;
+                    r = 0;
+                } else {                                                 // run interruption
+                    sel = w & 0x3Cu;
+                    r = ((uint32_t)((int)(w << 17) >> 23) & 0xFFFFu) | ((REC_BREAK | ((w >> 15) & 1u)) << 16);
+                }
+                *reinterpret_cast<uint32_t *>(tp + Cfg<NEAR>::RECW * 4) = r;
+                *reinterpret_cast<uint8_t *>(tp + Cfg<NEAR>::SELW * 4) = (uint8_t)sel;
+                tp += RS * 4;
+                w = *reinterpret_cast<const uint32_t *>(tp + sel);
             }
         }
         __syncthreads();

@@ -28,6 +28,7 @@ extern "C" long emu_hevc_encode_mode(uint8_t *stream, size_t cap, const uint8_t 
     P.scratch = scratch.data(); P.lists = lists.data(); P.overflow = &overflow; P.next_frame = &next;
     P.prof = nullptr;
     P.nq = 0;
+    for (int k = 0; k < 8; k++) P.qorder[k] = k;
     if (pair) emu::launch(1, NT, sizeof(Smem), [&] { hevc_pair_kernel(P); }, 2);
     else emu::launch(1, NT, sizeof(Smem), [&] { hevc_frame_kernel(P); });
     *ysz = hp; *xsz = wp;
@@ -51,6 +52,10 @@ extern "C" int emu_hevc_sweep(uint8_t *streams, size_t cap, const uint8_t *img, 
     P.prof = nullptr;
     P.nq = nq;
     for (int k = 0; k < 8; k++) P.qlist[k] = k < nq ? qlist[k] : 0;
+    // the queue order of the product's host side (hevc.cu): settings by ascending qpd6, ties in list order
+    for (int k = 0; k < 8; k++) P.qorder[k] = k;
+    for (int a = 1; a < nq; a++)
+        for (int b = a; b > 0 && qlist[P.qorder[b]] < qlist[P.qorder[b - 1]]; b--) { const int t = P.qorder[b]; P.qorder[b] = P.qorder[b - 1]; P.qorder[b - 1] = t; }
     if (pair) emu::launch(1, NT, sizeof(Smem), [&] { hevc_pair_kernel(P); }, 2);
     else emu::launch(1, NT, sizeof(Smem), [&] { hevc_frame_kernel(P); });
     return overflow;
