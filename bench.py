@@ -358,6 +358,33 @@ def parity_report(ctx, name, got, want, what):
     return {"frames": int(n), "equal": nbad == 0, "against": cpu_kind(), "what": what}
 
 
+def host_link_probe(ctx, nin, nout, iters=8):
+    """What the host side of the box gives when every rank moves its step's bytes at once: `nin` bytes page-locked host -> HBM
+    and `nout` bytes HBM -> page-locked host per rank and iteration, both directions in flight on two streams, all ranks
+    together (barrier on both sides, max over ranks).  Returns aggregate GB/s.  The e2e leg cannot move its bytes faster."""
+    torch = ctx.torch
+    h_in = torch.empty(nin, dtype=torch.uint8).pin_memory()
+    h_out = torch.empty(nout, dtype=torch.uint8).pin_memory()
+    d_in = torch.empty(nin, dtype=torch.uint8, device="cuda")
+    d_out = torch.zeros(nout, dtype=torch.uint8, device="cuda")
+    s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+
+    def once():
+        with torch.cuda.stream(s1):
+            d_in.copy_(h_in, non_blocking=True)
+        with torch.cuda.stream(s2):
+            h_out.copy_(d_out, non_blocking=True)
+
+    once()
+    ctx.barrier()
+    t = time.perf_counter()
+    for _ in range(iters):
+        once()
+    ctx.barrier()
+    dt = ctx.max_over_ranks([time.perf_counter() - t])[0]
+    return ctx.world * (nin + nout) * iters / dt / 1e9
+
+
 def measure(ctx, codec, steps, warmup, kind=KIND, with_host=True, with_cpu=True):
     """One codec on the 64 x 1080p batch; returns the JSON line's fields on rank 0 (None elsewhere)."""
     import torch
@@ -455,6 +482,9 @@ def measure(ctx, codec, steps, warmup, kind=KIND, with_host=True, with_cpu=True)
         for i in (0, n // 2, n - 1):
             assert d_host[i, :dev_lens[i]].tobytes() == host_streams[i], f"frame {i}: device-buffer and host-buffer paths differ"
         del h_frames, h_out
+    link_gbs = None
+    if with_host and codec == "jls" and kind == KIND:
+        link_gbs = host_link_probe(ctx, npix, max(1, total_bytes))
 
     # --- max over ranks ---
     dev_ms, e2e_ms, wall_ms = ctx.max_over_ranks([dev_ms, t_e2e * 1e3, t_wall * 1e3])
@@ -527,6 +557,11 @@ def measure(ctx, codec, steps, warmup, kind=KIND, with_host=True, with_cpu=True)
                        "transfer": ("page-locked host frames and slots through imcvtEncodeBatchJLS: the kernel reads the frames and writes "
                                     "the streams in place over PCIe every step (no staging copy in HBM)") if codec == "jls" else
                                    "page-locked host frames uploaded, streams downloaded through imcvtEncodeBatchHEVC every step"}
+    if with_host and link_gbs is not None:
+        line["e2e"]["host_link"] = {
+            "copy_ceiling_gbs": link_gbs, "achieved_gbs": world * (npix + d2h) * K / (e2e_ms / 1e3) / 1e9,
+            "what": ("copy_ceiling = all ranks copying this step's bytes (frames in, streams out) between page-locked host memory and "
+                     "HBM at once, both directions in flight, measured in this run; achieved = the same bytes over the e2e step time")}
     if parity is not None:
         line["parity"] = parity
     if cpu is not None:

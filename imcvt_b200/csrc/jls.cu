@@ -758,7 +758,7 @@ bool host_in_place_ok(int n, int is_rgb, uint32_t W, int near_)
     Engine &E = engine();
     const bool lossless = (near_ == 0) && !E.jls_force_serial;
     const bool use_tile = lossless && (int)W <= tile::WMAX && E.jls_path != 1;
-    const bool pair = E.jls_path == 3 || (E.jls_path == 0 && 2 * n <= E.sm_count);
+    const bool pair = E.jls_path == 3 || ((E.jls_path == 0 || E.jls_path == 6) && 2 * n <= E.sm_count);
     return !is_rgb && use_tile && pair;
 }
 
@@ -838,13 +838,14 @@ int encode_device(const uint8_t *d_frames, size_t frame_stride, int n, int is_rg
         }
         // Few planes: two SMs per plane (a cluster of two CTAs: rank 0 = producers, rank 1 = two chain stages + packers).
         // Many planes: one CTA per plane keeps every SM on a plane of its own.
-        const bool pair = E.jls_path == 3 || (E.jls_path == 0 && 2 * P <= E.sm_count);
+        const bool pair = E.jls_path == 3 || ((E.jls_path == 0 || E.jls_path == 6) && 2 * P <= E.sm_count);
         IMCVT_CUDA(cudaMemsetAsync(next, 0, sizeof(int), st));
         tile::Params TP;
         TP.pix = planes; TP.plane_stride = plane_stride; TP.P = P; TP.W = (int)W; TP.H = (int)H;
         TP.L = Lay; TP.plane_bytes = (unsigned long long *)plane_bytes; TP.next_plane = next;
         TP.prof = nullptr;
         TP.line_out = (out_is_host && ncomp == 1) ? 1 : 0;     // RGB scans 1, 2 go through device scratch and assemble_kernel
+        TP.tma = E.jls_path == 6 ? 0 : 1;                      // imcvtDebugJLSPath(6): row tiles through registers instead of bulk copies
 #ifdef IMCVT_JLS_PROF
         {
             if (!g_jls_prof) { IMCVT_CUDA(cudaMalloc(&g_jls_prof, 16 * 8)); IMCVT_CUDA(cudaMemset(g_jls_prof, 0, 16 * 8)); }

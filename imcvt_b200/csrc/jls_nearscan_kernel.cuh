@@ -380,18 +380,18 @@ nearscan_kernel(const uint8_t *__restrict__ pix, size_t plane_stride, int W, int
                     const uint32_t xo = *reinterpret_cast<const uint32_t *>(tp + Cfg<NEAR>::XW * 4) | ((uint32_t)sgn & 2048u);   // dq2[x + 255 | negative << 9]
                     const int hv = st.z >> 6;                                               // N >= 64: halve (:378-383; N never exceeds 64)
                     const int nn = (st.z >> hv) + 1;
-                    const int cm = max(st.y - 1, -128), cp = min(st.y + 1, 127);
                     int px = medn + (st.y ^ sgn);
                     px = min(max(px, 0), 255);
                     const uint32_t v = *reinterpret_cast<const uint32_t *>(dqb + xo - 4 * px);
                     sel = v >> 16;
                     const uint32_t wn = *reinterpret_cast<const uint32_t *>(tp + RS * 4 + sel);          // the next entry, before the state update
                     const int e = (int)(short)(v & 0xFFFFu);
-                    const int bh = (st.x + e * quant) >> hv;                                // :376-393, branch-free
-                    const bool c1 = bh <= -nn, c2 = bh > 0;
-                    const int b1 = max(bh + nn, 1 - nn), b2 = min(bh - nn, 0);
-                    st.x = c1 ? b1 : (c2 ? b2 : bh);
-                    st.y = c1 ? cm : (c2 ? cp : st.y);
+                    const int bh = (st.x + e * quant) >> hv;                                // :376-383
+                    // bias update :384-393 without branches: down = (B <= -N), up = (B > 0) as sign masks
+                    const int sdn = (bh + nn - 1) >> 31, sup = (-bh) >> 31;
+                    const int dc = sdn - sup;                                               // -1 / 0 / +1
+                    st.x = min(max(bh - nn * dc, 1 - nn), 0);
+                    st.y = min(max(st.y + dc, -128), 127);
                     st.z = nn;
                     *sp = st;
                     *reinterpret_cast<uint32_t *>(tp + Cfg<NEAR>::RECW * 4) = pack_halves(v, w);

@@ -138,6 +138,7 @@ struct Params {
     int *next_plane;                           // plane queue
     unsigned long long *prof;                  // role cycle counters (development build IMCVT_JLS_PROF only)
     int line_out;                              // 1: the output slots are page-locked HOST memory: write whole 128-byte lines
+    int tma;                                   // 1: row tiles are staged by bulk async copies (cp.async.bulk + mbarrier) when the plane allows it
 };
 
 #if defined(IMCVT_JLS_PROF) && !defined(IMCVT_HOST_EMU)
@@ -157,7 +158,8 @@ struct Smem {
     uint32_t ubits[UBITS_WORDS];    // packer: un-stuffed bits of one tile
     uint32_t chunk_bits[8];         // packer: code bits per chunk
     uint8_t  lens[2][LEN_SLOTS];    // code length per sample (0 = nothing), raster order (len_idx)
-    uint8_t  pix[3][PIXBUF];        // rows of a tile (+ the row above, + the sample two rows above column 0)
+    alignas(16) uint8_t pix[3][PIXBUF];     // rows of a tile (+ the row above, + the sample two rows above column 0); 16-byte aligned: bulk copies land here
+    alignas(8) unsigned long long stage_bar;   // mbarrier of the bulk copy in flight (one at a time: issued at the start of a tick, awaited at its end)
     int ctx[NCTX][4];               // (A, B, C, N) of every regular context of the plane in flight
     int ctx_a[NCTX];                // pair kernel: A lives with the second chain stage
     int run_state[8];               // run_index, A/B/N of the two run-interruption contexts, pending run length
@@ -266,6 +268,56 @@ __device__ __forceinline__ void pull_tile(uint8_t *dst, const uint8_t *remote, i
     const uint32_t *s4 = reinterpret_cast<const uint32_t *>(remote);
     uint32_t *d4 = reinterpret_cast<uint32_t *>(dst);
     for (int i = tid; i < words; i += nthr) d4[i] = s4[i];
+}
+
+// ---- row tiles by bulk asynchronous copy (TMA engine: cp.async.bulk global -> shared, completion on an mbarrier) -------------
+// One thread arms the barrier with the byte count and issues ONE copy for the rows of a tile (+ the row above it); nobody's
+// registers or issue slots move pixels.  The copy wants 16-byte aligned source, destination and size: planes whose width is
+// a multiple of 16 (and whose first byte is 16-byte aligned) qualify, the others keep the register staging.
+#ifdef IMCVT_HOST_EMU
+__device__ __forceinline__ void bulk_bar_init(unsigned long long *bar) { *bar = 0; }
+__device__ __forceinline__ void bulk_load(void *dst, const void *src, uint32_t bytes, unsigned long long *bar) { memcpy(dst, src, bytes); (void)bar; }
+__device__ __forceinline__ void bulk_wait(unsigned long long *bar, uint32_t parity) { (void)bar; (void)parity; }
+#else
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void bulk_bar_init(unsigned long long *bar)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(bar)) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void bulk_load(void *dst, const void *src, uint32_t bytes, unsigned long long *bar)
+{
+    const uint32_t b = smem_u32(bar);
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(b), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(b) : "memory");
+}
+__device__ __forceinline__ void bulk_wait(unsigned long long *bar, uint32_t parity)
+{
+    const uint32_t b = smem_u32(bar);
+    uint32_t done = 0;
+    while (!done) {
+        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                     : "=r"(done) : "r"(b), "r"(parity) : "memory");
+    }
+}
+#endif
+// whether the rows of this plane can be staged by bulk copies
+__device__ __forceinline__ bool bulk_ok(const Params &P, const uint8_t *img) { return P.tma && (P.W & 15) == 0 && ((size_t)img & 15) == 0; }
+// issue (one thread): the rows of tile t and the row above it, as stage_tile lays them out
+__device__ __forceinline__ void stage_bulk_issue(uint8_t *buf, const uint8_t *img, int W, int H, int rows_per_tile, int t, unsigned long long *bar)
+{
+    const int r0 = t * rows_per_tile, r1 = min(H, r0 + rows_per_tile);
+    const int first = r0 > 0 ? r0 - 1 : 0;
+    bulk_load(buf + 16 + (first - (r0 - 1)) * W, img + (size_t)first * W, (uint32_t)((r1 - first) * W), bar);
+}
+// the two things a bulk copy does not bring (all threads of the staging group; plain stores to other bytes than the copy's)
+__device__ __forceinline__ void stage_bulk_edges(uint8_t *buf, const uint8_t *img, int W, int rows_per_tile, int t, int tid, int nthr)
+{
+    const int r0 = t * rows_per_tile;
+    if (r0 == 0) for (int i = tid; i < W; i += nthr) buf[16 + i] = 0;     // the row above the picture reads as zeros (:47-49)
+    if (tid == 0) buf[0] = r0 >= 2 ? img[(size_t)(r0 - 2) * W] : 0;
 }
 
 // ---- producers ------------------------------------------------------------------------------------
@@ -387,7 +439,8 @@ constexpr int NBLK = (NBUCKET + 1 + 31) / 32;      // blocks of 32 histogram slo
 
 // sm: the producers' own shared memory; cons: where the sorted tile goes (the same image, or the partner CTA's)
 template <int NPW>
-__device__ __forceinline__ void producer_tick(Smem &sm, Smem &cons, const Params &P, const uint8_t *img, int rows_per_tile, int t, int ntiles, int nbuf, int pw, int lane)
+__device__ __forceinline__ void producer_tick(Smem &sm, Smem &cons, const Params &P, const uint8_t *img, int rows_per_tile, int t, int ntiles, int nbuf, int pw, int lane,
+                                              uint32_t &bulk_phase)
 {
     constexpr int PROD_WARPS = NPW, PROD_THREADS = NPW * 32;
     const int W = P.W, H = P.H;
@@ -398,7 +451,11 @@ __device__ __forceinline__ void producer_tick(Smem &sm, Smem &cons, const Params
     constexpr int NREG = SPLIT_STAGE ? (TSMAX + WMAX + 4 * NPW * 32 - 1) / (4 * NPW * 32) : 1;
     StageRegs<NREG> sregs;
     sregs.fast = false;
-    if (SPLIT_STAGE && t + 1 < ntiles) stage_issue<NREG>(sregs, sm.pix[(t + 1) % 3], img, W, H, rows_per_tile, t + 1, ptid, PROD_THREADS);
+    // the rows of the next tile: one bulk copy issued now and awaited at the end of the tick (its buffer was last read two
+    // ticks ago), or -- planes the copy engine cannot take -- loads into registers now, stores at the end
+    const bool bulk = bulk_ok(P, img);
+    if (bulk) { if (ptid == 0 && t + 1 < ntiles) stage_bulk_issue(sm.pix[(t + 1) % 3], img, W, H, rows_per_tile, t + 1, &sm.stage_bar); }
+    else if (SPLIT_STAGE && t + 1 < ntiles) stage_issue<NREG>(sregs, sm.pix[(t + 1) % 3], img, W, H, rows_per_tile, t + 1, ptid, PROD_THREADS);
     if (t < ntiles) {
         const int buf = t % nbuf;                  // tiles in flight: 2 (one CTA) or 3 (pair)
         uint8_t *pb = sm.pix[t % 3];
@@ -479,7 +536,12 @@ __device__ __forceinline__ void producer_tick(Smem &sm, Smem &cons, const Params
     }
     // rows of the next tile
     if (t + 1 < ntiles) {
-        if (SPLIT_STAGE) stage_commit<NREG>(sregs, sm.pix[(t + 1) % 3], img, W, H, rows_per_tile, t + 1, ptid, PROD_THREADS);
+        if (bulk) {
+            stage_bulk_edges(sm.pix[(t + 1) % 3], img, W, rows_per_tile, t + 1, ptid, PROD_THREADS);
+            bulk_wait(&sm.stage_bar, bulk_phase & 1u);                  // the barrier's phase flips with every copy of this CTA
+            bulk_phase++;
+        }
+        else if (SPLIT_STAGE) stage_commit<NREG>(sregs, sm.pix[(t + 1) % 3], img, W, H, rows_per_tile, t + 1, ptid, PROD_THREADS);
         else stage_tile(sm.pix[(t + 1) % 3], img, W, H, rows_per_tile, t + 1, ptid, PROD_THREADS);
     }
 }
@@ -952,6 +1014,8 @@ __device__ __forceinline__ void tile_body(const Params &P)
 
     if (consumer_cta) for (int i = tid; i < 2 * LEN_SLOTS / 4; i += NTHREADS) reinterpret_cast<uint32_t *>(&sm.lens[0][0])[i] = 0;
     if (producer_cta) build_qlut(sm.qlut, tid, NTHREADS);
+    uint32_t bulk_phase = 0;                        // bulk copies this CTA has awaited (every staging thread counts alike)
+    if (producer_cta && tid == 0) bulk_bar_init(&sm.stage_bar);     // in front of the first use: the barrier at the top of the plane loop
 
     for (;;) {
         if (PAIR) JLS_PAIR_SYNC(); else __syncthreads();
@@ -981,7 +1045,7 @@ __device__ __forceinline__ void tile_body(const Params &P)
 #endif
             if (PAIR) {
                 if (rank == 0) {
-                    producer_tick<NWARPS>(sm, cons, P, img, rows_per_tile, tick, ntiles, 3, warp, lane);
+                    producer_tick<NWARPS>(sm, cons, P, img, rows_per_tile, tick, ntiles, 3, warp, lane, bulk_phase);
                     JPROF(1, tid == 0);
                 } else if (warp < CHAIN_WARPS) {
                     if (tick >= 1 && tick - 1 < ntiles) chain1_tick(sm, tick - 1, tid);
@@ -1006,7 +1070,7 @@ __device__ __forceinline__ void tile_body(const Params &P)
                 JPROF(3, rank == 1 && tid == 0);
             } else {
                 if (warp >= CHAIN_WARPS && warp < CHAIN_WARPS + PROD_WARPS) {
-                    producer_tick<PROD_WARPS>(sm, sm, P, img, rows_per_tile, tick, ntiles, 2, warp - CHAIN_WARPS, lane);
+                    producer_tick<PROD_WARPS>(sm, sm, P, img, rows_per_tile, tick, ntiles, 2, warp - CHAIN_WARPS, lane, bulk_phase);
                     JPROF(1, warp == CHAIN_WARPS && lane == 0);
                     JPROF(5, warp == CHAIN_WARPS + PROD_WARPS - 1 && lane == 0);
                 } else if (warp < CHAIN_WARPS) {

@@ -25,6 +25,10 @@
  * (src/main.c:162-211) spread over the box.  A device only joins when its block is worth a CUDA context: at least 8 frames per
  * device for JPEG-LS, 2 for H.265.  The files are the same bytes whatever the number of devices.
  *
+ * The streams of a batch are written to their files by a writer thread while the main thread reads and encodes the next batch
+ * (the reference's fwrite per file, src/imageio_jls.c:467-472 / src/imageio_hevc.c:43-48, taken off the critical path); the
+ * files' lines are still printed in file order, and a file that reads or guards a name still being written waits for it.
+ *
  * Environment: IMCVT_DEVICE = CUDA device ordinal, that device only; IMCVT_DEVICES = "all" (default) | a count k (devices
  * 0..k-1) | a comma list of ordinals; IMCVT_BATCH = most frames per batch (default 256); IMCVT_TIMING = 1 prints where the
  * wall-clock time of the call went (stderr).
@@ -37,6 +41,7 @@
 #include <limits.h>
 #include <unistd.h>
 #include <time.h>
+#include <pthread.h>
 #include "imcvt_b200.h"
 #include "imcvt_pnm.h"
 
@@ -276,12 +281,65 @@ static int dump(const char *name, const uint8_t *buf, size_t len)
 
 /* ---- the pending batch ------------------------------------------------------------------------------------------- */
 
+/* the batch whose streams are being written (at most one in flight) */
+typedef struct {
+    pthread_t thread;
+    int active, n, encode_failed;
+    int idx[MAX_FILES];
+    uint8_t *out;
+    size_t *len, bound;
+    unsigned char write_failed[MAX_FILES];
+    double seconds;
+} Writer;
+static Writer g_writer;
+
+static void *writer_main(void *arg)
+{
+    Writer *Wr = (Writer *)arg;
+    const double t0 = now_s();
+    int i;
+    for (i = 0; i < Wr->n; i++) {
+        const Job *j = &g_jobs[Wr->idx[i]];
+        Wr->write_failed[i] = (unsigned char)(Wr->encode_failed || Wr->len[i] == 0 || dump(j->dst, Wr->out + (size_t)i * Wr->bound, Wr->len[i]));
+    }
+    Wr->seconds = now_s() - t0;
+    return NULL;
+}
+
+/* waits for the writer and settles its files' lines */
+static void writer_join(void)
+{
+    Writer *Wr = &g_writer;
+    int i;
+    if (!Wr->active)
+        return;
+    if (Wr->active == 1) {
+        const double t0 = now_s();
+        pthread_join(Wr->thread, NULL);
+        g_phase[T_WRITE] += now_s() - t0;           /* only what the main thread had to wait */
+    }
+    for (i = 0; i < Wr->n; i++) {
+        Job *j = &g_jobs[Wr->idx[i]];
+        if (Wr->write_failed[i]) {
+            fail(j, "write %s failed", j->dst);
+        } else {
+            j->ok = 1;
+            j->resolved = 1;
+        }
+    }
+    free(Wr->out);
+    free(Wr->len);
+    Wr->out = NULL; Wr->len = NULL;
+    Wr->active = 0;
+    print_resolved();
+}
+
 static void flush_batch(void)
 {
     Batch *B = &g_batch;
+    Writer *Wr = &g_writer;
     size_t bound, *len;
     uint8_t *out;
-    double t_write;
     int failed, i;
     if (B->n == 0)
         return;
@@ -310,21 +368,18 @@ static void flush_batch(void)
             fprintf(stderr, "imcvt_b200: %s\n", imcvtLastError());
         g_phase[T_ENCODE] += now_s() - t0;
     }
-    t_write = now_s();
-    for (i = 0; i < B->n; i++) {
-        Job *j = &g_jobs[B->idx[i]];
-        if (failed || len[i] == 0 || dump(j->dst, out + (size_t)i * bound, len[i])) {
-            fail(j, "write %s failed", j->dst);
-        } else {
-            j->ok = 1;
-            j->resolved = 1;
-        }
-    }
-    g_phase[T_WRITE] += now_s() - t_write;
-    free(out);
-    free(len);
+    /* the streams go to the writer thread; the arena is free for the next batch at once */
+    writer_join();
+    Wr->n = B->n; Wr->out = out; Wr->len = len; Wr->bound = bound; Wr->encode_failed = failed;
+    for (i = 0; i < B->n; i++) Wr->idx[i] = B->idx[i];
     B->n = 0;
-    print_resolved();
+    if (pthread_create(&Wr->thread, NULL, writer_main, Wr) == 0) {
+        Wr->active = 1;
+    } else {                                        /* no thread to be had: write here; writer_join() has nothing to wait for */
+        writer_main(Wr);
+        Wr->active = 2;
+        writer_join();
+    }
 }
 
 static void arena_release(void)
@@ -436,7 +491,18 @@ static void convert(int i_file, int force_write)
     int is_rgb = 0, failed = 0, i, staged = 0;
     FILE *fp;
 
-    /* sequential semantics: nothing this file reads or guards may still be owed by the pending batch */
+    /* sequential semantics: nothing this file reads or guards may still be owed by the writer thread or the pending batch */
+    if (g_writer.active) {
+        char *cs = canon_path(j->src);
+        for (i = 0; i < g_writer.n; i++) {
+            const char *pd = g_jobs[g_writer.idx[i]].canon_dst;
+            if (pd && ((cs && !strcmp(cs, pd)) || (j->canon_dst && !strcmp(j->canon_dst, pd)))) {
+                writer_join();
+                break;
+            }
+        }
+        free(cs);
+    }
     if (g_batch.n) {
         char *cs = canon_path(j->src);
         for (i = 0; i < g_batch.n; i++) {
@@ -571,6 +637,7 @@ int main(int argc, char **argv)
         print_resolved();
     }
     flush_batch();
+    writer_join();
     print_resolved();
     {
         const double t0 = now_s();

@@ -142,7 +142,8 @@ void imcvtDebugJLSForceSerial(int on);
  * multi-kernel pipeline that wider planes use, 2 = force one CTA per plane, 3 = force the two-CTA cluster (rank 0
  * produces sorted tiles into the shared memory of rank 1), 4 = NEAR > 0 / forced-serial scans on the plain
  * one-thread-per-plane kernel instead of the row-pipelined one, 5 = NEAR > 0 on the three-warp row scan instead of the
- * candidate-table kernel. */
+ * candidate-table kernel, 6 = default launch shapes, but the tile kernels stage their rows through registers instead of
+ * bulk asynchronous copies (cp.async.bulk). */
 void imcvtDebugJLSPath(int path);
 /* Debug / cross-check of the H.265 paths: 0 = default (a cluster of two CTAs per frame when the batch has at most SMs/2
  * frames, else one CTA per frame), 1 = force one CTA per frame, 2 = force the two-CTA cluster. */

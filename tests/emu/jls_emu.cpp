@@ -20,6 +20,7 @@ extern "C" size_t emu_jls_encode_mode(const uint8_t *img, int H, int W, uint8_t 
     P.L.ncomp = 1; P.L.hdr_len = 15; P.L.out = out; P.L.out_stride = cap - 2; P.L.scratch = nullptr; P.L.scratch_stride = 0;
     P.plane_bytes = &bytes; P.next_plane = &next;
     P.prof = nullptr;
+    P.tma = (W % 32 == 0) ? 1 : 0;      // both staging paths get exercised by the test shapes
     P.line_out = (pair >> 1) & 1;       // bit 1: stuffed bytes leave through the 128-byte line ring (output in host memory)
     pair &= 1;
     if (pair) emu::launch(1, 2 * tile::NTHREADS, 2 * tile::SMEM_STRIDE, [&] { tile::jls_pair_kernel(P); });

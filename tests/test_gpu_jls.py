@@ -130,6 +130,35 @@ def test_full_hd_frame_matches_oracle():
         check(f, 0)
 
 
+def test_row_tiles_by_bulk_copy_and_through_registers_give_the_same_streams(lossless_path):
+    """The tile kernels stage their rows with cp.async.bulk + mbarrier when the plane's width is a multiple of 16 (and fall back
+    to loads through registers otherwise); imcvtDebugJLSPath(6) forces the register path.  Same bytes either way, on both
+    launch shapes (64 frames: cluster pairs; 160: one CTA per plane), also with page-locked buffers coded in place."""
+    if lossless_path != 2:
+        pytest.skip("sets its own paths")
+    import ctypes as C
+    import torch
+    for n, h, w in ((3, 1080, 1920), (160, 33, 160), (5, 40, 1912)):
+        frames = synth.batch("natural", n, h, w)
+        imcvt_b200.debug_jls_path(0)
+        a = imcvt_b200.encode_jls_batch(frames, 0)
+        imcvt_b200.debug_jls_path(6)
+        b = imcvt_b200.encode_jls_batch(frames, 0)
+        imcvt_b200.debug_jls_path(0)
+        assert a == b, (n, h, w)
+        assert a[0] == oracle_jls(frames[0], 0) and a[-1] == oracle_jls(frames[-1], 0)
+    # page-locked frames and slots: the bulk copies read host memory over PCIe
+    frames = synth.batch("texture", 4, 270, 480)
+    stride = imcvt_b200.jls_bound(0, 270, 480)
+    h_in = torch.from_numpy(frames).pin_memory()
+    h_out = torch.zeros(4 * stride, dtype=torch.uint8).pin_memory()
+    lens = (C.c_size_t * 4)()
+    rc = imcvt_b200.lib().imcvtEncodeBatchJLS(h_in.numpy().ctypes.data, 270 * 480, 4, 0, 270, 480, 0, h_out.numpy().ctypes.data, stride, C.cast(lens, C.c_void_p))
+    assert rc == 0, imcvt_b200.last_error()
+    for i in range(4):
+        assert h_out.numpy()[i * stride:i * stride + lens[i]].tobytes() == oracle_jls(frames[i], 0), i
+
+
 def test_serial_kernel_equals_pipeline_at_full_size():
     frames = synth.batch("natural", 4, 1080, 1920)
     a = imcvt_b200.encode_jls_batch(frames, 0)
