@@ -638,11 +638,16 @@ def measure_c4(ctx):
     h_out = torch.empty(per * out_stride, dtype=torch.uint8).pin_memory()
     h_lens = (C.c_size_t * per)()
     hf, ho = h_frames.numpy(), h_out.numpy()
+
+    def step_host():
+        rc = imcvt_b200.lib().imcvtEncodeBatchJLS(hf.ctypes.data, fbytes, per, 1, BIG_H, BIG_W, C4_NEAR, ho.ctypes.data, out_stride, C.cast(h_lens, C.c_void_p))
+        if rc:
+            raise RuntimeError(imcvt_b200.last_error())
+
+    step_host()                                    # warm-up: the staging arena and the chunk workspaces (several GB) are allocated on first use
     ctx.barrier()
     t = time.perf_counter()
-    rc = imcvt_b200.lib().imcvtEncodeBatchJLS(hf.ctypes.data, fbytes, per, 1, BIG_H, BIG_W, C4_NEAR, ho.ctypes.data, out_stride, C.cast(h_lens, C.c_void_p))
-    if rc:
-        raise RuntimeError(imcvt_b200.last_error())
+    step_host()
     ctx.barrier()
     e2e_ms = (time.perf_counter() - t) * 1e3
     streams = [ho[i * out_stride:i * out_stride + h_lens[i]].tobytes() for i in range(per)]

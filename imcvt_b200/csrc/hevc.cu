@@ -70,8 +70,9 @@ int encode_device(const uint8_t *d_frames, size_t frame_stride, int n, uint32_t 
         const double t_single = makespan(jobs, E.sm_count), t_pair = makespan(jobs, E.sm_count / 2) / kPairGain;
         pair = t_pair < 0.97 * t_single;
     }
-    if (E.hevc_path == 1) pair = false;
-    if (E.hevc_path == 2) pair = true;
+    const int shape = E.hevc_path & 3, form = E.hevc_path >> 2;          // imcvtDebugHEVCPath: launch shape | search form << 2
+    if (shape == 1) pair = false;
+    if (shape == 2) pair = true;
     const int grid = pair ? 2 * (n < E.sm_count / 2 ? n : E.sm_count / 2)
                           : (n < E.sm_count ? n : E.sm_count);              // one CTA per SM; frames come from a queue
     const size_t rstride = (rbytes + 255) & ~(size_t)255;
@@ -99,6 +100,9 @@ int encode_device(const uint8_t *d_frames, size_t frame_stride, int n, uint32_t 
     P.nq = nq > 0 ? nq : 0;
     for (int k = 0; k < 8; k++) P.qlist[k] = (nq > 0 && k < nq) ? qlist[k] : 0;
     for (int k = 0; k < 8; k++) P.qorder[k] = qorder[k];
+    // 8x8 units: on a CTA pair the spine's warps walk the 4x4 rounds in lock step, a single CTA runs the alternatives as three
+    // warp groups side by side (measured, DESIGN.md section 4: the groups gain 14 % on one CTA per frame and lose on pairs)
+    P.cu8_lockstep = form == 1 ? 1 : form == 2 ? 0 : (pair ? 1 : 0);
     if (nq > 0) P.qpd6 = qlist[0];
 #ifdef IMCVT_HEVC_PROF
     {

@@ -146,7 +146,8 @@ void imcvtDebugJLSForceSerial(int on);
  * bulk asynchronous copies (cp.async.bulk). */
 void imcvtDebugJLSPath(int path);
 /* Debug / cross-check of the H.265 paths: 0 = default (a cluster of two CTAs per frame when the batch has at most SMs/2
- * frames, else one CTA per frame), 1 = force one CTA per frame, 2 = force the two-CTA cluster. */
+ * frames, else one CTA per frame), 1 = force one CTA per frame, 2 = force the two-CTA cluster; + 4 = search the 8x8 units with
+ * all warps in lock step, + 8 = with three warp groups side by side (default: lock step on pairs, groups on single CTAs). */
 void imcvtDebugHEVCPath(int path);
 
 #ifdef __cplusplus

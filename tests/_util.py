@@ -179,8 +179,9 @@ def fullsize_table():
         return json.load(f)
 
 
-def emu_hevc(img, qpd6, pair=False):
-    """The SOURCE of the CUDA HEVC kernel run under the CPU SIMT emulator (tests/emu, test infrastructure)."""
+def emu_hevc(img, qpd6, pair=False, lockstep=False):
+    """The SOURCE of the CUDA HEVC kernel run under the CPU SIMT emulator (tests/emu, test infrastructure).
+    lockstep: the 8x8 units searched with all warps in lock step (Params::cu8_lockstep) instead of by three warp groups."""
     if "emu" not in _libs:
         d = os.path.join(ROOT, "tests", "emu")
         subprocess.run(["make", "-C", d, "-s", "libhevc_emu.so"], check=True, capture_output=True)
@@ -196,7 +197,7 @@ def emu_hevc(img, qpd6, pair=False):
     out = np.zeros(2 * (wp + 32) * (hp + 32) + 65536, dtype=np.uint8)
     rcon = np.zeros(hp * wp, dtype=np.uint8)
     ch, cw = C.c_int(h), C.c_int(w)
-    n = _libs["emu"].emu_hevc_encode_mode(out.ctypes.data, out.size, img.ctypes.data, rcon.ctypes.data, C.byref(ch), C.byref(cw), qpd6, 1 if pair else 0)
+    n = _libs["emu"].emu_hevc_encode_mode(out.ctypes.data, out.size, img.ctypes.data, rcon.ctypes.data, C.byref(ch), C.byref(cw), qpd6, (1 if pair else 0) | (2 if lockstep else 0))
     assert n > 0 and ch.value == hp and cw.value == wp
     return out[:n].tobytes(), rcon.reshape(hp, wp).copy()
 

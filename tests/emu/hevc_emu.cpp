@@ -12,9 +12,12 @@ extern "C" long emu_hevc_encode(uint8_t *stream, size_t cap, const uint8_t *img,
 {
     return emu_hevc_encode_mode(stream, cap, img, img_rcon, ysz, xsz, qpd6, 0);
 }
-// pair = 1: the two-CTA cluster kernel (spine + upper), both CTAs' threads as fibers of one emulated cluster
+// pair bit 0: the two-CTA cluster kernel (spine + upper), both CTAs' threads as fibers of one emulated cluster;
+// bit 1: the 8x8 units searched in lock step (Params::cu8_lockstep) instead of by three warp groups
 extern "C" long emu_hevc_encode_mode(uint8_t *stream, size_t cap, const uint8_t *img, uint8_t *img_rcon, int *ysz, int *xsz, int qpd6, int pair)
 {
+    const int lockstep = (pair >> 1) & 1;
+    pair &= 1;
     const int H = *ysz, W = *xsz;
     const int hp = (std::min(H, 8192) + 31) / 32 * 32, wp = (std::min(W, 8192) + 31) / 32 * 32;
     Params P;
@@ -28,6 +31,7 @@ extern "C" long emu_hevc_encode_mode(uint8_t *stream, size_t cap, const uint8_t 
     P.scratch = scratch.data(); P.lists = lists.data(); P.overflow = &overflow; P.next_frame = &next;
     P.prof = nullptr;
     P.nq = 0;
+    P.cu8_lockstep = lockstep;
     for (int k = 0; k < 8; k++) P.qorder[k] = k;
     if (pair) emu::launch(1, NT, sizeof(Smem), [&] { hevc_pair_kernel(P); }, 2);
     else emu::launch(1, NT, sizeof(Smem), [&] { hevc_frame_kernel(P); });
@@ -51,6 +55,7 @@ extern "C" int emu_hevc_sweep(uint8_t *streams, size_t cap, const uint8_t *img, 
     P.scratch = scratch.data(); P.lists = lists.data(); P.overflow = &overflow; P.next_frame = &next;
     P.prof = nullptr;
     P.nq = nq;
+    P.cu8_lockstep = pair ? 1 : 0;                  // the product's defaults: pairs in lock step, single CTAs by groups
     for (int k = 0; k < 8; k++) P.qlist[k] = k < nq ? qlist[k] : 0;
     // the queue order of the product's host side (hevc.cu): settings by ascending qpd6, ties in list order
     for (int k = 0; k < 8; k++) P.qorder[k] = k;

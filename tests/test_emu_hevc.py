@@ -17,11 +17,14 @@ def images():
     yield "1x1", np.array([[77]], dtype=np.uint8)
 
 
+@pytest.mark.parametrize("lockstep", [False, True], ids=["warp-groups", "lock-step"])
 @pytest.mark.parametrize("pair", [False, True], ids=["one-cta", "cluster-pair"])
 @pytest.mark.parametrize("qpd6", [0, 2, 4])
-def test_kernel_source_matches_oracle(qpd6, pair):
+def test_kernel_source_matches_oracle(qpd6, pair, lockstep):
+    if lockstep and qpd6 == 2:
+        pytest.skip("two settings are enough for the second search form")
     for name, img in images():
-        s, r = emu_hevc(img, qpd6, pair)
+        s, r = emu_hevc(img, qpd6, pair, lockstep)
         s2, r2 = oracle_hevc(img, qpd6)
         assert s == s2, f"{name}: stream differs"
         assert np.array_equal(r, r2), f"{name}: reconstruction differs"

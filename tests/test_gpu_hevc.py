@@ -14,10 +14,11 @@ from tests.test_oracle_hevc import fixture_gray, hevc_edge_images
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(params=[1, 2], ids=["one-cta", "cluster-pair"], autouse=True)
+@pytest.fixture(params=[1, 2, 5, 10], ids=["one-cta", "cluster-pair", "one-cta-lockstep", "cluster-pair-groups"], autouse=True)
 def hevc_path(request):
-    """Every test runs on both device paths: one CTA per frame, and a cluster of two CTAs per frame (the default for
-    batches of at most SMs/2 frames)."""
+    """Every test runs on both launch shapes -- one CTA per frame, and a cluster of two CTAs per frame (the default for
+    batches of at most SMs/2 frames) -- and on both forms of the 8x8 search (imcvtDebugHEVCPath: + 4 lock step, + 8 warp
+    groups; each shape's default form first)."""
     imcvt_b200.debug_hevc_path(request.param)
     yield request.param
     imcvt_b200.debug_hevc_path(0)
@@ -91,6 +92,8 @@ def test_full_hd_streams_decode_to_the_encoders_reconstruction(hevc_path):
     independent decoder stands in: FFmpeg (through OpenCV) must decode every emitted stream to exactly the reconstruction
     the encoder kept -- at qpd6 <= 1 the stream's in-loop deblocking leaves the picture unchanged.
     The first CTU row of frame 0 is also compared with the oracle bit for bit."""
+    if hevc_path > 3:
+        pytest.skip("the default search form of each launch shape is enough at this size")
     cv2 = pytest.importorskip("cv2")
     frames = synth.batch("natural", 2, 1080, 1920)
     streams, rcon = imcvt_b200.encode_hevc_batch(frames, 1)
