@@ -2,7 +2,7 @@
 (oracle/_ref/libimcvt_ref.so) for synthetic frames at BASELINE.json's full sizes, where the reference needs
 30 s .. 5 min of CPU per frame (run in the build container, where /root/reference exists):
 
-    python tests/golden/make_golden_fullsize.py [threads]
+    python tests/golden/make_golden_fullsize.py [threads] [--all]
 
 The frames come from imcvt_b200/synth.py (integer-only, the same bytes on every machine), so the GPU tier can
 check byte-level parity at 1920x1080 and 3840x2160 against these hashes without re-running the reference; the
@@ -29,6 +29,9 @@ JOBS = [
     ("jls", "texture", 0, 1080, 1920, False, 0), ("jls", "noise", 0, 1080, 1920, False, 0),
     ("jls", "natural", 0, 1080, 1920, False, 2),
 ]
+# the sample frames of the 256-frame 3840x2160 batches (configs[3] / configs[4]) the reference is run on in full
+JOBS += [("hevc", "natural", i, 2160, 3840, False, q) for i in (85, 170, 255) for q in (1, 2, 3, 4)]
+JOBS += [("jls", "natural", i, 2160, 3840, True, 2) for i in (85, 170, 255)]
 
 
 def run(job):
@@ -43,8 +46,16 @@ def run(job):
 
 
 if __name__ == "__main__":
-    threads = int(sys.argv[1]) if len(sys.argv) > 1 else (os.cpu_count() or 1)
+    threads = int(sys.argv[1]) if len(sys.argv) > 1 and sys.argv[1].isdigit() else (os.cpu_count() or 1)
+    # entries already in the table are kept (the reference and synth.py are fixed); only missing jobs run
+    path = os.path.join(GOLDEN, "fullsize_answers.json")
+    have = json.load(open(path)) if os.path.exists(path) and "--all" not in sys.argv else []
+    key = lambda e: (e["codec"], e["kind"], e["index"], e["height"], e["width"], e["rgb"], e["setting"])
+    done = {key(e): e for e in have}
+    todo = [j for j in JOBS if j not in done]
     with ThreadPoolExecutor(max_workers=threads) as ex:
-        out = list(ex.map(run, JOBS))
+        for e in ex.map(run, todo):
+            done[key(e)] = e
+    out = [done[j] for j in JOBS]
     json.dump(out, open(os.path.join(GOLDEN, "fullsize_answers.json"), "w"), indent=1)
     print(len(out), "entries")

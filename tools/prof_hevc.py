@@ -1,5 +1,5 @@
 """Phase profile of hevc_frame_kernel (development aid; needs `make -C imcvt_b200/csrc PROF=1`).
-   python tools/prof_hevc.py [kind] [n] [qpd6] [h] [w]"""
+   python tools/prof_hevc.py [kind] [n] [qpd6] [h] [w] [path]"""
 import ctypes as C, os, sys
 os.environ.setdefault("IMCVT_B200_LIB", "libimcvt_b200_prof.so")
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -12,8 +12,10 @@ n = int(sys.argv[2]) if len(sys.argv) > 2 else 64
 q = int(sys.argv[3]) if len(sys.argv) > 3 else 4
 h = int(sys.argv[4]) if len(sys.argv) > 4 else 128
 w = int(sys.argv[5]) if len(sys.argv) > 5 else 256
+path = int(sys.argv[6]) if len(sys.argv) > 6 else 0          # imcvtDebugHEVCPath: launch shape | search form << 2
 frames = synth.batch(kind, n, h, w)
 imcvt_b200.init(0)
+imcvt_b200.debug_hevc_path(path)
 d = torch.from_numpy(frames).cuda()
 out = torch.empty((n, imcvt_b200.hevc_bound(h, w)), dtype=torch.uint8, device="cuda")
 lens = torch.zeros(n, dtype=torch.int64, device="cuda")
