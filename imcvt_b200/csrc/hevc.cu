@@ -100,9 +100,10 @@ int encode_device(const uint8_t *d_frames, size_t frame_stride, int n, uint32_t 
     P.nq = nq > 0 ? nq : 0;
     for (int k = 0; k < 8; k++) P.qlist[k] = (nq > 0 && k < nq) ? qlist[k] : 0;
     for (int k = 0; k < 8; k++) P.qorder[k] = qorder[k];
-    // 8x8 units: on a CTA pair the spine's warps walk the 4x4 rounds in lock step, a single CTA runs the alternatives as three
-    // warp groups side by side (measured, DESIGN.md section 4: the groups gain 14 % on one CTA per frame and lose on pairs)
-    P.cu8_lockstep = form == 1 ? 1 : form == 2 ? 0 : (pair ? 1 : 0);
+    // 8x8 units: the round form (warps 0-9 walk the four 4x4 rounds together, one-TU pipelines beside round 0) on both launch
+    // shapes; the three-warp-group form stays selectable as a cross-check (measured round 2, 96 frames on single CTAs: 3.38 s
+    // against 3.96 s; CTA pairs, 64 frames: 2.18 s against 2.62 s)
+    P.cu8_lockstep = form == 2 ? 0 : 1;
     if (nq > 0) P.qpd6 = qlist[0];
 #ifdef IMCVT_HEVC_PROF
     {

@@ -31,6 +31,7 @@
 #define HEVC_PAIR_SMEM(r) (emu::cluster_smem(r))
 #define HEVC_PAIR_SYNC() emu_cluster_sync()
 #define HEVC_CLUSTER_DIMS
+#define HEVC_SMEM(K) (*(K).sm)
 #else
 #include <cooperative_groups.h>
 #define IMCVT_CONSTANT __constant__ const
@@ -40,6 +41,9 @@ extern __shared__ __align__(16) unsigned char imcvt_dyn_smem[];
 #define HEVC_PAIR_SMEM(r) (cooperative_groups::this_cluster().map_shared_rank(imcvt_dyn_smem, (r)))
 #define HEVC_PAIR_SYNC() cooperative_groups::this_cluster().sync()
 #define HEVC_CLUSTER_DIMS __cluster_dims__(2, 1, 1)
+// A CTA's own shared memory, named through the __shared__ symbol in every function that uses it: read through the pointer kept
+// in Ctx it is a generic address, and every access becomes a 64-bit generic load / store instead of LDS / STS.
+#define HEVC_SMEM(K) (*reinterpret_cast<Smem *>(imcvt_dyn_smem))
 #endif
 
 namespace imcvt {
@@ -62,10 +66,15 @@ namespace hevc {
 #define TPROF_START(sm) do { } while (0)
 #endif
 
+// bar.sync id, count: `count` threads (whole warps) meet at barrier `id`.  bar.arrive: a producer warp counts towards the barrier
+// and goes on; only the consumers wait.  The fence in front of the arrive orders the producer's global-memory stores (bin lists)
+// as the barrier itself orders shared memory.
 #ifdef IMCVT_HOST_EMU
 #define HEVC_NAMED_BARRIER(id, count) emu_named_barrier(id, count)
+#define HEVC_NAMED_ARRIVE(id, count) emu_named_arrive(id, count)
 #else
 #define HEVC_NAMED_BARRIER(id, count) asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory")
+#define HEVC_NAMED_ARRIVE(id, count) do { __threadfence_block(); asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory"); } while (0)
 #endif
 // the transform-unit pipeline, the binariser and the block coder are inlined into the phases that use them
 #define HEVC_BIGFN __device__ __forceinline__
@@ -208,6 +217,14 @@ struct Smem {
 };
 
 static_assert(sizeof(Smem) <= SMEM_LIMIT, "hevc Smem does not fit the 227 KB a CTA can have");
+
+// a pointer into this CTA's shared memory that came through memory (a struct member, a function argument) and is therefore a
+// generic address: the same address, derived from the __shared__ symbol so that the compiler knows the address space
+template <class T> __device__ __forceinline__ T *own_smem(T *p)
+{
+    unsigned char *base = IMCVT_DYN_SMEM();
+    return reinterpret_cast<T *>(base + (unsigned)(reinterpret_cast<unsigned char *>(p) - base));
+}
 
 // ------------------------------------------------------------------------------------------------
 // small helpers
@@ -377,38 +394,12 @@ __device__ __forceinline__ void mpm_list(int l, int a, int m[3])                
 // produced, lanes would sit at different call sites and run one after the other.  So the syntax in front of a block's
 // coefficient groups (coding-unit head, cbf flags, last position) is first written as bin-list entries into a small
 // per-trial list, and the coder is only ever stepped from the loop of code_block / emit_list, where the lanes converge.
+__device__ __forceinline__ unsigned pack4(const int *v) { return (unsigned)v[0] | ((unsigned)v[1] << 8) | ((unsigned)v[2] << 16) | ((unsigned)v[3] << 24); }
 struct PreList {
     unsigned short *p; int n;
     __device__ __forceinline__ void ctx(int ci, int bin) { p[n++] = (unsigned short)((bin << 8) | ci); }                       // = ent_ctx(0, ci, bin)
     __device__ __forceinline__ void byp(int val, int len) { p[n++] = (unsigned short)((3 << 14) | (len << 8) | (val & ((1 << len) - 1))); }   // = ent_byp, len <= 8
 };
-
-// all prev_intra_luma_pred flags first, then mpm_idx / rem_intra_luma_pred_mode (putYpmode :984-1017)
-__device__ inline void build_luma_modes(PreList &L, int count, const int *mode, const int *left, const int *above)
-{
-    int hit[4];
-    for (int i = 0; i < count; i++) {
-        int m[3];
-        mpm_list(left[i], above[i], m);
-        hit[i] = -1;
-        for (int j = 0; j < 3; j++) if (m[j] == mode[i]) hit[i] = j;
-        L.ctx(CX_YMODE, hit[i] >= 0);
-    }
-    for (int i = 0; i < count; i++) {
-        if (hit[i] >= 0) {
-            L.byp(hit[i] > 0, 1);
-            if (hit[i] > 0) L.byp(hit[i] - 1, 1);
-        } else {
-            int m[3], t, rem = mode[i];
-            mpm_list(left[i], above[i], m);
-            if (m[0] < m[1]) { t = m[0]; m[0] = m[1]; m[1] = t; }
-            if (m[1] < m[2]) { t = m[1]; m[1] = m[2]; m[2] = t; }
-            if (m[0] < m[1]) { t = m[0]; m[0] = m[1]; m[1] = t; }
-            for (int j = 0; j < 3; j++) if (rem > m[j]) rem--;
-            L.byp(rem, 5);
-        }
-    }
-}
 
 __device__ __forceinline__ int pos_group(int v)        // last-position group index (:1046)
 {
@@ -628,17 +619,34 @@ __device__ __forceinline__ unsigned entry_of(const Entry8 &v, int k)
 }
 
 // Arithmetic coding of one transform unit from its bin lists (one lane).  slots / hdrs point at the unit's group 0.
-HEVC_BIGFN void code_block(Coder &c, int sz, int mode, int last, unsigned cgp0, unsigned cgp1, unsigned sg0, unsigned sg1,
-                                           const unsigned short *slots, const unsigned short *hdrs, const uint8_t (*scan_all)[2], PreList &pre)
+// sz == 0: no unit, only what waits in `pre` is coded (blocks without coefficients, the tail of a trial).
+// ONE copy of this function serves every trial of the kernel (a real call, HEVC_PHASE): the trials are single lanes walking
+// through code that nothing else keeps warm, and the kernel is bound by instruction fetch -- inlined
+// at its seven call sites the coder loop alone was 80 KB of a coding unit's instruction stream.
+HEVC_PHASE void code_stream(Coder &c_io, PreList &pre_io, const uint8_t (*scan_all)[2], int sz, int mode, int last,
+                            unsigned cgp0, unsigned cgp1, unsigned sg0, unsigned sg1, const unsigned short *slots, const unsigned short *hdrs)
 {
-    // the entries waiting in `pre` (head of the coding unit, cbf flags) go first, then the last position, then the groups
-    const int st = scan_type_for(sz, mode), ncg = sz >> 2;
-    const uint8_t (*scan)[2] = scan_all + scan_base(st, size_class(sz));
-    build_last_pos(pre, sz, st, scan[last][0], scan[last][1]);
-    int cg = last >> 4, prevbig = 0, add = 0, k = 0, pk = 0;
-    unsigned h = hdrs[cg];
+    Coder c = c_io;                                                     // registers inside; the caller's copy is in local memory across the call
+    PreList pre = pre_io;
+    // pointers that arrive through memory are generic addresses; contexts, tables and the prefix list live in this CTA's shared
+    // memory: named through the __shared__ symbol again, their accesses are LDS / STS
+    Smem &sm = *reinterpret_cast<Smem *>(IMCVT_DYN_SMEM());
+    c.ctx = own_smem(c.ctx); c.lps = sm.lpsw; c.nlps = sm.next_lps;
+    pre.p = own_smem(pre.p);
+    scan_all = sm.scan;
+    const int st = sz ? scan_type_for(sz, mode) : 0, ncg = sz >> 2;
+    const uint8_t (*scan)[2] = scan_all + (sz ? scan_base(st, size_class(sz)) : 0);
+    int cg = sz ? last >> 4 : 0, prevbig = 0, add = 0, k = 0, pk = 0;
+    // the first group's header and entries are requested before the last position is binarised: an L2 round trip (another warp
+    // wrote them) that the prefix work covers
+    unsigned h = 0;
     const Entry8 *sp = reinterpret_cast<const Entry8 *>(slots + cg * SLOT);
-    Entry8 ev = sp[0];
+    Entry8 ev; ev.w[0] = ev.w[1] = ev.w[2] = ev.w[3] = 0;
+    if (sz) {
+        h = hdrs[cg];
+        ev = sp[0];
+        build_last_pos(pre, sz, st, scan[last][0], scan[last][1]);
+    }
     int cnt = (int)(h & 0x7Fu);
     for (;;) {
         int isb = 0, a = 0, b = 0;
@@ -675,29 +683,63 @@ HEVC_BIGFN void code_block(Coder &c, int sz, int mode, int last, unsigned cgp0, 
         }
         if (emit) { if (isb) c.bypass_chunk(a, b); else c.bin(b, a); }
     }
-    pre.n = 0;
+    c_io.range = c.range; c_io.low = c.low; c_io.nbits = c.nbits; c_io.pending = c.pending; c_io.held = c.held; c_io.zeros = c.zeros; c_io.nout = c.nout;
+    pre_io.n = 0;
 }
-
+__device__ __forceinline__ void code_block(Coder &c, int sz, int mode, int last, unsigned cgp0, unsigned cgp1, unsigned sg0, unsigned sg1,
+                                           const unsigned short *slots, const unsigned short *hdrs, const uint8_t (*scan_all)[2], PreList &pre)
+{
+    code_stream(c, pre, scan_all, sz, mode, last, cgp0, cgp1, sg0, sg1, slots, hdrs);
+}
 // steps the coder through what is left in a prefix list (blocks without coefficients do not call code_block)
-__device__ __forceinline__ void emit_list(Coder &c, PreList &pre)
+__device__ __forceinline__ void emit_list(Coder &c, PreList &pre, const uint8_t (*scan_all)[2], const unsigned short *any_list)
 {
-    for (int k = 0; k < pre.n; k++) {
-        const unsigned e = pre.p[k];
-        if ((e >> 14) == 3) c.bypass_chunk((int)(e & 0xFFu), (int)((e >> 8) & 15u));
-        else c.bin((int)((e >> 8) & 1u), (int)(e & 0xFFu));
-    }
-    pre.n = 0;
+    if (pre.n) code_stream(c, pre, scan_all, 0, 0, 0, 0u, 0u, 0u, 0u, any_list, any_list);
 }
 
-// coding-unit syntax before the residual (putCU_* :1271-1339 up to the cbf flags)
-__device__ __forceinline__ void build_cu_head(PreList &L, int sz, int kind, const int *modes, const int *left, const int *above)
+// coding-unit syntax before the residual (putCU_* :1271-1339 up to the cbf flags).  modes / left / above: one byte per
+// prediction unit (kind 2 = NxN: four, else one).  All prev_intra_luma_pred flags first, then mpm_idx /
+// rem_intra_luma_pred_mode (putYpmode :984-1017).  One compact copy (a real call, rolled loops): it runs once per trial on one
+// lane, its size is its cost.
+HEVC_PHASE void build_cu_head(PreList &L_io, int sz, int kind, unsigned modes, unsigned left, unsigned above)
 {
+    PreList L = L_io;
+    L.p = own_smem(L.p);
     if (sz == 8) L.ctx(CX_PART, kind != 2);                                            // putPartSize :951-954
-    build_luma_modes(L, kind == 2 ? 4 : 1, modes, left, above);
+    const int count = kind == 2 ? 4 : 1;
+    unsigned hits = 0;                                                                 // two bits per unit: 0 = not a probable mode, else index + 1
+#pragma unroll 1
+    for (int i = 0; i < count; i++) {
+        int m[3];
+        mpm_list((int)((left >> (8 * i)) & 255u), (int)((above >> (8 * i)) & 255u), m);
+        const int md = (int)((modes >> (8 * i)) & 255u);
+        const unsigned hit = m[2] == md ? 3u : m[1] == md ? 2u : m[0] == md ? 1u : 0u;  // the last match of :990-993
+        hits |= hit << (2 * i);
+        L.ctx(CX_YMODE, hit != 0);
+    }
+#pragma unroll 1
+    for (int i = 0; i < count; i++) {
+        const int hit = (int)((hits >> (2 * i)) & 3u);
+        if (hit) {
+            L.byp(hit > 1, 1);
+            if (hit > 1) L.byp(hit - 2, 1);
+        } else {
+            int m[3], t, rem = (int)((modes >> (8 * i)) & 255u);
+            mpm_list((int)((left >> (8 * i)) & 255u), (int)((above >> (8 * i)) & 255u), m);
+            if (m[0] < m[1]) { t = m[0]; m[0] = m[1]; m[1] = t; }
+            if (m[1] < m[2]) { t = m[1]; m[1] = m[2]; m[2] = t; }
+            if (m[0] < m[1]) { t = m[0]; m[0] = m[1]; m[1] = t; }
+            if (rem > m[0]) rem--;
+            if (rem > m[1]) rem--;
+            if (rem > m[2]) rem--;
+            L.byp(rem, 5);
+        }
+    }
     L.ctx(CX_UVMODE, 0);                                                               // chroma mode "derived" :1020-1022
     if (kind != 2) L.ctx(CX_SPLIT_TU + (sz == 32 ? 0 : sz == 16 ? 1 : 2), kind == 1);  // :1025-1032
     L.ctx(CX_UVCBF + 0, 0);                                                            // cbf_cb, cbf_cr at depth 0
     L.ctx(CX_UVCBF + 0, 0);
+    L_io.n = L.n;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1162,14 +1204,14 @@ __device__ __forceinline__ void warp_best(Smem &sm, const RdK &rd, int first, in
 template <int SZ>
 HEVC_PHASE void trial_cu(Ctx &K, int c, const CoderRegs &entry, int entry_bits_rel, int split_ctx, int mode_l, int mode_a)
 {
-    Smem &sm = *K.sm;
+    Smem &sm = HEVC_SMEM(K);
     constexpr int H = SZ / 2, SET = Level<SZ>::set;
     const int kind = c >= NMODE, mode = c - kind * NMODE;
     Coder cd; cd.load(entry); cd.nout = 0;
     attach(cd, sm, sm.cctx[SET][c], K.scratch[SET] + (size_t)c * SCR_BYTES, SCR_BYTES);
     PreList pre; pre.p = sm.tpre[c]; pre.n = 0;
     if (SZ >= 16) pre.ctx(CX_SPLIT_CU + split_ctx, 0);               // putSplitCUflag :942-946
-    build_cu_head(pre, SZ, kind, &mode, &mode_l, &mode_a);
+    build_cu_head(pre, SZ, kind, (unsigned)mode, (unsigned)mode_l, (unsigned)mode_a);
     const unsigned short *lst = K.lists[SET] + (size_t)c * CAND_LIST_U16;
     const int tsz = kind ? H : SZ, ncg = (tsz / 4) * (tsz / 4);
     for (int i = 0; i < (kind ? 4 : 1); i++) {
@@ -1179,11 +1221,45 @@ HEVC_PHASE void trial_cu(Ctx &K, int c, const CoderRegs &entry, int entry_bits_r
         if (cbf) code_block(cd, tsz, mode, sm.clast[SET][c][i], g0, g1, sm.csg[SET][c][i][0], sm.csg[SET][c][i][1],
                             lst + (size_t)i * ncg * SLOT, lst + 64 * SLOT + i * ncg, sm.scan, pre);
     }
-    emit_list(cd, pre);
+    emit_list(cd, pre, sm.scan, lst);
     cd.store(sm.ccoder[SET][c]);
     sm.cbits[SET][c] = cd.bits() - entry_bits_rel;
 }
 
+
+// 8x8 units: CABAC trial of four-TU candidate NMODE + c (:1455-1473) block by block, as the blocks arrive -- block i of every
+// candidate is published by the warps that run its pipeline with bar.arrive on barrier bar0 + i; this trial waits there, so only
+// the last block's bins are left to code once the last pipelines are through.  Called by WHOLE warps (`nthreads` = the waiting
+// threads plus the arriving ones); lanes without a candidate (c < 0) only keep the barriers company.
+HEVC_PHASE void trial_cu8_four(Ctx &K, int c, const CoderRegs &entry, int entry_bits_rel, int mode_l, int mode_a, int bar0, int nthreads)
+{
+    Smem &sm = HEVC_SMEM(K);
+    constexpr int SET = 1;
+    const bool on = c >= 0;
+    const int mode = on ? c : 0, cand = NMODE + mode;
+    Coder cd; cd.load(entry); cd.nout = 0;
+    attach(cd, sm, sm.cctx[SET][cand], K.scratch[SET] + (size_t)cand * SCR_BYTES, SCR_BYTES);
+    PreList pre; pre.p = sm.tpre[cand]; pre.n = 0;
+    if (on) build_cu_head(pre, 8, 1, (unsigned)mode, (unsigned)mode_l, (unsigned)mode_a);
+    const unsigned short *lst = K.lists[SET] + (size_t)cand * CAND_LIST_U16;
+#pragma unroll 1
+    for (int i = 0; i < 4; i++) {
+        __syncwarp();
+        HEVC_NAMED_BARRIER(bar0 + i, nthreads);
+        if (on) {
+            const unsigned g0 = sm.ccg[SET][cand][i][0];
+            const int cbf = g0 != 0;
+            pre.ctx(CX_YCBF + 0, cbf);                                   // :1039
+            if (cbf) code_block(cd, 4, mode, sm.clast[SET][cand][i], g0, 0u, sm.csg[SET][cand][i][0], 0u,
+                                lst + (size_t)i * SLOT, lst + 64 * SLOT + i, sm.scan, pre);
+        }
+    }
+    if (on) {
+        emit_list(cd, pre, sm.scan, lst);
+        cd.store(sm.ccoder[SET][cand]);
+        sm.cbits[SET][cand] = cd.bits() - entry_bits_rel;
+    }
+}
 
 
 // ------------------------------------------------------------------------------------------------
@@ -1214,7 +1290,7 @@ template <int SZ> struct SubUnits {
 template <int SZ>
 __device__ __forceinline__ void cu_enter(Ctx &K, int y0, int x0, int avail)
 {
-    Smem &sm = *K.sm;
+    Smem &sm = HEVC_SMEM(K);
     constexpr int LV = Level<SZ>::v;
     const int tid = threadIdx.x, cy = y0 / 4, cx = x0 / 4;
     __syncthreads();
@@ -1233,7 +1309,7 @@ __device__ __forceinline__ void cu_enter(Ctx &K, int y0, int x0, int avail)
 template <int SZ>
 __device__ __forceinline__ void put_split_flag(Ctx &K)
 {
-    Smem &sm = *K.sm;
+    Smem &sm = HEVC_SMEM(K);
     if (threadIdx.x == 0) {
         Coder c; c.load(sm.cur); attach(c, sm, sm.cur_ctx, K.out, (unsigned)K.P->out_stride);
         c.bin(1, CX_SPLIT_CU + sm.par[Level<SZ>::v].split_ctx);
@@ -1244,7 +1320,7 @@ __device__ __forceinline__ void put_split_flag(Ctx &K)
 template <int SZ>
 __device__ __forceinline__ void cu_split_cost(Ctx &K)
 {
-    Smem &sm = *K.sm;
+    Smem &sm = HEVC_SMEM(K);
     constexpr int LV = Level<SZ>::v;
     const int tid = threadIdx.x, y0 = sm.par[LV].y0, x0 = sm.par[LV].x0;
     __syncthreads();
@@ -1266,7 +1342,7 @@ __device__ __forceinline__ void cu_split_cost(Ctx &K)
 template <int SZ>
 HEVC_PHASE void eval_a1(Ctx &K)
 {
-    Smem &sm = *K.sm;
+    Smem &sm = HEVC_SMEM(K);
     constexpr int LV = Level<SZ>::v, SET = Level<SZ>::set;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const CuPar q = sm.par[LV];
@@ -1293,7 +1369,7 @@ HEVC_PHASE void eval_a1(Ctx &K)
 template <int SZ>
 HEVC_PHASE void eval_a4(Ctx &K)
 {
-    Smem &sm = *K.sm;
+    Smem &sm = HEVC_SMEM(K);
     constexpr int LV = Level<SZ>::v, SET = Level<SZ>::set, H = SZ / 2;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const CuPar q = sm.par[LV];
@@ -1328,7 +1404,7 @@ HEVC_PHASE void eval_a4(Ctx &K)
 template <int SZ>
 HEVC_PHASE void eval_b(Ctx &K)
 {
-    Smem &sm = *K.sm;
+    Smem &sm = HEVC_SMEM(K);
     constexpr int LV = Level<SZ>::v, SET = Level<SZ>::set;
     const int tid = threadIdx.x;
     for (int i = tid; i < NCAND * (CXP / 4); i += NT)
@@ -1358,7 +1434,7 @@ HEVC_PHASE void eval_b(Ctx &K)
 template <int SZ, bool REMOTE>
 __device__ __forceinline__ void cu_decide_commit(Ctx &K)
 {
-    Smem &sm = *K.sm;
+    Smem &sm = HEVC_SMEM(K);
     constexpr int LV = Level<SZ>::v, SET = Level<SZ>::set;
     const int tid = threadIdx.x, y0 = sm.par[LV].y0, x0 = sm.par[LV].x0;
     const int win = sm.eval_win[LV];
@@ -1417,7 +1493,7 @@ __device__ void search_cu(Ctx &K, int y0, int x0, int avail)
 // body); the decision follows the reference order: one-TU modes, four-TU modes, NxN, a later candidate wins ties.
 HEVC_PHASE void search_cu8_groups(Ctx &K, int y0, int x0, int avail)
 {
-    Smem &sm = *K.sm;
+    Smem &sm = HEVC_SMEM(K);
     constexpr int SZ = 8, LV = 2, H = 4, SET = 1, RT = 320;                   // RT: threads of the round warps
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int qpd6 = K.qpd6;
@@ -1598,13 +1674,13 @@ HEVC_PHASE void search_cu8_groups(Ctx &K, int y0, int x0, int avail)
                     left[2] = sm.mmd[1 + cy + 1][cx];  above[2] = modes[0];
                     left[3] = modes[2];                above[3] = modes[1];
                     PreList pre; pre.p = sm.tpre[NXN]; pre.n = 0;
-                    build_cu_head(pre, 8, 2, modes, left, above);
+                    build_cu_head(pre, 8, 2, pack4(modes), pack4(left), pack4(above));
                     for (int i = 0; i < 4; i++) {
                         const int cbf = sm.nxn_cg[i] != 0;
                         pre.ctx(CX_YCBF + 0, cbf);
                         if (cbf) code_block(cd, 4, modes[i], sm.nxn_last[i], sm.nxn_cg[i], 0u, 1u, 0u, sm.nxn_list[i], &sm.nxn_hdr[i], sm.scan, pre);
                     }
-                    emit_list(cd, pre);
+                    emit_list(cd, pre, sm.scan, sm.nxn_list[0]);
                     cd.store(sm.ccoder[SET][NXN]);
                     sm.cbits[SET][NXN] = cd.bits() - entry_bits_rel;
                     sm.csse[SET][NXN] = sse;
@@ -1661,7 +1737,7 @@ HEVC_PHASE void search_cu8_groups(Ctx &K, int y0, int x0, int avail)
 // and the decision follows the reference order: one-TU modes, four-TU modes, NxN, a later candidate wins ties.
 HEVC_PHASE void search_cu8_lockstep(Ctx &K, int y0, int x0, int avail)
 {
-    Smem &sm = *K.sm;
+    Smem &sm = HEVC_SMEM(K);
     constexpr int SZ = 8, LV = 2, H = 4, SET = 1, RT = 320;                   // RT: threads of the round warps
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int qpd6 = K.qpd6;
@@ -1693,11 +1769,19 @@ HEVC_PHASE void search_cu8_lockstep(Ctx &K, int y0, int x0, int avail)
         1 | 0 | 4 | 0 };
     Src src; src.rc = &sm.rc[0][0]; src.priv = nullptr; src.py0 = y0; src.px0 = x0; src.psz = SZ; src.ppitch = SZ;
 
-    // ---- one-TU candidates 0..34 (:1419-1447), phase A: four transform units per warp ----
-    {
-        constexpr int G = 4;
-        if (warp * G < NMODE) {
-            const int item = warp * G + lane / SZ;
+    // Warps 0-4 start the chain of the four stand-alone PUs at once (round 0 = block 0 of the four-TU candidates, the same
+    // transform units); warps 5-11 run the one-TU pipelines meanwhile and warps 5-9 join the rounds when round 1 begins.
+    //   barrier 4   the round warps 0-9 (RT threads); in round 0 warps 5-9 only meet its last one
+    //   barrier 9   warps 0-4 inside round 0 (AT threads)
+    //   barrier 10  one-TU candidates 0..19 are in: warps 5-9 arrive, warps 10-11 wait (their own 20..34 included)
+    //   barriers 5-8  block i of the four-TU candidates is in: warps 0-4 arrive, warps 10-11 wait (trial_cu8_four)
+    constexpr int AT = 160, CT = 64;
+    if (warp >= 5) {
+        // ---- one-TU candidates 0..34 (:1419-1447), phase A: four transform units per warp and pass; the second pass is warps 10-11's ----
+#pragma unroll 1
+        for (int pass = 0; pass < 2; pass++) {
+            if (pass == 1 && warp < 10) break;
+            const int item = (pass == 0 ? (warp - 5) * 4 : 28 + (warp - 10) * 4) + lane / SZ;
             const bool active = item < NMODE;
             const int m = active ? item : 0;
             const int loff = (lane / SZ) * SZ * (SZ + 2);
@@ -1711,15 +1795,15 @@ HEVC_PHASE void search_cu8_lockstep(Ctx &K, int y0, int x0, int avail)
             __syncwarp();
         }
     }
-    __syncthreads();
     HPROF(K, LV * 16 + 2);
 
     if (warp >= 10) {
-        // ---- CABAC trials of the one-TU candidates and, once the last round's pipelines are done, of the four-TU ones ----
+        // ---- CABAC trials of the one-TU candidates, then of the four-TU ones block by block as the rounds deliver them ----
+        HEVC_NAMED_BARRIER(10, AT + CT);
         const int c = (warp - 10) * 18 + lane;
-        if (lane < 18 && c < NMODE) trial_cu<SZ>(K, c, entry, entry_bits_rel, 0, mode_l, mode_a);
-        HEVC_NAMED_BARRIER(5, NT);
-        if (lane < 18 && c < NMODE) trial_cu<SZ>(K, NMODE + c, entry, entry_bits_rel, 0, mode_l, mode_a);
+        const bool on = lane < 18 && c < NMODE;
+        if (on) trial_cu<SZ>(K, c, entry, entry_bits_rel, 0, mode_l, mode_a);
+        trial_cu8_four(K, on ? c : -1, entry, entry_bits_rel, mode_l, mode_a, 5, AT + CT);
     } else {
         // ---- four rounds over the 4x4 blocks ----
         const bool grp3 = warp < 5;                                         // four-TU candidates; else stand-alone PUs
@@ -1750,13 +1834,23 @@ HEVC_PHASE void search_cu8_lockstep(Ctx &K, int y0, int x0, int avail)
                 __syncwarp();
                 binarize_warp<H>(sm, warp, lane, K.lists[SET]);
                 __syncwarp();
+                if (grp3) HEVC_NAMED_ARRIVE(5 + i, AT + CT);                // block i of the four-TU candidates is in: warps 10, 11 may code it
             }
-            if (i == 3) HEVC_NAMED_BARRIER(5, NT);         // all four blocks of the four-TU candidates are in: warps 10, 11 code them
-            else HEVC_NAMED_BARRIER(4, RT);
+            // round 0 is warps 0-4's alone; warps 5-9 come from the one-TU pipelines and wait for the kept block 0
+            const bool solo = i == 0;
+            if (solo && !grp3) {
+                __syncwarp();
+                HEVC_NAMED_ARRIVE(10, AT + CT);                             // one-TU candidates 0..19 are in
+                HEVC_NAMED_BARRIER(4, RT);
+                continue;
+            }
+            const int rbar = solo ? 9 : 4, rthr = solo ? AT : RT;
+            HEVC_NAMED_BARRIER(rbar, rthr);
             HPROF(K, LV * 16 + 8);
-            // stand-alone trial of every mode on a fresh coder: cost = absolute length of the block's residual (:1504-1518)
+            // stand-alone trial of every mode on a fresh coder: cost = absolute length of the block's residual (:1504-1518);
+            // four lanes of warps 0-8, in round 0 seven lanes of warps 0-4
             {
-                const int c = candidate35_of_thread(tid, 0);
+                const int c = solo ? (lane < 7 ? warp * 7 + lane : -1) : candidate35_of_thread(tid, 0);
                 if (c >= 0) {
                     const int from = i == 0 ? NMODE + c : NCAND + c;
                     Coder cd; cd.fresh();
@@ -1769,7 +1863,7 @@ HEVC_PHASE void search_cu8_lockstep(Ctx &K, int y0, int x0, int avail)
                 }
             }
             HPROF(K, LV * 16 + 9);
-            HEVC_NAMED_BARRIER(4, RT);
+            HEVC_NAMED_BARRIER(rbar, rthr);
             HPROF(K, LV * 16 + 10);
             if (warp == 0) {
                 int bc, win;
@@ -1782,9 +1876,9 @@ HEVC_PHASE void search_cu8_lockstep(Ctx &K, int y0, int x0, int avail)
                 }
             }
             // fresh contexts for the next round's trials
-            for (int k = tid; k < NMODE * (CXP / 4); k += RT)
+            for (int k = tid; k < NMODE * (CXP / 4); k += rthr)
                 ((unsigned *)sm.cctx[SET][NCAND])[k] = ((const unsigned *)sm.init_ctx)[k % (CXP / 4)];
-            HEVC_NAMED_BARRIER(4, RT);
+            HEVC_NAMED_BARRIER(rbar, rthr);
             {
                 const int w = sm.win;
                 const int from = i == 0 ? NMODE + w : NCAND + w;
@@ -1796,7 +1890,7 @@ HEVC_PHASE void search_cu8_lockstep(Ctx &K, int y0, int x0, int avail)
                     sm.nxn_rec[(sub_y[i] - y0 + y) * 8 + (sub_x[i] - x0 + x)] = i == 0 ? sm.rec1[NMODE + w][y * 8 + x] : sm.rec4[w][y * 4 + x];
                 }
             }
-            HEVC_NAMED_BARRIER(4, RT);
+            HEVC_NAMED_BARRIER(4, RT);                                      // (round 0: warps 5-9 join here)
             HPROF(K, LV * 16 + 11);
         }
     }
@@ -1816,13 +1910,13 @@ HEVC_PHASE void search_cu8_lockstep(Ctx &K, int y0, int x0, int avail)
             left[2] = sm.mmd[1 + cy + 1][cx];  above[2] = modes[0];
             left[3] = modes[2];                above[3] = modes[1];
             PreList pre; pre.p = sm.tpre[NXN]; pre.n = 0;
-            build_cu_head(pre, 8, 2, modes, left, above);
+            build_cu_head(pre, 8, 2, pack4(modes), pack4(left), pack4(above));
             for (int i = 0; i < 4; i++) {
                 const int cbf = sm.nxn_cg[i] != 0;
                 pre.ctx(CX_YCBF + 0, cbf);
                 if (cbf) code_block(cd, 4, modes[i], sm.nxn_last[i], sm.nxn_cg[i], 0u, 1u, 0u, sm.nxn_list[i], &sm.nxn_hdr[i], sm.scan, pre);
             }
-            emit_list(cd, pre);
+            emit_list(cd, pre, sm.scan, sm.nxn_list[0]);
             cd.store(sm.ccoder[SET][NXN]);
             sm.cbits[SET][NXN] = cd.bits() - entry_bits_rel;
             sm.csse[SET][NXN] = sse;
@@ -1948,7 +2042,7 @@ __device__ inline void build_tables(Smem &sm, int qpd6)
 // size / mode maps, their borders
 __device__ __forceinline__ void load_ctu(Ctx &K, const uint8_t *img, const uint8_t *rcon, int y, int x, bool maps)
 {
-    Smem &sm = *K.sm;
+    Smem &sm = HEVC_SMEM(K);
     const Params &P = *K.P;
     const int tid = threadIdx.x, H = P.H, W = P.W, wp = P.wp;
     const bool hl = x > 0, ha = y > 0;
@@ -1974,7 +2068,7 @@ __device__ __forceinline__ void load_ctu(Ctx &K, const uint8_t *img, const uint8
 // reconstruction out (:1625-1627), map borders for the next CTUs, end_of_slice_segment_flag (:1629)
 __device__ __forceinline__ void finish_ctu(Ctx &K, uint8_t *rcon, int y, int x)
 {
-    Smem &sm = *K.sm;
+    Smem &sm = HEVC_SMEM(K);
     const Params &P = *K.P;
     const int tid = threadIdx.x, hp = P.hp, wp = P.wp;
     for (int i = tid; i < CTU * CTU / 4; i += NT) {
@@ -1995,7 +2089,7 @@ __device__ __forceinline__ void finish_ctu(Ctx &K, uint8_t *rcon, int y, int x)
 template <int SZ>
 __device__ __forceinline__ void push_entry(Ctx &K)
 {
-    Smem &sm = *K.sm, &pe = *K.peer;
+    Smem &sm = HEVC_SMEM(K), &pe = *K.peer;
     constexpr int LV = Level<SZ>::v;
     const int tid = threadIdx.x;
     copy_words(pe.entry_ctx[LV], sm.entry_ctx[LV], CXP / 4, tid, NT);
@@ -2005,7 +2099,7 @@ __device__ __forceinline__ void push_entry(Ctx &K)
 // spine -> upper: the final reconstruction of a 16x16 unit (reference samples of the units that follow)
 __device__ __forceinline__ void push_rc_block(Ctx &K, int y0, int x0)
 {
-    Smem &sm = *K.sm, &pe = *K.peer;
+    Smem &sm = HEVC_SMEM(K), &pe = *K.peer;
     const int tid = threadIdx.x;
     if (tid < 256) pe.rc[1 + y0 + (tid >> 4)][1 + x0 + (tid & 15)] = sm.rc[1 + y0 + (tid >> 4)][1 + x0 + (tid & 15)];
 }
@@ -2014,7 +2108,7 @@ __device__ __forceinline__ void push_rc_block(Ctx &K, int y0, int x0)
 template <int SZ>
 __device__ __forceinline__ void push_result(Ctx &K)
 {
-    Smem &sm = *K.sm, &pe = *K.peer;
+    Smem &sm = HEVC_SMEM(K), &pe = *K.peer;
     constexpr int LV = Level<SZ>::v, SET = Level<SZ>::set;
     const int tid = threadIdx.x, win = sm.eval_win[LV];
     copy_words(pe.res_ctx[LV], sm.cctx[SET][win], CXP / 4, tid, NT);
@@ -2032,7 +2126,7 @@ __device__ __forceinline__ void push_result(Ctx &K)
 template <bool PAIR>
 __device__ inline void encode_frame(Ctx &K, int job, int rank)
 {
-    Smem &sm = *K.sm;
+    Smem &sm = HEVC_SMEM(K);
     const Params &P = *K.P;
     const int tid = threadIdx.x;
     const int hp = P.hp, wp = P.wp, qpd6 = K.qpd6;

@@ -60,6 +60,7 @@ struct State {
     std::vector<Fiber> fibers;
     std::vector<uint64_t> slots;            // [warp][32] exchange slots for shuffles / ballots
     unsigned char *smem = nullptr;
+    int bar_arrived[24] = {0};              // bar.arrive: threads that announced themselves at named barrier id without waiting
     int cluster = 1;                        // CTAs per cluster: the fibers of one launch step are cluster x cta_threads
     int cta_threads = 0;                    // threads of one CTA
     size_t smem_stride = 0;                 // distance of the CTAs' shared-memory images
@@ -147,7 +148,8 @@ inline void launch(unsigned grid_x, unsigned block_x, size_t smem_bytes, std::fu
                 int waiting_n = 0, want = 0;
                 for (int t = 0; t < s.nthreads; t++)
                     if (s.fibers[t].state == AT_NAMED_BARRIER && s.fibers[t].bar_id == id) { waiting_n++; want = s.fibers[t].bar_count; }
-                if (waiting_n > 0 && waiting_n >= want) {
+                if (waiting_n > 0 && waiting_n + s.bar_arrived[id] >= want) {
+                    s.bar_arrived[id] = 0;
                     for (int t = 0; t < s.nthreads; t++)
                         if (s.fibers[t].state == AT_NAMED_BARRIER && s.fibers[t].bar_id == id) s.fibers[t].state = RUNNABLE;
                     released = true;
@@ -219,6 +221,12 @@ inline void emu_named_barrier(int id, int count)
     emu::Fiber &f = emu::S().fibers[emu::S().tid];
     f.bar_id = id; f.bar_count = count;
     emu::yield_as(emu::AT_NAMED_BARRIER);
+}
+// bar.arrive id, count: the calling thread counts towards barrier `id` and goes on (producer side of a producer / consumer pair)
+inline void emu_named_arrive(int id, int count)
+{
+    (void)count;
+    emu::S().bar_arrived[id]++;
 }
 inline void __syncthreads()
 {

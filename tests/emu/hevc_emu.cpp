@@ -55,7 +55,7 @@ extern "C" int emu_hevc_sweep(uint8_t *streams, size_t cap, const uint8_t *img, 
     P.scratch = scratch.data(); P.lists = lists.data(); P.overflow = &overflow; P.next_frame = &next;
     P.prof = nullptr;
     P.nq = nq;
-    P.cu8_lockstep = pair ? 1 : 0;                  // the product's defaults: pairs in lock step, single CTAs by groups
+    P.cu8_lockstep = 1;                             // the product's default on both launch shapes
     for (int k = 0; k < 8; k++) P.qlist[k] = k < nq ? qlist[k] : 0;
     // the queue order of the product's host side (hevc.cu): settings by ascending qpd6, ties in list order
     for (int k = 0; k < 8; k++) P.qorder[k] = k;

@@ -21,10 +21,13 @@ out = torch.empty((n, imcvt_b200.hevc_bound(h, w)), dtype=torch.uint8, device="c
 lens = torch.zeros(n, dtype=torch.int64, device="cuda")
 L = imcvt_b200.lib()
 buf = (C.c_ulonglong * 128)()
+import time
 for it in range(2):
+    torch.cuda.synchronize(); t0 = time.time()
     imcvt_b200.encode_hevc_device(d, q, out, lens)
-    torch.cuda.synchronize()
+    torch.cuda.synchronize(); wall = time.time() - t0
     L.imcvtDebugHevcProf(buf)
+print(f"wall {wall*1e3:.1f} ms for the batch")
 v = np.array(list(buf), dtype=np.float64)
 nctu = n * ((h + 31) // 32) * ((w + 31) // 32)
 names = ["entry", "split+children sse", "A one-TU", "A four-TU", "ctx copy", "B trials / CU8: wait for four-TU trials after NxN", "decide", "commit",
