@@ -107,6 +107,14 @@ constexpr int NALL = NXN + 1;
 constexpr int PRE_MAX = 40;             // entries of a trial's prefix list: head (<= 9; NxN 16) + <= 4 cbf flags + last position (<= 24; 4x4: 6)
 constexpr int SLOT = 112;               // bin-list entries per coefficient group (worst case 107)
 constexpr int CAND_LIST_U16 = 64 * SLOT + 64;   // 64 group slots + 64 group headers per candidate
+// Where the bin lists of a candidate live (entries of group g at CAND * (lid - BASE) + g * SLOT, its header at ... + HDR + g):
+//   ListsGlobal  the per-CTA lists in global memory, any transform size
+//   ListsCu8     the 4x4 blocks of an 8x8 unit's four-TU and stand-alone candidates (lid NMODE .. NXN-1, four groups each) in
+//                shared memory: they are written, read by the trials of the same round and dropped -- in global memory every one
+//                of those steps was an L2 round trip on the unit's critical chain.  The space is rec0, which only the 32x32
+//                evaluation uses and which is dead while 8x8 units are searched (both kernels).
+struct ListsGlobal { static constexpr int CAND = CAND_LIST_U16, HDR = 64 * SLOT, BASE = 0; };
+struct ListsCu8 { static constexpr int CAND = 4 * SLOT + 8, HDR = 4 * SLOT, BASE = 35; };
 
 // context offsets: member order of the reference's ContextSet (:744-758)
 enum { CX_SPLIT_CU = 0, CX_PART = 3, CX_YMODE = 4, CX_UVMODE = 5, CX_SPLIT_TU = 6, CX_YCBF = 9, CX_UVCBF = 11,
@@ -217,6 +225,11 @@ struct Smem {
 };
 
 static_assert(sizeof(Smem) <= SMEM_LIMIT, "hevc Smem does not fit the 227 KB a CTA can have");
+
+// the bin lists of an 8x8 unit's 4x4 blocks (ListsCu8): (NXN - NMODE) candidates x ListsCu8::CAND entries in the space of rec0
+static_assert((NXN - NMODE) * ListsCu8::CAND * 2 <= NCAND * REC_STRIDE, "ListsCu8 does not fit rec0");
+static_assert((ListsCu8::CAND * 2) % 16 == 0 && (SLOT * 2) % 16 == 0, "group slots must stay 16-byte aligned");
+__device__ __forceinline__ unsigned short *cu8_lists(Smem &sm) { return reinterpret_cast<unsigned short *>(&sm.rec0[0][0]); }
 
 // a pointer into this CTA's shared memory that came through memory (a struct member, a function argument) and is therefore a
 // generic address: the same address, derived from the __shared__ symbol so that the compiler knows the address space
@@ -469,6 +482,7 @@ __device__ __forceinline__ void emit_bypass(unsigned short *dst, int &o, int val
 
 // One coefficient group by the 16 lanes of a half-warp; lane hl codes scan position cg*16 + 15 - hl, so lane order is
 // coding order.  Executed by all 32 lanes (ballots / shuffles inside); `has` masks a half without a task.
+template <class LL>
 __device__ __forceinline__ void binarize_cg(bool has, const BinDesc &D, int sz, int cg, int hl, int half,
                                             const uint8_t (*scan_all)[2], const short *levbase,
                                             unsigned cgp0, unsigned cgp1, unsigned short *lists)
@@ -550,7 +564,7 @@ __device__ __forceinline__ void binarize_cg(bool has, const BinDesc &D, int sz, 
     const int total = n4 + __shfl_sync(0xffffffffu, incl, 15, 16);
 
     if (!has) return;
-    unsigned short *slot = lists + (size_t)D.lid * CAND_LIST_U16 + (size_t)(D.slot0 + cg) * SLOT;
+    unsigned short *slot = lists + (size_t)(D.lid - LL::BASE) * LL::CAND + (size_t)(D.slot0 + cg) * SLOT;
     if (sig_coded) slot[__popc(sball & lt)] = ent_ctx(0, CX_SIG + sig_ctx_index(sz, st, y, x, nb), nzf);
     if (nzf && nzidx < 8) {
         const int c1 = earlier_big ? 0 : (nzidx < 2 ? 1 + nzidx : 3);
@@ -566,12 +580,12 @@ __device__ __forceinline__ void binarize_cg(bool has, const BinDesc &D, int sz, 
         emit_bypass(slot, o, valA, lenA);
         emit_bypass(slot, o, valB, lenB);
     }
-    if (hl == 0) lists[(size_t)D.lid * CAND_LIST_U16 + 64 * SLOT + D.slot0 + cg] = (unsigned short)(total | (nz > 0 ? 0x80 : 0) | (anybig ? 0x100 : 0));
+    if (hl == 0) lists[(size_t)(D.lid - LL::BASE) * LL::CAND + LL::HDR + D.slot0 + cg] = (unsigned short)(total | (nz > 0 ? 0x80 : 0) | (anybig ? 0x100 : 0));
 }
 
 // Binarises the transform units a warp has just quantised (descriptors in sm.bdesc[warp][0..G-1], levels in sm.lev).
 // Tasks are the significant coefficient groups plus group 0 of every unit; each half-warp takes its share.
-template <int TS>
+template <int TS, class LL = ListsGlobal>
 HEVC_BIGFN void binarize_warp(Smem &sm, int warp, int lane, unsigned short *lists)
 {
     constexpr int G = 32 / TS;
@@ -602,7 +616,7 @@ HEVC_BIGFN void binarize_warp(Smem &sm, int warp, int lane, unsigned short *list
         const int blk = D.slot0 / ((TS / 4) * (TS / 4));
         const int cand = D.lid;
         const unsigned cgp0 = has ? sm.ccg[D.set][cand][blk][0] : 0u, cgp1 = has ? sm.ccg[D.set][cand][blk][1] : 0u;
-        binarize_cg(has, D, TS, cg, hl, half, sm.scan, &sm.lev[0][0], cgp0, cgp1, lists);
+        binarize_cg<LL>(has, D, TS, cg, hl, half, sm.scan, &sm.lev[0][0], cgp0, cgp1, lists);
     }
     TPROF(sm, 64 + SizeClass<TS>::v * 8 + 7);
 }
@@ -643,8 +657,8 @@ HEVC_PHASE void code_stream(Coder &c_io, PreList &pre_io, const uint8_t (*scan_a
     const Entry8 *sp = reinterpret_cast<const Entry8 *>(slots + cg * SLOT);
     Entry8 ev; ev.w[0] = ev.w[1] = ev.w[2] = ev.w[3] = 0;
     if (sz) {
-        h = hdrs[cg];
-        ev = sp[0];
+        // a unit without a significant group has an empty group 0 (publish_tu): nothing to fetch
+        if (sg0 | sg1) { h = hdrs[cg]; ev = sp[0]; }
         build_last_pos(pre, sz, st, scan[last][0], scan[last][1]);
     }
     int cnt = (int)(h & 0x7Fu);
@@ -1168,14 +1182,14 @@ __device__ __forceinline__ void fill_maps(Smem &sm, int y0, int x0, int mode)
 }
 
 // group leaders publish what binarize_warp needs about the unit they just quantised
-template <int SET>
+template <int SET, class LL = ListsGlobal>
 __device__ __forceinline__ void publish_tu(Smem &sm, unsigned short *lists, int warp, int g, bool active, int cand, int blk, int ncg, int mode, int lev_off, const TuResult &r)
 {
     BinDesc &D = sm.bdesc[warp][g];
     D.set = SET;
     D.active = active; D.lid = cand; D.slot0 = blk * ncg; D.mode = mode; D.lev_off = lev_off; D.last = r.last; D.sg0 = r.sg0; D.sg1 = r.sg1;
     if (active) {
-        if ((r.sg0 | r.sg1) == 0) lists[(size_t)cand * CAND_LIST_U16 + 64 * SLOT + blk * ncg] = 0;      // empty group 0 (stand-alone 4x4 trials read it)
+        if ((r.sg0 | r.sg1) == 0) lists[(size_t)(cand - LL::BASE) * LL::CAND + LL::HDR + blk * ncg] = 0;      // empty group 0 (stand-alone 4x4 trials read it)
         sm.clast[SET][cand][blk] = r.last;
         sm.ccg[SET][cand][blk][0] = r.cg0; sm.ccg[SET][cand][blk][1] = r.cg1;
         sm.csg[SET][cand][blk][0] = r.sg0; sm.csg[SET][cand][blk][1] = r.sg1;
@@ -1241,7 +1255,7 @@ HEVC_PHASE void trial_cu8_four(Ctx &K, int c, const CoderRegs &entry, int entry_
     attach(cd, sm, sm.cctx[SET][cand], K.scratch[SET] + (size_t)cand * SCR_BYTES, SCR_BYTES);
     PreList pre; pre.p = sm.tpre[cand]; pre.n = 0;
     if (on) build_cu_head(pre, 8, 1, (unsigned)mode, (unsigned)mode_l, (unsigned)mode_a);
-    const unsigned short *lst = K.lists[SET] + (size_t)cand * CAND_LIST_U16;
+    const unsigned short *lst = cu8_lists(sm) + (size_t)(cand - ListsCu8::BASE) * ListsCu8::CAND;
 #pragma unroll 1
     for (int i = 0; i < 4; i++) {
         __syncwarp();
@@ -1251,7 +1265,7 @@ HEVC_PHASE void trial_cu8_four(Ctx &K, int c, const CoderRegs &entry, int entry_
             const int cbf = g0 != 0;
             pre.ctx(CX_YCBF + 0, cbf);                                   // :1039
             if (cbf) code_block(cd, 4, mode, sm.clast[SET][cand][i], g0, 0u, sm.csg[SET][cand][i][0], 0u,
-                                lst + (size_t)i * SLOT, lst + 64 * SLOT + i, sm.scan, pre);
+                                lst + (size_t)i * SLOT, lst + ListsCu8::HDR + i, sm.scan, pre);
         }
     }
     if (on) {
@@ -1824,7 +1838,7 @@ HEVC_PHASE void search_cu8_lockstep(Ctx &K, int y0, int x0, int avail)
                                             sm.lev[warp] + loff, rec, grp3 ? SZ : H);
                 sse3 += r.sse;
                 if (lane % H == 0) {
-                    publish_tu<SET>(sm, K.lists[SET], warp, lane / H, active, cand, grp3 ? i : 0, 1, m, warp * LEV_STRIDE + loff, r);
+                    publish_tu<SET, ListsCu8>(sm, cu8_lists(sm), warp, lane / H, active, cand, grp3 ? i : 0, 1, m, warp * LEV_STRIDE + loff, r);
                     if (active) {
                         if (!grp3) sm.csse[SET][cand] = r.sse;
                         else if (i == 0) sm.sse0[m] = r.sse;
@@ -1832,7 +1846,7 @@ HEVC_PHASE void search_cu8_lockstep(Ctx &K, int y0, int x0, int avail)
                     }
                 }
                 __syncwarp();
-                binarize_warp<H>(sm, warp, lane, K.lists[SET]);
+                binarize_warp<H, ListsCu8>(sm, warp, lane, cu8_lists(sm));
                 __syncwarp();
                 if (grp3) HEVC_NAMED_ARRIVE(5 + i, AT + CT);                // block i of the four-TU candidates is in: warps 10, 11 may code it
             }
@@ -1855,9 +1869,9 @@ HEVC_PHASE void search_cu8_lockstep(Ctx &K, int y0, int x0, int avail)
                     const int from = i == 0 ? NMODE + c : NCAND + c;
                     Coder cd; cd.fresh();
                     attach(cd, sm, sm.cctx[SET][NCAND + c], K.scratch[SET] + (size_t)(NCAND + c) * SCR_BYTES, SCR_BYTES);
-                    const unsigned short *lst = K.lists[SET] + (size_t)from * CAND_LIST_U16;
+                    const unsigned short *lst = cu8_lists(sm) + (size_t)(from - ListsCu8::BASE) * ListsCu8::CAND;
                     PreList pre; pre.p = sm.tpre[NCAND + c]; pre.n = 0;
-                    code_block(cd, 4, c, sm.clast[SET][from][0], sm.ccg[SET][from][0][0], 0u, sm.csg[SET][from][0][0], 0u, lst, lst + 64 * SLOT, sm.scan, pre);
+                    code_block(cd, 4, c, sm.clast[SET][from][0], sm.ccg[SET][from][0][0], 0u, sm.csg[SET][from][0][0], 0u, lst, lst + ListsCu8::HDR, sm.scan, pre);
                     sm.cbits[SET][NCAND + c] = cd.bits();
                     if (i == 0) sm.csse[SET][NCAND + c] = sm.sse0[c];
                 }
@@ -1882,9 +1896,9 @@ HEVC_PHASE void search_cu8_lockstep(Ctx &K, int y0, int x0, int avail)
             {
                 const int w = sm.win;
                 const int from = i == 0 ? NMODE + w : NCAND + w;
-                const unsigned short *lst = K.lists[SET] + (size_t)from * CAND_LIST_U16;
+                const unsigned short *lst = cu8_lists(sm) + (size_t)(from - ListsCu8::BASE) * ListsCu8::CAND;
                 if (tid < SLOT) sm.nxn_list[i][tid] = lst[tid];               // keep the winner's bins for the NxN trial
-                if (tid == SLOT) sm.nxn_hdr[i] = lst[64 * SLOT];
+                if (tid == SLOT) sm.nxn_hdr[i] = lst[ListsCu8::HDR];
                 if (tid >= 128 && tid < 144) {
                     const int y = (tid - 128) >> 2, x = (tid - 128) & 3;
                     sm.nxn_rec[(sub_y[i] - y0 + y) * 8 + (sub_x[i] - x0 + x)] = i == 0 ? sm.rec1[NMODE + w][y * 8 + x] : sm.rec4[w][y * 4 + x];
