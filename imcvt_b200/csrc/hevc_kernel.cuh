@@ -333,19 +333,42 @@ struct Coder {
             held = lead;
         }
     }
+    // Shared-memory accesses of the bin step.  On the device they are ld / st.shared on 32-bit addresses kept in registers
+    // (ctx_s, lps_s, nlps_s, set by bind_shared): left to the compiler, every access re-derived the CTA's shared window base
+    // from a special register inside the bin loop -- on the one dependent chain a trial lane has.
+#ifdef IMCVT_HOST_EMU
+    __device__ __forceinline__ void bind_shared() {}
+    __device__ __forceinline__ int ld_ctx(int ci) const { return ctx[ci]; }
+    __device__ __forceinline__ void st_ctx(int ci, int v) { ctx[ci] = (uint8_t)v; }
+    __device__ __forceinline__ unsigned ld_lps(int row) const { return lps[row]; }
+    __device__ __forceinline__ int ld_nlps(int st) const { return nlps[st]; }
+#else
+    unsigned ctx_s, lps_s, nlps_s;
+    __device__ __forceinline__ void bind_shared()
+    {
+        ctx_s = (unsigned)__cvta_generic_to_shared(ctx); lps_s = (unsigned)__cvta_generic_to_shared(lps); nlps_s = (unsigned)__cvta_generic_to_shared(nlps);
+        // opaque to the optimiser: otherwise it re-materialises the table addresses (special-register read + shift + add) per bin
+        asm volatile("mov.u32 %0, %0;" : "+r"(lps_s));
+        asm volatile("mov.u32 %0, %0;" : "+r"(nlps_s));
+    }
+    __device__ __forceinline__ int ld_ctx(int ci) const { unsigned v; asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(ctx_s + (unsigned)ci) : "memory"); return (int)v; }
+    __device__ __forceinline__ void st_ctx(int ci, int v) { asm volatile("st.shared.u8 [%0], %1;" ::"r"(ctx_s + (unsigned)ci), "r"(v) : "memory"); }
+    __device__ __forceinline__ unsigned ld_lps(int row) const { unsigned v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(lps_s + 4u * (unsigned)row)); return v; }
+    __device__ __forceinline__ int ld_nlps(int st) const { unsigned v; asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(nlps_s + (unsigned)st)); return (int)v; }
+#endif
     __device__ __forceinline__ void bin(int b, int ci)                                 // CABACputBin :913-932
     {
-        const int st = ctx[ci];
-        const int l = (int)((lps[st >> 1] >> (((range >> 6) & 3) * 8)) & 0xFFu);
+        const int st = ld_ctx(ci);
+        const int l = (int)((ld_lps(st >> 1) >> (((range >> 6) & 3) * 8)) & 0xFFu);
         range -= l;
         if ((b != 0) != ((st & 1) != 0)) {
             const int n = __clz(l >> 3) - 26;           // renormalisation shift (table :712-714 in closed form)
-            ctx[ci] = nlps[st];
+            st_ctx(ci, ld_nlps(st));
             low = (low + range) << n;
             range = l << n;
             nbits -= n;
         } else {
-            ctx[ci] = (uint8_t)(st < 124 ? st + 2 : st);
+            st_ctx(ci, st < 124 ? st + 2 : st);
             if (range < 256) { low <<= 1; range <<= 1; nbits--; }
         }
         shift_out();
@@ -521,8 +544,7 @@ __device__ __forceinline__ void binarize_cg(bool has, const BinDesc &D, int sz, 
     const bool escape = nz > 8 || __popc(bball) > 1 || g2ball != 0;
     // sign bits, first coded level in the most significant position
     int signs = (nzf && v < 0) ? 1 << (nz - 1 - nzidx) : 0;
-#pragma unroll
-    for (int d = 1; d < 16; d <<= 1) signs |= __shfl_xor_sync(0xffffffffu, signs, d, 16);
+    signs = (int)__reduce_or_sync(0xFFFFu << sh, (unsigned)signs);       // one redux over the half-warp instead of four shuffle steps
     const int n4 = n3 + (nz > 8 ? 2 : nz > 0 ? 1 : 0);
 
     // remaining absolute levels: Rice parameter and base level evolve along the group (:1252-1263)
@@ -558,10 +580,12 @@ __device__ __forceinline__ void binarize_cg(bool has, const BinDesc &D, int sz, 
         }
     }
     const int mine = chunks_of(lenA) + chunks_of(lenB);
-    int incl = mine;
+    int incl = mine, total = n4;
+    if (__any_sync(0xffffffffu, mine != 0)) {                             // no escape codes in either half (the common case): nothing to scan
 #pragma unroll
-    for (int d = 1; d < 16; d <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, d, 16); if (hl >= d) incl += t; }
-    const int total = n4 + __shfl_sync(0xffffffffu, incl, 15, 16);
+        for (int d = 1; d < 16; d <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, d, 16); if (hl >= d) incl += t; }
+        total = n4 + __shfl_sync(0xffffffffu, incl, 15, 16);
+    }
 
     if (!has) return;
     unsigned short *slot = lists + (size_t)(D.lid - LL::BASE) * LL::CAND + (size_t)(D.slot0 + cg) * SLOT;
@@ -646,6 +670,7 @@ HEVC_PHASE void code_stream(Coder &c_io, PreList &pre_io, const uint8_t (*scan_a
     // memory: named through the __shared__ symbol again, their accesses are LDS / STS
     Smem &sm = *reinterpret_cast<Smem *>(IMCVT_DYN_SMEM());
     c.ctx = own_smem(c.ctx); c.lps = sm.lpsw; c.nlps = sm.next_lps;
+    c.bind_shared();
     pre.p = own_smem(pre.p);
     scan_all = sm.scan;
     const int st = sz ? scan_type_for(sz, mode) : 0, ncg = sz >> 2;
@@ -1167,6 +1192,7 @@ template <int SET> __device__ __forceinline__ uint8_t *rec_tile(Smem &sm, int c)
 __device__ __forceinline__ void attach(Coder &c, Smem &sm, uint8_t *ctx, uint8_t *out, unsigned cap)
 {
     c.ctx = ctx; c.out = out; c.cap = cap; c.lps = sm.lpsw; c.nlps = sm.next_lps;
+    c.bind_shared();
 }
 
 template <int SZ>
@@ -1880,30 +1906,24 @@ HEVC_PHASE void search_cu8_lockstep(Ctx &K, int y0, int x0, int avail)
             HEVC_NAMED_BARRIER(rbar, rthr);
             HPROF(K, LV * 16 + 10);
             if (warp == 0) {
+                // the choice, and what is kept of the winner for the rounds to come and for the NxN trial: its mode, last position and
+                // group mask, its bins, its reconstruction -- all by this warp, while the others refresh the trial contexts
                 int bc, win;
                 warp_best<SET>(sm, rd, NCAND, NMODE, lane, bc, win);
                 win -= NCAND;
-                if (lane == 0) {
-                    const int from = i == 0 ? NMODE + win : NCAND + win;
-                    sm.win = win;
-                    sm.nxn_mode[i] = win; sm.nxn_last[i] = sm.clast[SET][from][0]; sm.nxn_cg[i] = sm.ccg[SET][from][0][0];
+                const int from = i == 0 ? NMODE + win : NCAND + win;
+                if (lane == 0) { sm.nxn_mode[i] = win; sm.nxn_last[i] = sm.clast[SET][from][0]; sm.nxn_cg[i] = sm.ccg[SET][from][0][0]; }
+                const unsigned short *lst = cu8_lists(sm) + (size_t)(from - ListsCu8::BASE) * ListsCu8::CAND;
+                for (int k = lane; k < SLOT; k += 32) sm.nxn_list[i][k] = lst[k];
+                if (lane == 16) sm.nxn_hdr[i] = lst[ListsCu8::HDR];
+                if (lane < 16) {
+                    const int y = lane >> 2, x = lane & 3;
+                    sm.nxn_rec[(sub_y[i] - y0 + y) * 8 + (sub_x[i] - x0 + x)] = i == 0 ? sm.rec1[NMODE + win][y * 8 + x] : sm.rec4[win][y * 4 + x];
                 }
             }
             // fresh contexts for the next round's trials
             for (int k = tid; k < NMODE * (CXP / 4); k += rthr)
                 ((unsigned *)sm.cctx[SET][NCAND])[k] = ((const unsigned *)sm.init_ctx)[k % (CXP / 4)];
-            HEVC_NAMED_BARRIER(rbar, rthr);
-            {
-                const int w = sm.win;
-                const int from = i == 0 ? NMODE + w : NCAND + w;
-                const unsigned short *lst = cu8_lists(sm) + (size_t)(from - ListsCu8::BASE) * ListsCu8::CAND;
-                if (tid < SLOT) sm.nxn_list[i][tid] = lst[tid];               // keep the winner's bins for the NxN trial
-                if (tid == SLOT) sm.nxn_hdr[i] = lst[ListsCu8::HDR];
-                if (tid >= 128 && tid < 144) {
-                    const int y = (tid - 128) >> 2, x = (tid - 128) & 3;
-                    sm.nxn_rec[(sub_y[i] - y0 + y) * 8 + (sub_x[i] - x0 + x)] = i == 0 ? sm.rec1[NMODE + w][y * 8 + x] : sm.rec4[w][y * 4 + x];
-                }
-            }
             HEVC_NAMED_BARRIER(4, RT);                                      // (round 0: warps 5-9 join here)
             HPROF(K, LV * 16 + 11);
         }

@@ -243,6 +243,17 @@ template <class T> inline T __shfl_sync(unsigned, T v, int src, int width = 32)
     int lane = emu::lane_id();
     return emu::exchange(v, (lane & ~(width - 1)) | (src & (width - 1)));
 }
+// redux.sync.or over the lanes of `mask` (the calling lane is one of them; every lane of the warp executes it with its own mask)
+inline unsigned __reduce_or_sync(unsigned mask, unsigned v)
+{
+    uint64_t *sl = emu::warp_slots();
+    sl[emu::lane_id()] = emu::to_bits(v);
+    emu::yield_as(emu::AT_WARP_BARRIER);
+    unsigned r = 0;
+    for (int l = 0; l < 32; l++) if ((mask >> l) & 1u) r |= emu::from_bits<unsigned>(sl[l]);
+    emu::yield_as(emu::AT_WARP_BARRIER);
+    return r;
+}
 template <class T> inline T __shfl_xor_sync(unsigned, T v, int m, int width = 32)
 {
     int lane = emu::lane_id(), src = lane ^ m;

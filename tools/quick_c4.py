@@ -8,7 +8,7 @@ from imcvt_b200 import synth
 
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 32
 near = int(sys.argv[2]) if len(sys.argv) > 2 else 2
-iters = int(sys.argv[3]) if len(sys.argv) > 3 else 3
+iters = int(sys.argv[3]) if len(sys.argv) > 3 else 3          # host-buffer calls (0: device-resident path only)
 h, w = 2160, 3840
 base = np.stack([synth.frame("natural", i, h, w, True) for i in range(min(n, 4))])
 frames = np.concatenate([base] * ((n + len(base) - 1) // len(base)))[:n]
