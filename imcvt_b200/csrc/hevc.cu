@@ -18,10 +18,11 @@ static unsigned long long *g_prof = nullptr;
 static inline int pad32(uint32_t v) { uint32_t c = v > 8192 ? 8192 : v; return (int)((c + 31) / 32 * 32); }   // HEVCe.c:1580-1581
 
 // Relative cost of one job by quantiser and the gain of giving a job two SMs (the cluster-pair kernel), measured on B200 with
-// 16 "natural" 1920x1080 frames (tools/quick_hevc.py, round 2): one CTA per frame 14.9 / 11.9 / 8.5 / 3.1 s at qpd6 1 / 2 / 3 / 4
-// (the lower the quantiser, the more bins the CABAC trials step through), a CTA pair 9.4 / 7.3 / 5.2 / 1.9 s.  qpd6 0: extrapolated.
-static const double kJobCost[5] = {5.8, 4.8, 3.8, 2.75, 1.0};
-static const double kPairGain = 1.6;
+// 16 "natural" 1920x1080 frames on CTA pairs (tools/quick_hevc.py, end of round 2, profiles/quick_timings_r2.txt): 9.47 / 7.35 /
+// 5.29 / 1.60 s at qpd6 1 / 2 / 3 / 4 (the lower the quantiser, the more bins the CABAC trials step through); one CTA per frame
+// with every SM busy 2.97 s against 1.74 s on pairs at qpd6 4.  qpd6 0: extrapolated.
+static const double kJobCost[5] = {7.2, 5.9, 4.6, 3.3, 1.0};
+static const double kPairGain = 1.7;
 
 // Finishing time of jobs handed out longest first to `machines` workers (what the kernel's dynamic queue does).
 static double makespan(const std::vector<double> &jobs_desc, int machines)
