@@ -12,10 +12,11 @@
  * a pending job: the reference's sequential semantics (an output used as a later input, the "already exist" guard on a
  * name written earlier in the same call) stay observable.
  *
- * Formats: PNM in / out is this repo's own reader (pnm_io.c).  The PNG / BMP / QOI loaders and writers are the
- * reference's format files (out of scope for this engine); they are WEAK references here: linked
- * in (oracle/Makefile: _ref/ImCvt_batch) they work as in the reference, left out such inputs fail with the reference's
- * "open ... failed" line and such outputs with its "write ... failed" line.
+ * Formats: every input / output format of the reference, each written for this repo: PNM (pnm_io.c), BMP (fmt_bmp.c), QOI
+ * (fmt_qoi.c), PNG (fmt_png.c: the reference's stored-deflate writer, and an inflate + unfilter reader in place of its
+ * third-party uPNG) -- SURVEY section 8(f) row f4; tests/test_cli_formats.py holds them against the reference's CLI byte for
+ * byte.  Loaders are tried in the reference's order (PNM, PNG, BMP, QOI: src/main.c:142-160); their stdout lines are
+ * captured and printed in file order.
  *
  * Deliberate deviation: `-o <file>` in front of any input makes the reference write dst_fnames[-1];
  * here that output name is ignored.
@@ -46,12 +47,12 @@
 #include "imcvt_pnm.h"
 
 int      writePNMImageFile(const char *, const uint8_t *, int, uint32_t, uint32_t);
-extern uint8_t *loadPNGImageFile(const char *, int *, uint32_t *, uint32_t *) __attribute__((weak));
-extern uint8_t *loadBMPImageFile(const char *, int *, uint32_t *, uint32_t *) __attribute__((weak));
-extern uint8_t *loadQOIImageFile(const char *, int *, uint32_t *, uint32_t *) __attribute__((weak));
-extern int writePNGImageFile(const char *, const uint8_t *, int, uint32_t, uint32_t) __attribute__((weak));
-extern int writeBMPImageFile(const char *, const uint8_t *, int, uint32_t, uint32_t) __attribute__((weak));
-extern int writeQOIImageFile(const char *, const uint8_t *, int, uint32_t, uint32_t) __attribute__((weak));
+uint8_t *loadPNGImageFile(const char *, int *, uint32_t *, uint32_t *);        /* fmt_png.c */
+uint8_t *loadBMPImageFile(const char *, int *, uint32_t *, uint32_t *);        /* fmt_bmp.c */
+uint8_t *loadQOIImageFile(const char *, int *, uint32_t *, uint32_t *);        /* fmt_qoi.c */
+int writePNGImageFile(const char *, const uint8_t *, int, uint32_t, uint32_t);
+int writeBMPImageFile(const char *, const uint8_t *, int, uint32_t, uint32_t);
+int writeQOIImageFile(const char *, const uint8_t *, int, uint32_t, uint32_t);
 
 static const char *const USAGE_LINES[] = {
     "|------------------------------------------------------------------------------------|",
@@ -472,12 +473,10 @@ static void capture_end(Job *j)
 static uint8_t *load_other_formats(Job *j, const char *src, int *is_rgb, uint32_t *h, uint32_t *w)
 {
     uint8_t *img = NULL;
-    if (!loadPNGImageFile && !loadBMPImageFile && !loadQOIImageFile)
-        return NULL;
     capture_begin();
-    if (img == NULL && loadPNGImageFile) img = loadPNGImageFile(src, is_rgb, h, w);
-    if (img == NULL && loadBMPImageFile) img = loadBMPImageFile(src, is_rgb, h, w);
-    if (img == NULL && loadQOIImageFile) img = loadQOIImageFile(src, is_rgb, h, w);
+    if (img == NULL) img = loadPNGImageFile(src, is_rgb, h, w);
+    if (img == NULL) img = loadBMPImageFile(src, is_rgb, h, w);
+    if (img == NULL) img = loadQOIImageFile(src, is_rgb, h, w);
     capture_end(j);
     return img;
 }
@@ -573,9 +572,9 @@ static void convert(int i_file, int force_write)
     capture_begin();
     switch (kind) {
     case OUT_PNM: failed = writePNMImageFile(j->dst, img, is_rgb, h, w); break;
-    case OUT_PNG: failed = writePNGImageFile ? writePNGImageFile(j->dst, img, is_rgb, h, w) : 1; break;
-    case OUT_BMP: failed = writeBMPImageFile ? writeBMPImageFile(j->dst, img, is_rgb, h, w) : 1; break;
-    default:      failed = writeQOIImageFile ? writeQOIImageFile(j->dst, img, is_rgb, h, w) : 1; break;
+    case OUT_PNG: failed = writePNGImageFile(j->dst, img, is_rgb, h, w); break;
+    case OUT_BMP: failed = writeBMPImageFile(j->dst, img, is_rgb, h, w); break;
+    default:      failed = writeQOIImageFile(j->dst, img, is_rgb, h, w); break;
     }
     capture_end(j);
     free(img);
