@@ -401,8 +401,12 @@ static uint8_t *batch_slot(int kind, int is_rgb, uint32_t h, uint32_t w)
     if (B->n && (B->kind != kind || B->is_rgb != is_rgb || B->h != h || B->w != w || B->n >= B->max_n))
         flush_batch();
     if (B->n == 0) {
-        /* frames per batch: the limit, and at most about 2 GiB of staged pixels */
+        /* frames per batch: the limit, at most about 2 GiB of staged pixels, and at most about 4 GiB of worst-case stream
+         * slots (the slots exist once in host memory and once in device memory; real streams are ~10x smaller) */
         size_t fit = ((size_t)2 << 30) / frame_bytes, need;
+        const size_t slot = kind == OUT_JLS ? imcvtJLSBound(is_rgb, h, w) : imcvtHEVCBound(h, w);
+        if (slot && fit > ((size_t)4 << 30) / slot)
+            fit = ((size_t)4 << 30) / slot;
         B->kind = kind; B->is_rgb = is_rgb; B->h = h; B->w = w; B->frame_bytes = frame_bytes;
         B->max_n = (int)(fit < 1 ? 1 : fit > (size_t)g_batch_limit ? (size_t)g_batch_limit : fit);
         /* the arena only grows, and in whole batches of the CURRENT shape as long as files of it may follow */
