@@ -135,3 +135,36 @@ def test_pinned_staging_buffer_feeds_the_batch_call():
             assert got[i] == oracle_jls(frames[i], 0)
     finally:
         L.imcvtHostFree(p)
+
+
+def test_bmp_qoi_png_inputs_are_staged_into_codec_batches():
+    """Row f4 on the device: pictures that arrive as BMP / QOI / PNG (this repo's own readers, host/fmt_*.c) go through the same
+    staging and batch calls as PNM files; streams against the oracle, stdout / exit code / every file against the reference CLI."""
+    with tempfile.TemporaryDirectory() as d, tempfile.TemporaryDirectory() as d2:
+        for dd in (d, d2):
+            imgs = make_inputs(dd)
+            # the other formats of the same pictures, written by the command line itself (CPU paths; tests/test_cli_formats.py
+            # holds them against the reference byte for byte)
+            conv = ["-f"]
+            for n in ("n0.pgm", "n1.pgm", "c0.ppm", "c1.ppm", "t0.pgm"):
+                stem = os.path.splitext(n)[0]
+                conv += [n, "-o", stem + ".bmp", n, "-o", stem + ".png", n, "-o", stem + ".qoi"]
+            assert run(CLI, conv, dd)[0] == 0
+        args = ["-f", "-1", "n0.bmp", "-o", "a0.jls", "n1.png", "-o", "a1.jls", "n1.bmp", "-o", "a2.jls", "c0.png", "-o", "a3.jls", "c1.bmp", "-o", "a4.jls",
+                "c0.qoi", "-o", "a5.jls", "n0.qoi", "-o", "a6.jls", "n0.png", "-o", "b0.h265", "t0.bmp", "-o", "b1.h265", "c1.png", "-o", "b2.h265",
+                "t0.qoi", "-o", "b3.h265", "a0.jls", "-o", "nope.png"]
+        rc, out, err = run(CLI, args, d, {"IMCVT_BATCH": "4"})
+        assert rc == 1, (out, err)                                   # a .jls file is not a readable input
+        g = lambda n: np.repeat(imgs[n][:, :, None], 3, axis=2)     # a gray picture comes back from QOI as RGB (imageio_qoi.c:149-186)
+        want = {"a0.jls": oracle_jls(imgs["n0.pgm"], 1), "a1.jls": oracle_jls(imgs["n1.pgm"], 1), "a2.jls": oracle_jls(imgs["n1.pgm"], 1),
+                "a3.jls": oracle_jls(imgs["c0.ppm"], 1), "a4.jls": oracle_jls(imgs["c1.ppm"], 1), "a5.jls": oracle_jls(imgs["c0.ppm"], 1),
+                "a6.jls": oracle_jls(g("n0.pgm"), 1),
+                "b0.h265": oracle_hevc(imgs["n0.pgm"], 1)[0], "b1.h265": oracle_hevc(imgs["t0.pgm"], 1)[0],
+                "b2.h265": oracle_hevc(imgs["c1.ppm"][:, :, 1], 1)[0], "b3.h265": oracle_hevc(imgs["t0.pgm"], 1)[0]}
+        for name, stream in want.items():
+            assert open(os.path.join(d, name), "rb").read() == stream, name
+        if os.path.exists(REF):
+            rc2, out2, _ = run(REF, args, d2)
+            assert (rc2, out2) == (rc, out)
+            for name in want:
+                assert open(os.path.join(d, name), "rb").read() == open(os.path.join(d2, name), "rb").read(), name
