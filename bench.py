@@ -671,8 +671,10 @@ def measure_c4(ctx):
     if dom:
         cnt, ms = stats[dom]
         alg = per * fbytes + total_bytes
+        # the committed capture is of exactly this launch (configs[3]'s per-GPU share, default frame count and content)
+        traffic, traffic_src = traffic_of(dom) if not args.big_frames else (None, None)
         roof = {"bound": "hbm", "kernel": dom, "achieved": alg / (ms / cnt / 1e3) / 1e9, "peak": peak, "unit": "GB/s",
-                "frac": alg / (ms / cnt / 1e3) / 1e9 / peak, "traffic": None, "peak_source": peak_src,
+                "frac": alg / (ms / cnt / 1e3) / 1e9 / peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": alg, "avg_launch_ms": ms / cnt,
                 "kernel_ms_per_step": {k: v[1] for k, v in sorted(stats.items())}}
     sec = {"metric": f"Mpixels/s encode (JLS near={C4_NEAR}, RGB24: 3 samples per pixel)",
