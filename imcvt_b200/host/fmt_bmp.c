@@ -140,6 +140,12 @@ uint8_t *loadBMPImageFile(const char *p_filename, int *p_is_rgb, uint32_t *p_hei
     }
     *p_is_rgb = is_rgb;
     const size_t out_pp = is_rgb ? 3 : 1;
+    /* a BMP's sizes are 32-bit fields: pixel data of 4 GiB or more cannot be a BMP file (a damaged header would otherwise make
+     * this loader write tens of gigabytes of 0xFF; the reference does exactly that, fgetc by fgetc) */
+    if (((uint64_t)bytes_pp * width + 3) / 4 * 4 * (uint64_t)height > 0xFFFFFFFFull) {
+        free(file);
+        return NULL;
+    }
     uint8_t *img = (uint8_t *)malloc(out_pp * width * height);
     if (img == NULL) {
         free(file);
@@ -149,6 +155,15 @@ uint8_t *loadBMPImageFile(const char *p_filename, int *p_is_rgb, uint32_t *p_hei
     for (uint32_t y = 0; y < height; y++) {
         uint8_t *dst = img + out_pp * (size_t)(height - 1 - y) * width;
         b.pos = (size_t)offset + (size_t)y * row_padded;
+        if (b.pos >= b.n) {                     /* the whole row lies past the end of the file: every byte reads 0xFF */
+            if (bytes_pp > 1 || !is_rgb) {
+                memset(dst, bytes_pp > 1 ? 0xFF : pal[0xFF][0], out_pp * width);
+            } else {
+                for (uint32_t x = 0; x < width; x++, dst += 3)
+                    memcpy(dst, pal[0xFF], 3);
+            }
+            continue;
+        }
         for (uint32_t x = 0; x < width; x++) {
             if (bytes_pp > 1) {
                 dst[2] = get_byte(&b); dst[1] = get_byte(&b); dst[0] = get_byte(&b);

@@ -382,6 +382,10 @@ uint8_t *loadPNGImageFile(const char *p_filename, int *p_is_rgb, uint32_t *p_hei
         /* room for the inflated lines as the reference decoder sizes it (uPNG.c:1092): a stream that inflates to more is malformed */
         const size_t cap = (size_t)(uint32_t)(width * (height * (uint32_t)bits_pp + 7u)) / 8 + height;
         const size_t room = cap > raw_size ? cap : raw_size;
+        /* deflate expands at most 1032 : 1: a picture that the data cannot cover even then is a damaged header, not a picture (the
+         * reference would un-filter gigabytes of uninitialised memory) */
+        if (raw_size / 1032 > zn + 64)
+            goto fail;
         if (width == 0 || height == 0 || (raw = (uint8_t *)calloc(room + 1, 1)) == NULL || (pix = (uint8_t *)malloc(stride * height + 1)) == NULL)
             goto fail;
         if (zlib_inflate(z, zn, raw, cap) || unfilter(pix, raw, stride, height, bits_pp >= 8 ? bits_pp / 8 : 1))
