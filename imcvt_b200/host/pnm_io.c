@@ -27,9 +27,9 @@ static int next_number(FILE *fp, int *num)
             if (ch == EOF)
                 break;
         } else if (ch >= '0' && ch <= '9') {
-            int v = 0;
-            do { v = v * 10 + (ch - '0'); ch = fgetc(fp); } while (ch >= '0' && ch <= '9');
-            *num = v;
+            unsigned v = 0;                    /* wraps like the reference's int does in practice, without the undefined behaviour */
+            do { v = v * 10u + (unsigned)(ch - '0'); ch = fgetc(fp); } while (ch >= '0' && ch <= '9');
+            *num = (int)v;
             return ch;
         }
     }
