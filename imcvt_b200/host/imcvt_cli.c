@@ -587,11 +587,23 @@ static void convert(int i_file, int force_write)
     j->resolved = 1;
 }
 
-int main(int argc, char **argv)
+/* imcvt_serve.c: the resident engine (IMCVT_SERVE / IMCVT_SERVER) */
+int imcvtClientRun(const char *path, int argc, char **argv, int *rc);
+int imcvtServe(const char *path, int (*run)(int, char **));
+static int g_resident;                  /* this process serves requests: the engine and the staging arena outlive a command */
+
+/* one command line from argv to exit code (src/main.c:87-223) */
+static int run_command(int argc, char **argv)
 {
     int switches[128] = {0}, i, next_is_dst = 0, n_file = -1, force_write, n_success = 0, n_failed;
     const char *env;
     const double t_start = now_s();
+
+    memset(g_jobs, 0, sizeof(Job) * (size_t)(g_njobs > 0 ? g_njobs : 0));      /* a resident process runs many commands */
+    memset(g_phase, 0, sizeof g_phase);
+    g_njobs = g_printed = 0;
+    g_batch_limit = 256;
+    g_batch.n = 0;
 
     for (i = 1; i < argc; i++) {                                    /* src/main.c:87-132 */
         const char *arg = argv[i];
@@ -642,7 +654,7 @@ int main(int argc, char **argv)
     flush_batch();
     writer_join();
     print_resolved();
-    {
+    if (!g_resident) {
         const double t0 = now_s();
         arena_release();
         imcvtShutdown();
@@ -666,4 +678,26 @@ int main(int argc, char **argv)
         printf("\n");
     }
     return n_failed;
+}
+
+int main(int argc, char **argv)
+{
+    const char *env;
+    if ((env = getenv("IMCVT_SERVE")) != NULL && *env) {
+        /* resident engine: the CUDA context is created once, here, and every later command line finds it warm */
+        const char *dev = getenv("IMCVT_DEVICE");
+        int rc;
+        g_resident = 1;
+        imcvtInit(dev ? atoi(dev) : 0);                             /* without a device the server still converts between file formats */
+        rc = imcvtServe(env, run_command);
+        arena_release();
+        imcvtShutdown();
+        return rc;
+    }
+    if ((env = getenv("IMCVT_SERVER")) != NULL && *env) {
+        int rc;
+        if (imcvtClientRun(env, argc, argv, &rc) == 0)
+            return rc;                                              /* no server on that path: run here, as always */
+    }
+    return run_command(argc, argv);
 }

@@ -168,3 +168,43 @@ def test_bmp_qoi_png_inputs_are_staged_into_codec_batches():
             assert (rc2, out2) == (rc, out)
             for name in want:
                 assert open(os.path.join(d, name), "rb").read() == open(os.path.join(d2, name), "rb").read(), name
+
+
+def test_resident_engine_serves_codec_batches_warm():
+    """IMCVT_SERVE / IMCVT_SERVER (host/imcvt_serve.c): the same command lines executed by a resident process -- identical streams,
+    text and exit codes, and without the CUDA context creation a cold process pays (the wall-clock times are printed)."""
+    import signal
+    import time
+    with tempfile.TemporaryDirectory() as s, tempfile.TemporaryDirectory() as d, tempfile.TemporaryDirectory() as d2:
+        imgs = make_inputs(d)
+        make_inputs(d2)
+        sock = os.path.join(s, "sock")
+        srv = subprocess.Popen([CLI], env=dict(os.environ, IMCVT_SERVE=sock), cwd=s, stdout=subprocess.DEVNULL, stderr=subprocess.PIPE)
+        try:
+            for _ in range(1200):
+                if os.path.exists(sock):
+                    break
+                time.sleep(0.05)
+            assert os.path.exists(sock)
+            names = ["n0.pgm", "n1.pgm", "n2.pgm", "n3.pgm", "n4.pgm", "t0.pgm", "c0.ppm", "c1.ppm"]
+            args_j = ["-f", "-0"] + pairs(names, ".jls")
+            args_h = ["-f", "-4"] + pairs(["n0.pgm", "n1.pgm", "t0.pgm", "c0.ppm"], ".h265")
+            t = time.perf_counter(); cold = run(CLI, args_j, d2); t_cold = time.perf_counter() - t
+            walls = []
+            for rep in range(3):
+                t = time.perf_counter(); warm = run(CLI, args_j, d, {"IMCVT_SERVER": sock}); walls.append(time.perf_counter() - t)
+                assert warm[:2] == cold[:2]
+                for n in names:
+                    assert open(os.path.join(d, os.path.splitext(n)[0] + ".jls"), "rb").read() == oracle_jls(imgs[n], 0), n
+            h_cold = run(CLI, args_h, d2)
+            h_warm = run(CLI, args_h, d, {"IMCVT_SERVER": sock})
+            assert h_warm[:2] == h_cold[:2] and h_warm[0] == 0
+            for n in ("n0.pgm", "n1.pgm", "t0.pgm"):
+                assert open(os.path.join(d, os.path.splitext(n)[0] + ".h265"), "rb").read() == oracle_hevc(imgs[n], 4)[0], n
+            assert open(os.path.join(d, "c0.h265"), "rb").read() == oracle_hevc(imgs["c0.ppm"][:, :, 1], 4)[0]
+            print("resident engine: cold process %.3f s, through the server %s s" % (t_cold, ", ".join("%.3f" % w for w in walls)))
+            assert min(walls[1:]) < t_cold, (t_cold, walls)
+            assert srv.poll() is None
+        finally:
+            srv.send_signal(signal.SIGTERM)
+            assert srv.wait(timeout=120) == 0

@@ -40,6 +40,27 @@ def main():
             res[f"batch_cli_s_run{rep}"] = round(dt, 3)
             res[f"phases_run{rep}"] = p.stderr.decode().strip().splitlines()[-1]
         res["batch_cli_mpixel_s"] = round(n * h * w / dt / 1e6, 1)
+        # the same command line through a resident engine (IMCVT_SERVE / IMCVT_SERVER, host/imcvt_serve.c): no context creation
+        sock = os.path.join(d, "sock")
+        srv = subprocess.Popen([CLI], cwd=d, env=dict(os.environ, IMCVT_SERVE=sock), stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+        try:
+            for _ in range(1200):
+                if os.path.exists(sock):
+                    break
+                time.sleep(0.05)
+            cold = {f: open(os.path.join(d, f), "rb").read() for f in os.listdir(d) if f.endswith(suffix)}
+            for rep in range(3):                # the first request still pins the staging arena and sizes the workspaces
+                t0 = time.perf_counter()
+                p = subprocess.run([CLI] + args, cwd=d, capture_output=True, env=dict(os.environ, IMCVT_TIMING="1", IMCVT_SERVER=sock))
+                dt = time.perf_counter() - t0
+                assert p.returncode == 0, (p.stdout[-400:], p.stderr[-400:])
+                res[f"resident_cli_s_run{rep}"] = round(dt, 3)
+                res[f"resident_phases_run{rep}"] = p.stderr.decode().strip().splitlines()[-1]
+            res["resident_cli_mpixel_s"] = round(n * h * w / dt / 1e6, 1)
+            res["resident_same_bytes_as_cold"] = all(open(os.path.join(d, f), "rb").read() == b for f, b in cold.items())
+        finally:
+            srv.terminate()
+            srv.wait(timeout=120)
         if os.path.exists(REF):
             m = 4 if codec == "jls" else 1
             rargs = [switch, "-f"]
