@@ -117,6 +117,7 @@ static int g_njobs, g_printed, g_setting, g_batch_limit = 256;
 static Batch g_batch;
 /* devices a batch is sharded over: g_ndev < 0 = the engine's own device only (IMCVT_DEVICE), 0 = all visible, else the list */
 static int g_devs[64], g_ndev = 0;
+static int g_resident;                  /* this process serves requests (imcvt_serve.c): the engine and the arenas outlive a command */
 
 static void parse_devices(const char *env)
 {
@@ -285,7 +286,7 @@ static int dump(const char *name, const uint8_t *buf, size_t len)
 /* the batch whose streams are being written (at most one in flight) */
 typedef struct {
     pthread_t thread;
-    int active, n, encode_failed;
+    int active, n, encode_failed, out_kept;     /* out_kept: `out` is one of the resident process's stream arenas, not to be freed */
     int idx[MAX_FILES];
     uint8_t *out;
     size_t *len, bound;
@@ -328,11 +329,43 @@ static void writer_join(void)
             j->resolved = 1;
         }
     }
-    free(Wr->out);
+    if (!Wr->out_kept)
+        free(Wr->out);
     free(Wr->len);
     Wr->out = NULL; Wr->len = NULL;
     Wr->active = 0;
     print_resolved();
+}
+
+/* A resident process (imcvt_serve.c) keeps two PAGE-LOCKED stream arenas and alternates between them: the writer thread of batch k
+ * writes files out of one while batch k + 1 is encoded into the other.  With frames and slots both page-locked a gray NEAR = 0 batch is
+ * coded in place over PCIe (no staging copies); a one-shot process does not pin hundreds of megabytes of slots
+ * for a single use and takes pageable memory. */
+static struct { uint8_t *p; size_t cap; } g_out_arena[2];
+static int g_out_next;
+static uint8_t *stream_arena(size_t need)
+{
+    uint8_t *p;
+    const int k = g_out_next;
+    if (!g_resident)
+        return NULL;
+    if (g_out_arena[k].cap < need) {
+        if (g_out_arena[k].p) imcvtHostFree(g_out_arena[k].p);
+        g_out_arena[k].p = (uint8_t *)imcvtHostAlloc(need);
+        g_out_arena[k].cap = g_out_arena[k].p ? need : 0;
+    }
+    p = g_out_arena[k].p;
+    if (p) g_out_next = k ^ 1;
+    return p;
+}
+static void stream_arenas_release(void)
+{
+    int k;
+    for (k = 0; k < 2; k++) {
+        if (g_out_arena[k].p) imcvtHostFree(g_out_arena[k].p);
+        g_out_arena[k].p = NULL;
+        g_out_arena[k].cap = 0;
+    }
 }
 
 static void flush_batch(void)
@@ -341,11 +374,18 @@ static void flush_batch(void)
     Writer *Wr = &g_writer;
     size_t bound, *len;
     uint8_t *out;
-    int failed, i;
+    int failed, i, out_kept;
     if (B->n == 0)
         return;
     bound = B->kind == OUT_JLS ? imcvtJLSBound(B->is_rgb, B->h, B->w) : imcvtHEVCBound(B->h, B->w);
-    out = (uint8_t *)malloc((size_t)B->n * bound);
+    {
+        const double t0 = now_s();
+        out = stream_arena((size_t)B->n * bound);
+        g_phase[T_STAGE_ALLOC] += now_s() - t0;
+    }
+    out_kept = out != NULL;
+    if (out == NULL)
+        out = (uint8_t *)malloc((size_t)B->n * bound);
     len = (size_t *)calloc((size_t)B->n, sizeof *len);
     failed = (out == NULL || len == NULL);
     if (!failed) {
@@ -371,7 +411,7 @@ static void flush_batch(void)
     }
     /* the streams go to the writer thread; the arena is free for the next batch at once */
     writer_join();
-    Wr->n = B->n; Wr->out = out; Wr->len = len; Wr->bound = bound; Wr->encode_failed = failed;
+    Wr->n = B->n; Wr->out = out; Wr->len = len; Wr->bound = bound; Wr->encode_failed = failed; Wr->out_kept = out_kept;
     for (i = 0; i < B->n; i++) Wr->idx[i] = B->idx[i];
     B->n = 0;
     if (pthread_create(&Wr->thread, NULL, writer_main, Wr) == 0) {
@@ -590,7 +630,6 @@ static void convert(int i_file, int force_write)
 /* imcvt_serve.c: the resident engine (IMCVT_SERVE / IMCVT_SERVER) */
 int imcvtClientRun(const char *path, int argc, char **argv, int *rc);
 int imcvtServe(const char *path, int (*run)(int, char **));
-static int g_resident;                  /* this process serves requests: the engine and the staging arena outlive a command */
 
 /* one command line from argv to exit code (src/main.c:87-223) */
 static int run_command(int argc, char **argv)
@@ -691,6 +730,7 @@ int main(int argc, char **argv)
         imcvtInit(dev ? atoi(dev) : 0);                             /* without a device the server still converts between file formats */
         rc = imcvtServe(env, run_command);
         arena_release();
+        stream_arenas_release();
         imcvtShutdown();
         return rc;
     }
