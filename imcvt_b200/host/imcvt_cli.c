@@ -41,6 +41,8 @@
 #include <stdarg.h>
 #include <limits.h>
 #include <unistd.h>
+#include <sys/stat.h>
+#include <sys/types.h>
 #include <time.h>
 #include <pthread.h>
 #include "imcvt_b200.h"
@@ -286,7 +288,7 @@ static int dump(const char *name, const uint8_t *buf, size_t len)
 /* the batch whose streams are being written (at most one in flight) */
 typedef struct {
     pthread_t thread;
-    int active, n, encode_failed, out_kept;     /* out_kept: `out` is one of the resident process's stream arenas, not to be freed */
+    int active, n, next, encode_failed, out_kept;     /* out_kept: `out` is one of the resident process's stream arenas, not to be freed */
     int idx[MAX_FILES];
     uint8_t *out;
     size_t *len, bound;
@@ -295,15 +297,36 @@ typedef struct {
 } Writer;
 static Writer g_writer;
 
+/* the files of a batch are independent (no two pending jobs share a destination: convert() flushes first), so a large batch is
+ * written by a few threads that take files off one counter */
+static void *writer_worker(void *arg)
+{
+    Writer *Wr = (Writer *)arg;
+    for (;;) {
+        const int i = __atomic_fetch_add(&Wr->next, 1, __ATOMIC_RELAXED);
+        const Job *j;
+        if (i >= Wr->n)
+            break;
+        j = &g_jobs[Wr->idx[i]];
+        Wr->write_failed[i] = (unsigned char)(Wr->encode_failed || Wr->len[i] == 0 || dump(j->dst, Wr->out + (size_t)i * Wr->bound, Wr->len[i]));
+    }
+    return NULL;
+}
+
 static void *writer_main(void *arg)
 {
     Writer *Wr = (Writer *)arg;
     const double t0 = now_s();
-    int i;
-    for (i = 0; i < Wr->n; i++) {
-        const Job *j = &g_jobs[Wr->idx[i]];
-        Wr->write_failed[i] = (unsigned char)(Wr->encode_failed || Wr->len[i] == 0 || dump(j->dst, Wr->out + (size_t)i * Wr->bound, Wr->len[i]));
-    }
+    pthread_t helper[3];
+    int nh = 0, k;
+    Wr->next = 0;
+    if (Wr->n >= 8)
+        for (k = 0; k < 3; k++)
+            if (pthread_create(&helper[nh], NULL, writer_worker, Wr) == 0)
+                nh++;
+    writer_worker(Wr);
+    for (k = 0; k < nh; k++)
+        pthread_join(helper[k], NULL);
     Wr->seconds = now_s() - t0;
     return NULL;
 }
@@ -335,6 +358,74 @@ static void writer_join(void)
     Wr->out = NULL; Wr->len = NULL;
     Wr->active = 0;
     print_resolved();
+}
+
+/* Raw PGM / PPM pixels of codec jobs are not read where the file is looked at: the job only notes (file, offset, slot), and the
+ * notes of a batch are carried out together by a few threads (pread straight into the page-locked arena) -- the copy out of the page
+ * cache is what a staged file costs, and one thread moves ~6 GB/s.  A read is only postponed when the file is long enough for it to
+ * succeed, so the outcome of the job is known at once; and every postponed read is carried out before this process writes any file
+ * (read_pending_pixels() in front of the direct writers and of the batch's encode), so a later job can never change what an earlier
+ * one was going to read. */
+typedef struct { FILE *fp; long offset; size_t bytes; uint8_t *dst; int job; } PendingRead;
+static PendingRead g_reads[MAX_FILES];
+static int g_nreads, g_read_next;
+
+static void *read_worker(void *arg)
+{
+    (void)arg;
+    for (;;) {
+        const int i = __atomic_fetch_add(&g_read_next, 1, __ATOMIC_RELAXED);
+        PendingRead *r;
+        size_t done = 0;
+        if (i >= g_nreads)
+            break;
+        r = &g_reads[i];
+        while (done < r->bytes) {
+            const ssize_t k = pread(fileno(r->fp), r->dst + done, r->bytes - done, (off_t)r->offset + (off_t)done);
+            if (k <= 0)
+                break;
+            done += (size_t)k;
+        }
+        if (done != r->bytes)
+            memset(r->dst + done, 0, r->bytes - done);      /* the file shrank under us: the frame is coded as far as it was there */
+        fclose(r->fp);
+    }
+    return NULL;
+}
+
+static void read_pending_pixels(void)
+{
+    const double t0 = now_s();
+    pthread_t helper[3];
+    int nh = 0, k;
+    if (g_nreads == 0)
+        return;
+    g_read_next = 0;
+    if (g_nreads >= 4)
+        for (k = 0; k < 3; k++)
+            if (pthread_create(&helper[nh], NULL, read_worker, NULL) == 0)
+                nh++;
+    read_worker(NULL);
+    for (k = 0; k < nh; k++)
+        pthread_join(helper[k], NULL);
+    g_nreads = 0;
+    g_phase[T_READ] += now_s() - t0;
+}
+
+/* 1 = the pixels of this raw PNM file will be read later (fp is kept); 0 = read them now */
+static int postpone_read(FILE *fp, const ImcvtPNMHeader *hd, uint8_t *slot, int job)
+{
+    struct stat st;
+    long at;
+    if ((hd->type != 5 && hd->type != 6) || g_nreads >= MAX_FILES)
+        return 0;
+    at = ftell(fp);
+    if (at < 0 || fstat(fileno(fp), &st) != 0 || !S_ISREG(st.st_mode) || (uint64_t)st.st_size < (uint64_t)at + hd->bytes)
+        return 0;
+    g_reads[g_nreads].fp = fp; g_reads[g_nreads].offset = at; g_reads[g_nreads].bytes = hd->bytes;
+    g_reads[g_nreads].dst = slot; g_reads[g_nreads].job = job;
+    g_nreads++;
+    return 1;
 }
 
 /* A resident process (imcvt_serve.c) keeps two PAGE-LOCKED stream arenas and alternates between them: the writer thread of batch k
@@ -375,6 +466,7 @@ static void flush_batch(void)
     size_t bound, *len;
     uint8_t *out;
     int failed, i, out_kept;
+    read_pending_pixels();
     if (B->n == 0)
         return;
     bound = B->kind == OUT_JLS ? imcvtJLSBound(B->is_rgb, B->h, B->w) : imcvtHEVCBound(B->h, B->w);
@@ -534,24 +626,25 @@ static void convert(int i_file, int force_write)
     int is_rgb = 0, failed = 0, i, staged = 0;
     FILE *fp;
 
-    /* sequential semantics: nothing this file reads or guards may still be owed by the writer thread or the pending batch */
-    if (g_writer.active) {
-        char *cs = canon_path(j->src);
-        for (i = 0; i < g_writer.n; i++) {
-            const char *pd = g_jobs[g_writer.idx[i]].canon_dst;
-            if (pd && ((cs && !strcmp(cs, pd)) || (j->canon_dst && !strcmp(j->canon_dst, pd)))) {
-                writer_join();
-                break;
-            }
-        }
-        free(cs);
-    }
+    /* sequential semantics: nothing this file reads or guards may still be owed by the pending batch or by the writer thread.  The
+     * batch first: flushing it hands its files to the writer, and the writer check below then waits for them. */
     if (g_batch.n) {
         char *cs = canon_path(j->src);
         for (i = 0; i < g_batch.n; i++) {
             const char *pd = g_jobs[g_batch.idx[i]].canon_dst;
             if (pd && ((cs && !strcmp(cs, pd)) || (j->canon_dst && !strcmp(j->canon_dst, pd)))) {
                 flush_batch();
+                break;
+            }
+        }
+        free(cs);
+    }
+    if (g_writer.active) {
+        char *cs = canon_path(j->src);
+        for (i = 0; i < g_writer.n; i++) {
+            const char *pd = g_jobs[g_writer.idx[i]].canon_dst;
+            if (pd && ((cs && !strcmp(cs, pd)) || (j->canon_dst && !strcmp(j->canon_dst, pd)))) {
+                writer_join();
                 break;
             }
         }
@@ -571,7 +664,11 @@ static void convert(int i_file, int force_write)
                 double t0;
                 slot = batch_slot(kind, hd.is_rgb, hd.height, hd.width);
                 t0 = now_s();
-                if (slot && !imcvtPNMReadPixels(fp, &hd, slot)) {
+                if (slot && postpone_read(fp, &hd, slot, i_file)) {
+                    fp = NULL;                                      /* closed by the read */
+                    staged = 1;
+                    is_rgb = hd.is_rgb; h = hd.height; w = hd.width;
+                } else if (slot && !imcvtPNMReadPixels(fp, &hd, slot)) {
                     g_phase[T_READ] += now_s() - t0;
                     staged = 1;
                     is_rgb = hd.is_rgb; h = hd.height; w = hd.width;
@@ -585,7 +682,8 @@ static void convert(int i_file, int force_write)
                 }
             }
         }
-        fclose(fp);
+        if (fp)
+            fclose(fp);
     }
     if (!staged && img == NULL)
         img = load_other_formats(j, j->src, &is_rgb, &h, &w);
@@ -613,6 +711,7 @@ static void convert(int i_file, int force_write)
         g_batch.idx[g_batch.n++] = i_file;          /* resolved by flush_batch() */
         return;
     }
+    read_pending_pixels();                          /* nothing is written while an earlier job still has pixels to read */
     capture_begin();
     switch (kind) {
     case OUT_PNM: failed = writePNMImageFile(j->dst, img, is_rgb, h, w); break;
