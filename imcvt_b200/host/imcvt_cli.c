@@ -41,7 +41,9 @@
 #include <stdarg.h>
 #include <limits.h>
 #include <unistd.h>
+#include <errno.h>
 #include <sys/stat.h>
+#include <sys/resource.h>
 #include <sys/types.h>
 #include <time.h>
 #include <pthread.h>
@@ -425,6 +427,18 @@ static int postpone_read(FILE *fp, const ImcvtPNMHeader *hd, uint8_t *slot, int 
     g_reads[g_nreads].fp = fp; g_reads[g_nreads].offset = at; g_reads[g_nreads].bytes = hd->bytes;
     g_reads[g_nreads].dst = slot; g_reads[g_nreads].job = job;
     g_nreads++;
+    {
+        /* each note holds a file open: carried out in lots that stay far below RLIMIT_NOFILE */
+        static int lot;
+        if (lot == 0) {
+            struct rlimit rl;
+            lot = 32;
+            if (getrlimit(RLIMIT_NOFILE, &rl) == 0 && rl.rlim_cur != RLIM_INFINITY && rl.rlim_cur < 24 + 2 * 32)
+                lot = rl.rlim_cur > 26 ? (int)(rl.rlim_cur - 24) / 2 : 1;
+        }
+        if (g_nreads >= lot)
+            read_pending_pixels();
+    }
     return 1;
 }
 
@@ -656,7 +670,12 @@ static void convert(int i_file, int force_write)
     if (!force_write && file_exists(j->dst)) { fail(j, "%s already exist", j->dst); return; }
 
     /* load: PNM first (src/main.c:183); pixels of a codec job land in the staging arena, not in a buffer of their own */
-    if ((fp = fopen(j->src, "rb")) != NULL) {
+    fp = fopen(j->src, "rb");
+    if (fp == NULL && (errno == EMFILE || errno == ENFILE) && g_nreads) {
+        read_pending_pixels();                      /* out of descriptors: the postponed reads hold some */
+        fp = fopen(j->src, "rb");
+    }
+    if (fp != NULL) {
         ImcvtPNMHeader hd;
         if (!imcvtPNMReadHeader(fp, &hd)) {
             const int jls_dims_bad = hd.width > 32767 || hd.height > 32767;                 /* src/imageio_jls.c:436 */

@@ -167,3 +167,27 @@ def test_resident_process_reuses_its_arenas_across_requests_of_different_shapes(
         finally:
             srv.send_signal(signal.SIGTERM)
             assert srv.wait(timeout=60) == 0
+
+
+def test_many_small_files_in_one_batch_and_a_tight_descriptor_limit(cli):
+    """300 files in one batch (postponed reads are carried out in lots), once under RLIMIT_NOFILE = 40: every file still gets its
+    own pixels and nothing fails for want of descriptors."""
+    import resource
+    rng = np.random.default_rng(13)
+    with tempfile.TemporaryDirectory() as d:
+        imgs = {"s%03d.pgm" % i: rng.integers(0, 256, (8, 8), dtype=np.uint8) for i in range(300)}
+        args = ["-f"]
+        for n, img in imgs.items():
+            write_pnm(os.path.join(d, n), img)
+            args += [n, "-o", n + ".jls"]
+        for limit in (None, 40):
+            for n in imgs:
+                if os.path.exists(os.path.join(d, n + ".jls")):
+                    os.remove(os.path.join(d, n + ".jls"))
+            e = {k: v for k, v in os.environ.items() if not k.startswith("IMCVT_")}
+            e["IMCVT_BATCH"] = "999"
+            pre = (lambda: resource.setrlimit(resource.RLIMIT_NOFILE, (limit, limit))) if limit else None
+            p = subprocess.run([cli] + args, cwd=d, capture_output=True, timeout=600, env=e, preexec_fn=pre)
+            assert p.returncode == 0, (limit, p.stdout[-300:], p.stderr[-300:])
+            for n, img in imgs.items():
+                expect(os.path.join(d, n + ".jls"), "J", 0, img)
