@@ -230,6 +230,16 @@ int imcvtServe(const char *path, int (*run)(int, char **))
     struct sigaction act;
     const int fd = open_socket(path, &sa);
     if (fd < 0) { fprintf(stderr, "ImCvt_b200: bad socket path %s\n", path); return 1; }
+    {
+        /* a socket file may be left over from a server that died -- or belong to one that is alive: ask before taking the path */
+        struct sockaddr_un probe_sa;
+        const int probe = open_socket(path, &probe_sa);
+        if (probe >= 0) {
+            const int alive = connect(probe, (struct sockaddr *)&probe_sa, sizeof probe_sa) == 0;
+            close(probe);
+            if (alive) { fprintf(stderr, "ImCvt_b200: a server is already listening on %s\n", path); close(fd); return 1; }
+        }
+    }
     unlink(path);
     {
         const mode_t old = umask(0077);                 /* the socket is the owner's */

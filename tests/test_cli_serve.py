@@ -31,11 +31,19 @@ class Server:
         env = dict(os.environ, IMCVT_SERVE=self.path)
         env.pop("IMCVT_SERVER", None)
         self.p = subprocess.Popen([CLI], env=env, cwd=d, stdout=subprocess.DEVNULL, stderr=self.err)
+        up = False
         for _ in range(600):                       # engine start: a CUDA context on a GPU box, an error message here
-            if os.path.exists(self.path):
+            c = socket.socket(socket.AF_UNIX, socket.SOCK_STREAM)
+            try:
+                c.connect(self.path)               # (a connection that says nothing: the server drops it)
+                up = True
+            except OSError:
+                time.sleep(0.05)
+            finally:
+                c.close()
+            if up:
                 break
-            time.sleep(0.05)
-        assert os.path.exists(self.path), "server did not come up"
+        assert up, "server did not come up"
 
     def stop(self):
         self.p.send_signal(signal.SIGTERM)
@@ -125,3 +133,27 @@ def test_no_server_on_the_path_means_an_ordinary_run_and_the_server_survives_bad
             assert rc == 0 and srv.p.poll() is None
         finally:
             srv.stop()
+
+
+def test_a_second_server_does_not_take_a_live_servers_path_but_takes_a_stale_one():
+    with tempfile.TemporaryDirectory() as s, tempfile.TemporaryDirectory() as d:
+        stage(d)
+        srv = Server(s)
+        try:
+            env = dict(os.environ, IMCVT_SERVE=srv.path)
+            env.pop("IMCVT_SERVER", None)
+            second = subprocess.run([CLI], env=env, cwd=s, capture_output=True, timeout=60)
+            assert second.returncode == 1 and b"already listening" in second.stderr
+            rc, out, _ = run(["-f", "P5.pnm", "-o", "a.pgm"], d, srv.path)          # the first server is untouched
+            assert rc == 0 and srv.p.poll() is None
+        finally:
+            srv.p.kill()                                                            # dies without removing its socket file
+            srv.p.wait(timeout=60)
+            srv.err.close()
+        assert os.path.exists(srv.path)
+        third = Server(s)                                                           # the stale file is replaced
+        try:
+            rc, out, _ = run(["-f", "P6.pnm", "-o", "b.ppm"], d, third.path)
+            assert rc == 0 and b"(1/1)  P6.pnm -> b.ppm" in out
+        finally:
+            assert third.stop() == 0
